@@ -1,0 +1,172 @@
+// Shared device helpers for the cropnerf_b200 kernels (sm_100a).
+//
+// Bit-exactness notes: everything that decides a hash index is written with explicit
+// round-to-nearest intrinsics (__fmul_rn/__fadd_rn/__fdiv_rn) so nvcc cannot contract it into FMAs; the
+// torch reference evaluates each elementwise op as a separately rounded fp32 operation.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cropnerf_b200.h"
+
+#define CNB_HASH_P1 2654435761u
+#define CNB_HASH_P2 805459861u
+
+void cnb_set_error(const char* fmt, ...);
+int cnb_check_launch(const char* what);
+
+#define CNB_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      cnb_set_error(__VA_ARGS__);   \
+      return CNB_ERR_ARG;           \
+    }                               \
+  } while (0)
+
+static inline int cnb_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// positions
+// ---------------------------------------------------------------------------------------------------------
+
+// Frustums.get_positions (nerfstudio rays.py): o + d * (start + end) / 2, each op rounded separately.
+__device__ __forceinline__ float cnb_axis_position(float o, float d, float start, float end) {
+  return __fadd_rn(o, __fmul_rn(__fmul_rn(d, __fadd_rn(start, end)), 0.5f));
+}
+
+// fruit_field.py:171-180: contraction / aabb normalisation, strict (0,1) selector, masked positions -> 0.
+// Returns the selector.
+__device__ __forceinline__ bool cnb_warp_position(const cnb_warp& w, float& x, float& y, float& z) {
+  if (w.mode == CNB_WARP_CONTRACT_LINF) {
+    // SceneContraction(order=inf): where(mag < 1, x, (2 - 1/mag) * (x / mag))
+    float mag = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    if (!(mag < 1.0f)) {
+      float s = __fsub_rn(2.0f, __fdiv_rn(1.0f, mag));
+      x = __fmul_rn(s, __fdiv_rn(x, mag));
+      y = __fmul_rn(s, __fdiv_rn(y, mag));
+      z = __fmul_rn(s, __fdiv_rn(z, mag));
+    }
+    x = __fmul_rn(__fadd_rn(x, 2.0f), 0.25f);
+    y = __fmul_rn(__fadd_rn(y, 2.0f), 0.25f);
+    z = __fmul_rn(__fadd_rn(z, 2.0f), 0.25f);
+  } else {
+    x = __fdiv_rn(__fsub_rn(x, w.aabb_min[0]), __fsub_rn(w.aabb_max[0], w.aabb_min[0]));
+    y = __fdiv_rn(__fsub_rn(y, w.aabb_min[1]), __fsub_rn(w.aabb_max[1], w.aabb_min[1]));
+    z = __fdiv_rn(__fsub_rn(z, w.aabb_min[2]), __fsub_rn(w.aabb_max[2], w.aabb_min[2]));
+  }
+  bool sel = (x > 0.0f) && (x < 1.0f) && (y > 0.0f) && (y < 1.0f) && (z > 0.0f) && (z < 1.0f);
+  if (!sel) { x = 0.0f; y = 0.0f; z = 0.0f; }
+  return sel;
+}
+
+// normalised + masked position of sample i (= r*S + s) of a cnb_samples description
+__device__ __forceinline__ bool cnb_sample_position(const cnb_samples& sm, const cnb_warp& w, int64_t r, int32_t s,
+                                                    float& x, float& y, float& z) {
+  const float st = __ldg(sm.starts + r * sm.row_stride + s);
+  const float en = __ldg(sm.ends + r * sm.row_stride + s);
+  x = cnb_axis_position(__ldg(sm.origins + 3 * r + 0), __ldg(sm.directions + 3 * r + 0), st, en);
+  y = cnb_axis_position(__ldg(sm.origins + 3 * r + 1), __ldg(sm.directions + 3 * r + 1), st, en);
+  z = cnb_axis_position(__ldg(sm.origins + 3 * r + 2), __ldg(sm.directions + 3 * r + 2), st, en);
+  return cnb_warp_position(w, x, y, z);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// hash grid (nerfstudio encodings.py HashEncoding.pytorch_fwd / hash_fn)
+// ---------------------------------------------------------------------------------------------------------
+
+struct CnbCell {
+  uint32_t cx, cy, cz, fx, fy, fz;  // ceil / floor integer coordinates (>= 0)
+  float ox, oy, oz;                 // scaled - floor
+};
+
+__device__ __forceinline__ CnbCell cnb_cell(float x, float y, float z, float scale) {
+  CnbCell c;
+  const float sx = __fmul_rn(x, scale), sy = __fmul_rn(y, scale), sz = __fmul_rn(z, scale);
+  const float flx = floorf(sx), fly = floorf(sy), flz = floorf(sz);
+  c.cx = (uint32_t)(int32_t)ceilf(sx); c.cy = (uint32_t)(int32_t)ceilf(sy); c.cz = (uint32_t)(int32_t)ceilf(sz);
+  c.fx = (uint32_t)(int32_t)flx; c.fy = (uint32_t)(int32_t)fly; c.fz = (uint32_t)(int32_t)flz;
+  c.ox = __fsub_rn(sx, flx); c.oy = __fsub_rn(sy, fly); c.oz = __fsub_rn(sz, flz);
+  return c;
+}
+
+// int64 (x*1 ^ y*2654435761 ^ z*805459861) % 2^T of the reference == uint32 wrap-around arithmetic for
+// non-negative coordinates and power-of-two tables (verified there on 1.6 M triples).
+__device__ __forceinline__ uint32_t cnb_hash(uint32_t x, uint32_t y, uint32_t z, uint32_t mask) {
+  return (x ^ (y * CNB_HASH_P1) ^ (z * CNB_HASH_P2)) & mask;
+}
+
+// the 8 corner rows in the reference's h0..h7 order: ccc cfc ffc fcc ccf cff fff fcf
+__device__ __forceinline__ void cnb_corner_rows(const CnbCell& c, uint32_t mask, uint32_t level_offset, uint32_t (&h)[8]) {
+  const uint32_t xc = c.cx, xf = c.fx;
+  const uint32_t yc = c.cy * CNB_HASH_P1, yf = c.fy * CNB_HASH_P1;
+  const uint32_t zc = c.cz * CNB_HASH_P2, zf = c.fz * CNB_HASH_P2;
+  h[0] = ((xc ^ yc ^ zc) & mask) + level_offset;
+  h[1] = ((xc ^ yf ^ zc) & mask) + level_offset;
+  h[2] = ((xf ^ yf ^ zc) & mask) + level_offset;
+  h[3] = ((xf ^ yc ^ zc) & mask) + level_offset;
+  h[4] = ((xc ^ yc ^ zf) & mask) + level_offset;
+  h[5] = ((xc ^ yf ^ zf) & mask) + level_offset;
+  h[6] = ((xf ^ yf ^ zf) & mask) + level_offset;
+  h[7] = ((xf ^ yc ^ zf) & mask) + level_offset;
+}
+
+// trilinear blend in the reference's exact operation order (separately rounded ops)
+__device__ __forceinline__ float cnb_blend(const float (&f)[8], float ox, float oy, float oz) {
+  const float mx = __fsub_rn(1.0f, ox), my = __fsub_rn(1.0f, oy), mz = __fsub_rn(1.0f, oz);
+  const float f03 = __fadd_rn(__fmul_rn(f[0], ox), __fmul_rn(f[3], mx));
+  const float f12 = __fadd_rn(__fmul_rn(f[1], ox), __fmul_rn(f[2], mx));
+  const float f56 = __fadd_rn(__fmul_rn(f[5], ox), __fmul_rn(f[6], mx));
+  const float f47 = __fadd_rn(__fmul_rn(f[4], ox), __fmul_rn(f[7], mx));
+  const float f0312 = __fadd_rn(__fmul_rn(f03, oy), __fmul_rn(f12, my));
+  const float f4756 = __fadd_rn(__fmul_rn(f47, oy), __fmul_rn(f56, my));
+  return __fadd_rn(__fmul_rn(f0312, oz), __fmul_rn(f4756, mz));
+}
+
+// corner weights matching cnb_blend (d out / d f[i])
+__device__ __forceinline__ void cnb_corner_weights(float ox, float oy, float oz, float (&w)[8]) {
+  const float mx = 1.0f - ox, my = 1.0f - oy, mz = 1.0f - oz;
+  w[0] = ox * oy * oz;  w[3] = mx * oy * oz;
+  w[1] = ox * my * oz;  w[2] = mx * my * oz;
+  w[4] = ox * oy * mz;  w[7] = mx * oy * mz;
+  w[5] = ox * my * mz;  w[6] = mx * my * mz;
+}
+
+__device__ __forceinline__ float2 cnb_ldg2(const float* table, uint32_t row) {
+  return __ldg(reinterpret_cast<const float2*>(table) + row);
+}
+
+// vector reduction into the gradient table: one red.global.add.v2.f32 (sm_90+) per corner
+__device__ __forceinline__ void cnb_red2(float* table, uint32_t row, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(reinterpret_cast<float2*>(table) + row), "f"(a), "f"(b) : "memory");
+}
+
+// trunc_exp (nerfstudio activations.py): exp forward, g*exp(clamp(x,-15,15)) backward
+__device__ __forceinline__ float cnb_trunc_exp_grad(float x) { return expf(fminf(fmaxf(x, -15.0f), 15.0f)); }
+
+__device__ __forceinline__ float cnb_nan_to_num(float v) {
+  if (isnan(v)) return 0.0f;
+  if (isinf(v)) return v > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+  return v;
+}
+
+// spacing functions (nerfstudio ray_samplers.py UniformLinDispPiecewiseSampler / UniformSampler)
+__device__ __forceinline__ float cnb_spacing_fn(int kind, float x) {
+  if (kind == CNB_SPACING_LINDISP_PIECEWISE) return x < 1.0f ? __fmul_rn(x, 0.5f) : __fsub_rn(1.0f, __fdiv_rn(1.0f, __fmul_rn(2.0f, x)));
+  return x;
+}
+__device__ __forceinline__ float cnb_spacing_inv(int kind, float x) {
+  if (kind == CNB_SPACING_LINDISP_PIECEWISE) return x < 0.5f ? __fmul_rn(2.0f, x) : __fdiv_rn(1.0f, __fsub_rn(2.0f, __fmul_rn(2.0f, x)));
+  return x;
+}
+// spacing_to_euclidean_fn(x) = inv(x * s_far + (1 - x) * s_near)
+__device__ __forceinline__ float cnb_spacing_to_euclid(int kind, float x, float s_near, float s_far) {
+  return cnb_spacing_inv(kind, __fadd_rn(__fmul_rn(x, s_far), __fmul_rn(__fsub_rn(1.0f, x), s_near)));
+}

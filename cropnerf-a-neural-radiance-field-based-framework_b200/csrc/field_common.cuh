@@ -1,0 +1,37 @@
+// Pieces shared by the fp32 and mixed-precision FruitField kernels.
+#pragma once
+#include "cnb_common.cuh"
+
+// components_from_spherical_harmonics(degree=3) on the *shifted* direction (d+1)/2, exactly as the torch path of
+// nerfstudio's SHEncoding evaluates it for fruit_field.py:116-119,244-246.
+__device__ __forceinline__ void cnb_sh16(float dx, float dy, float dz, float (&c)[16]) {
+  const float x = __fmul_rn(__fadd_rn(dx, 1.0f), 0.5f);
+  const float y = __fmul_rn(__fadd_rn(dy, 1.0f), 0.5f);
+  const float z = __fmul_rn(__fadd_rn(dz, 1.0f), 0.5f);
+  const float xx = x * x, yy = y * y, zz = z * z;
+  c[0] = 0.28209479177387814f;
+  c[1] = 0.4886025119029199f * y;
+  c[2] = 0.4886025119029199f * z;
+  c[3] = 0.4886025119029199f * x;
+  c[4] = 1.0925484305920792f * x * y;
+  c[5] = 1.0925484305920792f * y * z;
+  c[6] = 0.9461746957575601f * zz - 0.31539156525251999f;
+  c[7] = 1.0925484305920792f * x * z;
+  c[8] = 0.5462742152960396f * (xx - yy);
+  c[9] = 0.5900435899266435f * y * (3.0f * xx - yy);
+  c[10] = 2.890611442640554f * x * y * z;
+  c[11] = 0.4570457994644658f * y * (5.0f * zz - 1.0f);
+  c[12] = 0.3731763325901154f * z * (5.0f * zz - 3.0f);
+  c[13] = 0.4570457994644658f * x * (5.0f * zz - 1.0f);
+  c[14] = 1.445305721320277f * z * (xx - yy);
+  c[15] = 0.5900435899266435f * x * (xx - 3.0f * yy);
+}
+
+int cnb_field_check(const cnb_field* f, const cnb_samples* s, bool bwd);
+
+// mixed-precision (tensor-core) implementation, field_mixed.cu
+int cnb_field_mixed_fwd(const cnb_field* f, const cnb_samples* s, float* density, float* geo, float* rgb, float* sem, float* positions_out,
+                        cudaStream_t stream);
+int cnb_field_mixed_bwd(const cnb_field* f, const cnb_samples* s, const float* d_density, const float* d_rgb, const float* d_sem,
+                        cudaStream_t stream);
+bool cnb_field_mixed_supported(const cnb_field* f);

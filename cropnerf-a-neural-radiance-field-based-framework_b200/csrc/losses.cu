@@ -1,0 +1,211 @@
+// Losses of the training step (row a16 of SURVEY.md section 8) and the optimiser (row f2).
+//  - cnb_interlevel_fwd/bwd : nerfstudio losses.py interlevel_loss / lossfun_outer / outer (fruit_nerf.py:610)
+//  - cnb_distortion_fwd     : nerfstudio losses.py distortion_loss / lossfun_distortion (fruit_nerf.py:643, metric)
+//  - cnb_pixel_losses       : MSELoss(image, rgb) + w * BCEWithLogitsLoss(sem, fruit_mask) (fruit_nerf.py:601-608)
+//  - cnb_adam_step          : torch.optim.Adam(lr, eps=1e-15) update (fruit_nerf_config.py:45-60)
+#include "cnb_common.cuh"
+#include "warp_scan.cuh"
+
+namespace {
+
+constexpr int WARPS = 4;
+constexpr float EPS7 = 1e-7f;
+
+// smem per warp: cp [Sp+1], cy1 [Sp+1]
+__global__ void __launch_bounds__(WARPS * 32) k_interlevel(const float* __restrict__ c, const float* __restrict__ w, const float* __restrict__ cp,
+                                                           const float* __restrict__ wp, int64_t R, int Sc, int Sp, float grad_scale,
+                                                           float* __restrict__ loss_out, float* __restrict__ d_wp) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* cps = smem + (size_t)warp * 3 * (Sp + 1);
+  float* cy1 = cps + (Sp + 1);
+  float* dcy = cy1 + (Sp + 1);
+  const float norm = 1.0f / (float)((double)R * (double)Sc);
+  float loss_acc = 0.0f;
+  for (int64_t r = blockIdx.x * (int64_t)WARPS + warp; r < R; r += (int64_t)gridDim.x * WARPS) {
+    for (int j = lane; j <= Sp; j += 32) { cps[j] = __ldg(cp + r * (Sp + 1) + j); dcy[j] = 0.0f; }
+    for (int j = lane; j < Sp; j += 32) cy1[1 + j] = __ldg(wp + r * Sp + j);
+    if (lane == 0) cy1[0] = 0.0f;
+    __syncwarp();
+    cnb_warp_cumsum(cy1 + 1, cy1 + 1, Sp, lane);
+    __syncwarp();
+    for (int i = lane; i < Sc; i += 32) {
+      const float t0s = __ldg(c + r * (Sc + 1) + i), t0e = __ldg(c + r * (Sc + 1) + i + 1);
+      int lo = cnb_search_right(cps, Sp, t0s) - 1;        // over t1_starts = cp[:-1]
+      lo = min(max(lo, 0), Sp - 1);
+      int hi = cnb_search_right(cps + 1, Sp, t0e);        // over t1_ends = cp[1:]
+      hi = min(max(hi, 0), Sp - 1);
+      const float w_outer = __fsub_rn(cy1[hi + 1], cy1[lo]);
+      const float wi = __ldg(w + r * Sc + i);
+      const float diff = fmaxf(__fsub_rn(wi, w_outer), 0.0f);
+      const float denom = __fadd_rn(wi, EPS7);
+      loss_acc += diff * diff / denom;
+      if (d_wp != nullptr && diff > 0.0f) {
+        const float g = -2.0f * diff / denom * norm * grad_scale;  // dL / d w_outer
+        atomicAdd(dcy + hi + 1, g);
+        atomicAdd(dcy + lo, -g);
+      }
+    }
+    if (d_wp != nullptr) {
+      __syncwarp();
+      // cy1[m] = sum_{k<m} wp_k  =>  d wp_k = sum_{m>k} dcy[m]
+      cnb_warp_suffix_excl(dcy, dcy, Sp + 1, lane);
+      __syncwarp();
+      for (int k = lane; k < Sp; k += 32) d_wp[r * Sp + k] = dcy[k];
+    }
+    __syncwarp();
+  }
+  if (loss_out != nullptr) {
+    loss_acc = cnb_warp_sum(loss_acc);
+    if (lane == 0 && loss_acc != 0.0f) atomicAdd(loss_out, loss_acc * norm);
+  }
+}
+
+// lossfun_distortion: sum_i w_i sum_j w_j |ut_i - ut_j| + sum_i w_i^2 (t_{i+1}-t_i)/3 ; mean over rays
+__global__ void __launch_bounds__(WARPS * 32) k_distortion(const float* __restrict__ c, const float* __restrict__ w, int64_t R, int S,
+                                                           float* __restrict__ loss_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ut = smem + (size_t)warp * 2 * S;
+  float* ws = ut + S;
+  float acc = 0.0f;
+  for (int64_t r = blockIdx.x * (int64_t)WARPS + warp; r < R; r += (int64_t)gridDim.x * WARPS) {
+    float intra = 0.0f;
+    for (int j = lane; j < S; j += 32) {
+      const float t0 = __ldg(c + r * (S + 1) + j), t1 = __ldg(c + r * (S + 1) + j + 1);
+      const float wj = __ldg(w + r * S + j);
+      ut[j] = (t1 + t0) * 0.5f;
+      ws[j] = wj;
+      intra += wj * wj * (t1 - t0);
+    }
+    __syncwarp();
+    float inter = 0.0f;
+    for (int i = lane; i < S; i += 32) {
+      float inner = 0.0f;
+      const float ui = ut[i];
+      for (int j = 0; j < S; ++j) inner = fmaf(ws[j], fabsf(ui - ut[j]), inner);
+      inter = fmaf(ws[i], inner, inter);
+    }
+    acc += inter + intra / 3.0f;
+    __syncwarp();
+  }
+  acc = cnb_warp_sum(acc);
+  if (lane == 0 && acc != 0.0f) atomicAdd(loss_out, acc / (float)R);
+}
+
+__global__ void __launch_bounds__(256) k_pixel_losses(const float* __restrict__ rgb, const float* __restrict__ sem, const float* __restrict__ image,
+                                                      const float* __restrict__ mask, int64_t R, float sem_weight, float grad_scale,
+                                                      float* __restrict__ losses_out, float* __restrict__ d_rgb, float* __restrict__ d_sem) {
+  float mse = 0.0f, bce = 0.0f;
+  const float inv3r = 1.0f / (3.0f * (float)R), invr = 1.0f / (float)R;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float d = __ldg(rgb + 3 * r + ch) - __ldg(image + 3 * r + ch);
+      mse = fmaf(d, d, mse);
+      if (d_rgb) d_rgb[3 * r + ch] = 2.0f * d * inv3r * grad_scale;
+    }
+    if (sem != nullptr) {
+      // BCEWithLogits: max(x,0) - x*y + log1p(exp(-|x|)) ; d/dx = sigmoid(x) - y
+      const float x = __ldg(sem + r), y = __ldg(mask + r);
+      bce += fmaxf(x, 0.0f) - x * y + log1pf(expf(-fabsf(x)));
+      if (d_sem) d_sem[r] = (1.0f / (1.0f + expf(-x)) - y) * invr * sem_weight * grad_scale;
+    }
+  }
+  mse = cnb_warp_sum(mse);
+  bce = cnb_warp_sum(bce);
+  if ((threadIdx.x & 31) == 0 && losses_out != nullptr) {
+    atomicAdd(losses_out, mse * inv3r);
+    if (sem != nullptr) atomicAdd(losses_out + 1, bce * invr * sem_weight);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                              int64_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_scale) {
+  const float step_size = lr / bc1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * inv_scale;
+    const float mi = m[i] + (1.0f - b1) * (gi - m[i]);  // torch: exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / denom);
+  }
+}
+
+int ray_grid(int64_t R) {
+  int64_t blocks = (R + WARPS - 1) / WARPS;
+  const int64_t cap = (int64_t)cnb_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+int launch_interlevel(const float* c, const float* w, const float* cp, const float* wp, int64_t R, int Sc, int Sp, float grad_scale, float* loss_out,
+                      float* d_wp, cudaStream_t stream) {
+  CNB_REQUIRE(R >= 0 && Sc >= 1 && Sp >= 1 && Sp <= 4096, "interlevel: bad sizes R=%lld Sc=%d Sp=%d", (long long)R, Sc, Sp);
+  if (R == 0) return CNB_OK;
+  CNB_REQUIRE(c && w && cp && wp, "interlevel: null pointer");
+  const size_t smem = sizeof(float) * WARPS * 3 * (size_t)(Sp + 1);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(k_interlevel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return cnb_check_launch("interlevel attr");
+    configured = smem;
+  }
+  k_interlevel<<<ray_grid(R), WARPS * 32, smem, stream>>>(c, w, cp, wp, R, Sc, Sp, grad_scale, loss_out, d_wp);
+  return cnb_check_launch("interlevel");
+}
+
+}  // namespace
+
+extern "C" int cnb_interlevel_fwd(const float* c, const float* w, const float* cp, const float* wp, int64_t R, int32_t Sc, int32_t Sp,
+                                  float* loss_out, cnb_stream_t stream) {
+  CNB_REQUIRE(loss_out != nullptr, "interlevel_fwd: null loss_out");
+  return launch_interlevel(c, w, cp, wp, R, Sc, Sp, 0.0f, loss_out, nullptr, stream);
+}
+
+extern "C" int cnb_interlevel_bwd(const float* c, const float* w, const float* cp, const float* wp, int64_t R, int32_t Sc, int32_t Sp,
+                                  float grad_scale, float* d_wp, cnb_stream_t stream) {
+  CNB_REQUIRE(d_wp != nullptr, "interlevel_bwd: null d_wp");
+  return launch_interlevel(c, w, cp, wp, R, Sc, Sp, grad_scale, nullptr, d_wp, stream);
+}
+
+extern "C" int cnb_distortion_fwd(const float* c, const float* w, int64_t R, int32_t S, float* loss_out, cnb_stream_t stream) {
+  CNB_REQUIRE(R >= 0 && S >= 1 && S <= 4096, "distortion: bad sizes R=%lld S=%d", (long long)R, S);
+  if (R == 0) return CNB_OK;
+  CNB_REQUIRE(c && w && loss_out, "distortion: null pointer");
+  const size_t smem = sizeof(float) * WARPS * 2 * (size_t)S;
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(k_distortion, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return cnb_check_launch("distortion attr");
+    configured = smem;
+  }
+  k_distortion<<<ray_grid(R), WARPS * 32, smem, stream>>>(c, w, R, S, loss_out);
+  return cnb_check_launch("distortion");
+}
+
+extern "C" int cnb_pixel_losses(const float* rgb, const float* sem, const float* image, const float* mask, int64_t R, float sem_weight,
+                                float grad_scale, float* losses_out, float* d_rgb, float* d_sem, cnb_stream_t stream) {
+  CNB_REQUIRE(R >= 0, "pixel_losses: bad R");
+  if (R == 0) return CNB_OK;
+  CNB_REQUIRE(rgb && image && (sem == nullptr || mask != nullptr), "pixel_losses: null pointer");
+  int64_t blocks = (R + 255) / 256;
+  const int64_t cap = (int64_t)cnb_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  k_pixel_losses<<<(int)blocks, 256, 0, stream>>>(rgb, sem, image, mask, R, sem_weight, grad_scale, losses_out, d_rgb, d_sem);
+  return cnb_check_launch("pixel_losses");
+}
+
+extern "C" int cnb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                             float eps, int32_t step, float inv_grad_scale, cnb_stream_t stream) {
+  CNB_REQUIRE(n >= 0 && step >= 1, "adam: bad n/step");
+  if (n == 0) return CNB_OK;
+  CNB_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam: null pointer");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)cnb_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  k_adam<<<(int)blocks, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), inv_grad_scale);
+  return cnb_check_launch("adam");
+}

@@ -1,0 +1,207 @@
+/*
+ * cropnerf_b200.h -- C ABI of the B200-native per-ray rendering hot path of FruitNeRF / CropNeRF.
+ *
+ * The reference (robotic-vision-lab/CropNeRF, /root/reference) is pure Python on top of nerfstudio 1.1.3; it
+ * has no FFI of its own.  The entry points below are what a binding for this path would call: one per
+ * nerfstudio primitive the reference imports (cited per function, paths relative to
+ * /root/reference/crop_nerf/fruit_nerf unless prefixed "nerfstudio/").  INTEGRATION.md shows the ctypes
+ * stubs a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain pointers + sizes only; every pointer is DEVICE memory owned by the caller unless stated; the
+ *    library never allocates persistent memory and never frees caller memory;
+ *  - all work is enqueued on `stream` (no hidden syncs, graph-capturable); stateless and re-entrant;
+ *  - return 0 on success, negative cnb_status otherwise; cnb_last_error() gives the thread-local message;
+ *  - tensors are contiguous row-major fp32 unless stated; "[R,S]" sample arrays may carry a row stride so
+ *    that bin-edge arrays [R,S+1] can be passed as starts (=edges) and ends (=edges+1) without copies;
+ *  - gradient pointers inside descriptor structs are ACCUMULATED into (caller zeroes them per step).
+ *  - there is no CPU fallback: without a CUDA device every compute entry returns CNB_ERR_CUDA.
+ */
+#ifndef CROPNERF_B200_H
+#define CROPNERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNB_VERSION 100
+#define CNB_MAX_LEVELS 16
+#define CNB_MAX_LAYERS 4
+#define CNB_MAX_WIDTH 64
+
+typedef struct CUstream_st* cnb_stream_t;
+
+typedef enum cnb_status {
+  CNB_OK = 0,
+  CNB_ERR_ARG = -1,         /* bad argument / unsupported configuration */
+  CNB_ERR_CUDA = -2,        /* CUDA runtime error (message in cnb_last_error) */
+  CNB_ERR_UNSUPPORTED = -3  /* configuration outside the compiled specialisations */
+} cnb_status;
+
+enum { CNB_PREC_FP32 = 0, CNB_PREC_MIXED = 1 };          /* MLP arithmetic: fp32 FFMA / fp16 tensor cores, fp32 accumulate */
+enum { CNB_ACT_NONE = 0, CNB_ACT_RELU = 1, CNB_ACT_SIGMOID = 2 };
+enum { CNB_WARP_AABB = 0, CNB_WARP_CONTRACT_LINF = 1 }; /* position normalisation (fruit_field.py:171-176) */
+enum { CNB_SPACING_UNIFORM = 0, CNB_SPACING_LINDISP_PIECEWISE = 1 };
+enum { CNB_BG_NONE = 0, CNB_BG_LAST_SAMPLE = 1, CNB_BG_CONSTANT = 2 };
+enum { CNB_APP_PER_CAMERA = 0, CNB_APP_MEAN = 1, CNB_APP_ZERO = 2 }; /* fruit_field.py:251-261, 219-221 */
+
+/* Multiresolution hash grid == nerfstudio/field_components/encodings.py HashEncoding (ctor: fruit_field.py:125-132;
+ * proposal grids: fruit_nerf.py:124-141).  table row index = hash(level corner) + level * 2^log2_hashmap_size. */
+typedef struct cnb_grid {
+  const float* table;        /* [num_levels * 2^log2_hashmap_size, 2] */
+  float* d_table;            /* same shape, accumulated by *_bwd; may be NULL for forward-only use */
+  int32_t num_levels;        /* 1..CNB_MAX_LEVELS */
+  int32_t log2_hashmap_size; /* <= 24 */
+  float scalings[CNB_MAX_LEVELS]; /* floor(min_res * growth^level) evaluated in fp32 by the host (top field level = 2047) */
+} cnb_grid;
+
+/* nn.Linear stack == nerfstudio/field_components/mlp.py MLP torch path (fruit_field.py:133-141,146-154,159-167);
+ * ReLU between layers, out_activation after the last.  W[l] is [dims[l+1], dims[l]] row-major (nn.Linear.weight). */
+typedef struct cnb_mlp {
+  int32_t num_layers;                 /* 1..CNB_MAX_LAYERS */
+  int32_t dims[CNB_MAX_LAYERS + 1];   /* in, hidden..., out ; each <= CNB_MAX_WIDTH */
+  int32_t out_activation;             /* CNB_ACT_* */
+  int32_t _pad;
+  const float* W[CNB_MAX_LAYERS];
+  const float* b[CNB_MAX_LAYERS];
+  float* dW[CNB_MAX_LAYERS];          /* accumulated by *_bwd; NULL entries are skipped */
+  float* db[CNB_MAX_LAYERS];
+} cnb_mlp;
+
+/* world position -> unit cube (fruit_field.py:171-180; nerfstudio/fields/density_fields.py get_density) */
+typedef struct cnb_warp {
+  int32_t mode;        /* CNB_WARP_* ; CONTRACT_LINF: x' = (contract(x) + 2) / 4 ; AABB: (x - min) / (max - min) */
+  float aabb_min[3];
+  float aabb_max[3];
+} cnb_warp;
+
+/* Ray samples == nerfstudio/cameras/rays.py RaySamples/Frustums restricted to what the field reads.
+ * position(r,s) = origins[r] + directions[r] * (starts[r,s] + ends[r,s]) / 2 . */
+typedef struct cnb_samples {
+  const float* origins;          /* [R,3] */
+  const float* directions;       /* [R,3] */
+  const float* starts;           /* element (r,s) at starts[r*row_stride + s] */
+  const float* ends;             /* same addressing */
+  const int32_t* camera_indices; /* [R] or NULL */
+  int64_t num_rays;
+  int64_t row_stride;
+  int32_t samples_per_ray;
+  int32_t _pad;
+} cnb_samples;
+
+/* HashMLPDensityField (nerfstudio/fields/density_fields.py; built fruit_nerf.py:118-142) */
+typedef struct cnb_density_field {
+  cnb_grid grid;
+  cnb_mlp mlp;               /* 2L -> hidden -> 1 (hidden <= 64), or a single Linear when use_linear */
+  cnb_warp warp;
+  float average_init_density;
+} cnb_density_field;
+
+/* FruitField (fruit_field.py:44-302) */
+typedef struct cnb_field {
+  cnb_grid grid;
+  cnb_mlp base;              /* 2L -> 64 -> 1+geo     (fruit_field.py:133-141) */
+  cnb_mlp sem;               /* geo -> 64 -> 64        (fruit_field.py:146-154) */
+  cnb_mlp sem_head;          /* 64 -> 1                (components/field_heads.py:29-40, fruit_field.py:155-157) */
+  cnb_mlp rgb;               /* 16+geo+app -> 64 -> 64 -> 3, sigmoid (fruit_field.py:159-167) */
+  const float* embedding;    /* [num_images, appearance_dim] (fruit_field.py:106) */
+  float* d_embedding;        /* accumulated (per-camera mode only); may be NULL */
+  const float* mean_embedding; /* [appearance_dim], required for CNB_APP_MEAN */
+  cnb_warp warp;
+  int32_t num_images;
+  int32_t appearance_dim;    /* 32 */
+  int32_t geo_feat_dim;      /* 15 */
+  int32_t appearance_mode;   /* CNB_APP_* */
+  int32_t pass_semantic_gradients; /* fruit_field.py:264-266 */
+  int32_t precision;         /* CNB_PREC_* */
+} cnb_field;
+
+int cnb_version(void);
+const char* cnb_last_error(void);
+/* number of CUDA devices visible, or a negative status; never throws */
+int cnb_device_count(void);
+
+/* ---- a2: HashEncoding.pytorch_fwd / its autograd (nerfstudio encodings.py) -------------------------------- */
+/* positions [n,3] in [0,1]; out [n, 2*L]; indices (optional) [n, L, 8] int32 table rows in h0..h7 order */
+int cnb_hashgrid_fwd(const cnb_grid* g, const float* positions, int64_t n, float* out, int32_t* indices, cnb_stream_t stream);
+/* accumulates g->d_table from d_out [n, 2*L] */
+int cnb_hashgrid_bwd(const cnb_grid* g, const float* positions, const float* d_out, int64_t n, cnb_stream_t stream);
+
+/* ---- a3/a4: MLP / FieldHead ------------------------------------------------------------------------------- */
+/* floats of `hidden` needed per sample when training (sum of hidden widths) */
+int64_t cnb_mlp_hidden_floats(const cnb_mlp* m);
+/* x: element (i,k) at x[i*x_stride+k]; y [n, out] dense; hidden (optional, for bwd) [sum_l n*width_l] */
+int cnb_mlp_fwd(const cnb_mlp* m, const float* x, int64_t x_stride, int64_t n, float* y, float* hidden, cnb_stream_t stream);
+/* y is the forward output (needed for sigmoid'); dx optional, element (i,k) at dx[i*dx_stride+k] (overwritten) */
+int cnb_mlp_bwd(const cnb_mlp* m, const float* x, int64_t x_stride, const float* hidden, const float* y, const float* dy,
+                int64_t n, float* dx, int64_t dx_stride, cnb_stream_t stream);
+
+/* ---- a7: HashMLPDensityField.get_density / density_fn ------------------------------------------------------ */
+/* density [R*S]; positions_out (optional) [R*S,3] normalised+masked positions */
+int cnb_density_field_fwd(const cnb_density_field* f, const cnb_samples* s, float* density, float* positions_out, cnb_stream_t stream);
+/* recomputes the forward per sample; accumulates grid.d_table, mlp.dW/db */
+int cnb_density_field_bwd(const cnb_density_field* f, const cnb_samples* s, const float* d_density, cnb_stream_t stream);
+
+/* ---- a1/a5/a6: FruitField.forward (get_density + get_outputs / get_inference_outputs) ---------------------- */
+/* floats of `ctx` scratch per call (activations kept for backward + backward scratch); 0 => ctx may be NULL */
+int64_t cnb_field_ctx_floats(const cnb_field* f, int64_t n, int32_t training);
+/* outputs (each optional except density): density [N], geo [N,1+geo] (col 0 = pre-activation density),
+ * rgb [N,3], sem [N], positions_out [N,3] (= FruitField._sample_locations) */
+int cnb_field_fwd(const cnb_field* f, const cnb_samples* s, float* density, float* geo, float* rgb, float* sem,
+                  float* positions_out, float* ctx, int32_t training, cnb_stream_t stream);
+/* d_geo (optional) [N,1+geo] external gradient on the geo embedding; accumulates all parameter gradients */
+int cnb_field_bwd(const cnb_field* f, const cnb_samples* s, const float* d_density, const float* d_rgb, const float* d_sem,
+                  const float* d_geo, float* ctx, cnb_stream_t stream);
+
+/* ---- a8/a9: samplers (nerfstudio ray_samplers.py; components/ray_samplers.py:54-104) ----------------------- */
+/* SpacedSampler: lin_bins = torch.linspace(0,1,S+1) supplied by the host (bit-exact u); t_rand NULL (eval) or
+ * [R*rand_stride] with rand_stride 1 (single_jitter) or S+1.  Outputs spacing/euclid bin edges [R,S+1]. */
+int cnb_sample_spaced(const float* nears, const float* fars, const float* lin_bins, const float* t_rand, int32_t rand_stride,
+                      int32_t spacing, int64_t R, int32_t S, float* spacing_bins, float* euclid_bins, cnb_stream_t stream);
+/* PDFSampler(include_original=False): weights [R,Sp] (raised to `anneal` in-kernel), prev spacing bins [R,Sp+1];
+ * u_base = torch.linspace(0, 1-1/(S+1), S+1) from the host; rand NULL (eval: + 1/(2(S+1))) or [R*rand_stride];
+ * inds (optional) [R,S+1] int32 = searchsorted(cdf,u,right). */
+int cnb_sample_pdf(const float* weights, float anneal, const float* prev_spacing_bins, const float* nears, const float* fars,
+                   int32_t spacing, const float* u_base, const float* rand, int32_t rand_stride, int64_t R, int32_t Sp, int32_t S,
+                   float histogram_padding, float eps, float* spacing_bins, float* euclid_bins, int32_t* inds, cnb_stream_t stream);
+
+/* ---- a10: RaySamples.get_weights -------------------------------------------------------------------------- */
+int cnb_weights_fwd(const float* density, const float* starts, const float* ends, int64_t row_stride, int64_t R, int32_t S,
+                    float* weights, cnb_stream_t stream);
+int cnb_weights_bwd(const float* density, const float* starts, const float* ends, int64_t row_stride, int64_t R, int32_t S,
+                    const float* d_weights, float* d_density, cnb_stream_t stream);
+
+/* ---- a11-a14: RGB / Depth(median) / Accumulation / Semantic renderers -------------------------------------- */
+/* Any of rgb/sem inputs and outputs may be NULL (that renderer is skipped).  eval_mode: nan_to_num(rgb) in, clamp out.
+ * median_index (optional) [R] int32. */
+int cnb_render_fwd(const float* weights, const float* rgb, const float* sem, const float* starts, const float* ends,
+                   int64_t row_stride, int64_t R, int32_t S, int32_t bg_mode, const float* bg_color, int32_t eval_mode,
+                   float* rgb_out, float* depth_out, float* acc_out, float* sem_out, int32_t* median_index, cnb_stream_t stream);
+/* d_weights gets d(rgb,acc[,sem if sem_weight_grad]) ; d_rgb [R,S,3]; d_sem [R,S]; NULL outputs skipped */
+int cnb_render_bwd(const float* weights, const float* rgb, const float* sem, int64_t R, int32_t S, int32_t bg_mode,
+                   const float* bg_color, const float* d_rgb_out, const float* d_acc_out, const float* d_sem_out,
+                   int32_t sem_weight_grad, float* d_weights, float* d_rgb, float* d_sem, cnb_stream_t stream);
+
+/* ---- a16: losses (nerfstudio losses.py interlevel_loss / distortion_loss; fruit_nerf.py:601-615,639-645) --- */
+/* loss_out[0] += sum_r mean-normalised lossfun_outer ; c [R,Sc+1], w [R,Sc] (final level, detached); cp/wp proposal */
+int cnb_interlevel_fwd(const float* c, const float* w, const float* cp, const float* wp, int64_t R, int32_t Sc, int32_t Sp,
+                       float* loss_out, cnb_stream_t stream);
+/* d_wp [R,Sp] overwritten with grad_scale * dLoss/dwp */
+int cnb_interlevel_bwd(const float* c, const float* w, const float* cp, const float* wp, int64_t R, int32_t Sc, int32_t Sp,
+                       float grad_scale, float* d_wp, cnb_stream_t stream);
+int cnb_distortion_fwd(const float* c, const float* w, int64_t R, int32_t S, float* loss_out, cnb_stream_t stream);
+/* MSE(rgb) + weight*BCEWithLogits(sem) forward and gradients in one pass; losses_out[0]+=mse, [1]+=bce */
+int cnb_pixel_losses(const float* rgb, const float* sem, const float* image, const float* mask, int64_t R, float sem_weight,
+                     float grad_scale, float* losses_out, float* d_rgb, float* d_sem, cnb_stream_t stream);
+
+/* ---- f2: optimiser (torch.optim.Adam semantics; fruit_nerf_config.py:45-60) -------------------------------- */
+int cnb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int32_t step, float inv_grad_scale, cnb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROPNERF_B200_H */
