@@ -1,0 +1,232 @@
+"""ctypes binding of ``libcropnerf_b200.so`` (C ABI declared in ``include/cropnerf_b200.h``).
+
+The product path has no CPU fallback: :func:`lib` raises if the shared library is missing, and every
+compute wrapper raises ``RuntimeError`` with ``cnb_last_error()`` when the library reports a failure
+(e.g. no CUDA device).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcropnerf_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "cropnerf_b200.h")
+
+MAX_LEVELS = 16
+MAX_LAYERS = 4
+MAX_WIDTH = 64
+
+PREC_FP32, PREC_MIXED = 0, 1
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+WARP_AABB, WARP_CONTRACT_LINF = 0, 1
+SPACING_UNIFORM, SPACING_LINDISP_PIECEWISE = 0, 1
+BG_NONE, BG_LAST_SAMPLE, BG_CONSTANT = 0, 1, 2
+APP_PER_CAMERA, APP_MEAN, APP_ZERO = 0, 1, 2
+
+
+class Grid(C.Structure):
+    _fields_ = [
+        ("table", C.c_void_p),
+        ("d_table", C.c_void_p),
+        ("num_levels", C.c_int32),
+        ("log2_hashmap_size", C.c_int32),
+        ("scalings", C.c_float * MAX_LEVELS),
+    ]
+
+
+class Mlp(C.Structure):
+    _fields_ = [
+        ("num_layers", C.c_int32),
+        ("dims", C.c_int32 * (MAX_LAYERS + 1)),
+        ("out_activation", C.c_int32),
+        ("_pad", C.c_int32),
+        ("W", C.c_void_p * MAX_LAYERS),
+        ("b", C.c_void_p * MAX_LAYERS),
+        ("dW", C.c_void_p * MAX_LAYERS),
+        ("db", C.c_void_p * MAX_LAYERS),
+    ]
+
+
+class Warp(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3)]
+
+
+class Samples(C.Structure):
+    _fields_ = [
+        ("origins", C.c_void_p),
+        ("directions", C.c_void_p),
+        ("starts", C.c_void_p),
+        ("ends", C.c_void_p),
+        ("camera_indices", C.c_void_p),
+        ("num_rays", C.c_int64),
+        ("row_stride", C.c_int64),
+        ("samples_per_ray", C.c_int32),
+        ("_pad", C.c_int32),
+    ]
+
+
+class DensityField(C.Structure):
+    _fields_ = [("grid", Grid), ("mlp", Mlp), ("warp", Warp), ("average_init_density", C.c_float)]
+
+
+class Field(C.Structure):
+    _fields_ = [
+        ("grid", Grid),
+        ("base", Mlp),
+        ("sem", Mlp),
+        ("sem_head", Mlp),
+        ("rgb", Mlp),
+        ("embedding", C.c_void_p),
+        ("d_embedding", C.c_void_p),
+        ("mean_embedding", C.c_void_p),
+        ("warp", Warp),
+        ("num_images", C.c_int32),
+        ("appearance_dim", C.c_int32),
+        ("geo_feat_dim", C.c_int32),
+        ("appearance_mode", C.c_int32),
+        ("pass_semantic_gradients", C.c_int32),
+        ("precision", C.c_int32),
+    ]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_I32 = C.c_int32
+_F = C.c_float
+
+# name -> (restype, argtypes); mirrors include/cropnerf_b200.h one to one (checked by tests/test_abi.py)
+SIGNATURES = {
+    "cnb_version": (C.c_int, []),
+    "cnb_last_error": (C.c_char_p, []),
+    "cnb_device_count": (C.c_int, []),
+    "cnb_hashgrid_fwd": (C.c_int, [C.POINTER(Grid), _P, _I64, _P, _P, _P]),
+    "cnb_hashgrid_bwd": (C.c_int, [C.POINTER(Grid), _P, _P, _I64, _P]),
+    "cnb_mlp_hidden_floats": (_I64, [C.POINTER(Mlp)]),
+    "cnb_mlp_fwd": (C.c_int, [C.POINTER(Mlp), _P, _I64, _I64, _P, _P, _P]),
+    "cnb_mlp_bwd": (C.c_int, [C.POINTER(Mlp), _P, _I64, _P, _P, _P, _I64, _P, _I64, _P]),
+    "cnb_density_field_fwd": (C.c_int, [C.POINTER(DensityField), C.POINTER(Samples), _P, _P, _P]),
+    "cnb_density_field_bwd": (C.c_int, [C.POINTER(DensityField), C.POINTER(Samples), _P, _P]),
+    "cnb_field_ctx_floats": (_I64, [C.POINTER(Field), _I64, _I32]),
+    "cnb_field_fwd": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), _P, _P, _P, _P, _P, _P, _I32, _P]),
+    "cnb_field_bwd": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), _P, _P, _P, _P, _P, _P]),
+    "cnb_sample_spaced": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I64, _I32, _P, _P, _P]),
+    "cnb_sample_pdf": (C.c_int, [_P, _F, _P, _P, _P, _I32, _P, _P, _I32, _I64, _I32, _I32, _F, _F, _P, _P, _P, _P]),
+    "cnb_weights_fwd": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P]),
+    "cnb_weights_bwd": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P, _P]),
+    "cnb_render_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, C.POINTER(_F), _I32, _P, _P, _P, _P, _P, _P]),
+    "cnb_render_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, C.POINTER(_F), _P, _P, _P, _I32, _P, _P, _P, _P]),
+    "cnb_interlevel_fwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P]),
+    "cnb_interlevel_bwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P]),
+    "cnb_distortion_fwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
+    "cnb_pixel_losses": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _P, _P, _P, _P]),
+    "cnb_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA sources in-tree for sm_100a (``csrc/Makefile``) and return the library path."""
+    res = subprocess.run(["make", "-C", CSRC, "-j", str(os.cpu_count() or 4)], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libcropnerf_b200.so failed:\n" + res.stdout[-4000:] + res.stderr[-4000:])
+    if verbose:
+        print(res.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load (once) the shared library; fail loudly if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C cropnerf-a-neural-radiance-field-based-framework_b200/csrc`). "
+                "cropnerf_b200 has no CPU / PyTorch fallback for its kernels."
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return lib().cnb_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"cropnerf_b200: {what} failed (status {rc}): {last_error()}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a contiguous CUDA tensor (None passes NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("cropnerf_b200 kernels need CUDA tensors; there is no CPU fallback")
+    if not t.is_contiguous():
+        raise RuntimeError("cropnerf_b200: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def make_grid(table: torch.Tensor, d_table: Optional[torch.Tensor], num_levels: int, log2_hashmap_size: int, scalings: Sequence[float]) -> Grid:
+    g = Grid()
+    g.table = ptr(table)
+    g.d_table = ptr(d_table)
+    g.num_levels = int(num_levels)
+    g.log2_hashmap_size = int(log2_hashmap_size)
+    for i in range(MAX_LEVELS):
+        g.scalings[i] = float(scalings[i]) if i < len(scalings) else 0.0
+    return g
+
+
+def make_mlp(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], out_activation: int,
+             d_weights: Optional[Sequence[Optional[torch.Tensor]]] = None, d_biases: Optional[Sequence[Optional[torch.Tensor]]] = None) -> Mlp:
+    m = Mlp()
+    n = len(weights)
+    if not 1 <= n <= MAX_LAYERS:
+        raise ValueError(f"MLP with {n} layers unsupported (1..{MAX_LAYERS})")
+    m.num_layers = n
+    m.out_activation = out_activation
+    m.dims[0] = weights[0].shape[1]
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        if w.shape[0] > MAX_WIDTH or w.shape[1] > MAX_WIDTH:
+            raise ValueError(f"MLP layer {i} of shape {tuple(w.shape)} exceeds the compiled maximum width {MAX_WIDTH}")
+        m.dims[i + 1] = w.shape[0]
+        m.W[i] = ptr(w)
+        m.b[i] = ptr(b)
+        m.dW[i] = ptr(d_weights[i]) if d_weights is not None else None
+        m.db[i] = ptr(d_biases[i]) if d_biases is not None else None
+    return m
+
+
+def make_warp(contraction: bool, aabb) -> Warp:
+    """``aabb``: host-side nested list [[xmin,ymin,zmin],[xmax,ymax,zmax]] (no device sync on the call path)."""
+    w = Warp()
+    w.mode = WARP_CONTRACT_LINF if contraction else WARP_AABB
+    box = [[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]] if aabb is None else (aabb.detach().cpu().tolist() if isinstance(aabb, torch.Tensor) else aabb)
+    for i in range(3):
+        w.aabb_min[i] = box[0][i]
+        w.aabb_max[i] = box[1][i]
+    return w

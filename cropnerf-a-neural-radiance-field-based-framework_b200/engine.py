@@ -1,0 +1,124 @@
+"""Training-step driver: what nerfstudio's ``Trainer.train_iteration`` does around the hot path for the ``fruit_nerf``
+method (``fruit_nerf_config.py:29-65``; call stack SURVEY.md section 3.1), on flat parameter / gradient buffers.
+
+* parameters of each param group (``proposal_networks`` / ``fields`` / ``camera_opt``, fruit_nerf.py:191-196) are
+  re-homed as views into one contiguous fp32 buffer per group, gradients likewise -- one fused Adam launch and one
+  NCCL all-reduce per group instead of one per tensor;
+* data parallelism = the reference's only strategy (DDP, ``fruit_pipeline.py:119-121``): every rank renders its own
+  rays, gradients are averaged with ``torch.distributed.all_reduce`` over the flat buffers (NCCL over NVLink on the
+  GPU box, gloo in the CPU tests of the host logic);
+* Adam(lr 1e-2, eps 1e-15) + ExponentialDecay(lr_final 1e-4, max_steps 200k) = ``fruit_nerf_config.py:45-60``.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor, nn
+
+from . import ops
+
+
+@dataclass
+class OptimizerSpec:
+    lr: float = 1e-2
+    eps: float = 1e-15
+    betas: tuple = (0.9, 0.999)
+    lr_final: Optional[float] = 1e-4
+    max_steps: int = 200000
+
+
+DEFAULT_OPTIMIZERS = {
+    "proposal_networks": OptimizerSpec(),
+    "fields": OptimizerSpec(),
+    "camera_opt": OptimizerSpec(lr=1e-3, lr_final=1e-4, max_steps=5000),
+}
+
+
+def exponential_decay_lr(step: int, spec: OptimizerSpec) -> float:
+    """nerfstudio ExponentialDecayScheduler (no warm-up): log-linear interpolation lr -> lr_final over max_steps."""
+    if spec.lr_final is None:
+        return spec.lr
+    t = min(max(step / spec.max_steps, 0.0), 1.0)
+    return math.exp(math.log(spec.lr) * (1 - t) + math.log(spec.lr_final) * t)
+
+
+class FlatGroup:
+    """One param group flattened: ``param.data`` and ``param.grad`` become views of two contiguous buffers."""
+
+    def __init__(self, params: List[nn.Parameter]):
+        uniq, seen = [], set()
+        for p in params:
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        self.params = uniq
+        n = sum(p.numel() for p in uniq)
+        dev = uniq[0].device
+        self.flat = torch.empty((n,), device=dev, dtype=torch.float32)
+        self.grad = torch.zeros((n,), device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        off = 0
+        for p in uniq:
+            k = p.numel()
+            self.flat[off : off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off : off + k].view(p.shape)
+            p.grad = self.grad[off : off + k].view(p.shape)
+            off += k
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+
+
+class Trainer:
+    """Minimal trainer for FruitModel: callbacks, forward, losses, backward, gradient all-reduce, Adam."""
+
+    def __init__(self, model, optimizers: Optional[Dict[str, OptimizerSpec]] = None, world_size: int = 1):
+        self.model = model
+        self.world_size = world_size
+        self.optimizers = optimizers or DEFAULT_OPTIMIZERS
+        self.groups: Dict[str, FlatGroup] = {name: FlatGroup(params) for name, params in model.get_param_groups().items() if len(params) > 0}
+        self.callbacks = model.get_training_callbacks()
+        self.opt_step = 0
+
+    def _run_callbacks(self, where: str, step: int) -> None:
+        for cb in self.callbacks:
+            if where in cb.where_to_run and step % cb.update_every_num_iters == 0:
+                cb.func(step)
+
+    def all_reduce_gradients(self) -> None:
+        """DDP semantics (fruit_pipeline.py:119-121): mean of the per-rank gradients.  The 1/world_size factor is
+        folded into the Adam kernel (``inv_grad_scale``)."""
+        if self.world_size > 1:
+            for g in self.groups.values():
+                dist.all_reduce(g.grad, op=dist.ReduceOp.SUM)
+
+    def optimizer_step(self, step: int) -> None:
+        self.opt_step += 1
+        for name, g in self.groups.items():
+            spec = self.optimizers[name]
+            lr = exponential_decay_lr(step, spec)
+            ops.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, lr, self.opt_step, spec.betas[0], spec.betas[1], spec.eps,
+                          inv_grad_scale=1.0 / self.world_size)
+
+    def train_iteration(self, step: int, ray_bundle, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        self.model.train()
+        self._run_callbacks("BEFORE_TRAIN_ITERATION", step)
+        for g in self.groups.values():
+            g.zero_grad()
+        outputs = self.model(ray_bundle)
+        metrics = self.model.get_metrics_dict(outputs, batch)
+        loss_dict = self.model.get_loss_dict(outputs, batch, metrics)
+        loss = sum(loss_dict.values())
+        loss.backward()
+        self.all_reduce_gradients()
+        self.optimizer_step(step)
+        self._run_callbacks("AFTER_TRAIN_ITERATION", step)
+        out = dict(loss_dict)
+        out.update(metrics)
+        out["loss"] = loss.detach()
+        return out

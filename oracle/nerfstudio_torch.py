@@ -131,6 +131,11 @@ class RayBundle:
         )
         if camera_indices is not None:
             camera_indices = camera_indices.expand(*bin_starts.shape[:-2], S, 1)
+        # TensorDataclass.__post_init__ broadcasts every field to the common batch shape (eval-mode bins are [1,S+1])
+        if spacing_starts is not None:
+            spacing_starts = spacing_starts.expand(bin_starts.shape)
+        if spacing_ends is not None:
+            spacing_ends = spacing_ends.expand(bin_ends.shape)
         return RaySamples(
             frustums=frustums,
             camera_indices=camera_indices,

@@ -1,0 +1,175 @@
+"""CPU tests: the C-ABI library loads and exports every symbol ``include/cropnerf_b200.h`` declares, ctypes mirrors of
+the descriptor structs have the C compiler's sizes, host-side logic (ray layout, flat param groups, schedules, the
+2-rank gradient all-reduce over gloo), and the product refuses to run without CUDA (no fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+import torch
+
+from helpers import ROOT
+
+from cropnerf_b200 import _lib as L
+from cropnerf_b200 import engine, ops, synthetic
+from cropnerf_b200.fruit_nerf import FruitModel, FruitNerfModelConfig
+from cropnerf_b200.rays import RayBundle, ray_layout
+
+HEADER = os.path.join(ROOT, "include", "cropnerf_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cnb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.lib()
+    names = _declared_symbols()
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert set(names) == set(L.SIGNATURES), set(names) ^ set(L.SIGNATURES)
+    assert lib.cnb_version() == 100
+
+
+def test_struct_sizes_match_c_compiler():
+    prog = r"""
+#include <stdio.h>
+#include "cropnerf_b200.h"
+int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(cnb_grid), sizeof(cnb_mlp), sizeof(cnb_warp), sizeof(cnb_samples), sizeof(cnb_density_field), sizeof(cnb_field)); return 0; }
+"""
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "s.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        sizes = [int(v) for v in subprocess.check_output([exe]).split()]
+    mine = [C.sizeof(t) for t in (L.Grid, L.Mlp, L.Warp, L.Samples, L.DensityField, L.Field)]
+    assert sizes == mine
+
+
+def test_no_cuda_means_loud_failure_not_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    assert L.lib().cnb_device_count() < 0
+    assert "cudaGetDeviceCount" in L.last_error()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.ray_weights(torch.rand(4, 8, 1), torch.rand(4, 8, 1), torch.rand(4, 8, 1))
+    model = FruitModel(FruitNerfModelConfig(log2_hashmap_size=8), num_train_data=4)
+    rays = synthetic.make_rays(8, num_cameras=4)
+    rb = RayBundle(rays["origins"], rays["directions"], rays["pixel_area"], rays["camera_indices"])
+    with pytest.raises(RuntimeError):
+        model(rb)
+
+
+def test_argument_validation_reports_through_last_error():
+    lib = L.lib()
+    g = L.Grid()
+    g.num_levels = 99
+    rc = lib.cnb_hashgrid_fwd(C.byref(g), None, 0, None, None, None)
+    assert rc == -1 and "hashgrid" in L.last_error()
+    m = L.Mlp()
+    m.num_layers = 9
+    assert lib.cnb_mlp_fwd(C.byref(m), None, 0, 0, None, None, None) == -1
+    assert lib.cnb_sample_spaced(None, None, None, None, 0, 0, 5, 0, None, None, None) == -1
+
+
+def test_ray_layout_uses_edge_views_without_copies():
+    R, S = 7, 5
+    rays = synthetic.make_rays(R, num_cameras=4)
+    rb = RayBundle(rays["origins"], rays["directions"], rays["pixel_area"], rays["camera_indices"])
+    edges = torch.arange(R * (S + 1), dtype=torch.float32).view(R, S + 1)
+    rs = rb.get_ray_samples(edges[:, :-1, None], edges[:, 1:, None])
+    o, d, starts, ends, cam, r, s, stride = ray_layout(rs)
+    assert (r, s, stride) == (R, S, S + 1)
+    assert starts.data_ptr() == edges.data_ptr() and ends.data_ptr() == edges.data_ptr() + 4
+    assert cam.dtype == torch.int32 and cam.shape == (R,)
+    # density_fn-style samples: arbitrary positions -> one ray per point
+    from cropnerf_b200.rays import Frustums, RaySamples
+
+    pos = torch.rand(3, 4, 3)
+    rs2 = RaySamples(Frustums(pos, torch.ones_like(pos), torch.zeros_like(pos[..., :1]), torch.zeros_like(pos[..., :1]), None))
+    o2, d2, st2, en2, cam2, r2, s2, stride2 = ray_layout(rs2)
+    assert (r2, s2) == (12, 1) and torch.equal(o2, pos.reshape(12, 3))
+
+
+def test_flat_groups_alias_parameters_and_lr_schedule():
+    model = FruitModel(FruitNerfModelConfig(log2_hashmap_size=8, proposal_net_args_list=[
+        {"hidden_dim": 16, "log2_hashmap_size": 8, "num_levels": 5, "max_res": 128, "use_linear": False}] * 2), num_train_data=4)
+    groups = model.get_param_groups()
+    assert set(groups) == {"proposal_networks", "fields"}  # camera_opt appears only when the optimizer is on (fruit_nerf.py:191-196)
+    tr = engine.Trainer(model)
+    fg = tr.groups["fields"]
+    n = sum(p.numel() for p in fg.params)
+    assert fg.flat.numel() == n == fg.grad.numel()
+    p = model.field.mlp_head.layers[0].weight
+    p.data.fill_(3.0)
+    assert (fg.flat == 3.0).sum() == p.numel()
+    p.grad.fill_(2.0)
+    assert (fg.grad == 2.0).sum() == p.numel()
+    spec = engine.OptimizerSpec()
+    assert abs(engine.exponential_decay_lr(0, spec) - 1e-2) < 1e-12
+    assert abs(engine.exponential_decay_lr(200000, spec) - 1e-4) < 1e-12
+    assert abs(engine.exponential_decay_lr(100000, spec) - 1e-3) < 1e-9
+
+
+def test_proposal_update_schedule_and_anneal():
+    model = FruitModel(FruitNerfModelConfig(log2_hashmap_size=8), num_train_data=4)
+    s = model.proposal_sampler
+    assert s.update_sched(0) == 1 and s.update_sched(5000) == 5 and s.update_sched(2500) == 2.5
+    cbs = model.get_training_callbacks()
+    assert len(cbs) == 2
+    cbs[0].func(0)
+    assert s._anneal == 0.0
+    cbs[0].func(1000)
+    assert abs(s._anneal - 1.0) < 1e-12
+    cbs[0].func(100)
+    assert abs(s._anneal - (10 * 0.1) / (9 * 0.1 + 1)) < 1e-12
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from cropnerf_b200 import engine
+from cropnerf_b200.fruit_nerf import FruitModel, FruitNerfModelConfig
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+torch.manual_seed(0)
+prop = [{"hidden_dim": 16, "log2_hashmap_size": 8, "num_levels": 5, "max_res": 128, "use_linear": False}] * 2
+model = FruitModel(FruitNerfModelConfig(log2_hashmap_size=8, proposal_net_args_list=prop), num_train_data=4)
+tr = engine.Trainer(model, world_size=world)
+for name, g in tr.groups.items():
+    g.grad.copy_(torch.arange(g.grad.numel(), dtype=torch.float32) * (rank + 1))
+tr.all_reduce_gradients()
+ok = True
+for name, g in tr.groups.items():
+    want = torch.arange(g.grad.numel(), dtype=torch.float32) * sum(r + 1 for r in range(world))
+    ok = ok and torch.equal(g.grad, want)
+# ray-range sharding used by export / projection: disjoint cover
+from cropnerf_b200.export import shard_range
+lo, hi = shard_range(1000003, rank, world)
+t = torch.tensor([lo, hi, hi - lo], dtype=torch.int64)
+parts = [torch.zeros_like(t) for _ in range(world)]
+dist.all_gather(parts, t)
+ok = ok and parts[0][0].item() == 0 and parts[-1][1].item() == 1000003 and all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_two_rank_gradient_allreduce_gloo():
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "w.py")
+        open(path, "w").write(_WORKER)
+        procs = []
+        for rank in range(2):
+            env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29617")
+            procs.append(subprocess.Popen([sys.executable, path, ROOT], env=env))
+        codes = [p.wait(timeout=300) for p in procs]
+    assert codes == [0, 0]

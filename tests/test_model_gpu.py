@@ -1,0 +1,212 @@
+"""End-to-end parity of the B200 FruitField / FruitModel against the oracle (fp32 mode: 1e-4 relative; semantic label
+agreement >= 99.9 %), against the committed golden fixtures, and gradient parity of one training step."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, assert_close, product_bundle, product_model, rel_err
+
+from cropnerf_b200 import synthetic
+from cropnerf_b200.field_components import FieldHeadNames
+from cropnerf_b200.rays import ray_layout
+from oracle import cases
+from oracle import nerfstudio_torch as ns
+
+pytestmark = pytest.mark.gpu
+
+RTOL_FP32 = 1e-4  # north_star: per-ray RGB / depth / accumulation within 1e-4 relative in fp32
+
+
+def _field_samples(R, S, seed):
+    rays = synthetic.make_rays(R, seed=seed, num_cameras=20)
+    g = torch.Generator().manual_seed(seed)
+    edges = torch.sort(torch.rand((R, S + 1), generator=g) * 3.0, dim=-1).values
+    edges[0] = torch.linspace(0, 2000.0, S + 1)  # far samples: contraction branch
+    return rays, edges
+
+
+@pytest.mark.parametrize("contraction", [True, False])
+@pytest.mark.parametrize("training", [True, False])
+def test_field_forward_backward(dev, contraction, training):
+    R, S, num_images = 160, 48, 20
+    cfg = cases.make_config(dict(log2_hashmap_size=14, disable_scene_contraction=not contraction))
+    oracle, state = cases.build_oracle(cfg, num_images, seed=0, table_scale=0.5)
+    oracle.train(training)
+    model = product_model(cfg, state, num_images, dev, training)
+    rays, edges = _field_samples(R, S, 3)
+    rb = cases.oracle_bundle(rays)
+    rs = rb.get_ray_samples(edges[:, :-1, None], edges[:, 1:, None])
+    out_ref = oracle.field(rs)
+    rbm = product_bundle(rays, dev)
+    e = edges.to(dev)
+    rsm = rbm.get_ray_samples(e[:, :-1, None], e[:, 1:, None])
+    out = model.field(rsm)
+    assert_close(out[FieldHeadNames.DENSITY], out_ref["density"], RTOL_FP32, "density", floor=1e-3)
+    assert_close(out[FieldHeadNames.RGB], out_ref["rgb"], RTOL_FP32, "rgb")
+    assert_close(out[FieldHeadNames.SEMANTICS], out_ref["semantics"], 5e-4, "semantics", floor=1e-2)
+    # _sample_locations (BayesRays hook): normalised + masked positions, bit-exact
+    assert torch.equal(model.field._sample_locations.cpu(), oracle.field._sample_locations.detach())
+    if not training:
+        return
+    g = torch.Generator().manual_seed(11)
+    gd, gr, gs = torch.randn((R, S, 1), generator=g) * 0.01, torch.randn((R, S, 3), generator=g), torch.randn((R, S, 1), generator=g)
+    (out_ref["density"] * gd).sum().add((out_ref["rgb"] * gr).sum()).add((out_ref["semantics"] * gs).sum()).backward()
+    (out[FieldHeadNames.DENSITY] * gd.to(dev)).sum().add((out[FieldHeadNames.RGB] * gr.to(dev)).sum()).add(
+        (out[FieldHeadNames.SEMANTICS] * gs.to(dev)).sum()).backward()
+    ref_params = dict(oracle.field.named_parameters())
+    for name, p in model.field.named_parameters():
+        gr_ = ref_params[name].grad
+        assert gr_ is not None and p.grad is not None, name
+        scale = gr_.abs().max().item() + 1e-20
+        err = (p.grad.cpu() - gr_).abs().max().item() / scale
+        assert err < 5e-4, f"field grad {name}: {err:.3e}"
+
+
+def test_density_field_forward_backward(dev):
+    R, S, num_images = 200, 64, 20
+    cfg = cases.make_config(dict(log2_hashmap_size=14))
+    oracle, state = cases.build_oracle(cfg, num_images, seed=0, table_scale=0.5)
+    model = product_model(cfg, state, num_images, dev, True)
+    rays, edges = _field_samples(R, S, 4)
+    rs = cases.oracle_bundle(rays).get_ray_samples(edges[:, :-1, None], edges[:, 1:, None])
+    e = edges.to(dev)
+    rsm = product_bundle(rays, dev).get_ray_samples(e[:, :-1, None], e[:, 1:, None])
+    for i in range(2):
+        ref_net, net = oracle.proposal_networks[i], model.proposal_networks[i]
+        d_ref, _ = ref_net.get_density(rs)
+        d, _ = net.get_density(rsm)
+        assert_close(d, d_ref, RTOL_FP32, f"proposal {i} density", floor=1e-3)
+        # density_fn(positions) path (arbitrary positions, one zero-length frustum per point)
+        pos = rs.frustums.get_positions()
+        d2 = net.density_fn(pos.to(dev))
+        assert_close(d2, ref_net.density_fn(pos), RTOL_FP32, f"proposal {i} density_fn", floor=1e-3)
+        g = torch.Generator().manual_seed(i)
+        gd = torch.randn(d_ref.shape, generator=g) * 0.1
+        (d_ref * gd).sum().backward()
+        (d * gd.to(dev)).sum().backward()
+        ref_params = dict(ref_net.named_parameters())
+        for name, p in net.named_parameters():
+            gr_ = ref_params[name].grad
+            scale = gr_.abs().max().item() + 1e-20
+            err = (p.grad.cpu() - gr_).abs().max().item() / scale
+            assert err < 5e-4, f"proposal {i} grad {name}: {err:.3e}"
+
+
+def _run_product(name, dev, spec=None, num_images=20, seed=0):
+    spec = spec or cases.CASES[name]
+    R = spec["num_rays"]
+    cfg = cases.make_config(spec.get("cfg"))
+    oracle, state = cases.build_oracle(cfg, num_images, seed, spec["table_scale"])
+    model = product_model(cfg, state, num_images, dev, spec["training"])
+    rays = synthetic.make_rays(R, seed=1, num_cameras=num_images)
+    if spec["training"]:
+        feed = synthetic.JitterFeed(synthetic.make_jitter(R, 3, seed=2))
+        model.proposal_sampler.initial_sampler.rand_fn = feed
+        model.proposal_sampler.pdf_sampler.rand_fn = feed
+        for cb in model.get_training_callbacks():
+            if "BEFORE_TRAIN_ITERATION" in cb.where_to_run:
+                cb.func(500)
+    model.proposal_sampler.pdf_sampler.keep_inds = True
+    outputs = model(product_bundle(rays, dev))
+    return model, outputs
+
+
+def _check_outputs(outputs, ref, tag):
+    # per-ray outputs: within 1e-4 relative for (nearly) every ray; the median depth is a discontinuous pick of one
+    # sample, so a last-ulp difference in the cumulative weights may move a few rays by one sample
+    assert_close(outputs["rgb"], ref["rgb"], RTOL_FP32, tag + " rgb")
+    assert_close(outputs["accumulation"], ref["accumulation"], RTOL_FP32, tag + " accumulation")
+    assert_close(outputs["depth"], ref["depth"], RTOL_FP32, tag + " depth", frac=0.98)
+    assert_close(outputs["prop_depth_0"], ref["prop_depth_0"], RTOL_FP32, tag + " prop_depth_0", frac=0.98)
+    assert_close(outputs["prop_depth_1"], ref["prop_depth_1"], RTOL_FP32, tag + " prop_depth_1", frac=0.98)
+    assert_close(outputs["semantics"], ref["semantics"], 5e-4, tag + " semantics", floor=1e-2)
+    agree = (outputs["semantics_colormap"].cpu().numpy() == ref["semantics_colormap"]).mean()
+    assert agree >= 0.999, f"{tag}: semantic label agreement {agree}"
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_model_against_golden(dev, name):
+    ref = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    model, outputs = _run_product(name, dev)
+    _check_outputs(outputs, ref, name)
+    inds = model.proposal_sampler.pdf_sampler.last_inds.cpu().numpy()
+    same = (inds == ref["pdf_inds_last"]).mean()
+    assert same >= 0.995, f"{name}: resampling bins agree on {same*100:.2f}%"
+    assert inds.shape == ref["pdf_inds_last"].shape  # proposal sample counts
+
+
+def test_training_step_losses_and_gradients(dev):
+    name = "tiny_train"
+    ref = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    model, outputs = _run_product(name, dev)
+    R = cases.CASES[name]["num_rays"]
+    targets = {k: v.to(dev) for k, v in synthetic.make_targets(R, seed=3).items()}
+    loss_dict = model.get_loss_dict(outputs, targets)
+    metrics = model.get_metrics_dict(outputs, targets)
+    for k, v in loss_dict.items():
+        r = float(ref["loss_" + k])
+        assert abs(v.item() - r) <= 2e-4 * abs(r) + 1e-8, f"{k}: {v.item()} vs {r}"
+    assert abs(metrics["distortion"].item() - float(ref["metric_distortion"])) <= 1e-3 * abs(float(ref["metric_distortion"]))
+    assert abs(metrics["psnr"].item() - float(ref["metric_psnr"])) <= 1e-3
+    sum(loss_dict.values()).backward()
+    checked = 0
+    for pname, p in model.named_parameters():
+        key = "gradnorm/" + pname
+        if key not in ref:
+            continue
+        assert p.grad is not None, pname
+        gn = p.grad.double().norm().item()
+        rn = float(ref[key])
+        assert abs(gn - rn) <= 2e-3 * rn + 1e-12, f"grad norm {pname}: {gn} vs {rn}"
+        if "grad/" + pname in ref:
+            g_ref = ref["grad/" + pname]
+            scale = np.abs(g_ref).max() + 1e-20
+            err = np.abs(p.grad.cpu().numpy().reshape(-1) - g_ref).max() / scale
+            assert err < 2e-3, f"grad {pname}: {err:.3e}"
+        checked += 1
+    assert checked >= 20
+
+
+def test_full_size_config_vs_oracle(dev):
+    """The fruit_nerf preset at full table sizes (2^19 x 16 field, 2^17 x 5 proposals), 384 rays, eval mode."""
+    spec = dict(num_rays=384, training=False, cfg=dict(), table_scale=0.5)
+    cfg = cases.make_config(spec["cfg"], small=False)
+    oracle, state = cases.build_oracle(cfg, 20, 0, 0.5)
+    oracle.eval()
+    rays = synthetic.make_rays(spec["num_rays"], seed=1, num_cameras=20)
+    with torch.no_grad():
+        ref = oracle(cases.oracle_bundle(rays))
+    model = product_model(cfg, state, 20, dev, False)
+    with torch.no_grad():
+        out = model(product_bundle(rays, dev))
+    ref_np = {k: v.numpy() for k, v in ref.items() if isinstance(v, torch.Tensor)}
+    _check_outputs(out, ref_np, "full-size")
+
+
+def test_export_mode_and_density_projection(dev):
+    """setup_inference (uniform sampler, contraction off) + get_export_outputs, and the opacity-in-front-of-AABB
+    path of semantic_projection (get_density_for_camera_ray_bundle with injected near/far)."""
+    cfg = cases.make_config(dict(log2_hashmap_size=14))
+    oracle, state = cases.build_oracle(cfg, 20, 0, 0.5)
+    oracle.eval()
+    model = product_model(cfg, state, 20, dev, False)
+    rays = synthetic.make_rays(100, seed=5, num_cameras=20)
+    with torch.no_grad():
+        acc_ref = oracle.get_density_for_ray_bundle(cases.oracle_bundle(rays, with_near_far=(0.0, 0.8)))
+        acc = model.get_density_for_camera_ray_bundle(product_bundle(rays, dev, near_far=(0.0, 0.8)))
+    assert_close(acc, acc_ref, RTOL_FP32, "opacity in front of box")
+    oracle.test_mode = model.test_mode = "export"
+    oracle.field.test_mode = model.field.test_mode = "export"
+    oracle.setup_inference(True, 200)
+    model.setup_inference(True, 200)
+    oracle.eval()
+    model.eval()
+    with torch.no_grad():
+        ref = oracle(cases.oracle_bundle(rays, with_near_far=(0.0, 1.5)))
+        out = model(product_bundle(rays, dev, near_far=(0.0, 1.5)))
+    assert_close(out["density"], ref["density"], RTOL_FP32, "export density", floor=1e-3)
+    assert_close(out["rgb"], ref["rgb"], RTOL_FP32, "export rgb")
+    assert_close(out["point_location"], ref["point_location"], 1e-6, "export positions")
+    assert (out["semantics_colormap"].cpu() == ref["semantics_colormap"]).float().mean() >= 0.999
