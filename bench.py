@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the FruitNeRF per-ray rendering hot path (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision fp32|mixed]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Headline `value`: training rays/s (fwd + bwd + gradient all-reduce + Adam) of the `fruit_nerf` preset
+(BASELINE.json configs[1]: 4096-ray batch per GPU, proposal 256/96 + 48 NeRF samples, full-size hash tables), inputs
+resident in HBM.  `e2e`: the same step through the public API with HOST ray/target buffers (pinned) copied in and the
+loss read back every step.  `render`: eval-mode render (the export / projection loop body) in rays/s.
+`roofline`: dominant C-ABI call, algorithmic bytes / CUDA-event time.  `cpu_baseline`: the oracle
+(torch CPU restatement of the reference path) on the box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+RAYS_PER_GPU = 4096
+PROPOSAL_SAMPLES = (256, 96)
+NERF_SAMPLES = 48
+NUM_IMAGES = 300
+# algorithmic bytes per ray (SURVEY.md section 8d / BASELINE.md section 3), fp32 tables: 8 corners * 2 floats per (sample, level)
+FETCH_BYTES = {"prop0": 256 * 5 * 8 * 8, "prop1": 96 * 5 * 8 * 8, "field": 48 * 16 * 8 * 8}
+RENDER_BYTES_PER_RAY = sum(FETCH_BYTES.values()) + 40 + 24                    # 161 856
+TRAIN_BYTES_PER_RAY = 3 * sum(FETCH_BYTES.values()) + 64 + 16                 # 485 456 (update step: gather + scatter RMW)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(dev, precision, seed=0):
+    from cropnerf_b200 import synthetic
+    from cropnerf_b200.fruit_nerf import FruitModel, FruitNerfModelConfig
+
+    torch.manual_seed(seed)
+    cfg = FruitNerfModelConfig(precision=precision)
+    model = FruitModel(cfg, num_train_data=NUM_IMAGES)
+    state = synthetic.randomize_state(model.state_dict(), seed=seed, table_scale=0.5)
+    model.load_state_dict(state)
+    return model.to(dev)
+
+
+def host_batch(R, seed):
+    from cropnerf_b200 import synthetic
+
+    rays = synthetic.make_rays(R, seed=seed, num_cameras=NUM_IMAGES)
+    tgt = synthetic.make_targets(R, seed=seed + 7)
+    out = {**rays, **tgt}
+    return {k: v.pin_memory() for k, v in out.items()}
+
+
+def to_bundle(batch, dev, non_blocking=True):
+    from cropnerf_b200.rays import RayBundle
+
+    g = {k: v.to(dev, non_blocking=non_blocking) for k, v in batch.items()}
+    rb = RayBundle(g["origins"], g["directions"], g["pixel_area"], g["camera_indices"])
+    return rb, {"image": g["image"], "fruit_mask": g["fruit_mask"]}
+
+
+def bytes_of(batch):
+    return int(sum(v.numel() * v.element_size() for v in batch.values()))
+
+
+def run_product(args):
+    from cropnerf_b200 import _lib as L
+    from cropnerf_b200 import engine
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
+
+    model = build_model(dev, args.precision)
+    trainer = engine.Trainer(model, world_size=world)
+    R = RAYS_PER_GPU
+    nb = 8  # distinct ray batches cycled through (fresh rays every step, like next_train)
+    host = [host_batch(R, seed=100 * rank + i) for i in range(nb)]
+    resident = [to_bundle(b, dev, non_blocking=False) for b in host]
+    l2_flush = torch.empty((192 << 20,), dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def train_step(step, rb, tg):
+        from cropnerf_b200.rays import RayBundle
+        rb = RayBundle(rb.origins, rb.directions, rb.pixel_area, rb.camera_indices)  # the collider mutates the bundle
+        return trainer.train_iteration(step, rb, tg)
+
+    # ---- warm-up -----------------------------------------------------------------------------------------
+    step = 0
+    for _ in range(max(args.warmup, 3)):
+        train_step(step, *resident[step % nb]); step += 1
+    barrier()
+
+    # ---- timed: resident inputs ----------------------------------------------------------------------------
+    prof = L.Profile(timing=False)
+    L.set_profile(prof)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        l2_flush.fill_(i & 0xFF)  # flush L2 between timed iterations (the 74 MiB of tables would otherwise stay resident)
+        ev[i][0].record()
+        train_step(step, *resident[step % nb]); step += 1
+        ev[i][1].record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    L.set_profile(None)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    t_local = sum(step_ms) / 1e3
+    launches = prof.launches()
+
+    # ---- timed: end to end through the public API with host buffers ------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss_host = 0.0
+    for i in range(args.steps):
+        rb, tg = to_bundle(host[step % nb], dev)       # H2D from pinned memory, every step
+        stats = trainer.train_iteration(step, rb, tg); step += 1
+        loss_host = float(stats["loss"].item())        # D2H read of the step's result
+    e1.record()
+    barrier()
+    t_e2e_local = e0.elapsed_time(e1) / 1e3
+
+    # ---- per-call device times for the roofline (separate pass so the events do not perturb the timed region) ----
+    prof_t = L.Profile(timing=True)
+    L.set_profile(prof_t)
+    n_prof = min(args.steps, 5)
+    for i in range(n_prof):
+        l2_flush.fill_(i & 0xFF)
+        train_step(step, *resident[step % nb]); step += 1
+    call_ms = prof_t.times_ms()
+    L.set_profile(None)
+
+    # ---- render (export / projection loop body), eval mode ----------------------------------------------------
+    model.eval()
+    Rr = 32768
+    rhost = host_batch(Rr, seed=999 + rank)
+    rres, _ = to_bundle(rhost, dev, non_blocking=False)
+
+    def render_once(rb):
+        from cropnerf_b200.rays import RayBundle
+        with torch.no_grad():
+            return model(RayBundle(rb.origins, rb.directions, rb.pixel_area, rb.camera_indices))
+
+    for _ in range(3):
+        render_once(rres)
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_r = max(3, min(args.steps, 10))
+    r0.record()
+    for _ in range(n_r):
+        render_once(rres)
+    r1.record()
+    barrier()
+    t_render_local = r0.elapsed_time(r1) / 1e3
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    d2h_render = 0
+    for _ in range(n_r):
+        rb, _ = to_bundle(rhost, dev)
+        out = render_once(rb)
+        host_out = {k: out[k].cpu() for k in ("rgb", "depth", "accumulation", "semantics")}
+        d2h_render = sum(v.numel() * v.element_size() for v in host_out.values())
+    h1.record()
+    barrier()
+    t_render_e2e_local = h0.elapsed_time(h1) / 1e3
+    model.train()
+
+    # ---- reduce over ranks (max time) -----------------------------------------------------------------------
+    times = torch.tensor([t_local, t_e2e_local, t_render_local, t_render_e2e_local], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t, t_e2e, t_render, t_render_e2e = times.tolist()
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        total_rays = world * R * args.steps
+        value = total_rays / t
+        # dominant C-ABI call by accumulated device time
+        tot = {k: sum(v) / n_prof for k, v in call_ms.items()}
+        dom = max(tot, key=tot.get)
+        counts = {k: len(v) / n_prof for k, v in call_ms.items()}
+        per_launch_ms = tot[dom] / counts[dom]
+        # algorithmic bytes of one call of the dominant op (fp32 tables; see DESIGN.md "algorithmic bytes")
+        per_ray = {
+            "cnb_field_bwd": 2 * FETCH_BYTES["field"],                     # fp32 path keeps activations: scatter RMW only
+            "cnb_field_fwd": FETCH_BYTES["field"],
+            "cnb_density_field_fwd": (FETCH_BYTES["prop0"] + FETCH_BYTES["prop1"]) / 2,   # averaged over the two levels
+            "cnb_density_field_bwd": 3 * (FETCH_BYTES["prop0"] + FETCH_BYTES["prop1"]) / 2,
+        }.get(dom)
+        if args.precision == "mixed":
+            per_ray = {"cnb_field_bwd": 3 * FETCH_BYTES["field"], "cnb_field_fwd": FETCH_BYTES["field"]}.get(dom, per_ray)
+        roofline = {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": None,
+                    "ms_per_launch": per_launch_ms, "share_of_step": tot[dom] / (sum(tot.values()) + 1e-12)}
+        if per_ray is not None:
+            ach = per_ray * R / (per_launch_ms * 1e-3) / 1e9
+            roofline.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": per_ray * R})
+        else:
+            roofline.update({"achieved": None, "frac": None})
+        step_achieved = TRAIN_BYTES_PER_RAY * total_rays / t / 1e9
+        line = {
+            "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "f16 tensor-core MLPs, f32 tables/accumulate/compositing", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: fruit_nerf preset training step, 4096 rays/GPU, proposal 256/96 + 48 NeRF samples, "
+                                   "field 16x2^19x2 + 2 proposal 5x2^17x2 fp32 hash tables, 300 synthetic 1080p cameras",
+                       "rays_per_gpu": R, "samples_per_ray": 400, "precision": args.precision, "l2": "flushed between timed iterations (192 MiB fill)",
+                       "includes": "fwd + bwd (all three networks updated) + gradient all-reduce + Adam"},
+            "samples_per_s": value * 400,
+            "step_roofline": {"algorithmic_bytes_per_ray": TRAIN_BYTES_PER_RAY, "achieved_GBps": step_achieved, "frac": step_achieved / peak,
+                              "roofline_rays_per_s_per_gpu": peak * 1e9 / TRAIN_BYTES_PER_RAY},
+            "e2e": {"value": total_rays / t_e2e, "unit": "rays/s", "h2d_bytes_per_step": bytes_of(host[0]), "d2h_bytes_per_step": 4,
+                    "last_loss": loss_host},
+            "render": {"value": world * Rr * n_r / t_render, "unit": "rays/s", "rays_per_call": Rr,
+                       "e2e": {"value": world * Rr * n_r / t_render_e2e, "unit": "rays/s", "h2d_bytes_per_step": bytes_of({k: rhost[k] for k in ("origins", "directions", "pixel_area", "camera_indices")}),
+                               "d2h_bytes_per_step": int(d2h_render)},
+                       "roofline_frac": (RENDER_BYTES_PER_RAY * world * Rr * n_r / t_render / 1e9) / (peak * world)},
+            "roofline": roofline,
+            "call_ms_per_step": {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])},
+            "gpu_launches": launches,
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(sample_rays=4 * args.cpu_rays, steps=2, warmup=1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sample_rays: int, steps: int, warmup: int):
+    """The oracle (port of the reference's torch path) timed on the host cores: one training step (fwd+bwd) of
+    `sample_rays` rays of the same workload.  The only place bench.py executes oracle/."""
+    from cropnerf_b200 import synthetic
+    from oracle import cases
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = cases.make_config({}, small=False)
+    model, _ = cases.build_oracle(cfg, NUM_IMAGES, 0, 0.5)
+    model.train()
+    rays = synthetic.make_rays(sample_rays, seed=5, num_cameras=NUM_IMAGES)
+    tgt = synthetic.make_targets(sample_rays, seed=6)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        model.zero_grad(set_to_none=True)
+        out = model(cases.oracle_bundle(rays))
+        loss = sum(model.get_loss_dict(out, tgt).values())
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    return {"value": sample_rays / t, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_rays}-ray training step (fwd+bwd, no optimizer) of the same fruit_nerf preset, torch {torch.__version__} CPU, "
+                      f"{warmup} warm-up + mean of {steps}", "seconds_per_step": t}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path = the oracle port (nerfstudio itself cannot be
+    installed here), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = args.cpu_rays
+    res = cpu_baseline(sample_rays=sample, steps=max(1, min(args.steps, 50)), warmup=max(1, min(args.warmup, 5)))
+    line = {
+        "impl": "reference", "metric": "train_rays_per_s", "value": res["value"], "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: fruit_nerf preset training step (bounded sample of the 4096-ray batch)", "rays_per_step": sample,
+                   "samples_per_ray": 400},
+        "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("CNB_PRECISION", "fp32"), choices=["fp32", "mixed"])
+    ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per CPU-baseline step (bounded sample of the 4096-ray batch)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

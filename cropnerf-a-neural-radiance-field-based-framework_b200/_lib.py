@@ -128,7 +128,71 @@ SIGNATURES = {
     "cnb_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P]),
 }
 
-_lib: Optional[C.CDLL] = None
+_lib: Optional["_Proxy"] = None
+
+# kernels launched per C-ABI call (fp32 field path is a chain of kernels; see csrc/field_fp32.cu)
+KERNELS_PER_CALL = {
+    "cnb_hashgrid_fwd": 1, "cnb_hashgrid_bwd": 1, "cnb_mlp_fwd": 1, "cnb_mlp_bwd": 1, "cnb_density_field_fwd": 1, "cnb_density_field_bwd": 1,
+    "cnb_field_fwd": 7, "cnb_field_bwd": 8, "cnb_sample_spaced": 1, "cnb_sample_pdf": 1, "cnb_weights_fwd": 1, "cnb_weights_bwd": 1,
+    "cnb_render_fwd": 1, "cnb_render_bwd": 1, "cnb_interlevel_fwd": 1, "cnb_interlevel_bwd": 1, "cnb_distortion_fwd": 1, "cnb_pixel_losses": 1,
+    "cnb_adam_step": 1,
+}
+
+
+class Profile:
+    """Optional per-call instrumentation: counts every C-ABI call and, when ``timing`` is set, brackets it with CUDA
+    events recorded on the launching (current) stream."""
+
+    def __init__(self, timing: bool = False):
+        self.timing = timing
+        self.calls = {}
+        self.events = {}
+
+    def launches(self) -> int:
+        return sum(n * KERNELS_PER_CALL.get(k, 1) for k, n in self.calls.items())
+
+    def times_ms(self) -> dict:
+        torch.cuda.synchronize()
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.events.items()}
+
+
+_profile: Optional[Profile] = None
+
+
+def set_profile(p: Optional[Profile]) -> None:
+    global _profile
+    _profile = p
+
+
+class _Proxy:
+    """Attribute access returns the ctypes function wrapped with the optional profiler."""
+
+    def __init__(self, handle: C.CDLL):
+        self._h = handle
+        self._cache = {}
+
+    def __getattr__(self, name):
+        c = self.__dict__["_cache"]
+        if name in c:
+            return c[name]
+        fn = getattr(self.__dict__["_h"], name)
+
+        def wrapped(*args, _fn=fn, _name=name):
+            prof = _profile
+            if prof is None:
+                return _fn(*args)
+            prof.calls[_name] = prof.calls.get(_name, 0) + 1
+            if not prof.timing:
+                return _fn(*args)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = _fn(*args)
+            e1.record()
+            prof.events.setdefault(_name, []).append((e0, e1))
+            return rc
+
+        c[name] = wrapped
+        return wrapped
 
 
 def build(verbose: bool = False) -> str:
@@ -141,7 +205,7 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
-def lib() -> C.CDLL:
+def lib() -> "_Proxy":
     """Load (once) the shared library; fail loudly if it has not been built -- there is no fallback."""
     global _lib
     if _lib is None:
@@ -156,7 +220,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = handle
+        _lib = _Proxy(handle)
     return _lib
 
 

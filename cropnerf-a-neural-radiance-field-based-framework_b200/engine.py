@@ -49,6 +49,8 @@ def exponential_decay_lr(step: int, spec: OptimizerSpec) -> float:
 class FlatGroup:
     """One param group flattened: ``param.data`` and ``param.grad`` become views of two contiguous buffers."""
 
+    ALIGN = 64  # floats
+
     def __init__(self, params: List[nn.Parameter]):
         uniq, seen = [], set()
         for p in params:
@@ -56,19 +58,22 @@ class FlatGroup:
                 seen.add(id(p))
                 uniq.append(p)
         self.params = uniq
-        n = sum(p.numel() for p in uniq)
+        # every tensor starts on a 256-byte boundary: the kernels use 8/16-byte vector loads and reductions on the tables
+        offsets, n = [], 0
+        for p in uniq:
+            offsets.append(n)
+            n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         dev = uniq[0].device
         self.flat = torch.empty((n,), device=dev, dtype=torch.float32)
         self.grad = torch.zeros((n,), device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
-        off = 0
-        for p in uniq:
+        self.flat.zero_()
+        for p, off in zip(uniq, offsets):
             k = p.numel()
             self.flat[off : off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off : off + k].view(p.shape)
             p.grad = self.grad[off : off + k].view(p.shape)
-            off += k
 
     def zero_grad(self) -> None:
         self.grad.zero_()

@@ -31,6 +31,16 @@ def assert_close(a, b, rtol, name, floor=1e-3, frac=1.0):
     return e
 
 
+def assert_close_scaled(a, b, tol, name):
+    """max |a-b| <= tol * max |b|  (for quantities with cancellation, e.g. dot products / gradients)."""
+    a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, dtype=np.float64)
+    b = np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b, dtype=np.float64)
+    scale = np.abs(b).max() + 1e-30
+    err = np.abs(a - b).max() / scale
+    assert err <= tol, f"{name}: max abs err / max |ref| = {err:.3e} > {tol}"
+    return err
+
+
 def product_model(oracle_cfg, state, num_images, dev, training, precision="fp32", test_mode="val"):
     kw = {k: getattr(oracle_cfg, k) for k in oracle_cfg.__dataclass_fields__ if k in FruitNerfModelConfig.__dataclass_fields__}
     cfg = FruitNerfModelConfig(**kw)

@@ -106,7 +106,8 @@ def test_flat_groups_alias_parameters_and_lr_schedule():
     tr = engine.Trainer(model)
     fg = tr.groups["fields"]
     n = sum(p.numel() for p in fg.params)
-    assert fg.flat.numel() == n == fg.grad.numel()
+    assert fg.flat.numel() >= n and fg.flat.numel() == fg.grad.numel()
+    assert all((q.data_ptr() - fg.flat.data_ptr()) % 256 == 0 and (q.grad.data_ptr() - fg.grad.data_ptr()) % 256 == 0 for q in fg.params)  # vector loads / red.v2 need aligned tables
     p = model.field.mlp_head.layers[0].weight
     p.data.fill_(3.0)
     assert (fg.flat == 3.0).sum() == p.numel()

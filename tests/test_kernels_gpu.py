@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import assert_close, rel_err
+from helpers import assert_close, assert_close_scaled, rel_err
 
 from cropnerf_b200 import _lib as L
 from cropnerf_b200 import ops
@@ -57,8 +57,9 @@ def test_hashgrid_backward(dev):
     ref(pos).backward(dout)
     mine(pos.to(dev)).backward(dout.to(dev))
     # scatter-add order differs (atomics): fp32 sums of <= a few thousand terms
-    e = rel_err(mine.hash_table.grad, ref.hash_table.grad, floor=1e-4)
-    assert e.max() < 2e-4, e.max()
+    gr = ref.hash_table.grad
+    err = (mine.hash_table.grad.cpu() - gr).abs().max().item() / gr.abs().max().item()
+    assert err < 1e-5, err
     nz = ref.hash_table.grad.abs().sum(-1) > 0
     assert torch.equal((mine.hash_table.grad.cpu().abs().sum(-1) > 0), nz), "touched rows must coincide"
 
@@ -90,14 +91,15 @@ def test_mlp_forward_backward(dev, dims, act):
         mine.zero_grad()
         yr = ref(xr)
         ym = mine(xm)
-        assert_close(ym, yr, 2e-5, f"mlp{dims} fwd n={n}")
+        # dot products of O(1) terms: compare against the output scale (fp32 FMA order differs from oneDNN's)
+        assert_close_scaled(ym, yr, 1e-5, f"mlp{dims} fwd n={n}")
         yr.backward(dy)
         ym.backward(dy.to(dev))
-        assert_close(xm.grad, xr.grad, 1e-4, f"mlp{dims} dx n={n}")
+        assert_close_scaled(xm.grad, xr.grad, 1e-5, f"mlp{dims} dx n={n}")
         for (k, pr), (_, pm) in zip(ref.named_parameters(), mine.named_parameters()):
             scale = pr.grad.abs().max().item() + 1e-12
             err = (pm.grad.cpu() - pr.grad).abs().max().item() / scale
-            assert err < 1e-4, f"mlp{dims} grad {k} n={n}: {err}"
+            assert err < 2e-5, f"mlp{dims} grad {k} n={n}: {err}"
 
 
 def _ray_case(R, S, seed, near=0.05, far=1000.0):
@@ -193,18 +195,20 @@ def test_weights_and_renderers(dev, S):
     rm = rgb.to(dev).requires_grad_(True)
     sm = sem.to(dev).requires_grad_(True)
     w = ops.ray_weights(dm, e_dev[:, :-1, None], e_dev[:, 1:, None])
-    assert_close(w, w_ref, 1e-5, "weights", floor=1e-6)
+    # alpha = 1 - exp(-dd) cancels for small dd, so one ulp of expf (CUDA vs CPU libm) is a large *relative* error of a
+    # tiny weight; weights live in [0,1] and every renderer sums them, so the bound that matters is absolute
+    assert (w.detach().cpu() - w_ref.detach()).abs().max().item() < 5e-7, "weights"
     rgb_o, acc_o, sem_o = ops.render(w, rm, sm, L.BG_LAST_SAMPLE, None, False)
     assert_close(rgb_o, rgb_ref, 1e-5, "rgb", floor=1e-3)
-    assert_close(acc_o, acc_ref, 1e-5, "acc", floor=1e-3)
+    assert_close(acc_o, acc_ref, 1e-4, "acc", floor=1e-3)
     assert_close(sem_o, sem_ref, 1e-4, "sem", floor=1e-2)
     # median index: bit-exact given identical weights (cumsum in double like torch's CPU cumsum)
     depth, idx = ops.render_median_depth(w_ref.detach().to(dev), e_dev[:, :-1, None], e_dev[:, 1:, None], want_index=True)
     assert torch.equal(idx.cpu().to(torch.int64), depth_r.last_median_index[:, 0])
     assert torch.equal(depth.cpu(), depth_ref)
     (rgb_o * g1.to(dev)).sum().add((acc_o * g2.to(dev)).sum()).add((sem_o * g3.to(dev)).sum()).backward()
-    assert_close(rm.grad, rr.grad, 1e-4, "d_rgb", floor=1e-4)
-    assert_close(sm.grad, sr.grad, 1e-4, "d_sem", floor=1e-4)
+    assert_close_scaled(rm.grad, rr.grad, 1e-5, "d_rgb")  # = g * w: same absolute-error argument as the weights
+    assert_close_scaled(sm.grad, sr.grad, 1e-5, "d_sem")
     scale = dr.grad.abs().max().item()
     assert ((dm.grad.cpu() - dr.grad).abs().max().item() / scale) < 1e-4, "d_density"
 
