@@ -148,7 +148,7 @@ int cnb_field_check(const cnb_field* f, const cnb_samples* s, bool bwd) {
 
 extern "C" int64_t cnb_field_ctx_floats(const cnb_field* f, int64_t n, int32_t training) {
   if (!f || n <= 0) return 0;
-  if (f->precision == CNB_PREC_MIXED) return 0;
+  if (f->precision == CNB_PREC_MIXED) return cnb_field_mixed_ctx_floats(n, training);
   return make_layout(f, n, training != 0).total;
 }
 
@@ -165,7 +165,8 @@ extern "C" int cnb_field_fwd(const cnb_field* f, const cnb_samples* s, float* de
       return CNB_ERR_UNSUPPORTED;
     }
     CNB_REQUIRE(geo == nullptr, "field_fwd: mixed precision path does not export the geo embedding");
-    return cnb_field_mixed_fwd(f, s, density, geo, rgb, sem, positions_out, stream);
+    CNB_REQUIRE(!training || ctx != nullptr, "field_fwd: mixed training forward needs ctx scratch (cnb_field_ctx_floats)");
+    return cnb_field_mixed_fwd(f, s, density, rgb, sem, positions_out, ctx, training, stream);
   }
   CNB_REQUIRE(ctx != nullptr, "field_fwd: fp32 path needs ctx scratch (cnb_field_ctx_floats)");
   const CtxLayout c = make_layout(f, N, training != 0);
@@ -203,7 +204,9 @@ extern "C" int cnb_field_bwd(const cnb_field* f, const cnb_samples* s, const flo
       return CNB_ERR_UNSUPPORTED;
     }
     CNB_REQUIRE(d_geo == nullptr, "field_bwd: mixed precision path takes no external geo gradient");
-    return cnb_field_mixed_bwd(f, s, d_density, d_rgb, d_sem, stream);
+    CNB_REQUIRE(ctx != nullptr, "field_bwd: mixed path needs the ctx written by cnb_field_fwd(training=1)");
+    CNB_REQUIRE(!f->pass_semantic_gradients, "field_bwd: pass_semantic_gradients is not compiled for the mixed path");
+    return cnb_field_mixed_bwd(f, s, d_density, d_rgb, d_sem, ctx, stream);
   }
   CNB_REQUIRE(ctx != nullptr, "field_bwd: fp32 path needs the ctx written by cnb_field_fwd(training=1)");
   const CtxLayout c = make_layout(f, N, true);

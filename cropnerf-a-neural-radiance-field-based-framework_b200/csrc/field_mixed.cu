@@ -1,14 +1,215 @@
-// FruitField on tensor cores (mixed precision) -- placeholder until the fused kernel lands.
-#include "field_common.cuh"
+// FruitField on tensor cores, mixed precision (rows a1/a5/a6 of SURVEY.md section 8; the hot-path version of
+// fruit_field.py:169-302): hash-grid gather -> base MLP -> trunc_exp density -> semantic MLP + head -> SH | geo |
+// appearance -> RGB MLP, ONE kernel, activations never leave registers.
+//
+// Mapping.  A warp owns an m-tile of 16 samples; lane (g = lane/4, t = lane%4) is wired exactly like the
+// mma.sync.m16n8k16 fragments:
+//   * the multiresolution gather lands directly in the A-operand registers of the first GEMM: feature pair of level
+//     8*kt + t (+4) of sample g (+8) IS fragment register a0..a3 of k-tile kt, so the 16 levels x 16 samples of a tile
+//     are spread over the 32 lanes with no shuffle and no shared-memory staging (64 independent 8-byte gathers/lane);
+//   * each layer's fp32 accumulator fragment (C layout) is bias-added, ReLU'd, packed to fp16 and re-used as the next
+//     layer's A fragment (two adjacent n-tiles of C == one k-tile of A);
+//   * weights live in shared memory as fp16 [out][in] rows padded by 8 halves (conflict-free 32-bit B-fragment loads).
+// Column bookkeeping: the 16 base-MLP outputs [dba | geo15] are fed unchanged as one k-tile to the semantic MLP and to
+// the RGB MLP (whose input becomes [SH16 | dba,geo15 | emb32] = 64 = 4 k-tiles) with the weight column of the dba
+// slot zeroed and the slot itself cleared, which is arithmetically the reference's concat([d, geo, emb]).
+//
+// Why mma.sync and not tcgen05 here: the dense work is ~8 K FLOP per sample in 7 dependent 16x64x64-sized steps; it
+// needs ~5 % of the tensor peak at the gather roofline.  Register-resident fragment chaining
+// has no smem/TMEM round trip between layers, whereas tcgen05 would need TMEM->reg->smem->fence per layer for the
+// activation.  DESIGN.md ("tensor-core path") records the measurement this choice rests on.
+#include "field_mixed.cuh"
 
-bool cnb_field_mixed_supported(const cnb_field*) { return false; }
+using namespace cnbmix;
 
-int cnb_field_mixed_fwd(const cnb_field*, const cnb_samples*, float*, float*, float*, float*, float*, cudaStream_t) {
-  cnb_set_error("field mixed: not built");
-  return CNB_ERR_UNSUPPORTED;
+namespace {
+
+// gather + trilinear blend of one (sample, level): returns the packed fp16 feature pair
+__device__ __forceinline__ uint32_t encode_level(const MixArgs& a, int level, float x, float y, float z) {
+  if (level >= a.L) return 0u;
+  const CnbCell c = cnb_cell(x, y, z, a.scalings[level]);
+  uint32_t h[8];
+  cnb_corner_rows(c, a.mask, (uint32_t)level * a.T, h);
+  float2 v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = cnb_ldg2(a.table, h[k]);
+  const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
+  // same pairing as the reference blend (f03,f12,f56,f47 -> f0312,f4756), FMA-contracted
+  float2 f03, f12, f56, f47;
+  f03.x = v[0].x * c.ox + v[3].x * mx; f03.y = v[0].y * c.ox + v[3].y * mx;
+  f12.x = v[1].x * c.ox + v[2].x * mx; f12.y = v[1].y * c.ox + v[2].y * mx;
+  f56.x = v[5].x * c.ox + v[6].x * mx; f56.y = v[5].y * c.ox + v[6].y * mx;
+  f47.x = v[4].x * c.ox + v[7].x * mx; f47.y = v[4].y * c.ox + v[7].y * mx;
+  const float a0 = (f03.x * c.oy + f12.x * my) * c.oz + (f47.x * c.oy + f56.x * my) * mz;
+  const float a1 = (f03.y * c.oy + f12.y * my) * c.oz + (f47.y * c.oy + f56.y * my) * mz;
+  return pack_h2(a0, a1);
 }
 
-int cnb_field_mixed_bwd(const cnb_field*, const cnb_samples*, const float*, const float*, const float*, cudaStream_t) {
-  cnb_set_error("field mixed: not built");
-  return CNB_ERR_UNSUPPORTED;
+__global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_constant__ MixArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __half* Wsm = reinterpret_cast<__half*>(smem_raw);
+  float* Bf = reinterpret_cast<float*>(smem_raw + HALVES * sizeof(__half));
+  load_weights(a, Wsm, Bf);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int S = a.sm.samples_per_ray;
+  const int64_t N = a.sm.num_rays * S;
+  const int64_t ntiles = (N + 15) >> 4;
+  for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * WARPS) {
+    int64_t row[2] = {tile * 16 + g, tile * 16 + g + 8};
+    bool valid[2], sel[2];
+    float px[2], py[2], pz[2];
+    int64_t ray[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      valid[h] = row[h] < N;
+      const int64_t r = valid[h] ? row[h] : N - 1;
+      ray[h] = r / S;
+      sel[h] = cnb_sample_position(a.sm, a.warp, ray[h], (int)(r - ray[h] * S), px[h], py[h], pz[h]);
+      if (a.pos_out && t == 0 && valid[h]) { a.pos_out[3 * r] = px[h]; a.pos_out[3 * r + 1] = py[h]; a.pos_out[3 * r + 2] = pz[h]; }
+    }
+    // ---- multiresolution gather straight into the A fragments of the first GEMM -------------------------------
+    uint32_t A0[2][4];
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) A0[kt][2 * q + h] = encode_level(a, 8 * kt + 4 * q + t, px[h], py[h], pz[h]);
+    if (a.x0_out) {
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (valid[h]) *reinterpret_cast<uint32_t*>(a.x0_out + row[h] * 32 + 16 * kt + 8 * q + 2 * t) = A0[kt][2 * q + h];
+    }
+    // ---- base MLP: 32 -> 64 -> 16 --------------------------------------------------------------------------------
+    uint32_t Abo[1][4];
+    {
+      float acc[8][4];
+      init_bias<8>(acc, Bf + F_BB1, t);
+      layer<8, 2, S32>(Wsm + O_WB1, A0, acc, g, t);
+      uint32_t AH[4][4];
+      to_afrag<4, true>(acc, AH);
+      float acc2[2][4];
+      init_bias<2>(acc2, Bf + F_BB2, t);
+      layer<2, 4, S64>(Wsm + O_WB2, AH, acc2, g, t);
+      if (t == 0) {  // column 0 = density before activation (fruit_field.py:185-193: trunc_exp in fp32, times the selector)
+        if (valid[0]) a.density[row[0]] = sel[0] ? expf(acc2[0][0]) : 0.f;
+        if (valid[1]) a.density[row[1]] = sel[1] ? expf(acc2[0][2]) : 0.f;
+        acc2[0][0] = 0.f; acc2[0][2] = 0.f;  // clear the dba slot: its weight columns downstream are zero
+      }
+      to_afrag<1, false>(acc2, Abo);
+    }
+    // ---- semantic MLP 15 -> 64 -> 64 and head 64 -> 1 (fruit_field.py:264-269) ------------------------------------
+    if (a.sem) {
+      float acc[8][4];
+      init_bias<8>(acc, Bf + F_BS1, t);
+      layer<8, 1, S16>(Wsm + O_WS1, Abo, acc, g, t);
+      uint32_t AS1[4][4];
+      to_afrag<4, true>(acc, AS1);
+      init_bias<8>(acc, Bf + F_BS2, t);
+      layer<8, 4, S64>(Wsm + O_WS2, AS1, acc, g, t);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 w = *reinterpret_cast<const float2*>(Bf + F_WH + nt * 8 + 2 * t);
+        s0 = fmaf(acc[nt][0], w.x, fmaf(acc[nt][1], w.y, s0));
+        s1 = fmaf(acc[nt][2], w.x, fmaf(acc[nt][3], w.y, s1));
+      }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      if (t == 0) {
+        const float bh = Bf[F_BH];
+        if (valid[0]) a.sem[row[0]] = s0 + bh;
+        if (valid[1]) a.sem[row[1]] = s1 + bh;
+      }
+    }
+    // ---- RGB MLP [SH16 | geo15 | emb32] -> 64 -> 64 -> 3, sigmoid (fruit_field.py:271-280) ---------------------------
+    if (a.rgb) {
+      uint32_t Ain[4][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float c[16];
+        cnb_sh16(__ldg(a.sm.directions + 3 * ray[h]), __ldg(a.sm.directions + 3 * ray[h] + 1), __ldg(a.sm.directions + 3 * ray[h] + 2), c);
+        Ain[0][h] = pack_h2(pick4(t, c[0], c[2], c[4], c[6]), pick4(t, c[1], c[3], c[5], c[7]));
+        Ain[0][2 + h] = pack_h2(pick4(t, c[8], c[10], c[12], c[14]), pick4(t, c[9], c[11], c[13], c[15]));
+        const float* e = nullptr;
+        if (a.app_mode == CNB_APP_PER_CAMERA) e = a.embedding + (int64_t)__ldg(a.sm.camera_indices + ray[h]) * 32;
+        else if (a.app_mode == CNB_APP_MEAN) e = a.embedding;
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+          float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+          if (e) { lo = __ldg(reinterpret_cast<const float2*>(e + 16 * kt + 2 * t)); hi = __ldg(reinterpret_cast<const float2*>(e + 16 * kt + 8 + 2 * t)); }
+          Ain[2 + kt][h] = pack_h2(lo.x, lo.y);
+          Ain[2 + kt][2 + h] = pack_h2(hi.x, hi.y);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Ain[1][i] = Abo[0][i];
+      float acc[8][4];
+      init_bias<8>(acc, Bf + F_BR1, t);
+      layer<8, 4, S64>(Wsm + O_WR1, Ain, acc, g, t);
+      uint32_t AR[4][4];
+      to_afrag<4, true>(acc, AR);
+      init_bias<8>(acc, Bf + F_BR2, t);
+      layer<8, 4, S64>(Wsm + O_WR2, AR, acc, g, t);
+      to_afrag<4, true>(acc, AR);
+      float acc3[1][4];
+      init_bias<1>(acc3, Bf + F_BR3, t);
+      layer<1, 4, S64>(Wsm + O_WR3, AR, acc3, g, t);
+      if (t < 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (!valid[h]) continue;
+          const float v0 = 1.f / (1.f + __expf(-acc3[0][2 * h])), v1 = 1.f / (1.f + __expf(-acc3[0][2 * h + 1]));
+          if (t == 0) { a.rgb[3 * row[h]] = v0; a.rgb[3 * row[h] + 1] = v1; }
+          else a.rgb[3 * row[h] + 2] = v0;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+bool cnb_field_mixed_supported(const cnb_field* f) {
+  const cnb_mlp &b = f->base, &s = f->sem, &r = f->rgb;
+  return f->grid.num_levels <= 16 && b.num_layers == 2 && b.dims[0] == 2 * f->grid.num_levels && b.dims[1] == H && b.dims[2] == 16 &&
+         s.num_layers == 2 && s.dims[0] == 15 && s.dims[1] == H && s.dims[2] == H && f->sem_head.dims[0] == H && f->sem_head.dims[1] == 1 &&
+         r.num_layers == 3 && r.dims[0] == 63 && r.dims[1] == H && r.dims[2] == H && r.dims[3] == 3 && f->appearance_dim == 32 && f->geo_feat_dim == 15;
+}
+
+// ctx (mixed, training): [x0: N*32 fp16 = N*16 floats][positions: N*3 floats][d_x0: N*32 floats]
+int64_t cnb_field_mixed_ctx_floats(int64_t n, int training) { return training ? n * (16 + 3 + 32) + 16 : 0; }
+
+int cnb_field_mixed_fwd(const cnb_field* f, const cnb_samples* s, float* density, float* rgb, float* sem, float* positions_out, float* ctx,
+                        int training, cudaStream_t stream) {
+  MixArgs a;
+  fill_args(f, s, a);
+  const int64_t N = s->num_rays * s->samples_per_ray;
+  a.density = density; a.rgb = rgb; a.sem = sem; a.pos_out = positions_out; a.x0_out = nullptr;
+  if (training) {
+    a.x0_out = reinterpret_cast<__half*>(ctx);
+    a.pos_out = ctx + N * 16;
+  }
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(k_field_mixed_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD) != cudaSuccess) return cnb_check_launch("field_mixed_fwd attr");
+    configured = true;
+  }
+  const int64_t ntiles = (N + 15) / 16;
+  int64_t blocks = (ntiles + WARPS - 1) / WARPS;
+  const int64_t cap = (int64_t)cnb_num_sms() * 2;
+  if (blocks > cap) blocks = cap;
+  k_field_mixed_fwd<<<(int)blocks, THREADS, SMEM_FWD, stream>>>(a);
+  int rc = cnb_check_launch("field_mixed_fwd");
+  if (rc) return rc;
+  if (training && positions_out != nullptr &&
+      cudaMemcpyAsync(positions_out, a.pos_out, sizeof(float) * 3 * N, cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+    return cnb_check_launch("field_mixed_fwd positions copy");
+  return CNB_OK;
 }
