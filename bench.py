@@ -119,22 +119,14 @@ def bytes_of(batch):
     return int(sum(v.numel() * v.element_size() for v in batch.values()))
 
 
-def run_product(args):
+def measure(args, precision, dev, world, rank, local_rank, full=True):
+    """One precision mode: training step (resident + end-to-end), per-stage device times, eval render."""
     from cropnerf_b200 import _lib as L
     from cropnerf_b200 import engine
+    from cropnerf_b200.rays import RayBundle
     import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
-
-    model = build_model(dev, args.precision)
+    model = build_model(dev, precision)
     trainer = engine.Trainer(model, world_size=world)
     R = RAYS_PER_GPU
     nb = 8  # distinct ray batches cycled through (fresh rays every step, like next_train)
@@ -148,10 +140,10 @@ def run_product(args):
         torch.cuda.synchronize()
 
     def train_step(step, rb, tg):
-        from cropnerf_b200.rays import RayBundle
         rb = RayBundle(rb.origins, rb.directions, rb.pixel_area, rb.camera_indices)  # the collider mutates the bundle
         return trainer.train_iteration(step, rb, tg)
 
+    steps = args.steps if full else max(3, args.steps // 2)
     # ---- warm-up -----------------------------------------------------------------------------------------
     step = 0
     for _ in range(max(args.warmup, 3)):
@@ -159,32 +151,26 @@ def run_product(args):
     barrier()
 
     # ---- timed: resident inputs ----------------------------------------------------------------------------
-    prof = L.Profile(timing=False)
-    L.set_profile(prof)
     clocks = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and full:
         clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
-    for i in range(args.steps):
+    for i in range(steps):
         l2_flush.fill_(i & 0xFF)  # flush L2 between timed iterations (the 74 MiB of tables would otherwise stay resident)
         ev[i][0].record()
         train_step(step, *resident[step % nb]); step += 1
         ev[i][1].record()
     barrier()
-    clk = clocks.stop() if rank == 0 else None
-    L.set_profile(None)
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    t_local = sum(step_ms) / 1e3
-    launches = prof.launches()
+    clk = clocks.stop() if (rank == 0 and full) else None
+    t_local = sum(a.elapsed_time(b) for a, b in ev) / 1e3
 
     # ---- timed: end to end through the public API with host buffers ------------------------------------------
     barrier()
-    t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     loss_host = 0.0
-    for i in range(args.steps):
+    for i in range(steps):
         rb, tg = to_bundle(host[step % nb], dev)       # H2D from pinned memory, every step
         stats = trainer.train_iteration(step, rb, tg); step += 1
         loss_host = float(stats["loss"].item())        # D2H read of the step's result
@@ -192,15 +178,26 @@ def run_product(args):
     barrier()
     t_e2e_local = e0.elapsed_time(e1) / 1e3
 
-    # ---- per-call device times for the roofline (separate pass so the events do not perturb the timed region) ----
-    prof_t = L.Profile(timing=True)
-    L.set_profile(prof_t)
-    n_prof = min(args.steps, 5)
-    for i in range(n_prof):
-        l2_flush.fill_(i & 0xFF)
-        train_step(step, *resident[step % nb]); step += 1
-    call_ms = prof_t.times_ms()
-    L.set_profile(None)
+    # ---- per-stage device times (separate pass so the events do not perturb the timed region) ----------------
+    stage, adam_ms, n_prof = {}, 0.0, min(steps, 5)
+    if full:
+        L.lib().cnb_profile_enable(1)
+        a_ev = []
+        orig_opt = trainer.optimizer_step
+
+        def timed_opt(s):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(); orig_opt(s); a1.record()
+            a_ev.append((a0, a1))
+
+        trainer.optimizer_step = timed_opt
+        for i in range(n_prof):
+            l2_flush.fill_(i & 0xFF)
+            train_step(step, *resident[step % nb]); step += 1
+        stage = L.stage_profile_read()
+        L.lib().cnb_profile_enable(0)
+        trainer.optimizer_step = orig_opt
+        adam_ms = sum(a.elapsed_time(b) for a, b in a_ev) / n_prof
 
     # ---- render (export / projection loop body), eval mode ----------------------------------------------------
     model.eval()
@@ -209,21 +206,21 @@ def run_product(args):
     rres, _ = to_bundle(rhost, dev, non_blocking=False)
 
     def render_once(rb):
-        from cropnerf_b200.rays import RayBundle
         with torch.no_grad():
             return model(RayBundle(rb.origins, rb.directions, rb.pixel_area, rb.camera_indices))
 
     for _ in range(3):
         render_once(rres)
     barrier()
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_r = max(3, min(args.steps, 10))
-    r0.record()
-    for _ in range(n_r):
+    n_r = max(3, min(steps, 10))
+    rev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_r)]
+    for i in range(n_r):
+        l2_flush.fill_(i & 0xFF)
+        rev[i][0].record()
         render_once(rres)
-    r1.record()
+        rev[i][1].record()
     barrier()
-    t_render_local = r0.elapsed_time(r1) / 1e3
+    t_render_local = sum(a.elapsed_time(b) for a, b in rev) / 1e3
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h0.record()
     d2h_render = 0
@@ -235,6 +232,14 @@ def run_product(args):
     h1.record()
     barrier()
     t_render_e2e_local = h0.elapsed_time(h1) / 1e3
+    render_stage = {}
+    if full:
+        L.lib().cnb_profile_enable(1)
+        for i in range(3):
+            l2_flush.fill_(i & 0xFF)
+            render_once(rres)
+        render_stage = {k: v["ms"] / 3 for k, v in L.stage_profile_read().items()}
+        L.lib().cnb_profile_enable(0)
     model.train()
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------------------
@@ -242,55 +247,89 @@ def run_product(args):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     t, t_e2e, t_render, t_render_e2e = times.tolist()
+    del trainer, model, l2_flush
+    torch.cuda.empty_cache()
+    return {"steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
+            "stage": stage, "n_prof": n_prof, "adam_ms": adam_ms, "render_stage": render_stage, "loss": loss_host,
+            "h2d_train": bytes_of(host[0]), "h2d_render": bytes_of({k: rhost[k] for k in ("origins", "directions", "pixel_area", "camera_indices")}),
+            "d2h_render": int(d2h_render)}
+
+
+# algorithmic bytes per ray of each pipeline stage (fp32 tables, 8 corners x 8 B per (sample, level)):
+# forward = one gather; proposal backward = re-gather + scatter read-modify-write; field backward = scatter RMW only
+# (the encoded features are kept by the forward)
+STAGE_BYTES_PER_RAY = {
+    "proposal0_fwd": FETCH_BYTES["prop0"], "proposal1_fwd": FETCH_BYTES["prop1"], "field_fwd": FETCH_BYTES["field"],
+    "proposal0_bwd": 3 * FETCH_BYTES["prop0"], "proposal1_bwd": 3 * FETCH_BYTES["prop1"], "field_bwd": 2 * FETCH_BYTES["field"],
+}
+
+
+def run_product(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
+
+    m = measure(args, args.precision, dev, world, rank, local_rank, full=True)
+    other = "fp32" if args.precision == "mixed" else "mixed"
+    m2 = measure(args, other, dev, world, rank, local_rank, full=False) if not args.single_precision else None
+    R = RAYS_PER_GPU
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        total_rays = world * R * args.steps
-        value = total_rays / t
-        # dominant C-ABI call by accumulated device time
-        tot = {k: sum(v) / n_prof for k, v in call_ms.items()}
-        dom = max(tot, key=tot.get)
-        counts = {k: len(v) / n_prof for k, v in call_ms.items()}
-        per_launch_ms = tot[dom] / counts[dom]
-        # algorithmic bytes of one call of the dominant op (fp32 tables; see DESIGN.md "algorithmic bytes")
-        per_ray = {
-            "cnb_field_bwd": 2 * FETCH_BYTES["field"],                     # fp32 path keeps activations: scatter RMW only
-            "cnb_field_fwd": FETCH_BYTES["field"],
-            "cnb_density_field_fwd": (FETCH_BYTES["prop0"] + FETCH_BYTES["prop1"]) / 2,   # averaged over the two levels
-            "cnb_density_field_bwd": 3 * (FETCH_BYTES["prop0"] + FETCH_BYTES["prop1"]) / 2,
-        }.get(dom)
-        if args.precision == "mixed":
-            per_ray = {"cnb_field_bwd": 3 * FETCH_BYTES["field"], "cnb_field_fwd": FETCH_BYTES["field"]}.get(dom, per_ray)
-        roofline = {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": None,
-                    "ms_per_launch": per_launch_ms, "share_of_step": tot[dom] / (sum(tot.values()) + 1e-12)}
-        if per_ray is not None:
-            ach = per_ray * R / (per_launch_ms * 1e-3) / 1e9
-            roofline.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": per_ray * R})
-        else:
-            roofline.update({"achieved": None, "frac": None})
-        step_achieved = TRAIN_BYTES_PER_RAY * total_rays / t / 1e9
+        steps = m["steps"]
+        total_rays = world * R * steps
+        value = total_rays / m["t"]
+        n_prof = m["n_prof"]
+        tot = {k: v["ms"] / n_prof for k, v in m["stage"].items()}
+        tot["adam (fused Adam + grad clear, 2 flat groups)"] = m["adam_ms"]
+        launches = sum(v["kernels"] for v in m["stage"].values()) / n_prof + 2
+        cand = {k: v for k, v in tot.items() if k in STAGE_BYTES_PER_RAY}
+        dom = max(cand, key=cand.get)
+        calls = m["stage"][dom]["calls"] / n_prof
+        per_launch_ms = tot[dom] / calls
+        per_ray = STAGE_BYTES_PER_RAY[dom]
+        ach = per_ray * R / (per_launch_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "ms_per_launch": per_launch_ms, "share_of_step": tot[dom] / (sum(tot.values()) + 1e-12),
+                    "algorithmic_bytes_per_launch": per_ray * R,
+                    "note": "algorithmic bytes = 8-byte corner fetches of SURVEY.md 8d; the 74 MiB of tables are L2-resident, so DRAM traffic is far below this"}
+        step_achieved = TRAIN_BYTES_PER_RAY * total_rays / m["t"] / 1e9
+        n_r, Rr = m["n_r"], m["Rr"]
         line = {
-            "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "f16 tensor-core MLPs, f32 tables/accumulate/compositing", "data": "synthetic",
+            "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * m["t"] / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "f16 tensor-core MLPs (bf16 gradients), f32 hash tables / accumulation / compositing",
+            "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: fruit_nerf preset training step, 4096 rays/GPU, proposal 256/96 + 48 NeRF samples, "
                                    "field 16x2^19x2 + 2 proposal 5x2^17x2 fp32 hash tables, 300 synthetic 1080p cameras",
                        "rays_per_gpu": R, "samples_per_ray": 400, "precision": args.precision, "l2": "flushed between timed iterations (192 MiB fill)",
-                       "includes": "fwd + bwd (all three networks updated) + gradient all-reduce + Adam"},
+                       "includes": "fwd + losses + bwd (all three networks updated) + gradient all-reduce + Adam, one cnb_train_step call per step"},
             "samples_per_s": value * 400,
-            "step_roofline": {"algorithmic_bytes_per_ray": TRAIN_BYTES_PER_RAY, "achieved_GBps": step_achieved, "frac": step_achieved / peak,
+            "step_roofline": {"algorithmic_bytes_per_ray": TRAIN_BYTES_PER_RAY, "achieved_GBps": step_achieved, "frac": step_achieved / (peak * world),
                               "roofline_rays_per_s_per_gpu": peak * 1e9 / TRAIN_BYTES_PER_RAY},
-            "e2e": {"value": total_rays / t_e2e, "unit": "rays/s", "h2d_bytes_per_step": bytes_of(host[0]), "d2h_bytes_per_step": 4,
-                    "last_loss": loss_host},
-            "render": {"value": world * Rr * n_r / t_render, "unit": "rays/s", "rays_per_call": Rr,
-                       "e2e": {"value": world * Rr * n_r / t_render_e2e, "unit": "rays/s", "h2d_bytes_per_step": bytes_of({k: rhost[k] for k in ("origins", "directions", "pixel_area", "camera_indices")}),
-                               "d2h_bytes_per_step": int(d2h_render)},
-                       "roofline_frac": (RENDER_BYTES_PER_RAY * world * Rr * n_r / t_render / 1e9) / (peak * world)},
+            "e2e": {"value": total_rays / m["t_e2e"], "unit": "rays/s", "h2d_bytes_per_step": m["h2d_train"], "d2h_bytes_per_step": 4,
+                    "last_loss": m["loss"]},
+            "render": {"value": world * Rr * n_r / m["t_render"], "unit": "rays/s", "rays_per_call": Rr, "l2": "flushed between calls",
+                       "e2e": {"value": world * Rr * n_r / m["t_render_e2e"], "unit": "rays/s", "h2d_bytes_per_step": m["h2d_render"],
+                               "d2h_bytes_per_step": m["d2h_render"]},
+                       "roofline_frac": (RENDER_BYTES_PER_RAY * world * Rr * n_r / m["t_render"] / 1e9) / (peak * world),
+                       "stage_ms_per_call": {k: round(v, 4) for k, v in sorted(m["render_stage"].items(), key=lambda kv: -kv[1])}},
             "roofline": roofline,
-            "call_ms_per_step": {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])},
-            "gpu_launches": launches,
-            "clocks": clk,
+            "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])},
+            "gpu_launches": int(round(launches * steps)),
+            "clocks": m["clk"],
         }
+        if m2 is not None:
+            line["other_precision"] = {"precision": other, "train_rays_per_s": world * R * m2["steps"] / m2["t"], "ms_per_step": 1e3 * m2["t"] / m2["steps"],
+                                       "render_rays_per_s": world * m2["Rr"] * m2["n_r"] / m2["t_render"]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sample_rays=4 * args.cpu_rays, steps=2, warmup=1)
         print(json.dumps(line), flush=True)
@@ -354,7 +393,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CNB_PRECISION", "fp32"), choices=["fp32", "mixed"])
+    ap.add_argument("--precision", default=os.environ.get("CNB_PRECISION", "mixed"), choices=["fp32", "mixed"],
+                    help="mixed = fp16 tensor-core MLPs like the reference's autocast training (fruit_nerf_config.py:35); fp32 = exact mode")
+    ap.add_argument("--single-precision", action="store_true", help="skip the short pass in the other precision mode")
     ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per CPU-baseline step (bounded sample of the 4096-ray batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -95,6 +95,69 @@ class Field(C.Structure):
     ]
 
 
+class Rays(C.Structure):
+    _fields_ = [
+        ("origins", C.c_void_p),
+        ("directions", C.c_void_p),
+        ("nears", C.c_void_p),
+        ("fars", C.c_void_p),
+        ("camera_indices", C.c_void_p),
+        ("num_rays", C.c_int64),
+        ("near_plane", C.c_float),
+        ("far_plane", C.c_float),
+    ]
+
+
+class Sampler(C.Structure):
+    _fields_ = [
+        ("num_proposal_iterations", C.c_int32),
+        ("proposal_samples", C.c_int32 * 2),
+        ("nerf_samples", C.c_int32),
+        ("initial_spacing", C.c_int32),
+        ("single_jitter", C.c_int32),
+        ("histogram_padding", C.c_float),
+        ("pdf_eps", C.c_float),
+        ("lin_bins", C.c_void_p),
+        ("u_base", C.c_void_p * 2),
+    ]
+
+
+class Model(C.Structure):
+    _fields_ = [
+        ("field", Field),
+        ("proposal", DensityField * 2),
+        ("sampler", Sampler),
+        ("bg_mode", C.c_int32),
+        ("bg_color", C.c_float * 3),
+        ("_pad", C.c_int32),
+    ]
+
+
+class RayOutputs(C.Structure):
+    _fields_ = [
+        ("rgb", C.c_void_p),
+        ("depth", C.c_void_p),
+        ("accumulation", C.c_void_p),
+        ("semantics", C.c_void_p),
+        ("prop_depth", C.c_void_p * 2),
+        ("pdf_inds", C.c_void_p),
+    ]
+
+
+class TrainCfg(C.Structure):
+    _fields_ = [
+        ("image", C.c_void_p),
+        ("fruit_mask", C.c_void_p),
+        ("jitter", C.c_void_p),
+        ("anneal", C.c_float),
+        ("semantic_loss_weight", C.c_float),
+        ("interlevel_loss_mult", C.c_float),
+        ("grad_scale", C.c_float),
+        ("update_proposals", C.c_int32),
+        ("want_metrics", C.c_int32),
+    ]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _I32 = C.c_int32
@@ -126,6 +189,12 @@ SIGNATURES = {
     "cnb_distortion_fwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "cnb_pixel_losses": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _P, _P, _P, _P]),
     "cnb_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P]),
+    "cnb_adam_step_zero": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P]),
+    "cnb_profile_enable": (None, [_I32]),
+    "cnb_profile_read": (C.c_int, [C.c_char_p, _I32]),
+    "cnb_render_workspace_floats": (_I64, [C.POINTER(Model), _I64, _I32]),
+    "cnb_render_rays": (C.c_int, [C.POINTER(Model), C.POINTER(Rays), C.POINTER(RayOutputs), _P, _P]),
+    "cnb_train_step": (C.c_int, [C.POINTER(Model), C.POINTER(Rays), C.POINTER(TrainCfg), C.POINTER(RayOutputs), _P, _P, _P]),
 }
 
 _lib: Optional["_Proxy"] = None
@@ -294,3 +363,15 @@ def make_warp(contraction: bool, aabb) -> Warp:
         w.aabb_min[i] = box[0][i]
         w.aabb_max[i] = box[1][i]
     return w
+
+
+def stage_profile_read() -> dict:
+    """{stage: {"calls", "kernels", "ms"}} recorded by the fused pipeline since ``cnb_profile_enable(1)`` (synchronises)."""
+    buf = C.create_string_buffer(8192)
+    check(lib().cnb_profile_read(buf, 8192), "profile_read")
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if item:
+            name, calls, kernels, ms = item.split(":")
+            out[name] = {"calls": int(calls), "kernels": int(kernels), "ms": float(ms)}
+    return out

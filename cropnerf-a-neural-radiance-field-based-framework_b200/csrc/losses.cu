@@ -134,6 +134,26 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
   }
 }
 
+// Adam + gradient clear in one pass over a flat group (float4 lanes; n is a multiple of 4 for the flat groups):
+// 4 reads + 4 writes of 16 B per 4 parameters, nothing else touches the group between backward and the next forward.
+__global__ void __launch_bounds__(256) k_adam_zero4(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                                                    int64_t n4, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_scale) {
+  const float step_size = lr / bc1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 gi = g[i], mi = m[i], vi = v[i], pi = p[i];
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* gp = &gi.x; float* mp = &mi.x; float* vp = &vi.x; float* pp = &pi.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = gp[k] * inv_scale;
+      mp[k] = mp[k] + (1.0f - b1) * (gk - mp[k]);
+      vp[k] = b2 * vp[k] + (1.0f - b2) * gk * gk;
+      pp[k] -= step_size * (mp[k] / (sqrtf(vp[k]) / bc2_sqrt + eps));
+    }
+    m[i] = mi; v[i] = vi; p[i] = pi;
+  }
+}
+
 int ray_grid(int64_t R) {
   int64_t blocks = (R + WARPS - 1) / WARPS;
   const int64_t cap = (int64_t)cnb_num_sms() * 16;
@@ -208,4 +228,27 @@ extern "C" int cnb_adam_step(float* param, const float* grad, float* exp_avg, fl
   if (blocks > cap) blocks = cap;
   k_adam<<<(int)blocks, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), inv_grad_scale);
   return cnb_check_launch("adam");
+}
+
+extern "C" int cnb_adam_step_zero(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                                  float eps, int32_t step, float inv_grad_scale, cnb_stream_t stream) {
+  CNB_REQUIRE(n >= 0 && step >= 1, "adam: bad n/step");
+  if (n == 0) return CNB_OK;
+  CNB_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam: null pointer");
+  const bool vec = (n % 4 == 0) && ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0);
+  if (!vec) {
+    int rc = cnb_adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, inv_grad_scale, stream);
+    if (rc) return rc;
+    if (cudaMemsetAsync(grad, 0, sizeof(float) * n, stream) != cudaSuccess) return cnb_check_launch("adam memset");
+    return CNB_OK;
+  }
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  const int64_t cap = (int64_t)cnb_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  k_adam_zero4<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(param), reinterpret_cast<float4*>(grad), reinterpret_cast<float4*>(exp_avg),
+                                                reinterpret_cast<float4*>(exp_avg_sq), n4, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), inv_grad_scale);
+  return cnb_check_launch("adam_zero");
 }

@@ -1,0 +1,281 @@
+// The ray-render loop body as ONE C call (row a15 of SURVEY.md section 8): what FruitModel.get_outputs /
+// get_inference_outputs (fruit_nerf.py:497-599) do per chunk of rays, plus -- for training -- get_loss_dict /
+// get_metrics_dict (fruit_nerf.py:601-615,639-645) and the full backward.  Everything is enqueued on the caller's
+// stream into a caller-provided workspace: no allocation, no host synchronisation, CUDA-graph capturable.
+//
+// Workspace layout (floats, every block 64-float aligned), for S_l = samples of level l (proposal levels then the field):
+//   nears,fars [R] | per level: spacing edges [R,S_l+1], euclid edges [R,S_l+1], density [R,S_l], weights [R,S_l]
+//   | field rgb [R,S,3], sem [R,S] | per-ray outputs | (training) per-ray output grads, d_weights/d_density per level,
+//   d_rgb, d_sem | field ctx (cnb_field_ctx_floats)
+#include "cnb_common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr int MAX_LEVELS_P = 3;
+
+// Optional per-stage device timing of the calls below (cudaEvents on the launching stream); off by default and never
+// enabled during graph capture.  Read with cnb_profile_read.
+struct StageEv { const char* name; int kernels; cudaEvent_t e0, e1; };
+bool g_prof_on = false;
+std::vector<StageEv> g_prof;
+
+struct StageTimer {
+  cudaStream_t st; bool on; StageEv ev;
+  StageTimer(const char* name, int kernels, cudaStream_t s) : st(s), on(g_prof_on) {
+    if (!on) return;
+    ev.name = name; ev.kernels = kernels;
+    cudaEventCreate(&ev.e0); cudaEventCreate(&ev.e1);
+    cudaEventRecord(ev.e0, st);
+  }
+  ~StageTimer() {
+    if (!on) return;
+    cudaEventRecord(ev.e1, st);
+    g_prof.push_back(ev);
+  }
+};
+#define STAGE(name, kernels, call) do { StageTimer _t(name, kernels, st); rc = (call); } while (0)
+
+struct Layout {
+  int levels;            // proposal iterations + 1
+  int S[MAX_LEVELS_P];
+  int64_t nears, fars;
+  int64_t sp[MAX_LEVELS_P], eu[MAX_LEVELS_P], dens[MAX_LEVELS_P], w[MAX_LEVELS_P];
+  int64_t rgb, sem;
+  int64_t o_rgb, o_acc, o_sem, o_depth, o_pd[2];
+  int64_t g_rgb, g_sem, d_w[MAX_LEVELS_P], d_dens[MAX_LEVELS_P], d_rgb, d_sem;
+  int64_t ctx, ctx_floats;
+  int64_t total;
+};
+
+int make_layout(const cnb_model* m, int64_t R, bool training, Layout& L) {
+  const cnb_sampler& s = m->sampler;
+  CNB_REQUIRE(s.num_proposal_iterations >= 1 && s.num_proposal_iterations <= 2, "render: num_proposal_iterations %d outside 1..2", s.num_proposal_iterations);
+  L.levels = s.num_proposal_iterations + 1;
+  for (int i = 0; i < s.num_proposal_iterations; ++i) L.S[i] = s.proposal_samples[i];
+  L.S[L.levels - 1] = s.nerf_samples;
+  for (int i = 0; i < L.levels; ++i) CNB_REQUIRE(L.S[i] >= 1 && L.S[i] <= 4096, "render: samples per ray %d outside 1..4096", L.S[i]);
+  int64_t o = 0;
+  auto take = [&](int64_t n) { int64_t r = o; o += (n + 63) & ~(int64_t)63; return r; };
+  L.nears = take(R); L.fars = take(R);
+  for (int i = 0; i < L.levels; ++i) {
+    L.sp[i] = take(R * (L.S[i] + 1)); L.eu[i] = take(R * (L.S[i] + 1));
+    L.dens[i] = take(R * L.S[i]); L.w[i] = take(R * L.S[i]);
+  }
+  const int Sf = L.S[L.levels - 1];
+  L.rgb = take(R * Sf * 3); L.sem = take(R * Sf);
+  L.o_rgb = take(R * 3); L.o_acc = take(R); L.o_sem = take(R); L.o_depth = take(R); L.o_pd[0] = take(R); L.o_pd[1] = take(R);
+  if (training) {
+    L.g_rgb = take(R * 3); L.g_sem = take(R);
+    for (int i = 0; i < L.levels; ++i) { L.d_w[i] = take(R * L.S[i]); L.d_dens[i] = take(R * L.S[i]); }
+    L.d_rgb = take(R * Sf * 3); L.d_sem = take(R * Sf);
+  }
+  L.ctx_floats = cnb_field_ctx_floats(&m->field, R * Sf, training ? 1 : 0);
+  L.ctx = take(L.ctx_floats);
+  L.total = o;
+  return CNB_OK;
+}
+
+__global__ void __launch_bounds__(256) k_fill_near_far(const float* __restrict__ nears, const float* __restrict__ fars, float near_plane, float far_plane,
+                                                        int64_t R, float* __restrict__ n_out, float* __restrict__ f_out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R; i += (int64_t)gridDim.x * blockDim.x) {
+    n_out[i] = nears ? __ldg(nears + i) : near_plane;
+    f_out[i] = fars ? __ldg(fars + i) : far_plane;
+  }
+}
+
+__global__ void k_scale(float* __restrict__ v, int n, float s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] *= s;
+}
+
+cnb_samples make_samples(const cnb_rays* rays, const float* edges, int S) {
+  cnb_samples sm;
+  sm.origins = rays->origins; sm.directions = rays->directions;
+  sm.starts = edges; sm.ends = edges + 1;
+  sm.camera_indices = rays->camera_indices;
+  sm.num_rays = rays->num_rays; sm.row_stride = S + 1; sm.samples_per_ray = S; sm._pad = 0;
+  return sm;
+}
+
+int check_common(const cnb_model* m, const cnb_rays* rays, const float* ws) {
+  CNB_REQUIRE(m && rays, "render: null model/rays");
+  CNB_REQUIRE(rays->num_rays >= 0, "render: negative ray count");
+  if (rays->num_rays == 0) return CNB_OK;
+  CNB_REQUIRE(rays->origins && rays->directions, "render: null ray arrays");
+  CNB_REQUIRE(ws != nullptr, "render: null workspace (cnb_render_workspace_floats)");
+  CNB_REQUIRE(m->sampler.lin_bins != nullptr, "render: sampler.lin_bins missing");
+  for (int i = 1; i <= m->sampler.num_proposal_iterations; ++i) CNB_REQUIRE(m->sampler.u_base[i - 1] != nullptr, "render: sampler.u_base[%d] missing", i - 1);
+  return CNB_OK;
+}
+
+// sampler + proposal networks + field + compositing.  jitter == nullptr: deterministic (eval) samplers.
+int forward_chain(const cnb_model* m, const cnb_rays* rays, const Layout& L, float* ws, bool training, const float* jitter, float anneal,
+                  const cnb_ray_outputs* out, cudaStream_t st) {
+  const int64_t R = rays->num_rays;
+  const cnb_sampler& sp = m->sampler;
+  int rc;
+  int64_t blocks = (R + 255) / 256;
+  if (blocks > 4 * cnb_num_sms()) blocks = 4 * cnb_num_sms();
+  {
+    StageTimer _t("near_far", 1, st);
+    k_fill_near_far<<<(int)blocks, 256, 0, st>>>(rays->nears, rays->fars, rays->near_plane, rays->far_plane, R, ws + L.nears, ws + L.fars);
+  }
+  if ((rc = cnb_check_launch("render near/far"))) return rc;
+  const bool mixed = m->field.precision == CNB_PREC_MIXED;
+  const float* jit = jitter;
+  for (int lv = 0; lv < L.levels; ++lv) {
+    const int S = L.S[lv];
+    const int rstride = sp.single_jitter ? 1 : S + 1;
+    if (lv == 0) {
+      STAGE("sample_spaced", 1, cnb_sample_spaced(ws + L.nears, ws + L.fars, sp.lin_bins, jit, rstride, sp.initial_spacing, R, S, ws + L.sp[0], ws + L.eu[0], st));
+    } else {
+      const int Sp = L.S[lv - 1];
+      STAGE("sample_pdf", 1, cnb_sample_pdf(ws + L.w[lv - 1], anneal, ws + L.sp[lv - 1], ws + L.nears, ws + L.fars, sp.initial_spacing, sp.u_base[lv - 1], jit,
+                                            rstride, R, Sp, S, sp.histogram_padding, sp.pdf_eps, ws + L.sp[lv], ws + L.eu[lv],
+                                            (lv == L.levels - 1 && out) ? out->pdf_inds : nullptr, st));
+    }
+    if (rc) return rc;
+    if (jit) jit += R * rstride;
+    const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
+    if (lv < L.levels - 1) {
+      STAGE(lv == 0 ? "proposal0_fwd" : "proposal1_fwd", 1, cnb_density_field_fwd(&m->proposal[lv], &sm, ws + L.dens[lv], nullptr, st));
+      if (rc) return rc;
+    } else {
+      STAGE("field_fwd", mixed ? 1 : 7, cnb_field_fwd(&m->field, &sm, ws + L.dens[lv], nullptr, ws + L.rgb, ws + L.sem, nullptr,
+                                                        L.ctx_floats > 0 ? ws + L.ctx : nullptr, training ? 1 : 0, st));
+      if (rc) return rc;
+    }
+    STAGE("weights_fwd", 1, cnb_weights_fwd(ws + L.dens[lv], ws + L.eu[lv], ws + L.eu[lv] + 1, S + 1, R, S, ws + L.w[lv], st));
+    if (rc) return rc;
+  }
+  const int lf = L.levels - 1, Sf = L.S[lf];
+  const bool user = out != nullptr;
+  float* o_rgb = (user && out->rgb) ? out->rgb : ws + L.o_rgb;
+  float* o_acc = (user && out->accumulation) ? out->accumulation : ws + L.o_acc;
+  float* o_sem = (user && out->semantics) ? out->semantics : ws + L.o_sem;
+  float* o_depth = (user && out->depth) ? out->depth : nullptr;
+  STAGE("render_fwd", 1, cnb_render_fwd(ws + L.w[lf], ws + L.rgb, ws + L.sem, ws + L.eu[lf], ws + L.eu[lf] + 1, Sf + 1, R, Sf, m->bg_mode, m->bg_color,
+                                        training ? 0 : 1, o_rgb, o_depth, o_acc, o_sem, nullptr, st));
+  if (rc) return rc;
+  for (int lv = 0; lv < lf; ++lv) {
+    if (user && out->prop_depth[lv]) {
+      STAGE("prop_depth", 1, cnb_render_fwd(ws + L.w[lv], nullptr, nullptr, ws + L.eu[lv], ws + L.eu[lv] + 1, L.S[lv] + 1, R, L.S[lv], CNB_BG_NONE, nullptr,
+                                            0, nullptr, out->prop_depth[lv], nullptr, nullptr, nullptr, st));
+      if (rc) return rc;
+    }
+  }
+  return CNB_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t cnb_render_workspace_floats(const cnb_model* m, int64_t num_rays, int32_t training) {
+  if (!m || num_rays <= 0) return 0;
+  Layout L;
+  if (make_layout(m, num_rays, training != 0, L)) return 0;
+  return L.total;
+}
+
+extern "C" int cnb_render_rays(const cnb_model* m, const cnb_rays* rays, const cnb_ray_outputs* out, float* workspace, cnb_stream_t stream) {
+  int rc = check_common(m, rays, workspace);
+  if (rc) return rc;
+  if (rays->num_rays == 0) return CNB_OK;
+  Layout L;
+  if ((rc = make_layout(m, rays->num_rays, false, L))) return rc;
+  return forward_chain(m, rays, L, workspace, false, nullptr, 1.0f, out, stream);
+}
+
+extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cnb_train_cfg* cfg, const cnb_ray_outputs* out, float* losses_out,
+                              float* workspace, cnb_stream_t stream) {
+  int rc = check_common(m, rays, workspace);
+  if (rc) return rc;
+  CNB_REQUIRE(cfg && cfg->image && cfg->fruit_mask && losses_out, "train_step: null cfg/image/fruit_mask/losses_out");
+  const int64_t R = rays->num_rays;
+  if (R == 0) return CNB_OK;
+  Layout L;
+  if ((rc = make_layout(m, R, true, L))) return rc;
+  float* ws = workspace;
+  cudaStream_t st = stream;
+  const bool mixed = m->field.precision == CNB_PREC_MIXED;
+  if (cudaMemsetAsync(losses_out, 0, 8 * sizeof(float), stream) != cudaSuccess) return cnb_check_launch("train_step memset");
+  if ((rc = forward_chain(m, rays, L, ws, true, cfg->jitter, cfg->anneal, out, stream))) return rc;
+  const int lf = L.levels - 1, Sf = L.S[lf];
+  const float gs = cfg->grad_scale == 0.0f ? 1.0f : cfg->grad_scale;
+  const float* o_rgb = (out && out->rgb) ? out->rgb : ws + L.o_rgb;
+  const float* o_sem = (out && out->semantics) ? out->semantics : ws + L.o_sem;
+  // ---- losses (fruit_nerf.py:601-615) --------------------------------------------------------------------------------------
+  STAGE("pixel_losses", 1, cnb_pixel_losses(o_rgb, o_sem, cfg->image, cfg->fruit_mask, R, cfg->semantic_loss_weight, gs, losses_out, ws + L.g_rgb, ws + L.g_sem, stream));
+  if (rc) return rc;
+  for (int lv = 0; lv < lf; ++lv) {
+    STAGE("interlevel_fwd", 1, cnb_interlevel_fwd(ws + L.sp[lf], ws + L.w[lf], ws + L.sp[lv], ws + L.w[lv], R, Sf, L.S[lv], losses_out + 2, stream));
+    if (rc) return rc;
+  }
+  if (cfg->interlevel_loss_mult != 1.0f) {
+    k_scale<<<1, 32, 0, stream>>>(losses_out + 2, 1, cfg->interlevel_loss_mult);
+    if ((rc = cnb_check_launch("train_step scale"))) return rc;
+  }
+  if (cfg->want_metrics) {
+    STAGE("distortion", 1, cnb_distortion_fwd(ws + L.sp[lf], ws + L.w[lf], R, Sf, losses_out + 3, stream));
+    if (rc) return rc;
+  }
+  // ---- backward: renderers -> get_weights -> field ----------------------------------------------------------------------------
+  STAGE("render_bwd", 1, cnb_render_bwd(ws + L.w[lf], ws + L.rgb, ws + L.sem, R, Sf, m->bg_mode, m->bg_color, ws + L.g_rgb, nullptr, ws + L.g_sem,
+                                        m->field.pass_semantic_gradients, ws + L.d_w[lf], ws + L.d_rgb, ws + L.d_sem, stream));
+  if (rc) return rc;
+  STAGE("weights_bwd", 1, cnb_weights_bwd(ws + L.dens[lf], ws + L.eu[lf], ws + L.eu[lf] + 1, Sf + 1, R, Sf, ws + L.d_w[lf], ws + L.d_dens[lf], stream));
+  if (rc) return rc;
+  {
+    const cnb_samples sm = make_samples(rays, ws + L.eu[lf], Sf);
+    STAGE("field_bwd", mixed ? 2 : 8, cnb_field_bwd(&m->field, &sm, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, nullptr, ws + L.ctx, stream));
+    if (rc) return rc;
+  }
+  // ---- backward: interlevel loss -> proposal networks (only on "updated" steps, ray_samplers.py ProposalNetworkSampler) ---
+  if (cfg->update_proposals) {
+    for (int lv = 0; lv < lf; ++lv) {
+      const int S = L.S[lv];
+      STAGE("interlevel_bwd", 1, cnb_interlevel_bwd(ws + L.sp[lf], ws + L.w[lf], ws + L.sp[lv], ws + L.w[lv], R, Sf, S, gs * cfg->interlevel_loss_mult, ws + L.d_w[lv], stream));
+      if (rc) return rc;
+      STAGE("weights_bwd", 1, cnb_weights_bwd(ws + L.dens[lv], ws + L.eu[lv], ws + L.eu[lv] + 1, S + 1, R, S, ws + L.d_w[lv], ws + L.d_dens[lv], stream));
+      if (rc) return rc;
+      const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
+      STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd(&m->proposal[lv], &sm, ws + L.d_dens[lv], stream));
+      if (rc) return rc;
+    }
+  }
+  return CNB_OK;
+}
+
+// ---- optional stage profiling ---------------------------------------------------------------------------------------------
+extern "C" void cnb_profile_enable(int32_t on) {
+  for (auto& e : g_prof) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+  g_prof.clear();
+  g_prof_on = on != 0;
+}
+
+// Synchronises the device, sums the recorded stages by name and writes "name:calls:kernels:ms;..." into buf; clears the log.
+extern "C" int cnb_profile_read(char* buf, int32_t buflen) {
+  if (!buf || buflen <= 0) return CNB_ERR_ARG;
+  if (cudaDeviceSynchronize() != cudaSuccess) return cnb_check_launch("profile_read");
+  struct Acc { std::string name; int calls; int kernels; double ms; };
+  std::vector<Acc> acc;
+  for (auto& e : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.e0, e.e1);
+    cudaEventDestroy(e.e0); cudaEventDestroy(e.e1);
+    bool found = false;
+    for (auto& a : acc) if (a.name == e.name) { a.calls++; a.kernels += e.kernels; a.ms += ms; found = true; break; }
+    if (!found) acc.push_back({e.name, 1, e.kernels, ms});
+  }
+  g_prof.clear();
+  std::string out;
+  char tmp[160];
+  for (auto& a : acc) { snprintf(tmp, sizeof(tmp), "%s:%d:%d:%.6f;", a.name.c_str(), a.calls, a.kernels, a.ms); out += tmp; }
+  if ((int)out.size() + 1 > buflen) return CNB_ERR_ARG;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return CNB_OK;
+}

@@ -82,8 +82,11 @@ class FlatGroup:
 class Trainer:
     """Minimal trainer for FruitModel: callbacks, forward, losses, backward, gradient all-reduce, Adam."""
 
-    def __init__(self, model, optimizers: Optional[Dict[str, OptimizerSpec]] = None, world_size: int = 1):
+    def __init__(self, model, optimizers: Optional[Dict[str, OptimizerSpec]] = None, world_size: int = 1, fused: bool = True):
+        from .pipeline import FusedPipeline
+
         self.model = model
+        self.fused = FusedPipeline(model) if fused else None
         self.world_size = world_size
         self.optimizers = optimizers or DEFAULT_OPTIMIZERS
         self.groups: Dict[str, FlatGroup] = {name: FlatGroup(params) for name, params in model.get_param_groups().items() if len(params) > 0}
@@ -107,14 +110,31 @@ class Trainer:
         for name, g in self.groups.items():
             spec = self.optimizers[name]
             lr = exponential_decay_lr(step, spec)
+            # Adam and the gradient clear of the next step in one pass over the flat group
             ops.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, lr, self.opt_step, spec.betas[0], spec.betas[1], spec.eps,
-                          inv_grad_scale=1.0 / self.world_size)
+                          inv_grad_scale=1.0 / self.world_size, zero_grad=True)
+        self._grads_clean = True
+
+    def _use_fused(self) -> bool:
+        return (self.fused is not None and self.model.camera_optimizer.mode == "off" and self.model.collider is not None
+                and self.fused.eligible())
 
     def train_iteration(self, step: int, ray_bundle, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
         self.model.train()
         self._run_callbacks("BEFORE_TRAIN_ITERATION", step)
-        for g in self.groups.values():
-            g.zero_grad()
+        if not getattr(self, "_grads_clean", False):
+            for g in self.groups.values():
+                g.zero_grad()
+        self._grads_clean = False
+        if self._use_fused():
+            # one C call: samplers + proposal networks + field + renderers + losses + backward (csrc/pipeline.cu)
+            losses, outputs = self.fused.train_step(ray_bundle, batch)
+            self.all_reduce_gradients()
+            self.optimizer_step(step)
+            self._run_callbacks("AFTER_TRAIN_ITERATION", step)
+            out = {"rgb_loss": losses[0], "semantics_loss": losses[1], "interlevel_loss": losses[2], "distortion": losses[3],
+                   "psnr": -10.0 * torch.log10(losses[0]), "loss": losses[0] + losses[1] + losses[2]}
+            return out
         outputs = self.model(ray_bundle)
         metrics = self.model.get_metrics_dict(outputs, batch)
         loss_dict = self.model.get_loss_dict(outputs, batch, metrics)

@@ -159,6 +159,8 @@ class FruitModel(nn.Module):
         colors = getattr(semantics, "colors", None)
         self.register_buffer("colormap", torch.as_tensor(colors, dtype=torch.float32).clone() if colors is not None else torch.tensor([0.0, 1.0]))
         self.step = 0
+        self.fused_render = True       # one-call render path for no-grad eval (set False to force the per-module operators)
+        self._fused_pipeline = None
         self.populate_modules()
         if device is not None:
             self.to(device)
@@ -292,7 +294,21 @@ class FruitModel(nn.Module):
     # fruit_nerf.py:543-599
     def get_outputs(self, ray_bundle: RayBundle) -> Dict:
         self.camera_optimizer.apply_to_raybundle(ray_bundle)
+        if not self.training and not torch.is_grad_enabled() and self.fused_render and ray_bundle.origins.dim() == 2 and self._fused().eligible():
+            # export / projection / eval-image loops: the whole chunk in one C call (csrc/pipeline.cu)
+            outputs = self._fused().render(ray_bundle, want_inds=self.proposal_sampler.pdf_sampler.keep_inds)
+            if "pdf_inds" in outputs:
+                self.proposal_sampler.pdf_sampler.last_inds = outputs.pop("pdf_inds")
+            outputs["semantics_colormap"] = self._semantic_colormap(outputs["semantics"])
+            return outputs
         return self._render(ray_bundle, depth_no_grad=True, keep_lists=self.training)
+
+    def _fused(self):
+        if self._fused_pipeline is None:
+            from .pipeline import FusedPipeline
+
+            self._fused_pipeline = FusedPipeline(self)
+        return self._fused_pipeline
 
     # fruit_nerf.py:497-541
     def get_inference_outputs(self, ray_bundle: RayBundle) -> Dict:

@@ -545,10 +545,11 @@ def pixel_losses(rgb: Tensor, sem: Tensor, image: Tensor, mask: Tensor, sem_weig
 
 
 def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, step: int, beta1: float = 0.9, beta2: float = 0.999,
-              eps: float = 1e-15, inv_grad_scale: float = 1.0) -> None:
+              eps: float = 1e-15, inv_grad_scale: float = 1.0, zero_grad: bool = False) -> None:
     dev = _dev(param)
+    fn = L.lib().cnb_adam_step_zero if zero_grad else L.lib().cnb_adam_step
     L.check(
-        L.lib().cnb_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(), lr, beta1, beta2, eps,
+        fn(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(), lr, beta1, beta2, eps,
                               int(step), inv_grad_scale, L.stream_ptr(dev)),
         "adam_step",
     )

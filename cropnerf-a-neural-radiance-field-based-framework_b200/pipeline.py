@@ -1,0 +1,220 @@
+"""Fused ray-render pipeline: one C-ABI call per chunk of rays (``cnb_render_rays``) or per training batch
+(``cnb_train_step``) instead of one call per nerfstudio module.
+
+This is the fast path behind ``FruitModel.forward`` in no-grad mode (the export / projection / eval-image loops,
+``fruit_nerf.py:320-404`` and ``export/exporter_utils_nerfacto.py:126-183``) and behind ``engine.Trainer`` (the training
+step).  The per-module operators in ``ops.py`` stay available for callers that compose the
+nerfstudio modules themselves (BayesRays, custom density_fns); both routes run the same kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+from . import ops
+from .density_fields import HashMLPDensityField
+from .field_components import SceneContraction
+from .renderers import resolve_background
+
+
+class FusedPipeline:
+    def __init__(self, model) -> None:
+        self.model = model
+        self._ws: Dict[Tuple[int, bool, str], Tensor] = {}
+        self._tables: Dict[Tuple, Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------------
+    def eligible(self) -> bool:
+        """True when the model is wired the way ``FruitModel.populate_modules`` wires it (fruit_nerf.py:87-183)."""
+        from .ray_samplers import PDFSampler, ProposalNetworkSampler, SpacedSampler
+
+        m = self.model
+        s = m.proposal_sampler
+        if not isinstance(s, ProposalNetworkSampler) or m.test_mode == "export":
+            return False
+        if not isinstance(s.initial_sampler, SpacedSampler) or not isinstance(s.pdf_sampler, PDFSampler):
+            return False
+        if s.num_proposal_network_iterations not in (1, 2) or len(m.density_fns) < s.num_proposal_network_iterations:
+            return False
+        for fn in m.density_fns[: s.num_proposal_network_iterations]:
+            owner = getattr(fn, "__self__", None)
+            if not isinstance(owner, HashMLPDensityField) or getattr(fn, "__func__", None) is not HashMLPDensityField.density_fn or owner.use_linear:
+                return False
+        sd = m.field.spatial_distortion
+        return sd is None or isinstance(sd, SceneContraction)
+
+    def _table(self, kind: str, n: int, dev) -> Tensor:
+        key = (kind, n, str(dev))
+        if key not in self._tables:  # torch.linspace on the host: bit-identical to the bins the reference samplers build
+            t = torch.linspace(0.0, 1.0, n + 1) if kind == "lin" else torch.linspace(0.0, 1.0 - (1.0 / (n + 1)), steps=n + 1)
+            self._tables[key] = t.to(dev)
+        return self._tables[key]
+
+    def _model_struct(self, dev, training: bool, with_grads: bool):
+        m = self.model
+        keep = []
+        field = m.field
+        inference = field.test_mode in ("inference", "export")
+        fcfg = field._cfg(inference)
+        fcfg["training"] = training
+        params = field.kernel_params()
+        grads = None
+        if with_grads:
+            grads = []
+            for p in params:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                grads.append(p.grad)
+        fs, k = ops._build_field(fcfg, params, grads)
+        keep.append(k)
+        ms = L.Model()
+        ms.field = fs
+        s = m.proposal_sampler
+        n = s.num_proposal_network_iterations
+        for i in range(n):
+            net = m.density_fns[i].__self__
+            mlp = net.mlp_base[1]
+            ws, bs = [mlp.layers[0].weight, mlp.layers[1].weight], [mlp.layers[0].bias, mlp.layers[1].bias]
+            tab = net.encoding.hash_table
+            if with_grads:
+                for p in (tab, *ws, *bs):
+                    if p.grad is None:
+                        p.grad = torch.zeros_like(p)
+            nl, t, sc = net.encoding.grid_cfg()
+            d = L.DensityField()
+            d.grid = L.make_grid(tab.detach(), tab.grad if with_grads else None, nl, t, sc)
+            d.mlp = L.make_mlp([w.detach() for w in ws], [b.detach() for b in bs], L.ACT_NONE, [w.grad for w in ws] if with_grads else None,
+                               [b.grad for b in bs] if with_grads else None)
+            d.warp = net._warp()
+            d.average_init_density = float(net.average_init_density)
+            ms.proposal[i] = d
+        sp = ms.sampler
+        sp.num_proposal_iterations = n
+        for i in range(n):
+            sp.proposal_samples[i] = int(s.num_proposal_samples_per_ray[i])
+        sp.nerf_samples = int(s.num_nerf_samples_per_ray)
+        sp.initial_spacing = s.initial_sampler.spacing_kind
+        sp.single_jitter = int(bool(s.initial_sampler.single_jitter))
+        sp.histogram_padding = float(s.pdf_sampler.histogram_padding)
+        sp.pdf_eps = 1e-5
+        sp.lin_bins = self._table("lin", sp.proposal_samples[0], dev).data_ptr()
+        counts = [sp.proposal_samples[i] for i in range(1, n)] + [sp.nerf_samples]
+        for i, cnt in enumerate(counts):
+            sp.u_base[i] = self._table("u", cnt, dev).data_ptr()
+        mode, color = resolve_background(m.renderer_rgb.background_color)
+        ms.bg_mode = mode
+        for i in range(3):
+            ms.bg_color[i] = float(color[i]) if color is not None else 0.0
+        return ms, keep
+
+    def _rays_struct(self, ray_bundle, training: bool):
+        m = self.model
+        R = ray_bundle.origins.shape[0]
+        keep = []
+
+        def f32c(t):
+            t = L.f32(t)
+            keep.append(t)
+            return t
+
+        r = L.Rays()
+        o, d = f32c(ray_bundle.origins.reshape(R, 3)), f32c(ray_bundle.directions.reshape(R, 3))
+        r.origins, r.directions = o.data_ptr(), d.data_ptr()
+        if ray_bundle.nears is not None and ray_bundle.fars is not None:
+            r.nears = f32c(ray_bundle.nears.reshape(R)).data_ptr()
+            r.fars = f32c(ray_bundle.fars.reshape(R)).data_ptr()
+        col = m.collider
+        r.near_plane = float(col.near_plane if (training or not getattr(col, "reset_near_plane", True)) else 0.0)
+        r.far_plane = float(col.far_plane)
+        cam = ray_bundle.camera_indices
+        if cam is not None:
+            cam = cam.reshape(R).to(torch.int32).contiguous()
+            keep.append(cam)
+            r.camera_indices = cam.data_ptr()
+        r.num_rays = R
+        return r, keep
+
+    def _workspace(self, ms, R: int, training: bool, dev) -> Tensor:
+        n = int(L.lib().cnb_render_workspace_floats(C.byref(ms), R, int(training)))
+        key = (R, training, str(dev))
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < n:
+            ws = torch.empty((max(n, 1),), device=dev, dtype=torch.float32)
+            self._ws[key] = ws
+        return ws
+
+    def _outputs(self, R: int, dev, n_prop: int, want_inds: bool, nerf_samples: int):
+        out = L.RayOutputs()
+        t = {
+            "rgb": torch.empty((R, 3), device=dev, dtype=torch.float32),
+            "depth": torch.empty((R, 1), device=dev, dtype=torch.float32),
+            "accumulation": torch.empty((R, 1), device=dev, dtype=torch.float32),
+            "semantics": torch.empty((R, 1), device=dev, dtype=torch.float32),
+        }
+        out.rgb, out.depth, out.accumulation, out.semantics = (t[k].data_ptr() for k in ("rgb", "depth", "accumulation", "semantics"))
+        for i in range(n_prop):
+            t[f"prop_depth_{i}"] = torch.empty((R, 1), device=dev, dtype=torch.float32)
+            out.prop_depth[i] = t[f"prop_depth_{i}"].data_ptr()
+        if want_inds:
+            t["pdf_inds"] = torch.empty((R, nerf_samples + 1), device=dev, dtype=torch.int32)
+            out.pdf_inds = t["pdf_inds"].data_ptr()
+        return out, t
+
+    # ------------------------------------------------------------------------------------------------
+    def render(self, ray_bundle, want_inds: bool = False) -> Dict[str, Tensor]:
+        """Eval-mode render of a flat bundle of rays -> the per-ray output dict of ``FruitModel.get_outputs``."""
+        dev = ray_bundle.origins.device
+        if dev.type != "cuda":
+            raise RuntimeError("cropnerf_b200 renders on CUDA devices only; there is no CPU fallback")
+        ms, keep = self._model_struct(dev, training=False, with_grads=False)
+        rays, keep2 = self._rays_struct(ray_bundle, training=False)
+        R = rays.num_rays
+        ws = self._workspace(ms, R, False, dev)
+        n_prop = ms.sampler.num_proposal_iterations
+        out, tensors = self._outputs(R, dev, n_prop, want_inds, ms.sampler.nerf_samples)
+        L.check(L.lib().cnb_render_rays(C.byref(ms), C.byref(rays), C.byref(out), ws.data_ptr(), L.stream_ptr(dev)), "render_rays")
+        del keep, keep2
+        return tensors
+
+    def train_step(self, ray_bundle, batch: Dict[str, Tensor], grad_scale: float = 1.0, want_metrics: bool = True):
+        """forward + losses + backward of one batch; gradients are accumulated into ``param.grad``.
+        Returns (losses [8] device tensor: rgb, semantics, interlevel, distortion, ...; per-ray outputs)."""
+        m = self.model
+        dev = ray_bundle.origins.device
+        s = m.proposal_sampler
+        ms, keep = self._model_struct(dev, training=True, with_grads=True)
+        rays, keep2 = self._rays_struct(ray_bundle, training=True)
+        R = rays.num_rays
+        ws = self._workspace(ms, R, True, dev)
+        n_prop = ms.sampler.num_proposal_iterations
+        out, tensors = self._outputs(R, dev, n_prop, False, ms.sampler.nerf_samples)
+        # jitter in the order the samplers draw it (initial sampler, then one draw per PDF resampling)
+        counts = [ms.sampler.proposal_samples[i] for i in range(n_prop)] + [ms.sampler.nerf_samples]
+        single = bool(ms.sampler.single_jitter)
+        fns = [s.initial_sampler.rand_fn] + [s.pdf_sampler.rand_fn] * n_prop
+        if single and all(fn is torch.rand for fn in fns):
+            jitter = torch.rand((n_prop + 1, R), device=dev, dtype=torch.float32)
+        else:
+            jitter = torch.cat([fn((R, 1) if single else (R, c + 1), dtype=torch.float32, device=dev).reshape(-1) for fn, c in zip(fns, counts)])
+        updated = s._steps_since_update > s.update_sched(s._step) or s._step < 10
+        cfg = L.TrainCfg()
+        image = L.f32(batch["image"].to(dev)[:, :3])
+        mask = L.f32(batch["fruit_mask"].to(dev)).reshape(R)
+        cfg.image, cfg.fruit_mask, cfg.jitter = image.data_ptr(), mask.data_ptr(), jitter.data_ptr()
+        cfg.anneal = float(s._anneal)
+        cfg.semantic_loss_weight = float(m.config.semantic_loss_weight)
+        cfg.interlevel_loss_mult = float(m.config.interlevel_loss_mult)
+        cfg.grad_scale = float(grad_scale)
+        cfg.update_proposals = int(bool(updated))
+        cfg.want_metrics = int(want_metrics)
+        losses = torch.empty((8,), device=dev, dtype=torch.float32)
+        L.check(L.lib().cnb_train_step(C.byref(ms), C.byref(rays), C.byref(cfg), C.byref(out), losses.data_ptr(), ws.data_ptr(), L.stream_ptr(dev)),
+                "train_step")
+        if updated:
+            s._steps_since_update = 0
+        del keep, keep2
+        return losses, tensors

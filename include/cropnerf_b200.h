@@ -201,6 +201,86 @@ int cnb_pixel_losses(const float* rgb, const float* sem, const float* image, con
 int cnb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float inv_grad_scale, cnb_stream_t stream);
 
+/* ---- a15: the ray-render loop body (FruitModel.get_outputs / get_inference_outputs, fruit_nerf.py:497-599) -------
+ * One call = collider -> ProposalNetworkSampler (piecewise/uniform bins -> proposal density -> weights -> PDF resample,
+ * per proposal iteration) -> FruitField -> get_weights -> RGB / accumulation / semantic / median-depth renderers, all
+ * enqueued on `stream` into a caller-provided workspace.  The training entry also runs the losses of
+ * FruitModel.get_loss_dict / get_metrics_dict (fruit_nerf.py:601-615,639-645) and the whole backward. */
+
+/* RayBundle (nerfstudio/cameras/rays.py) restricted to what the path reads */
+typedef struct cnb_rays {
+  const float* origins;          /* [R,3] */
+  const float* directions;       /* [R,3] */
+  const float* nears;            /* [R] or NULL => near_plane (NearFarCollider, fruit_nerf.py:167) */
+  const float* fars;             /* [R] or NULL => far_plane */
+  const int32_t* camera_indices; /* [R]; required for per-camera appearance (training) */
+  int64_t num_rays;
+  float near_plane, far_plane;
+} cnb_rays;
+
+/* ProposalNetworkSampler configuration (fruit_nerf.py:155-164) */
+typedef struct cnb_sampler {
+  int32_t num_proposal_iterations; /* 1..2 */
+  int32_t proposal_samples[2];     /* num_proposal_samples_per_ray */
+  int32_t nerf_samples;            /* num_nerf_samples_per_ray */
+  int32_t initial_spacing;         /* CNB_SPACING_* of the initial sampler */
+  int32_t single_jitter;
+  float histogram_padding;         /* 0.01 */
+  float pdf_eps;                   /* 1e-5 */
+  const float* lin_bins;           /* device [proposal_samples[0]+1] = torch.linspace(0,1,S0+1) */
+  const float* u_base[2];          /* device [S+1] = torch.linspace(0, 1-1/(S+1), S+1) for resampled level 1, 2 */
+} cnb_sampler;
+
+typedef struct cnb_model {
+  cnb_field field;
+  cnb_density_field proposal[2];   /* use_same_proposal_network: both entries describe the same network */
+  cnb_sampler sampler;
+  int32_t bg_mode;                 /* CNB_BG_* (renderer_rgb background_color / override context) */
+  float bg_color[3];
+  int32_t _pad;
+} cnb_model;
+
+/* per-ray outputs, each optional (NULL = not wanted) */
+typedef struct cnb_ray_outputs {
+  float* rgb;            /* [R,3] */
+  float* depth;          /* [R]  median depth of the final level */
+  float* accumulation;   /* [R] */
+  float* semantics;      /* [R]  composited semantic logit */
+  float* prop_depth[2];  /* [R]  median depth of each proposal level */
+  int32_t* pdf_inds;     /* [R, nerf_samples+1] searchsorted bins of the last resampling (bit-exactness tests) */
+} cnb_ray_outputs;
+
+/* floats of workspace for R rays (training != 0: forward activations + backward scratch are kept) */
+int64_t cnb_render_workspace_floats(const cnb_model* m, int64_t num_rays, int32_t training);
+/* eval-mode render (deterministic samplers, nan_to_num/clamp in the RGB renderer) */
+int cnb_render_rays(const cnb_model* m, const cnb_rays* rays, const cnb_ray_outputs* out, float* workspace, cnb_stream_t stream);
+
+typedef struct cnb_train_cfg {
+  const float* image;        /* [R,3] target colours */
+  const float* fruit_mask;   /* [R] 0/1 */
+  const float* jitter;       /* [levels][R] uniform(0,1) draws (single_jitter) in sampler order, or [levels][R*(S_l+1)] */
+  float anneal;              /* proposal weight annealing exponent (fruit_nerf.py:202-216) */
+  float semantic_loss_weight;
+  float interlevel_loss_mult;
+  float grad_scale;          /* GradScaler factor applied to every gradient (1 = none) */
+  int32_t update_proposals;  /* ProposalNetworkSampler "updated": proposal networks receive gradients this step */
+  int32_t want_metrics;      /* distortion metric + psnr inputs (get_metrics_dict) */
+} cnb_train_cfg;
+
+/* forward + losses + backward of one batch; parameter gradients are ACCUMULATED into the d_* pointers of `m`;
+ * losses_out (device, 8 floats, overwritten): [0] rgb mse, [1] weighted semantic bce, [2] interlevel (x mult), [3] distortion */
+int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cnb_train_cfg* cfg, const cnb_ray_outputs* out, float* losses_out,
+                   float* workspace, cnb_stream_t stream);
+
+/* ---- f2: fused optimiser over one flat parameter group: Adam update + gradient clear in one pass ----------------- */
+int cnb_adam_step_zero(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                       float eps, int32_t step, float inv_grad_scale, cnb_stream_t stream);
+
+/* ---- measurement aid: per-stage device times of cnb_render_rays / cnb_train_step (CUDA events on the launching stream).
+ * cnb_profile_read synchronises, writes "stage:calls:kernels:ms;..." (summed since enable) into buf and clears the log. */
+void cnb_profile_enable(int32_t on);
+int cnb_profile_read(char* buf, int32_t buflen);
+
 #ifdef __cplusplus
 }
 #endif
