@@ -1,0 +1,60 @@
+"""Pins the oracle's restated wiring (oracle/fruit_torch.py) to the reference's OWN code.
+
+``tests/golden/ref_*.npz`` were produced by importing ``/root/reference/crop_nerf/fruit_nerf/{fruit_field,fruit_nerf}.py``
+and ``components/*.py`` unmodified and executing them with nerfstudio's primitives shimmed by the oracle's restatement
+(``oracle/ref_shim.py``, generating script committed).  The restated wiring must reproduce them bit for bit; the
+``live`` tests redo the import where the reference is present (this container; not the GPU box)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN
+
+from oracle import cases, ref_shim
+
+OUTPUT_KEYS = ("rgb", "accumulation", "depth", "prop_depth_0", "prop_depth_1", "semantics", "semantics_colormap")
+
+
+def _check_case(name, ref):
+    got = cases.run_case(name)
+    for k in OUTPUT_KEYS:
+        assert np.array_equal(got[k], ref[k]), f"{name}/{k}: oracle differs from the reference-executed fixture"
+    for k, v in ref.items():
+        if k.startswith("loss_") or k.startswith("metric_"):
+            assert np.array_equal(got[k], v), f"{name}/{k}: {got[k]} vs {v}"
+        if k.startswith("gradnorm/"):
+            # the reference keeps both aliases of a proposal table (encoding.* and mlp_base.0.*); the oracle fixture stores one
+            ok = k if k in got else k.replace("encoding.hash_table", "mlp_base.0.hash_table")
+            if ok in got:
+                assert abs(float(got[ok]) - float(v)) <= 1e-6 * abs(float(v)) + 1e-30, k  # fp32 scatter-add order
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_oracle_reproduces_reference_executed_fixture(name):
+    _check_case(name, dict(np.load(os.path.join(GOLDEN, "ref_" + name + ".npz"))))
+
+
+@pytest.mark.parametrize("kind", list(ref_shim.MODE_CASES))
+def test_oracle_inference_and_export_modes_match_reference(kind):
+    ref = dict(np.load(os.path.join(GOLDEN, "ref_mode_" + kind + ".npz")))
+    got = ref_shim.run_mode_case(kind, "oracle")
+    assert set(got) == set(ref), (sorted(got), sorted(ref))
+    for k, v in ref.items():
+        assert np.array_equal(got[k], v), f"{kind}/{k}"
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present (GPU box): fixtures only")
+def test_live_reference_code_matches_fixtures():
+    """Re-import the reference's files and re-run them: the committed fixtures are what the reference code computes."""
+    ref = ref_shim.run_reference_case("tiny_eval")
+    fix = dict(np.load(os.path.join(GOLDEN, "ref_tiny_eval.npz")))
+    for k in OUTPUT_KEYS:
+        assert np.array_equal(ref[k], fix[k]), k
+    ref_field, ref_model = ref_shim.load_reference()
+    assert ref_field.__file__.startswith("/root/reference/") and ref_model.__file__.startswith("/root/reference/")
+    live = ref_shim.run_mode_case("export", "reference")
+    fix = dict(np.load(os.path.join(GOLDEN, "ref_mode_export.npz")))
+    for k, v in fix.items():
+        assert np.array_equal(live[k], v), k
