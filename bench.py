@@ -127,7 +127,9 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
     import torch.distributed as dist
 
     model = build_model(dev, precision)
-    trainer = engine.Trainer(model, world_size=world)
+    # every timed step back-propagates into all three networks (the update step SURVEY.md 8d's 485 456 B/ray describes;
+    # in steady state only 1 step in 6 does, ProposalNetworkSampler update_sched) and is replayed as one CUDA graph
+    trainer = engine.Trainer(model, world_size=world, cuda_graph=not args.no_graph, force_proposal_update=True)
     R = RAYS_PER_GPU
     nb = 8  # distinct ray batches cycled through (fresh rays every step, like next_train)
     host = [host_batch(R, seed=100 * rank + i) for i in range(nb)]
@@ -145,7 +147,7 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
 
     steps = args.steps if full else max(3, args.steps // 2)
     # ---- warm-up -----------------------------------------------------------------------------------------
-    step = 0
+    step = 2000  # past proposal_weights_anneal_max_num_iters (1000): anneal == 1 as in 39 000 of the 40 000 training iterations
     for _ in range(max(args.warmup, 3)):
         train_step(step, *resident[step % nb]); step += 1
     barrier()
@@ -183,7 +185,25 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
 
     # ---- per-stage device times (separate pass so the events do not perturb the timed region) ----------------
     stage, adam_ms, n_prof = {}, 0.0, min(steps, 5)
+    nonupdate_ms = None
     if full:
+        # steady-state step kind: proposal networks frozen this step (5 of every 6 steps after proposal_warmup)
+        trainer.force_proposal_update = False
+        model.proposal_sampler._step = 20000
+        nu = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps + 2):
+            model.proposal_sampler._steps_since_update = 1   # keeps "updated" false
+            l2_flush.fill_(i & 0xFF)
+            if i >= 2:
+                nu[i - 2][0].record()
+            train_step(step, *resident[step % nb]); step += 1
+            model.proposal_sampler._step = 20000
+            if i >= 2:
+                nu[i - 2][1].record()
+        torch.cuda.synchronize()
+        nonupdate_ms = sum(a.elapsed_time(b) for a, b in nu) / steps
+        trainer.force_proposal_update = True
+        trainer.cuda_graph = False  # the stage timers live in the C call, which a graph replay does not re-enter
         L.lib().cnb_profile_enable(1)
         a_ev = []
         orig_opt = trainer.optimizer_step
@@ -200,6 +220,7 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
         stage = L.stage_profile_read()
         L.lib().cnb_profile_enable(0)
         trainer.optimizer_step = orig_opt
+        trainer.cuda_graph = not args.no_graph
         adam_ms = sum(a.elapsed_time(b) for a, b in a_ev) / n_prof
 
     # ---- render (export / projection loop body), eval mode ----------------------------------------------------
@@ -253,7 +274,7 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
     del trainer, model, l2_flush
     torch.cuda.empty_cache()
     return {"steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
-            "stage": stage, "n_prof": n_prof, "adam_ms": adam_ms, "render_stage": render_stage, "loss": loss_host,
+            "stage": stage, "n_prof": n_prof, "nonupdate_ms": nonupdate_ms, "adam_ms": adam_ms, "render_stage": render_stage, "loss": loss_host,
             "h2d_train": bytes_of(host[0]), "h2d_render": bytes_of({k: rhost[k] for k in ("origins", "directions", "pixel_area", "camera_indices")}),
             "d2h_render": int(d2h_render)}
 
@@ -314,7 +335,10 @@ def run_product(args):
             "config": {"workload": "BASELINE configs[1]: fruit_nerf preset training step, 4096 rays/GPU, proposal 256/96 + 48 NeRF samples, "
                                    "field 16x2^19x2 + 2 proposal 5x2^17x2 fp32 hash tables, 300 synthetic 1080p cameras",
                        "rays_per_gpu": R, "samples_per_ray": 400, "precision": args.precision, "l2": "flushed between timed iterations (192 MiB fill)",
-                       "includes": "fwd + losses + bwd (all three networks updated) + gradient all-reduce + Adam, one cnb_train_step call per step"},
+                       "includes": "fwd + losses + bwd (all three networks updated EVERY step) + gradient all-reduce + Adam; "
+                                   + ("cnb_train_step eager" if args.no_graph else "cnb_train_step replayed as one CUDA graph"),
+                       "non_update_step_ms": m["nonupdate_ms"],
+                       "steady_state_rays_per_s": (world * R / ((m["t"] / steps + 5 * m["nonupdate_ms"] * 1e-3) / 6)) if m["nonupdate_ms"] else None},
             "samples_per_s": value * 400,
             "step_roofline": {"algorithmic_bytes_per_ray": TRAIN_BYTES_PER_RAY, "achieved_GBps": step_achieved, "frac": step_achieved / (peak * world),
                               "roofline_rays_per_s_per_gpu": peak * 1e9 / TRAIN_BYTES_PER_RAY},
@@ -398,6 +422,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CNB_PRECISION", "mixed"), choices=["fp32", "mixed"],
                     help="mixed = fp16 tensor-core MLPs like the reference's autocast training (fruit_nerf_config.py:35); fp32 = exact mode")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--single-precision", action="store_true", help="skip the short pass in the other precision mode")
     ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per CPU-baseline step (bounded sample of the 4096-ray batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

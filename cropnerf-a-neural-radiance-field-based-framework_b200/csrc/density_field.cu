@@ -261,7 +261,7 @@ int launch_bwd(const DfArgs& a, const float* d_density, cudaStream_t st) {
     configured = smem;
   }
   int64_t blocks = (total + BLOCK - 1) / BLOCK;
-  const int64_t cap = (int64_t)cnb_num_sms() * 4;
+  const int64_t cap = (int64_t)cnb_num_sms() * 8;  // 8 resident CTAs/SM (smem 25 KB, 76 regs): the gathers and reds need the warps
   if (blocks > cap) blocks = cap;
   k_density_bwd<LMAX, H><<<(int)blocks, BLOCK, smem, st>>>(a, d_density);
   return cnb_check_launch("density_field_bwd");

@@ -136,15 +136,15 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
 
 // Adam + gradient clear in one pass over a flat group (float4 lanes; n is a multiple of 4 for the flat groups):
 // 4 reads + 4 writes of 16 B per 4 parameters, nothing else touches the group between backward and the next forward.
-// The stores are write-through (st.global.wt): updating FOUR arrays in place with default write-back stores runs at
-// 2.0 TB/s on B200 (3 in-place arrays: 5.9 TB/s; measured with tests/micro/stream_bench*.cu), because every read miss
-// then has to evict a dirty line of one of the other streams; writing through keeps L2 clean and restores 6.0 TB/s.
+// The gradient clear is issued LAST, with a fake data dependency on the updated parameter: left to itself the compiler
+// hoists the (independent) zero store right behind the loads, and a store to a line whose load is still in flight
+// serialises the LSU -- the pass then runs at 2.0 TB/s instead of 6.3 TB/s on B200 (tests/micro/adam_bench.cu:
+// a_current vs f_late_zero; store cache policy makes no difference).
 __global__ void __launch_bounds__(256) k_adam_zero4(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
                                                     int64_t n4, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_scale) {
   const float step_size = lr / bc1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 gi = g[i], mi = m[i], vi = v[i], pi = p[i];
-    __stwt(g + i, make_float4(0.f, 0.f, 0.f, 0.f));
     float* gp = &gi.x; float* mp = &mi.x; float* vp = &vi.x; float* pp = &pi.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -153,7 +153,10 @@ __global__ void __launch_bounds__(256) k_adam_zero4(float4* __restrict__ p, floa
       vp[k] = b2 * vp[k] + (1.0f - b2) * gk * gk;
       pp[k] -= step_size * (mp[k] / (sqrtf(vp[k]) / bc2_sqrt + eps));
     }
-    __stwt(m + i, mi); __stwt(v + i, vi); __stwt(p + i, pi);
+    float z;
+    asm volatile("mov.f32 %0, 0f00000000;" : "=f"(z) : "f"(pi.w));  // zero that "depends" on the finished update
+    m[i] = mi; v[i] = vi; p[i] = pi;
+    g[i] = make_float4(z, z, z, z);
   }
 }
 

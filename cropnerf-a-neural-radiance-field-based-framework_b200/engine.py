@@ -79,14 +79,63 @@ class FlatGroup:
         self.grad.zero_()
 
 
+class _GraphedStep:
+    """One captured CUDA graph of ``cnb_train_step`` for a fixed (ray count, proposal-update flag, anneal) combination.
+    Inputs are copied into static buffers, jitter is drawn eagerly into a static buffer, then the graph is replayed: the
+    ~50 kernels of a step are submitted with one launch."""
+
+    def __init__(self, trainer: "Trainer", ray_bundle, batch, update: bool):
+        dev = ray_bundle.origins.device
+        R = ray_bundle.origins.shape[0]
+        fp = trainer.fused
+        self.static = {
+            "origins": torch.empty((R, 3), device=dev), "directions": torch.empty((R, 3), device=dev),
+            "camera_indices": torch.empty((R, 1), device=dev, dtype=torch.int32),
+            "image": torch.empty((R, 3), device=dev), "fruit_mask": torch.empty((R, 1), device=dev),
+        }
+        self.jitter = fp.draw_jitter(R, dev).clone()
+        self._load(ray_bundle, batch)
+        from .rays import RayBundle
+
+        self.bundle = RayBundle(self.static["origins"], self.static["directions"], None, self.static["camera_indices"])
+        self.batch = {"image": self.static["image"], "fruit_mask": self.static["fruit_mask"]}
+        self.update = update
+        self.graph = torch.cuda.CUDAGraph()
+        # parameter gradients are accumulated by the captured kernels: snapshot + restore around the capture run
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph):
+            self.losses, self.outputs = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update)
+        for g in trainer.groups.values():  # whatever the capture-time warm-up left in the gradients
+            g.zero_grad()
+
+    def _load(self, ray_bundle, batch) -> None:
+        st = self.static
+        R = st["origins"].shape[0]
+        st["origins"].copy_(ray_bundle.origins.reshape(R, 3), non_blocking=True)
+        st["directions"].copy_(ray_bundle.directions.reshape(R, 3), non_blocking=True)
+        st["camera_indices"].copy_(ray_bundle.camera_indices.reshape(R, 1), non_blocking=True)
+        st["image"].copy_(batch["image"][:, :3], non_blocking=True)
+        st["fruit_mask"].copy_(batch["fruit_mask"].reshape(R, 1), non_blocking=True)
+
+    def run(self, trainer: "Trainer", ray_bundle, batch):
+        self._load(ray_bundle, batch)
+        trainer.fused.draw_jitter(self.static["origins"].shape[0], self.static["origins"].device, out=self.jitter)
+        self.graph.replay()
+        return self.losses, self.outputs
+
+
 class Trainer:
     """Minimal trainer for FruitModel: callbacks, forward, losses, backward, gradient all-reduce, Adam."""
 
-    def __init__(self, model, optimizers: Optional[Dict[str, OptimizerSpec]] = None, world_size: int = 1, fused: bool = True):
+    def __init__(self, model, optimizers: Optional[Dict[str, OptimizerSpec]] = None, world_size: int = 1, fused: bool = True,
+                 cuda_graph: bool = False, force_proposal_update: bool = False):
         from .pipeline import FusedPipeline
 
         self.model = model
         self.fused = FusedPipeline(model) if fused else None
+        self.cuda_graph = cuda_graph                      # replay one captured graph per step when the step's scalars allow it
+        self.force_proposal_update = force_proposal_update  # benchmark aid: every step back-propagates into the proposal networks
+        self._graphs: Dict[tuple, _GraphedStep] = {}
         self.world_size = world_size
         self.optimizers = optimizers or DEFAULT_OPTIMIZERS
         self.groups: Dict[str, FlatGroup] = {name: FlatGroup(params) for name, params in model.get_param_groups().items() if len(params) > 0}
@@ -128,7 +177,24 @@ class Trainer:
         self._grads_clean = False
         if self._use_fused():
             # one C call: samplers + proposal networks + field + renderers + losses + backward (csrc/pipeline.cu)
-            losses, outputs = self.fused.train_step(ray_bundle, batch)
+            fp = self.fused
+            updated = True if self.force_proposal_update else fp.proposals_updated()
+            sampler = self.model.proposal_sampler
+            if self.cuda_graph and ray_bundle.nears is None:
+                key = (int(ray_bundle.origins.shape[0]), updated, float(sampler._anneal))
+                gs = self._graphs.get(key)
+                if gs is None:
+                    if len(self._graphs) >= 8:  # anneal still moving (first 1000 steps): do not hoard graphs
+                        self._graphs.pop(next(iter(self._graphs)))
+                    fp.train_step(ray_bundle, batch, update_proposals=False, want_metrics=True)  # eager warm-up (func attributes, workspace)
+                    for g in self.groups.values():
+                        g.zero_grad()
+                    gs = self._graphs[key] = _GraphedStep(self, ray_bundle, batch, updated)
+                losses, outputs = gs.run(self, ray_bundle, batch)
+                if updated:
+                    sampler._steps_since_update = 0
+            else:
+                losses, outputs = fp.train_step(ray_bundle, batch, update_proposals=updated)
             self.all_reduce_gradients()
             self.optimizer_step(step)
             self._run_callbacks("AFTER_TRAIN_ITERATION", step)

@@ -180,7 +180,27 @@ class FusedPipeline:
         del keep, keep2
         return tensors
 
-    def train_step(self, ray_bundle, batch: Dict[str, Tensor], grad_scale: float = 1.0, want_metrics: bool = True):
+    def proposals_updated(self) -> bool:
+        """ProposalNetworkSampler's "updated" rule (nerfstudio ray_samplers.py)."""
+        s = self.model.proposal_sampler
+        return bool(s._steps_since_update > s.update_sched(s._step) or s._step < 10)
+
+    def draw_jitter(self, R: int, dev, out: Optional[Tensor] = None) -> Tensor:
+        """Jitter in the order the samplers draw it (initial sampler, then one draw per PDF resampling), flat."""
+        s = self.model.proposal_sampler
+        n_prop = s.num_proposal_network_iterations
+        counts = [int(c) for c in s.num_proposal_samples_per_ray[:n_prop]] + [int(s.num_nerf_samples_per_ray)]
+        single = bool(s.initial_sampler.single_jitter)
+        fns = [s.initial_sampler.rand_fn] + [s.pdf_sampler.rand_fn] * n_prop
+        if single and all(fn is torch.rand for fn in fns):
+            if out is not None:
+                return out.uniform_()
+            return torch.rand(((n_prop + 1) * R,), device=dev, dtype=torch.float32)
+        j = torch.cat([fn((R, 1) if single else (R, c + 1), dtype=torch.float32, device=dev).reshape(-1) for fn, c in zip(fns, counts)])
+        return out.copy_(j) if out is not None else j
+
+    def train_step(self, ray_bundle, batch: Dict[str, Tensor], grad_scale: float = 1.0, want_metrics: bool = True,
+                   jitter: Optional[Tensor] = None, update_proposals: Optional[bool] = None):
         """forward + losses + backward of one batch; gradients are accumulated into ``param.grad``.
         Returns (losses [8] device tensor: rgb, semantics, interlevel, distortion, ...; per-ray outputs)."""
         m = self.model
@@ -192,15 +212,9 @@ class FusedPipeline:
         ws = self._workspace(ms, R, True, dev)
         n_prop = ms.sampler.num_proposal_iterations
         out, tensors = self._outputs(R, dev, n_prop, False, ms.sampler.nerf_samples)
-        # jitter in the order the samplers draw it (initial sampler, then one draw per PDF resampling)
-        counts = [ms.sampler.proposal_samples[i] for i in range(n_prop)] + [ms.sampler.nerf_samples]
-        single = bool(ms.sampler.single_jitter)
-        fns = [s.initial_sampler.rand_fn] + [s.pdf_sampler.rand_fn] * n_prop
-        if single and all(fn is torch.rand for fn in fns):
-            jitter = torch.rand((n_prop + 1, R), device=dev, dtype=torch.float32)
-        else:
-            jitter = torch.cat([fn((R, 1) if single else (R, c + 1), dtype=torch.float32, device=dev).reshape(-1) for fn, c in zip(fns, counts)])
-        updated = s._steps_since_update > s.update_sched(s._step) or s._step < 10
+        if jitter is None:
+            jitter = self.draw_jitter(R, dev)
+        updated = self.proposals_updated() if update_proposals is None else bool(update_proposals)
         cfg = L.TrainCfg()
         image = L.f32(batch["image"].to(dev)[:, :3])
         mask = L.f32(batch["fruit_mask"].to(dev)).reshape(R)

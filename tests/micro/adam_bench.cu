@@ -66,6 +66,25 @@ __global__ void __launch_bounds__(256) k_d(float4* __restrict__ p, float4* __res
     m[i] = mi; v[i] = vi; p[i] = pi;
   }
 }
+// g cleared LATE: the zero store carries a fake dependency on the computed parameter, so it cannot be hoisted above the math
+__global__ void __launch_bounds__(256) k_f(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v, long n4) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 gi = g[i], mi = m[i], vi = v[i], pi = p[i];
+    upd(gi, mi, vi, pi, 1e-2f, 0.9f, 0.999f, 1e-15f, 0.5f, 1.f);
+    float z;
+    asm volatile("mov.f32 %0, 0f00000000;" : "=f"(z) : "f"(pi.w));
+    m[i] = mi; v[i] = vi; p[i] = pi; g[i] = make_float4(z, z, z, z);
+  }
+}
+__global__ void __launch_bounds__(256) k_g(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v, long n4) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 gi = g[i], mi = m[i], vi = v[i], pi = p[i];
+    upd(gi, mi, vi, pi, 1e-2f, 0.9f, 0.999f, 1e-15f, 0.5f, 1.f);
+    float z;
+    asm volatile("mov.f32 %0, 0f00000000;" : "=f"(z) : "f"(pi.w));
+    __stwt(m + i, mi); __stwt(v + i, vi); __stwt(p + i, pi); __stwt(g + i, make_float4(z, z, z, z));
+  }
+}
 // pure copy-like baseline: read 4 write 4, no math
 __global__ void __launch_bounds__(256) k_e(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v, long n4) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
@@ -83,9 +102,9 @@ int main() {
   CK(cudaMalloc(&p, n * 4)); CK(cudaMalloc(&g, n * 4)); CK(cudaMalloc(&m, n * 4)); CK(cudaMalloc(&v, n * 4)); CK(cudaMalloc(&flush, 256 << 20));
   CK(cudaMemset(p, 0, n * 4)); CK(cudaMemset(g, 0, n * 4)); CK(cudaMemset(m, 0, n * 4)); CK(cudaMemset(v, 0, n * 4));
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const char* names[] = {"a_current", "b_streaming", "c_unroll2", "d_fastmath", "e_nomath"};
-  for (int grid_mul : {16, 8, 32, 64}) {
-    for (int var = 0; var < 5; ++var) {
+  const char* names[] = {"a_current", "b_streaming", "c_unroll2", "d_fastmath", "e_nomath", "f_late_zero", "g_late_zero_wt"};
+  for (int grid_mul : {16, 64}) {
+    for (int var = 0; var < 7; ++var) {
       float best = 1e9, sum = 0;
       for (int it = 0; it < 6; ++it) {
         CK(cudaMemsetAsync(flush, it, 256 << 20));
@@ -97,6 +116,8 @@ int main() {
           case 2: k_c<<<blocks, 256>>>(p, g, m, v, n4); break;
           case 3: k_d<<<blocks, 256>>>(p, g, m, v, n4); break;
           case 4: k_e<<<blocks, 256>>>(p, g, m, v, n4); break;
+          case 5: k_f<<<blocks, 256>>>(p, g, m, v, n4); break;
+          case 6: k_g<<<blocks, 256>>>(p, g, m, v, n4); break;
         }
         cudaEventRecord(e1);
         CK(cudaEventSynchronize(e1));

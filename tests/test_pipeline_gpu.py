@@ -128,3 +128,29 @@ def test_adam_zero_matches_torch_adam(dev):
         ops.adam_step(p, gd, m, v, 1e-2, step, zero_grad=True)
         assert float(gd.abs().max()) == 0.0
     assert_close(p, ref.detach(), 1e-5, "adam params")
+
+
+def test_cuda_graph_step_equals_eager(dev):
+    """The captured-graph training step replays exactly the kernels of the eager one-call step."""
+    R = 256
+    a, b = _models(dev, True, "mixed", small=False)
+    rays = synthetic.make_rays(R, seed=6, num_cameras=20)
+    targets = {k: v.to(dev) for k, v in synthetic.make_targets(R, seed=3).items()}
+    jit = synthetic.make_jitter(R, 3, seed=2)
+    stats, params = [], []
+    for model, graph in ((a, True), (b, False)):
+        feed = synthetic.JitterFeed(jit)
+        model.proposal_sampler.initial_sampler.rand_fn = feed
+        model.proposal_sampler.pdf_sampler.rand_fn = feed
+        tr = engine.Trainer(model, cuda_graph=graph, force_proposal_update=True)
+        for step in (3000, 3001, 3002):
+            feed.reset()
+            st = tr.train_iteration(step, product_bundle(rays, dev), targets)
+        stats.append({k: float(v) for k, v in st.items()})
+        params.append({n: g.flat.clone() for n, g in tr.groups.items()})
+        if graph:
+            assert len(tr._graphs) == 1
+    for k in ("rgb_loss", "semantics_loss", "interlevel_loss", "distortion"):
+        assert abs(stats[0][k] - stats[1][k]) <= 2e-4 * abs(stats[1][k]) + 1e-7, (k, stats[0][k], stats[1][k])
+    for n in params[0]:
+        assert (params[0][n] - params[1][n]).abs().max().item() < 5e-2, n
