@@ -148,6 +148,66 @@ __device__ __forceinline__ void cnb_red2(float* table, uint32_t row, float a, fl
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(reinterpret_cast<float2*>(table) + row), "f"(a), "f"(b) : "memory");
 }
 
+__device__ __forceinline__ void cnb_red4(float* table, uint32_t even_row, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<float2*>(table) + even_row), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// Gradient scatter of one (sample, level) with WARP AGGREGATION.  Must be called by all 32 lanes (inactive lanes pass
+// active = false).  Lanes are consecutive samples of a ray, so samples that fall into the same grid cell form runs of
+// consecutive lanes; a run (capped at 8 lanes) is summed with a segmented warp scan and only its last lane issues the
+// reductions.  The two x-neighbours of a corner pair (hash prime of x is 1) are adjacent table
+// rows whenever floor(x) is even: those go out as ONE 16-byte red.global.add.v4.f32.
+// Requires integer cell coordinates < 65536 (scalings < 65535).
+__device__ __forceinline__ void cnb_scatter_cell(float* d_table, const CnbCell& c, uint32_t mask, uint32_t level_offset, float d0, float d1,
+                                                 bool active) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  if (!active) { d0 = 0.0f; d1 = 0.0f; }
+  // cell identity: floor coordinates + which coordinates are exact integers (ceil == floor)
+  const uint32_t k0 = active ? (c.fx | (c.fy << 16)) : FULL;
+  const uint32_t k1 = active ? (c.fz | ((c.cx - c.fx) << 16) | ((c.cy - c.fy) << 17) | ((c.cz - c.fz) << 18)) : (uint32_t)lane;
+  const uint32_t p0 = __shfl_up_sync(FULL, k0, 1), p1 = __shfl_up_sync(FULL, k1, 1);
+  const bool head = (lane & 7) == 0 || k0 != p0 || k1 != p1;
+  const uint32_t heads = __ballot_sync(FULL, head);
+  float w[8];
+  cnb_corner_weights(c.ox, c.oy, c.oz, w);
+  float v0[8], v1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { v0[k] = w[k] * d0; v1[k] = w[k] * d1; }
+  if (heads != FULL) {  // at least one run of two or more lanes in this warp
+    const int start = 31 - __clz(heads & (FULL >> (31 - lane)));
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+      const bool take = lane - off >= start;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float t0 = __shfl_up_sync(FULL, v0[k], off), t1 = __shfl_up_sync(FULL, v1[k], off);
+        if (take) { v0[k] += t0; v1[k] += t1; }
+      }
+    }
+  }
+  const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+  if (!tail || !active) return;
+  uint32_t h[8];
+  cnb_corner_rows(c, mask, level_offset, h);
+  if (c.cx == c.fx + 1u && (c.fx & 1u) == 0u) {
+    // pairs (ceil-x, floor-x) of the reference's corner order: (0,3) (1,2) (5,6) (4,7)
+    const int pc[4] = {0, 1, 5, 4}, pf[4] = {3, 2, 6, 7};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kc = pc[q], kf = pf[q];
+      if (v0[kc] == 0.0f && v1[kc] == 0.0f && v0[kf] == 0.0f && v1[kf] == 0.0f) continue;
+      if ((h[kf] & 1u) == 0u) cnb_red4(d_table, h[kf], v0[kf], v1[kf], v0[kc], v1[kc]);
+      else cnb_red4(d_table, h[kc], v0[kc], v1[kc], v0[kf], v1[kf]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (v0[k] != 0.0f || v1[k] != 0.0f) cnb_red2(d_table, h[k], v0[k], v1[k]);
+  }
+}
+
 // trunc_exp (nerfstudio activations.py): exp forward, g*exp(clamp(x,-15,15)) backward
 __device__ __forceinline__ float cnb_trunc_exp_grad(float x) { return expf(fminf(fmaxf(x, -15.0f), 15.0f)); }
 

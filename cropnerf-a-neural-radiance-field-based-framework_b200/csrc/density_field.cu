@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(BLOCK) k_density_fwd(DfArgs a, float* __restri
 //   U_s = [dh_s (H) | g_s]      V_s = [x_s (in) | 1 | h_s (H)]
 // and the parameter gradients are the pair sums (dh_j,x_k) (dh_j,1) (g,h_j) (g,1).
 template <int LMAX, int H>
-__global__ void __launch_bounds__(BLOCK) k_density_bwd(DfArgs a, const float* __restrict__ d_density) {
+__global__ void __launch_bounds__(BLOCK, (H <= 16 && LMAX <= 8) ? 5 : 1) k_density_bwd(DfArgs a, const float* __restrict__ d_density) {
   constexpr int INP = 2 * LMAX;
   constexpr int LD = BLOCK + 1;
   extern __shared__ float4 smem4[];
@@ -143,10 +143,10 @@ __global__ void __launch_bounds__(BLOCK) k_density_bwd(DfArgs a, const float* __
         }
       }
     }
-    if (active) {
-      float dfeat[INP];
+    float dfeat[INP];
 #pragma unroll
-      for (int k = 0; k < INP; ++k) dfeat[k] = 0.0f;
+    for (int k = 0; k < INP; ++k) dfeat[k] = 0.0f;
+    if (active) {
 #pragma unroll
       for (int j = 0; j < H; ++j) {
         const float dh = hid[j] > 0.0f ? g * Ws[H * INP + H + j] : 0.0f;
@@ -164,26 +164,20 @@ __global__ void __launch_bounds__(BLOCK) k_density_bwd(DfArgs a, const float* __
       for (int k = 0; k < INP; ++k)
         if (k < a.in) V[k * LD + tid] = feat[k];
       V[a.in * LD + tid] = 1.0f;
-      // table gradient
-#pragma unroll
-      for (int l = 0; l < LMAX; ++l) {
-        if (l < a.L) {
-          const float d0 = dfeat[2 * l], d1 = dfeat[2 * l + 1];
-          if (d0 != 0.0f || d1 != 0.0f) {
-            const CnbCell c = cnb_cell(x, y, z, a.scalings[l]);
-            uint32_t h[8];
-            cnb_corner_rows(c, a.mask, (uint32_t)l * a.T, h);
-            float w[8];
-            cnb_corner_weights(c.ox, c.oy, c.oz, w);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (w[k] != 0.0f) cnb_red2(a.d_table, h[k], w[k] * d0, w[k] * d1);
-          }
-        }
-      }
     } else {
       for (int j = 0; j <= H; ++j) U[j * LD + tid] = 0.0f;
       for (int k = 0; k < nv; ++k) V[k * LD + tid] = 0.0f;
+    }
+    // table gradient: the lanes of a warp are consecutive samples of a ray -> warp-aggregated scatter (all lanes take part)
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      if (l < a.L) {
+        const float d0 = dfeat[2 * l], d1 = dfeat[2 * l + 1];
+        const bool on = active && (d0 != 0.0f || d1 != 0.0f);
+        CnbCell c = {};
+        if (on) c = cnb_cell(x, y, z, a.scalings[l]);
+        cnb_scatter_cell(a.d_table, c, a.mask, (uint32_t)l * a.T, d0, d1, on);
+      }
     }
     __syncthreads();
     for (int o = tid; o < nout; o += BLOCK) {
@@ -227,6 +221,8 @@ int make_args(const cnb_density_field* f, const cnb_samples* s, bool bwd, DfArgs
   CNB_REQUIRE(s->origins && s->directions && s->starts && s->ends, "density_field: null sample arrays");
   CNB_REQUIRE(s->samples_per_ray >= 1 && s->num_rays >= 0, "density_field: bad sample counts");
   CNB_REQUIRE(!bwd || g.d_table != nullptr, "density_field_bwd: d_table required");
+  if (bwd)
+    for (int i = 0; i < g.num_levels; ++i) CNB_REQUIRE(g.scalings[i] < 65535.0f, "density_field_bwd: level resolution %g too large for the aggregated scatter", g.scalings[i]);
   a.table = g.table; a.d_table = g.d_table; a.L = g.num_levels;
   a.T = 1u << g.log2_hashmap_size; a.mask = a.T - 1u;
   for (int i = 0; i < CNB_MAX_LEVELS; ++i) a.scalings[i] = g.scalings[i];

@@ -183,8 +183,7 @@ bool cnb_field_mixed_supported(const cnb_field* f) {
          r.num_layers == 3 && r.dims[0] == 63 && r.dims[1] == H && r.dims[2] == H && r.dims[3] == 3 && f->appearance_dim == 32 && f->geo_feat_dim == 15;
 }
 
-// ctx (mixed, training): [x0: N*32 fp16 = N*16 floats][positions: N*3 floats][d_x0: N*32 floats]
-int64_t cnb_field_mixed_ctx_floats(int64_t n, int training) { return training ? n * (16 + 3 + 32) + 16 : 0; }
+int64_t cnb_field_mixed_ctx_floats(int64_t n, int training) { return training ? ctx_total(n) : 0; }
 
 int cnb_field_mixed_fwd(const cnb_field* f, const cnb_samples* s, float* density, float* rgb, float* sem, float* positions_out, float* ctx,
                         int training, cudaStream_t stream) {
@@ -194,7 +193,7 @@ int cnb_field_mixed_fwd(const cnb_field* f, const cnb_samples* s, float* density
   a.density = density; a.rgb = rgb; a.sem = sem; a.pos_out = positions_out; a.x0_out = nullptr;
   if (training) {
     a.x0_out = reinterpret_cast<__half*>(ctx);
-    a.pos_out = ctx + N * 16;
+    a.pos_out = ctx + ctx_pos_off(N);
   }
   static bool configured = false;
   if (!configured) {

@@ -497,8 +497,8 @@ int cnb_field_mixed_bwd(const cnb_field* f, const cnb_samples* s, const float* d
   fill_args(f, s, b.m);
   const int64_t N = s->num_rays * s->samples_per_ray;
   b.x0 = reinterpret_cast<const __half*>(ctx);
-  b.pos = ctx + N * 16;
-  b.d_x0 = ctx + N * 19;
+  b.pos = ctx + ctx_pos_off(N);
+  b.d_x0 = ctx + ctx_dx0_off(N);
   b.d_density = d_density; b.d_rgb = d_rgb; b.d_sem = d_sem;
   b.dWb1 = f->base.dW[0]; b.dbb1 = f->base.db[0]; b.dWb2 = f->base.dW[1]; b.dbb2 = f->base.db[1];
   b.dWs1 = f->sem.dW[0]; b.dbs1 = f->sem.db[0]; b.dWs2 = f->sem.dW[1]; b.dbs2 = f->sem.db[1];

@@ -56,22 +56,26 @@ __global__ void __launch_bounds__(256) k_hashgrid_fwd(const __grid_constant__ Gr
   }
 }
 
+// Backward: a warp owns 32 CONSECUTIVE samples of one level (samples are ray-major, so neighbouring lanes are
+// neighbouring samples of a ray and often share a cell): cnb_scatter_cell aggregates those runs before the reductions.
 __global__ void __launch_bounds__(256) k_hashgrid_bwd(const __grid_constant__ GridArgs g, const float* __restrict__ pos, const float* __restrict__ d_out, int64_t n) {
-  const int64_t total = n * g.L;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const float2 d = __ldg(reinterpret_cast<const float2*>(d_out) + i);
-    if (d.x == 0.0f && d.y == 0.0f) continue;  // zero gradients add nothing (masked samples, App. B-3)
-    const int64_t s = i / g.L;
-    const int l = (int)(i - s * g.L);
-    const float x = __ldg(pos + 3 * s), y = __ldg(pos + 3 * s + 1), z = __ldg(pos + 3 * s + 2);
-    const CnbCell c = cnb_cell(x, y, z, g.scalings[l]);
-    uint32_t h[8];
-    cnb_corner_rows(c, g.mask, (uint32_t)l * g.T, h);
-    float w[8];
-    cnb_corner_weights(c.ox, c.oy, c.oz, w);
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (w[k] != 0.0f) cnb_red2(g.d_table, h[k], w[k] * d.x, w[k] * d.y);
+  const int lane = threadIdx.x & 31;
+  const int64_t nblk = (n + 31) >> 5;
+  const int64_t nwork = nblk * g.L;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t w = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); w < nwork; w += wstride) {
+    const int64_t sb = w / g.L;
+    const int l = (int)(w - sb * g.L);
+    const int64_t s = sb * 32 + lane;
+    bool active = s < n;
+    float2 d = make_float2(0.f, 0.f);
+    if (active) {
+      d = __ldg(reinterpret_cast<const float2*>(d_out) + s * g.L + l);
+      active = d.x != 0.0f || d.y != 0.0f;  // zero gradients add nothing (masked samples, App. B-3)
+    }
+    CnbCell c = {};
+    if (active) c = cnb_cell(__ldg(pos + 3 * s), __ldg(pos + 3 * s + 1), __ldg(pos + 3 * s + 2), g.scalings[l]);
+    cnb_scatter_cell(g.d_table, c, g.mask, (uint32_t)l * g.T, d.x, d.y, active);
   }
 }
 
@@ -109,6 +113,7 @@ extern "C" int cnb_hashgrid_bwd(const cnb_grid* g, const float* positions, const
   CNB_REQUIRE(n >= 0 && (n == 0 || (positions && d_out)), "hashgrid_bwd: null positions/d_out");
   if (n == 0) return CNB_OK;
   GridArgs a = make_args(g);
-  k_hashgrid_bwd<<<grid_for(n * a.L, 256), 256, 0, stream>>>(a, positions, d_out, n);
+  for (int i = 0; i < a.L; ++i) CNB_REQUIRE(a.scalings[i] < 65535.0f, "hashgrid_bwd: level resolution %g too large for the aggregated scatter", a.scalings[i]);
+  k_hashgrid_bwd<<<grid_for(((n + 31) / 32) * 32 * a.L, 256), 256, 0, stream>>>(a, positions, d_out, n);
   return cnb_check_launch("hashgrid_bwd");
 }
