@@ -7,6 +7,8 @@
 // MLP (193 parameters for H=16) is read from shared memory as warp-wide broadcasts.  Backward recomputes the
 // forward, scatters the table gradient with vector reductions (red.global.add.v2.f32) and reduces the MLP
 // parameter gradients per CTA through a shared-memory tile before one atomic flush per CTA.
+#include <cuda_bf16.h>
+
 #include "cnb_common.cuh"
 
 namespace {
@@ -205,6 +207,196 @@ __global__ void __launch_bounds__(BLOCK, (H <= 16 && LMAX <= 8) ? 5 : 1) k_densi
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward for the fruit_nerf proposal architecture (<= 7 levels, hidden 16): the MLP parameter gradients are the
+// products U^T V of the per-sample rows
+//     U_s = [dh_s (16) | g_s | 0 ...] (32 cols)        V_s = [x_s (in <= 14) | 0.. | 1 (col 15) | h_s (16)] (32 cols)
+// contracted over SAMPLES, i.e. a GEMM whose K dimension is the 128 samples of the CTA's tile: the rows are staged in
+// shared memory and contracted with mma.sync.m16n8k16 through ldmatrix.trans.  To keep fp32-level accuracy (this kernel
+// also serves the exact-fp32 mode, 5e-4 gradient parity) every value is split into bf16 hi + bf16 lo and the three
+// significant cross products are accumulated (relative error ~1e-5).  Each warp takes two of the tile's eight 16-sample
+// k-steps and keeps its 5 output tiles in registers across the whole kernel; one cross-warp reduction + flush per CTA.
+constexpr int TC_SW = 40;  // staging row stride in halves (32 + 8 pad): 80-byte rows, 16-byte aligned, conflict-free
+
+__device__ __forceinline__ void tc_ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void tc_mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 8 floats -> 8 bf16 hi (uint4) + 8 bf16 lo (uint4)
+__device__ __forceinline__ void tc_split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+    const float2 back = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * q] - back.x, v[2 * q + 1] - back.y);
+    h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[q] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(BLOCK, 5) k_density_bwd_tc(DfArgs a, const float* __restrict__ d_density) {
+  constexpr int LMAX = 8, H = 16, INP = 16;
+  extern __shared__ float4 smem4[];
+  float* Ws = reinterpret_cast<float*>(smem4);                         // H*INP + 2H + 4 floats (= 292)
+  __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(Ws + 296);     // Uh, Ul, Vh, Vl: 4 x [BLOCK][TC_SW]
+  load_weights<LMAX, H>(a, Ws);
+  __syncthreads();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t stg_s = (uint32_t)__cvta_generic_to_shared(stg);
+  constexpr uint32_t MAT = BLOCK * TC_SW * 2;  // bytes per staged matrix
+  const int S = a.sm.samples_per_ray;
+  const int64_t total = a.sm.num_rays * S;
+  const int64_t ntiles = (total + BLOCK - 1) / BLOCK;
+  // output tiles: t0 = dh x V[0:8], t1 = dh x V[8:16] (col 15 = bias 1), t2 = [g] x V[8:16], t3 = [g] x h[0:8], t4 = [g] x h[8:16]
+  float acc[5][4];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) { acc[q][0] = 0.f; acc[q][1] = 0.f; acc[q][2] = 0.f; acc[q][3] = 0.f; }
+  const int j = lane >> 3, r8 = lane & 7;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t i = tile * BLOCK + tid;
+    float g = 0.0f;
+    float feat[INP], hid[H];
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool active = false;
+    if (i < total) {
+      const float dd = __ldg(d_density + i);
+      if (dd != 0.0f) {
+        const int64_t r = i / S;
+        const int s = (int)(i - r * S);
+        const bool sel = cnb_sample_position(a.sm, a.warp, r, s, x, y, z);
+        if (sel) {
+          encode<LMAX>(a, x, y, z, feat);
+          const float out = mlp_forward<LMAX, H>(Ws, feat, hid);
+          g = dd * a.avg * cnb_trunc_exp_grad(out);
+          active = (g != 0.0f);
+        }
+      }
+    }
+    float dfeat[INP];
+#pragma unroll
+    for (int k = 0; k < INP; ++k) dfeat[k] = 0.0f;
+    uint4* row = reinterpret_cast<uint4*>(stg + tid * TC_SW);
+    constexpr int MATQ = BLOCK * TC_SW / 8;  // uint4 per matrix
+    if (active) {
+      float dh[H];
+#pragma unroll
+      for (int jj = 0; jj < H; ++jj) {
+        dh[jj] = hid[jj] > 0.0f ? g * Ws[H * INP + H + jj] : 0.0f;
+#pragma unroll
+        for (int k = 0; k < INP; k += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(Ws + jj * INP + k);
+          dfeat[k] = fmaf(dh[jj], w.x, dfeat[k]); dfeat[k + 1] = fmaf(dh[jj], w.y, dfeat[k + 1]);
+          dfeat[k + 2] = fmaf(dh[jj], w.z, dfeat[k + 2]); dfeat[k + 3] = fmaf(dh[jj], w.w, dfeat[k + 3]);
+        }
+      }
+      uint4 hi, lo;
+      float v8[8];
+      // U = [dh0..15 | g 0 0 0 0 0 0 0 | 0 x8]
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v8[k] = dh[8 * c + k];
+        tc_split8(v8, hi, lo);
+        row[c] = hi; row[MATQ + c] = lo;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v8[k] = 0.0f;
+      v8[0] = g;
+      tc_split8(v8, hi, lo);
+      row[2] = hi; row[MATQ + 2] = lo;
+      row[3] = make_uint4(0, 0, 0, 0); row[MATQ + 3] = make_uint4(0, 0, 0, 0);
+      // V = [x0..x(in-1) 0.. 1 | h0..15]
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v8[k] = (8 * c + k < a.in) ? feat[8 * c + k] : 0.0f;
+        if (c == 1) v8[7] = 1.0f;
+        tc_split8(v8, hi, lo);
+        row[2 * MATQ + c] = hi; row[3 * MATQ + c] = lo;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v8[k] = hid[8 * c + k];
+        tc_split8(v8, hi, lo);
+        row[2 * MATQ + 2 + c] = hi; row[3 * MATQ + 2 + c] = lo;
+      }
+    } else {
+      const uint4 zq = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) row[m * MATQ + c] = zq;
+    }
+    // table gradient: the lanes of a warp are consecutive samples of a ray -> warp-aggregated scatter (all lanes take part)
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      if (l < a.L) {
+        const float d0 = dfeat[2 * l], d1 = dfeat[2 * l + 1];
+        const bool on = active && (d0 != 0.0f || d1 != 0.0f);
+        CnbCell c = {};
+        if (on) c = cnb_cell(x, y, z, a.scalings[l]);
+        cnb_scatter_cell(a.d_table, c, a.mask, (uint32_t)l * a.T, d0, d1, on);
+      }
+    }
+    __syncthreads();
+    // ---- parameter gradients: this warp contracts k-steps 2*warp, 2*warp+1 of the tile ----------------------------------------
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int ks = 2 * warp + kk;
+      uint32_t A0[2][4], A1[2][4], B01[2][4], B23[2][4];  // [hi/lo]
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const uint32_t ubase = stg_s + p * MAT, vbase = stg_s + (2 + p) * MAT;
+        const uint32_t arow = 2u * ((16 * ks + (j >> 1) * 8 + r8) * TC_SW + (j & 1) * 8);
+        tc_ldsm_x4_t(A0[p], ubase + arow);
+        tc_ldsm_x4_t(A1[p], ubase + arow + 2u * 16);
+        const uint32_t brow = 2u * ((16 * ks + (j & 1) * 8 + r8) * TC_SW + 8 * (j >> 1));
+        tc_ldsm_x4_t(B01[p], vbase + brow);
+        tc_ldsm_x4_t(B23[p], vbase + brow + 2u * 16);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {  // hi*hi, hi*lo, lo*hi
+        const int pa = c == 2 ? 1 : 0, pb = c == 1 ? 1 : 0;
+        tc_mma_bf16(acc[0], A0[pa], B01[pb][0], B01[pb][1]);
+        tc_mma_bf16(acc[1], A0[pa], B01[pb][2], B01[pb][3]);
+        tc_mma_bf16(acc[2], A1[pa], B01[pb][2], B01[pb][3]);
+        tc_mma_bf16(acc[3], A1[pa], B23[pb][0], B23[pb][1]);
+        tc_mma_bf16(acc[4], A1[pa], B23[pb][2], B23[pb][3]);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- cross-warp reduction + one flush per CTA -----------------------------------------------------------------------------------
+  float* red = reinterpret_cast<float*>(stg);  // [4 warps][5][4][32]
+#pragma unroll
+  for (int q = 0; q < 5; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[((warp * 5 + q) * 4 + e) * 32 + lane] = acc[q][e];
+  __syncthreads();
+  for (int o = tid; o < 5 * 4 * 32; o += BLOCK) {
+    const float v = red[o] + red[640 + o] + red[1280 + o] + red[1920 + o];
+    if (v == 0.0f) continue;
+    const int q = o / 128, e = (o >> 5) & 3, ln = o & 31;
+    const int rowi = (ln >> 2) + (e >> 1) * 8, col = 2 * (ln & 3) + (e & 1);  // within the 16x8 tile
+    if (q == 0) { if (col < a.in && a.dW1) atomicAdd(a.dW1 + rowi * a.in + col, v); }
+    else if (q == 1) {
+      if (8 + col < a.in) { if (a.dW1) atomicAdd(a.dW1 + rowi * a.in + 8 + col, v); }
+      else if (col == 7 && a.db1) atomicAdd(a.db1 + rowi, v);
+    } else if (rowi == 0) {
+      if (q == 2) { if (col == 7 && a.db2) atomicAdd(a.db2, v); }
+      else if (a.dW2) atomicAdd(a.dW2 + (q - 3) * 8 + col, v);
+    }
+  }
+}
+
 int make_args(const cnb_density_field* f, const cnb_samples* s, bool bwd, DfArgs& a) {
   CNB_REQUIRE(f && s, "density_field: null descriptor");
   const cnb_grid& g = f->grid;
@@ -244,9 +436,20 @@ int launch_fwd(const DfArgs& a, float* density, float* pos_out, cudaStream_t st)
   return cnb_check_launch("density_field_fwd");
 }
 
+int launch_bwd_tc(const DfArgs& a, const float* d_density, cudaStream_t st) {
+  const int64_t total = a.sm.num_rays * a.sm.samples_per_ray;
+  const size_t smem = sizeof(float) * 296 + (size_t)4 * BLOCK * TC_SW * 2;
+  int64_t blocks = (total + BLOCK - 1) / BLOCK;
+  const int64_t cap = (int64_t)cnb_num_sms() * 5;
+  if (blocks > cap) blocks = cap;
+  k_density_bwd_tc<<<(int)blocks, BLOCK, smem, st>>>(a, d_density);
+  return cnb_check_launch("density_field_bwd");
+}
+
 template <int LMAX, int H>
 int launch_bwd(const DfArgs& a, const float* d_density, cudaStream_t st) {
   constexpr int INP = 2 * LMAX;
+  if (LMAX == 8 && H == 16 && a.in <= 14) return launch_bwd_tc(a, d_density, st);
   const int64_t total = a.sm.num_rays * a.sm.samples_per_ray;
   const int nv = a.in + 1 + H, nout = H * a.in + 2 * H + 1;
   const size_t smem = sizeof(float) * ((H * INP + 2 * H + 4) + (size_t)(H + 1 + nv) * (BLOCK + 1) + nout + 4);
