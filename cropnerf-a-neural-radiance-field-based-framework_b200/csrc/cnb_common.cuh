@@ -143,6 +143,29 @@ __device__ __forceinline__ float2 cnb_ldg2(const float* table, uint32_t row) {
   return __ldg(reinterpret_cast<const float2*>(table) + row);
 }
 
+// The 8 corner rows of a cell.  The hash prime of x is 1, so the ceil-x / floor-x rows of a corner pair differ only in
+// bit 0 whenever floor(x) is even: those pairs -- (0,3) (1,2) (5,6) (4,7) in the reference's corner order -- are fetched
+// with ONE 16-byte load.  The gathers are bound by the L1TEX data pipe (one wavefront per distinct sector per request),
+// so where the lanes of a request hit unrelated sectors (fine levels of the 16-level field grid) this removes up to a
+// quarter of the wavefronts.  Measured: field forward -5 %; proposal forward +20 % (its lanes are consecutive samples
+// that already share sectors, so the divergent second path only adds requests) -- used by the field kernel only.
+// Values are bit-identical to eight 8-byte loads.
+__device__ __forceinline__ void cnb_gather8(const float* __restrict__ table, const CnbCell& c, const uint32_t (&h)[8], float2 (&v)[8]) {
+  if (c.cx == c.fx + 1u && (c.fx & 1u) == 0u) {
+    const int pc[4] = {0, 1, 5, 4}, pf[4] = {3, 2, 6, 7};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(table) + (h[pf[q]] >> 1));
+      const bool f_even = (h[pf[q]] & 1u) == 0u;
+      v[pf[q]] = f_even ? make_float2(w.x, w.y) : make_float2(w.z, w.w);
+      v[pc[q]] = f_even ? make_float2(w.z, w.w) : make_float2(w.x, w.y);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = cnb_ldg2(table, h[k]);
+  }
+}
+
 // vector reduction into the gradient table: one red.global.add.v2.f32 (sm_90+) per corner
 __device__ __forceinline__ void cnb_red2(float* table, uint32_t row, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(reinterpret_cast<float2*>(table) + row), "f"(a), "f"(b) : "memory");

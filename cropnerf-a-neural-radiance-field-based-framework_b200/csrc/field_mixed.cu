@@ -24,15 +24,19 @@ using namespace cnbmix;
 
 namespace {
 
-// gather + trilinear blend of one (sample, level): returns the packed fp16 feature pair
-__device__ __forceinline__ uint32_t encode_level(const MixArgs& a, int level, float x, float y, float z) {
-  if (level >= a.L) return 0u;
-  const CnbCell c = cnb_cell(x, y, z, a.scalings[level]);
+constexpr int TILE = WARPS * 16;   // samples per CTA tile
+constexpr int XS = 40;             // row stride (halves) of the staged feature tile: conflict-free A-fragment reads
+constexpr size_t SMEM_FWD2 = SMEM_FWD + (size_t)TILE * XS * sizeof(__half);
+
+// gather + trilinear blend of one (sample, level) -> packed fp16 feature pair.  When floor(x) is even the two x-neighbours
+// of each corner pair are adjacent table rows (hash prime of x is 1): one 16-byte load instead of two 8-byte loads.
+__device__ __forceinline__ uint32_t gather_level(const float* __restrict__ table, uint32_t mask, uint32_t level_offset, float scale, float x, float y,
+                                                 float z) {
+  const CnbCell c = cnb_cell(x, y, z, scale);
   uint32_t h[8];
-  cnb_corner_rows(c, a.mask, (uint32_t)level * a.T, h);
+  cnb_corner_rows(c, mask, level_offset, h);
   float2 v[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = cnb_ldg2(a.table, h[k]);
+  cnb_gather8(table, c, h, v);
   const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
   // same pairing as the reference blend (f03,f12,f56,f47 -> f0312,f4756), FMA-contracted
   float2 f03, f12, f56, f47;
@@ -45,6 +49,13 @@ __device__ __forceinline__ uint32_t encode_level(const MixArgs& a, int level, fl
   return pack_h2(a0, a1);
 }
 
+// A warp owns a 16-sample m-tile end to end (no block-level barriers: the 16 resident warps of an SM drift apart, so the
+// L1-bound gathers of some overlap the tensor-pipe work of others).
+//   gather: lane = (level parity, sample 0..15), so each half-warp request covers 16 CONSECUTIVE samples of one level
+//     (neighbouring samples of a ray share cells / sectors at the coarse and middle levels) and x-neighbour rows go out
+//     as one 16-byte load.  The forward gathers are bound by the L1TEX data pipe (one wavefront per distinct sector per
+//     request; ncu: l1tex__data_pipe_lsu_wavefronts 85 % busy, L2 16-42 %), so wavefronts are what is minimised.
+//   features are staged (fp16) in a warp-private 16x32 shared-memory tile and re-read as mma A fragments.
 __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_constant__ MixArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* Wsm = reinterpret_cast<__half*>(smem_raw);
@@ -56,35 +67,53 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
   const int S = a.sm.samples_per_ray;
   const int64_t N = a.sm.num_rays * S;
   const int64_t ntiles = (N + 15) >> 4;
+  __half* X0 = reinterpret_cast<__half*>(smem_raw + SMEM_FWD) + warp * 16 * XS;
+  uint32_t* X32 = reinterpret_cast<uint32_t*>(X0);
+  const int sidx = lane & 15, lpar = lane >> 4;
   for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * WARPS) {
-    int64_t row[2] = {tile * 16 + g, tile * 16 + g + 8};
+    const int64_t base = tile * 16;
+    // ---- position of this lane's gather sample -------------------------------------------------------------------------------
+    float px = 0.f, py = 0.f, pz = 0.f;
+    bool my_sel = false;
+    {
+      const int64_t i = base + sidx;
+      if (i < N) {
+        const int64_t r = i / S;
+        my_sel = cnb_sample_position(a.sm, a.warp, r, (int)(i - r * S), px, py, pz);
+        if (a.pos_out && lpar == 0) { a.pos_out[3 * i] = px; a.pos_out[3 * i + 1] = py; a.pos_out[3 * i + 2] = pz; }
+      }
+    }
+    __syncwarp();  // the previous tile's fragment reads of X0 are complete
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+      const int l = 2 * it + lpar;
+      uint32_t f = 0u;
+      if (l < a.L) f = gather_level(a.table, a.mask, (uint32_t)l * a.T, a.scalings[l], px, py, pz);
+      X32[sidx * (XS / 2) + l] = f;
+    }
+    __syncwarp();
+    int64_t row[2] = {base + g, base + g + 8};
     bool valid[2], sel[2];
-    float px[2], py[2], pz[2];
     int64_t ray[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       valid[h] = row[h] < N;
-      const int64_t r = valid[h] ? row[h] : N - 1;
-      ray[h] = r / S;
-      sel[h] = cnb_sample_position(a.sm, a.warp, ray[h], (int)(r - ray[h] * S), px[h], py[h], pz[h]);
-      if (a.pos_out && t == 0 && valid[h]) { a.pos_out[3 * r] = px[h]; a.pos_out[3 * r + 1] = py[h]; a.pos_out[3 * r + 2] = pz[h]; }
+      ray[h] = (valid[h] ? row[h] : N - 1) / S;
+      sel[h] = __shfl_sync(0xffffffffu, my_sel ? 1 : 0, g + 8 * h) != 0;
     }
-    // ---- multiresolution gather straight into the A fragments of the first GEMM -------------------------------
     uint32_t A0[2][4];
 #pragma unroll
     for (int kt = 0; kt < 2; ++kt)
 #pragma unroll
       for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) A0[kt][2 * q + h] = encode_level(a, 8 * kt + 4 * q + t, px[h], py[h], pz[h]);
-    if (a.x0_out) {
+        for (int h = 0; h < 2; ++h) A0[kt][2 * q + h] = X32[(g + 8 * h) * (XS / 2) + 8 * kt + 4 * q + t];
+    if (a.x0_out) {  // encoded features kept for the backward: the tile is one contiguous 1 KB block of the [N,32] fp16 array
 #pragma unroll
-      for (int kt = 0; kt < 2; ++kt)
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            if (valid[h]) *reinterpret_cast<uint32_t*>(a.x0_out + row[h] * 32 + 16 * kt + 8 * q + 2 * t) = A0[kt][2 * q + h];
+      for (int e = lane; e < 64; e += 32) {
+        const int rw = e >> 2, q = e & 3;
+        if (base + rw < N) reinterpret_cast<uint4*>(a.x0_out + (base + rw) * 32)[q] = reinterpret_cast<const uint4*>(X0 + rw * XS)[q];
+      }
     }
     // ---- base MLP: 32 -> 64 -> 16 --------------------------------------------------------------------------------
     uint32_t Abo[1][4];
@@ -197,14 +226,13 @@ int cnb_field_mixed_fwd(const cnb_field* f, const cnb_samples* s, float* density
   }
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(k_field_mixed_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD) != cudaSuccess) return cnb_check_launch("field_mixed_fwd attr");
+    if (cudaFuncSetAttribute(k_field_mixed_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD2) != cudaSuccess) return cnb_check_launch("field_mixed_fwd attr");
     configured = true;
   }
-  const int64_t ntiles = (N + 15) / 16;
-  int64_t blocks = (ntiles + WARPS - 1) / WARPS;
+  int64_t blocks = (N + TILE - 1) / TILE;  // one 16-sample m-tile per warp and round
   const int64_t cap = (int64_t)cnb_num_sms() * 2;
   if (blocks > cap) blocks = cap;
-  k_field_mixed_fwd<<<(int)blocks, THREADS, SMEM_FWD, stream>>>(a);
+  k_field_mixed_fwd<<<(int)blocks, THREADS, SMEM_FWD2, stream>>>(a);
   int rc = cnb_check_launch("field_mixed_fwd");
   if (rc) return rc;
   if (training && positions_out != nullptr &&

@@ -28,12 +28,20 @@ GridArgs make_args(const cnb_grid* g) {
   return a;
 }
 
+// Forward: a warp owns 32 CONSECUTIVE samples of one level, so one load instruction touches few distinct 128-byte lines at
+// the coarse / middle levels (the gathers are bound by the L1TEX t-stage: one wavefront per distinct line per request).
 __global__ void __launch_bounds__(256) k_hashgrid_fwd(const __grid_constant__ GridArgs g, const float* __restrict__ pos, int64_t n, float* __restrict__ out,
                                                        int32_t* __restrict__ indices) {
-  const int64_t total = n * g.L;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t s = i / g.L;
-    const int l = (int)(i - s * g.L);
+  const int lane = threadIdx.x & 31;
+  const int64_t nblk = (n + 31) >> 5;
+  const int64_t nwork = nblk * g.L;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t w = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); w < nwork; w += wstride) {
+    const int64_t sb = w / g.L;
+    const int l = (int)(w - sb * g.L);
+    const int64_t s = sb * 32 + lane;
+    if (s >= n) continue;
+    const int64_t i = s * g.L + l;
     const float x = __ldg(pos + 3 * s), y = __ldg(pos + 3 * s + 1), z = __ldg(pos + 3 * s + 2);
     const CnbCell c = cnb_cell(x, y, z, g.scalings[l]);
     uint32_t h[8];
@@ -103,7 +111,7 @@ extern "C" int cnb_hashgrid_fwd(const cnb_grid* g, const float* positions, int64
   CNB_REQUIRE(n >= 0 && (n == 0 || (positions && out)), "hashgrid_fwd: null positions/out");
   if (n == 0) return CNB_OK;
   GridArgs a = make_args(g);
-  k_hashgrid_fwd<<<grid_for(n * a.L, 256), 256, 0, stream>>>(a, positions, n, out, indices);
+  k_hashgrid_fwd<<<grid_for(((n + 31) / 32) * 32 * a.L, 256), 256, 0, stream>>>(a, positions, n, out, indices);
   return cnb_check_launch("hashgrid_fwd");
 }
 
