@@ -128,48 +128,44 @@ int forward_chain(const cnb_model* m, const cnb_rays* rays, const Layout& L, flo
   if ((rc = cnb_check_launch("render near/far"))) return rc;
   const bool mixed = m->field.precision == CNB_PREC_MIXED;
   const float* jit = jitter;
-  for (int lv = 0; lv < L.levels; ++lv) {
-    const int S = L.S[lv];
-    const int rstride = sp.single_jitter ? 1 : S + 1;
-    if (lv == 0) {
-      STAGE("sample_spaced", 1, cnb_sample_spaced(ws + L.nears, ws + L.fars, sp.lin_bins, jit, rstride, sp.initial_spacing, R, S, ws + L.sp[0], ws + L.eu[0], st));
-    } else {
-      const int Sp = L.S[lv - 1];
-      STAGE("sample_pdf", 1, cnb_sample_pdf(ws + L.w[lv - 1], anneal, ws + L.sp[lv - 1], ws + L.nears, ws + L.fars, sp.initial_spacing, sp.u_base[lv - 1], jit,
-                                            rstride, R, Sp, S, sp.histogram_padding, sp.pdf_eps, ws + L.sp[lv], ws + L.eu[lv],
-                                            (lv == L.levels - 1 && out) ? out->pdf_inds : nullptr, st));
-    }
+  const int lf = L.levels - 1;
+  const bool user = out != nullptr;
+  {
+    const int rstride = sp.single_jitter ? 1 : L.S[0] + 1;
+    STAGE("sample_spaced", 1, cnb_sample_spaced(ws + L.nears, ws + L.fars, sp.lin_bins, jit, rstride, sp.initial_spacing, R, L.S[0], ws + L.sp[0], ws + L.eu[0], st));
     if (rc) return rc;
     if (jit) jit += R * rstride;
+  }
+  for (int lv = 0; lv < L.levels; ++lv) {
+    const int S = L.S[lv];
     const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
-    if (lv < L.levels - 1) {
+    if (lv < lf) {
       STAGE(lv == 0 ? "proposal0_fwd" : "proposal1_fwd", 1, cnb_density_field_fwd(&m->proposal[lv], &sm, ws + L.dens[lv], nullptr, st));
       if (rc) return rc;
+      // get_weights -> median depth -> PDF resampling of the next level, one kernel
+      const int Sn = L.S[lv + 1];
+      const int rstride = sp.single_jitter ? 1 : Sn + 1;
+      STAGE("level_resample", 1, cnb_level_resample(ws + L.dens[lv], ws + L.eu[lv], ws + L.sp[lv], ws + L.nears, ws + L.fars, sp.initial_spacing, anneal,
+                                                    sp.u_base[lv], jit, rstride, R, S, Sn, sp.histogram_padding, sp.pdf_eps, training ? ws + L.w[lv] : nullptr,
+                                                    user ? out->prop_depth[lv] : nullptr, ws + L.sp[lv + 1], ws + L.eu[lv + 1],
+                                                    (lv + 1 == lf && user) ? out->pdf_inds : nullptr, st));
+      if (rc) return rc;
+      if (jit) jit += R * rstride;
     } else {
       STAGE("field_fwd", mixed ? 1 : 7, cnb_field_fwd(&m->field, &sm, ws + L.dens[lv], nullptr, ws + L.rgb, ws + L.sem, nullptr,
                                                         L.ctx_floats > 0 ? ws + L.ctx : nullptr, training ? 1 : 0, st));
       if (rc) return rc;
     }
-    STAGE("weights_fwd", 1, cnb_weights_fwd(ws + L.dens[lv], ws + L.eu[lv], ws + L.eu[lv] + 1, S + 1, R, S, ws + L.w[lv], st));
-    if (rc) return rc;
   }
-  const int lf = L.levels - 1, Sf = L.S[lf];
-  const bool user = out != nullptr;
+  const int Sf = L.S[lf];
   float* o_rgb = (user && out->rgb) ? out->rgb : ws + L.o_rgb;
   float* o_acc = (user && out->accumulation) ? out->accumulation : ws + L.o_acc;
   float* o_sem = (user && out->semantics) ? out->semantics : ws + L.o_sem;
   float* o_depth = (user && out->depth) ? out->depth : nullptr;
-  STAGE("render_fwd", 1, cnb_render_fwd(ws + L.w[lf], ws + L.rgb, ws + L.sem, ws + L.eu[lf], ws + L.eu[lf] + 1, Sf + 1, R, Sf, m->bg_mode, m->bg_color,
-                                        training ? 0 : 1, o_rgb, o_depth, o_acc, o_sem, nullptr, st));
-  if (rc) return rc;
-  for (int lv = 0; lv < lf; ++lv) {
-    if (user && out->prop_depth[lv]) {
-      STAGE("prop_depth", 1, cnb_render_fwd(ws + L.w[lv], nullptr, nullptr, ws + L.eu[lv], ws + L.eu[lv] + 1, L.S[lv] + 1, R, L.S[lv], CNB_BG_NONE, nullptr,
-                                            0, nullptr, out->prop_depth[lv], nullptr, nullptr, nullptr, st));
-      if (rc) return rc;
-    }
-  }
-  return CNB_OK;
+  // get_weights -> RGB / accumulation / semantic / median-depth renderers of the final level, one kernel
+  STAGE("final_composite", 1, cnb_final_composite(ws + L.dens[lf], ws + L.rgb, ws + L.sem, ws + L.eu[lf], R, Sf, m->bg_mode, m->bg_color, training ? 0 : 1,
+                                                  training ? ws + L.w[lf] : nullptr, o_rgb, o_depth, o_acc, o_sem, st));
+  return rc;
 }
 
 }  // namespace
@@ -208,12 +204,27 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   const float gs = cfg->grad_scale == 0.0f ? 1.0f : cfg->grad_scale;
   const float* o_rgb = (out && out->rgb) ? out->rgb : ws + L.o_rgb;
   const float* o_sem = (out && out->semantics) ? out->semantics : ws + L.o_sem;
-  // ---- losses (fruit_nerf.py:601-615) --------------------------------------------------------------------------------------
-  STAGE("pixel_losses", 1, cnb_pixel_losses(o_rgb, o_sem, cfg->image, cfg->fruit_mask, R, cfg->semantic_loss_weight, gs, losses_out, ws + L.g_rgb, ws + L.g_sem, stream));
+  // ---- losses + backward of the final level: MSE / BCE gradients -> renderers -> get_weights, one kernel (fruit_nerf.py:601-608) ----
+  STAGE("final_composite_bwd", 1, cnb_final_composite_bwd(ws + L.dens[lf], ws + L.rgb, ws + L.sem, ws + L.eu[lf], ws + L.w[lf], o_rgb, o_sem, cfg->image,
+                                                          cfg->fruit_mask, R, Sf, m->bg_mode, m->bg_color, cfg->semantic_loss_weight, gs,
+                                                          m->field.pass_semantic_gradients, losses_out, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, stream));
   if (rc) return rc;
-  for (int lv = 0; lv < lf; ++lv) {
-    STAGE("interlevel_fwd", 1, cnb_interlevel_fwd(ws + L.sp[lf], ws + L.w[lf], ws + L.sp[lv], ws + L.w[lv], R, Sf, L.S[lv], losses_out + 2, stream));
+  {
+    const cnb_samples sm = make_samples(rays, ws + L.eu[lf], Sf);
+    STAGE("field_bwd", mixed ? 2 : 8, cnb_field_bwd(&m->field, &sm, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, nullptr, ws + L.ctx, stream));
     if (rc) return rc;
+  }
+  // ---- interlevel loss (fruit_nerf.py:610) and, on "updated" steps, its backward into the proposal networks ---------------------
+  for (int lv = 0; lv < lf; ++lv) {
+    const int S = L.S[lv];
+    STAGE("interlevel", 1, cnb_interlevel_fused(ws + L.sp[lf], ws + L.w[lf], ws + L.sp[lv], ws + L.w[lv], ws + L.dens[lv], ws + L.eu[lv], R, Sf, S,
+                                                gs * cfg->interlevel_loss_mult, losses_out + 2, cfg->update_proposals ? ws + L.d_dens[lv] : nullptr, stream));
+    if (rc) return rc;
+    if (cfg->update_proposals) {
+      const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
+      STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd(&m->proposal[lv], &sm, ws + L.d_dens[lv], stream));
+      if (rc) return rc;
+    }
   }
   if (cfg->interlevel_loss_mult != 1.0f) {
     k_scale<<<1, 32, 0, stream>>>(losses_out + 2, 1, cfg->interlevel_loss_mult);
@@ -222,30 +233,6 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   if (cfg->want_metrics) {
     STAGE("distortion", 1, cnb_distortion_fwd(ws + L.sp[lf], ws + L.w[lf], R, Sf, losses_out + 3, stream));
     if (rc) return rc;
-  }
-  // ---- backward: renderers -> get_weights -> field ----------------------------------------------------------------------------
-  STAGE("render_bwd", 1, cnb_render_bwd(ws + L.w[lf], ws + L.rgb, ws + L.sem, R, Sf, m->bg_mode, m->bg_color, ws + L.g_rgb, nullptr, ws + L.g_sem,
-                                        m->field.pass_semantic_gradients, ws + L.d_w[lf], ws + L.d_rgb, ws + L.d_sem, stream));
-  if (rc) return rc;
-  STAGE("weights_bwd", 1, cnb_weights_bwd(ws + L.dens[lf], ws + L.eu[lf], ws + L.eu[lf] + 1, Sf + 1, R, Sf, ws + L.d_w[lf], ws + L.d_dens[lf], stream));
-  if (rc) return rc;
-  {
-    const cnb_samples sm = make_samples(rays, ws + L.eu[lf], Sf);
-    STAGE("field_bwd", mixed ? 2 : 8, cnb_field_bwd(&m->field, &sm, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, nullptr, ws + L.ctx, stream));
-    if (rc) return rc;
-  }
-  // ---- backward: interlevel loss -> proposal networks (only on "updated" steps, ray_samplers.py ProposalNetworkSampler) ---
-  if (cfg->update_proposals) {
-    for (int lv = 0; lv < lf; ++lv) {
-      const int S = L.S[lv];
-      STAGE("interlevel_bwd", 1, cnb_interlevel_bwd(ws + L.sp[lf], ws + L.w[lf], ws + L.sp[lv], ws + L.w[lv], R, Sf, S, gs * cfg->interlevel_loss_mult, ws + L.d_w[lv], stream));
-      if (rc) return rc;
-      STAGE("weights_bwd", 1, cnb_weights_bwd(ws + L.dens[lv], ws + L.eu[lv], ws + L.eu[lv] + 1, S + 1, R, S, ws + L.d_w[lv], ws + L.d_dens[lv], stream));
-      if (rc) return rc;
-      const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
-      STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd(&m->proposal[lv], &sm, ws + L.d_dens[lv], stream));
-      if (rc) return rc;
-    }
   }
   return CNB_OK;
 }

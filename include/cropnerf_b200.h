@@ -197,6 +197,27 @@ int cnb_distortion_fwd(const float* c, const float* w, int64_t R, int32_t S, flo
 int cnb_pixel_losses(const float* rgb, const float* sem, const float* image, const float* mask, int64_t R, float sem_weight,
                      float grad_scale, float* losses_out, float* d_rgb, float* d_sem, cnb_stream_t stream);
 
+/* ---- fused per-ray stages (csrc/fused_ray.cu): the same arithmetic as the per-primitive entries above, chained in one
+ * warp-per-ray kernel per pipeline stage; results are bit-identical to calling the primitives one after the other ---- */
+/* get_weights(density) -> DepthRenderer(median) [depth_out optional] -> PDFSampler to S bins; weights_out optional [R,Sp] */
+int cnb_level_resample(const float* density, const float* euclid_bins_prev, const float* spacing_bins_prev, const float* nears,
+                       const float* fars, int32_t spacing, float anneal, const float* u_base, const float* rand, int32_t rand_stride,
+                       int64_t R, int32_t Sp, int32_t S, float histogram_padding, float eps, float* weights_out, float* depth_out,
+                       float* spacing_bins, float* euclid_bins, int32_t* inds, cnb_stream_t stream);
+/* get_weights -> RGB / accumulation / semantic / median-depth renderers of the final level (outputs optional) */
+int cnb_final_composite(const float* density, const float* rgb, const float* sem, const float* euclid_bins, int64_t R, int32_t S,
+                        int32_t bg_mode, const float* bg_color, int32_t eval_mode, float* weights_out, float* rgb_out, float* depth_out,
+                        float* acc_out, float* sem_out, cnb_stream_t stream);
+/* MSE + weighted BCE-with-logits (losses_out[0], [1] accumulated) and their gradients through the renderers and get_weights */
+int cnb_final_composite_bwd(const float* density, const float* rgb, const float* sem, const float* euclid_bins, const float* weights,
+                            const float* rgb_out, const float* sem_out, const float* image, const float* mask, int64_t R, int32_t S,
+                            int32_t bg_mode, const float* bg_color, float sem_weight, float grad_scale, int32_t sem_weight_grad,
+                            float* losses_out, float* d_density, float* d_rgb, float* d_sem, cnb_stream_t stream);
+/* interlevel loss of one proposal level (loss_out[0] accumulated); d_density_p != NULL also runs its backward through
+ * get_weights of that level and overwrites d_density_p [R,Sp] */
+int cnb_interlevel_fused(const float* c, const float* w, const float* cp, const float* wp, const float* density_p, const float* euclid_bins_p,
+                         int64_t R, int32_t Sc, int32_t Sp, float grad_scale, float* loss_out, float* d_density_p, cnb_stream_t stream);
+
 /* ---- f2: optimiser (torch.optim.Adam semantics; fruit_nerf_config.py:45-60) -------------------------------- */
 int cnb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float inv_grad_scale, cnb_stream_t stream);
