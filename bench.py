@@ -245,13 +245,16 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
         rev[i][1].record()
     barrier()
     t_render_local = sum(a.elapsed_time(b) for a, b in rev) / 1e3
+    # end to end through the public chunked-render API (host rays in, host outputs out)
+    host_bundle = RayBundle(rhost["origins"], rhost["directions"], rhost["pixel_area"], rhost["camera_indices"])
+    for _ in range(2):
+        model.get_outputs_for_camera_jagged_ray_bundle(host_bundle)
+    barrier()
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h0.record()
     d2h_render = 0
     for _ in range(n_r):
-        rb, _ = to_bundle(rhost, dev)
-        out = render_once(rb)
-        host_out = {k: out[k].cpu() for k in ("rgb", "depth", "accumulation", "semantics")}
+        host_out = model.get_outputs_for_camera_jagged_ray_bundle(host_bundle)
         d2h_render = sum(v.numel() * v.element_size() for v in host_out.values())
     h1.record()
     barrier()

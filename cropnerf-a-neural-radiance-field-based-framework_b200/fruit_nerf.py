@@ -161,6 +161,7 @@ class FruitModel(nn.Module):
         self.step = 0
         self.fused_render = True       # one-call render path for no-grad eval (set False to force the per-module operators)
         self._fused_pipeline = None
+        self._pinned: Dict[tuple, Tensor] = {}
         self.populate_modules()
         if device is not None:
             self.to(device)
@@ -366,6 +367,7 @@ class FruitModel(nn.Module):
             yield camera_ray_bundle.get_row_major_sliced_ray_bundle(i, i + step).to(self.device)
 
     # fruit_nerf.py:320-344: accumulated opacity in front of the cluster AABB
+    @torch.no_grad()
     def get_density_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Tensor:
         out = []
         for ray_bundle in self._chunks(camera_ray_bundle):
@@ -375,15 +377,32 @@ class FruitModel(nn.Module):
             out.append(self.renderer_accumulation(weights)[:, 0])
         return torch.cat(out).cpu()
 
+    @torch.no_grad()
     def _render_chunks(self, camera_ray_bundle: RayBundle) -> Dict[str, Tensor]:
-        outputs_lists = defaultdict(list)
-        for ray_bundle in self._chunks(camera_ray_bundle):
+        """Chunked render of a (host or device) ray bundle -> host tensors.  Chunks go up with non-blocking copies, every
+        chunk's outputs come down with non-blocking copies into PINNED host buffers that are cached per output shape (valid
+        until the next call), and the stream is synchronised once at the end -- not one ``.cpu()`` per output per chunk as in
+        fruit_nerf.py:363-369."""
+        n = len(camera_ray_bundle)
+        step = self.config.eval_num_rays_per_chunk
+        flat = camera_ray_bundle.flatten()
+        host: Dict[str, Tensor] = {}
+        for i in range(0, n, step):
+            ray_bundle = flat._map(lambda t: t[i : i + step].to(self.device, non_blocking=True))
             outputs = self.forward(ray_bundle=ray_bundle)
             for name, output in outputs.items():
-                if isinstance(output, torch.Tensor):
-                    outputs_lists[name].append(output)
-        # one device->host copy per output instead of one per chunk
-        return {name: torch.cat(chunks).cpu() for name, chunks in outputs_lists.items()}
+                if not isinstance(output, torch.Tensor):
+                    continue
+                if name not in host:
+                    key = (name, n, tuple(output.shape[1:]), output.dtype)
+                    buf = self._pinned.get(key)
+                    if buf is None:
+                        buf = torch.empty((n, *output.shape[1:]), dtype=output.dtype, pin_memory=True)
+                        self._pinned[key] = buf
+                    host[name] = buf
+                host[name][i : i + output.shape[0]].copy_(output, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host
 
     # fruit_nerf.py:346-374
     def get_outputs_for_camera_jagged_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, Tensor]:
