@@ -34,7 +34,7 @@ constexpr int A_R3 = 0, A_R2 = 1, A_R1 = 5, A_H = 9, A_S2 = 10, A_S1 = 14, A_B2 
 // bias accumulators (floats)
 constexpr int B_R3 = 0, B_R2 = 16, B_R1 = 80, B_H = 144, B_S2 = 160, B_S1 = 224, B_B2 = 288, B_B1 = 304, B_FLOATS = 368;
 
-constexpr size_t SMEM_BWD = (size_t)(HALVES + T_HALVES + 2 * BATCH * ST) * 2 + (size_t)(FLOATS + B_FLOATS + WARPS * A_TILES * 128) * 4;
+constexpr size_t SMEM_BWD = (size_t)(HALVES + T_HALVES + 4 * BATCH * ST) * 2 + (size_t)(FLOATS + B_FLOATS + WARPS * A_TILES * 128) * 4;  // 228 272 B
 
 struct BwdArgs {
   MixArgs m;
@@ -207,9 +207,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
   const MixArgs& a = b.m;
   __half* Wsm = reinterpret_cast<__half*>(smem_raw);
   __nv_bfloat16* WT = reinterpret_cast<__nv_bfloat16*>(Wsm + HALVES);
-  __nv_bfloat16* st_in = WT + T_HALVES;
-  __nv_bfloat16* st_out = st_in + BATCH * ST;
-  float* Bf = reinterpret_cast<float*>(st_out + BATCH * ST);
+  // two staging buffer pairs (X, dY), used alternately: a warp may stage GEMM k+1 while others still contract GEMM k, so one
+  // block barrier per GEMM suffices (the buffer being overwritten was last read two GEMMs ago, i.e. before the previous barrier)
+  __nv_bfloat16* st_base = WT + T_HALVES;
+  float* Bf = reinterpret_cast<float*>(st_base + 4 * BATCH * ST);
   float* bias_acc = Bf + FLOATS;
   float* acc_all = bias_acc + B_FLOATS;
   load_weights(a, Wsm, Bf);
@@ -221,33 +222,100 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   float* acc_w = acc_all + warp * A_TILES * 128;
-  uint32_t* in32 = reinterpret_cast<uint32_t*>(st_in);
-  uint32_t* out32 = reinterpret_cast<uint32_t*>(st_out);
-  const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(st_in), out_s = (uint32_t)__cvta_generic_to_shared(st_out);
+  uint32_t* const st32 = reinterpret_cast<uint32_t*>(st_base);
+  const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(st_base);
+  constexpr int MATW = BATCH * ST / 2;  // 32-bit words per staged matrix
+  int buf = 0;
   const int row0 = warp * 16;
   const int S = a.sm.samples_per_ray;
   const int64_t N = a.sm.num_rays * S;
   const int64_t nbatches = (N + BATCH - 1) / BATCH;
 
+  // Software pipeline over the batches of this CTA: the encoded features and camera indices of the NEXT tile are requested
+  // while the current one is processed, and every other global input of the current tile (directions, embedding row,
+  // incoming gradients) is requested at the top of the iteration, long before its first use -- with one CTA (2 warps per
+  // scheduler) on the SM nothing else hides these latencies (ncu: long-scoreboard was 32 % of all issue stalls).
+  struct TileIn {           // every global input of one m-tile, as this lane needs it
+    uint32_t A0[2][4];      // encoded features (A fragments)
+    float dirv[2][3];
+    float2 embv[2][2][2];
+    float drgb[2][2], dsem[2], ddens[2], posx[2];
+    int cam[2];
+  };
+  auto load_cam = [&](int64_t tl, int (&cam)[2]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t rw = tl * 16 + g + 8 * h;
+      cam[h] = 0;
+      if (a.app_mode == CNB_APP_PER_CAMERA) cam[h] = __ldg(a.sm.camera_indices + (rw < N ? rw : N - 1) / S);
+    }
+  };
+  auto load_tile = [&](int64_t tl, const int (&cam)[2], TileIn& in) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t rw = tl * 16 + g + 8 * h;
+      const bool ok = rw < N;
+      const int64_t ry = (ok ? rw : N - 1) / S;
+      in.cam[h] = cam[h];
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) in.A0[kt][2 * q + h] = ok ? __ldg(reinterpret_cast<const uint32_t*>(b.x0 + rw * 32 + 16 * kt + 8 * q + 2 * t)) : 0u;
+      in.dirv[h][0] = __ldg(a.sm.directions + 3 * ry); in.dirv[h][1] = __ldg(a.sm.directions + 3 * ry + 1); in.dirv[h][2] = __ldg(a.sm.directions + 3 * ry + 2);
+      const float* e = nullptr;
+      if (a.app_mode == CNB_APP_PER_CAMERA) e = a.embedding + (int64_t)cam[h] * 32;
+      else if (a.app_mode == CNB_APP_MEAN) e = a.embedding;
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt) {
+        in.embv[h][kt][0] = e ? __ldg(reinterpret_cast<const float2*>(e + 16 * kt + 2 * t)) : make_float2(0.f, 0.f);
+        in.embv[h][kt][1] = e ? __ldg(reinterpret_cast<const float2*>(e + 16 * kt + 8 + 2 * t)) : make_float2(0.f, 0.f);
+      }
+      in.drgb[h][0] = 0.f; in.drgb[h][1] = 0.f; in.dsem[h] = 0.f; in.ddens[h] = 0.f; in.posx[h] = 0.f;
+      if (ok) {
+        if (b.d_rgb && t < 2) {
+          in.drgb[h][0] = __ldg(b.d_rgb + 3 * rw + 2 * t);
+          if (t == 0) in.drgb[h][1] = __ldg(b.d_rgb + 3 * rw + 1);
+        }
+        if (b.d_sem) in.dsem[h] = __ldg(b.d_sem + rw);
+        if (t == 0 && b.d_density) { in.ddens[h] = __ldg(b.d_density + rw); in.posx[h] = __ldg(b.pos + 3 * rw); }
+      }
+    }
+  };
+  // Software pipeline over the batches of this CTA (one CTA, i.e. 2 warps per scheduler, per SM: nothing else hides global
+  // latency; ncu: long-scoreboard was 32 % of all issue stalls): all inputs of tile i+1 and the camera indices of tile i+2
+  // are requested while tile i is processed; they are loop-carried registers, so the compiler cannot sink the loads.
+  const int64_t tstride = (int64_t)gridDim.x * WARPS;
+  TileIn nxt;
+  int cam2[2];
+  {
+    const int64_t t0 = (int64_t)blockIdx.x * WARPS + warp;
+    int cam1[2];
+    load_cam(t0, cam1);
+    load_tile(t0, cam1, nxt);
+    load_cam(t0 + tstride, cam2);
+  }
+
   for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
     const int64_t tile = batch * WARPS + warp;
     const int64_t row[2] = {tile * 16 + g, tile * 16 + g + 8};
     bool valid[2];
-    int64_t ray[2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      valid[h] = row[h] < N;
-      ray[h] = (valid[h] ? row[h] : N - 1) / S;
-    }
-    // ---- encoded features kept by the forward -> A fragments -------------------------------------------------------
+    for (int h = 0; h < 2; ++h) valid[h] = row[h] < N;
+    const TileIn cur = nxt;
+    load_tile(tile + tstride, cam2, nxt);
+    load_cam(tile + 2 * tstride, cam2);
     uint32_t A0[2][4];
 #pragma unroll
     for (int kt = 0; kt < 2; ++kt)
 #pragma unroll
-      for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          A0[kt][2 * q + h] = valid[h] ? __ldg(reinterpret_cast<const uint32_t*>(b.x0 + row[h] * 32 + 16 * kt + 8 * q + 2 * t)) : 0u;
+      for (int q = 0; q < 4; ++q) A0[kt][q] = cur.A0[kt][q];
+    const int cam[2] = {cur.cam[0], cur.cam[1]};
+    const float (&dirv)[2][3] = cur.dirv;
+    const float2 (&embv)[2][2][2] = cur.embv;
+    const float (&drgb)[2][2] = cur.drgb;
+    const float (&dsem)[2] = cur.dsem;
+    const float (&ddens)[2] = cur.ddens;
+    const float (&posx)[2] = cur.posx;
     // ---- base MLP forward ---------------------------------------------------------------------------------------------
     uint32_t AH[4][4], Abo[1][4];
     float dba[2] = {0.f, 0.f};
@@ -272,18 +340,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float c[16];
-        cnb_sh16(__ldg(a.sm.directions + 3 * ray[h]), __ldg(a.sm.directions + 3 * ray[h] + 1), __ldg(a.sm.directions + 3 * ray[h] + 2), c);
+        cnb_sh16(dirv[h][0], dirv[h][1], dirv[h][2], c);
         Ain[0][h] = pack_h2(pick4(t, c[0], c[2], c[4], c[6]), pick4(t, c[1], c[3], c[5], c[7]));
         Ain[0][2 + h] = pack_h2(pick4(t, c[8], c[10], c[12], c[14]), pick4(t, c[9], c[11], c[13], c[15]));
-        const float* e = nullptr;
-        if (a.app_mode == CNB_APP_PER_CAMERA) e = a.embedding + (int64_t)__ldg(a.sm.camera_indices + ray[h]) * 32;
-        else if (a.app_mode == CNB_APP_MEAN) e = a.embedding;
 #pragma unroll
         for (int kt = 0; kt < 2; ++kt) {
-          float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
-          if (e) { lo = __ldg(reinterpret_cast<const float2*>(e + 16 * kt + 2 * t)); hi = __ldg(reinterpret_cast<const float2*>(e + 16 * kt + 8 + 2 * t)); }
-          Ain[2 + kt][h] = pack_h2(lo.x, lo.y);
-          Ain[2 + kt][2 + h] = pack_h2(hi.x, hi.y);
+          Ain[2 + kt][h] = pack_h2(embv[h][kt][0].x, embv[h][kt][0].y);
+          Ain[2 + kt][2 + h] = pack_h2(embv[h][kt][1].x, embv[h][kt][1].y);
         }
       }
 #pragma unroll
@@ -306,36 +369,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
           if (!valid[h]) continue;
           const float s0 = 1.f / (1.f + __expf(-acc3[0][2 * h])), s1 = 1.f / (1.f + __expf(-acc3[0][2 * h + 1]));
           float d0, d1 = 0.f;
-          if (t == 0) { d0 = __ldg(b.d_rgb + 3 * row[h]) * s0 * (1.f - s0); d1 = __ldg(b.d_rgb + 3 * row[h] + 1) * s1 * (1.f - s1); }
-          else d0 = __ldg(b.d_rgb + 3 * row[h] + 2) * s0 * (1.f - s0);
+          if (t == 0) { d0 = drgb[h][0] * s0 * (1.f - s0); d1 = drgb[h][1] * s1 * (1.f - s1); }
+          else d0 = drgb[h][0] * s0 * (1.f - s0);
           D3[0][h] = pack_bf2(d0, d1);
         }
       }
       // ---- layer 3: dW = D3^T r2 ; d_r2 = D3 W3 -------------------------------------------------------------------------
-      stage<1, false>(out32, row0, D3, g, t);
-      stage<4, true>(in32, row0, AR2, g, t);
+      stage<1, false>(st32 + (2 * buf + 1) * MATW, row0, D3, g, t);
+      stage<4, true>(st32 + (2 * buf) * MATW, row0, AR2, g, t);
       __syncthreads();
-      dw_gemm<1, 8>(out_s, in_s, acc_w + A_R3 * 128, bias_acc + B_R3, warp, lane);
-      __syncthreads();
+      dw_gemm<1, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_R3 * 128, bias_acc + B_R3, warp, lane);
+      buf ^= 1;
       uint32_t D[4][4];
       zero_acc<8>(acc);
       layer_bf<8, 1, 24>(WT + T_R3, D3, acc, g, t);
       relu_mask_pack<4>(acc, AR2, D);
       // ---- layer 2 ----------------------------------------------------------------------------------------------------------
-      stage<4, false>(out32, row0, D, g, t);
-      stage<4, true>(in32, row0, AR1, g, t);
+      stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
+      stage<4, true>(st32 + (2 * buf) * MATW, row0, AR1, g, t);
       __syncthreads();
-      dw_gemm<4, 8>(out_s, in_s, acc_w + A_R2 * 128, bias_acc + B_R2, warp, lane);
-      __syncthreads();
+      dw_gemm<4, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_R2 * 128, bias_acc + B_R2, warp, lane);
+      buf ^= 1;
       zero_acc<8>(acc);
       layer_bf<8, 4, 72>(WT + T_R2, D, acc, g, t);
       relu_mask_pack<4>(acc, AR1, D);
       // ---- layer 1 ----------------------------------------------------------------------------------------------------------
-      stage<4, false>(out32, row0, D, g, t);
-      stage<4, true>(in32, row0, Ain, g, t);
+      stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
+      stage<4, true>(st32 + (2 * buf) * MATW, row0, Ain, g, t);
       __syncthreads();
-      dw_gemm<4, 8>(out_s, in_s, acc_w + A_R1 * 128, bias_acc + B_R1, warp, lane);
-      __syncthreads();
+      dw_gemm<4, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_R1 * 128, bias_acc + B_R1, warp, lane);
+      buf ^= 1;
       float din[6][4];  // d(rgb input) columns 16..63: [0, geo15 | emb32]
       zero_acc<6>(din);
       layer_bf<6, 4, 72>(WT + T_R1 + 16 * 72, D, din, g, t);
@@ -347,7 +410,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
       if (a.app_mode == CNB_APP_PER_CAMERA && b.d_embedding != nullptr) {
         const int64_t first = tile * 16, last = tile * 16 + 15;
         if (last < N && first / S == last / S) {  // whole m-tile on one ray: reduce over its 16 samples first
-          float* dst = b.d_embedding + (int64_t)__ldg(a.sm.camera_indices + ray[0]) * 32;
+          float* dst = b.d_embedding + (int64_t)cam[0] * 32;
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
             float v0 = din[2 + nt][0] + din[2 + nt][2], v1 = din[2 + nt][1] + din[2 + nt][3];
@@ -359,7 +422,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (!valid[h]) continue;
-            float* dst = b.d_embedding + (int64_t)__ldg(a.sm.camera_indices + ray[h]) * 32;
+            float* dst = b.d_embedding + (int64_t)cam[h] * 32;
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) { atomicAdd(dst + 8 * nt + 2 * t, din[2 + nt][2 * h]); atomicAdd(dst + 8 * nt + 2 * t + 1, din[2 + nt][2 * h + 1]); }
           }
@@ -384,19 +447,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
           S2f[kt][2 * h] = pack_bf2(acc[2 * kt + h][0], acc[2 * kt + h][1]);
           S2f[kt][2 * h + 1] = pack_bf2(acc[2 * kt + h][2], acc[2 * kt + h][3]);
         }
-      float dsem[2] = {0.f, 0.f};
-      if (b.d_sem) {
-        if (valid[0]) dsem[0] = __ldg(b.d_sem + row[0]);
-        if (valid[1]) dsem[1] = __ldg(b.d_sem + row[1]);
-      }
       // ---- head: dWh = d_sem^T s2 ------------------------------------------------------------------------------------------
       uint32_t Dh[1][4] = {{0u, 0u, 0u, 0u}};
       if (t == 0) { Dh[0][0] = pack_bf2(dsem[0], 0.f); Dh[0][1] = pack_bf2(dsem[1], 0.f); }
-      stage<1, false>(out32, row0, Dh, g, t);
-      stage<4, false>(in32, row0, S2f, g, t);
+      stage<1, false>(st32 + (2 * buf + 1) * MATW, row0, Dh, g, t);
+      stage<4, false>(st32 + (2 * buf) * MATW, row0, S2f, g, t);
       __syncthreads();
-      dw_gemm<1, 8>(out_s, in_s, acc_w + A_H * 128, bias_acc + B_H, warp, lane);
-      __syncthreads();
+      dw_gemm<1, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_H * 128, bias_acc + B_H, warp, lane);
+      buf ^= 1;
       // d_s2 = d_sem * Wh (no activation after the last semantic layer)
 #pragma unroll
       for (int kt = 0; kt < 4; ++kt)
@@ -407,20 +465,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
           D[kt][2 * h + 1] = pack_bf2(dsem[1] * w.x, dsem[1] * w.y);
         }
       // ---- semantic layer 2 ------------------------------------------------------------------------------------------------
-      stage<4, false>(out32, row0, D, g, t);
-      stage<4, true>(in32, row0, AS1, g, t);
+      stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
+      stage<4, true>(st32 + (2 * buf) * MATW, row0, AS1, g, t);
       __syncthreads();
-      dw_gemm<4, 8>(out_s, in_s, acc_w + A_S2 * 128, bias_acc + B_S2, warp, lane);
-      __syncthreads();
+      dw_gemm<4, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_S2 * 128, bias_acc + B_S2, warp, lane);
+      buf ^= 1;
       zero_acc<8>(acc);
       layer_bf<8, 4, 72>(WT + T_S2, D, acc, g, t);
       relu_mask_pack<4>(acc, AS1, D);
       // ---- semantic layer 1 (input = [0 | geo15]) -----------------------------------------------------------------------------
-      stage<4, false>(out32, row0, D, g, t);
-      stage<1, true>(in32, row0, Abo, g, t);
+      stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
+      stage<1, true>(st32 + (2 * buf) * MATW, row0, Abo, g, t);
       __syncthreads();
-      dw_gemm<4, 2>(out_s, in_s, acc_w + A_S1 * 128, bias_acc + B_S1, warp, lane);
-      __syncthreads();
+      dw_gemm<4, 2>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_S1 * 128, bias_acc + B_S1, warp, lane);
+      buf ^= 1;
     }
 
     // ===================================== base MLP ========================================================================
@@ -429,28 +487,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float gd = 0.f;
-          if (valid[h] && __ldg(b.pos + 3 * row[h]) > 0.f) gd = __ldg(b.d_density + row[h]) * cnb_trunc_exp_grad(dba[h]);
+          if (valid[h] && posx[h] > 0.f) gd = ddens[h] * cnb_trunc_exp_grad(dba[h]);
           dbo[0][2 * h] = gd;
         }
       } else if (t == 0) { dbo[0][0] = 0.f; dbo[0][2] = 0.f; }
       uint32_t Dbo[1][4];
       Dbo[0][0] = pack_bf2(dbo[0][0], dbo[0][1]); Dbo[0][1] = pack_bf2(dbo[0][2], dbo[0][3]);
       Dbo[0][2] = pack_bf2(dbo[1][0], dbo[1][1]); Dbo[0][3] = pack_bf2(dbo[1][2], dbo[1][3]);
-      stage<1, false>(out32, row0, Dbo, g, t);
-      stage<4, true>(in32, row0, AH, g, t);
+      stage<1, false>(st32 + (2 * buf + 1) * MATW, row0, Dbo, g, t);
+      stage<4, true>(st32 + (2 * buf) * MATW, row0, AH, g, t);
       __syncthreads();
-      dw_gemm<1, 8>(out_s, in_s, acc_w + A_B2 * 128, bias_acc + B_B2, warp, lane);
-      __syncthreads();
+      dw_gemm<1, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_B2 * 128, bias_acc + B_B2, warp, lane);
+      buf ^= 1;
       float acc[8][4];
       zero_acc<8>(acc);
       layer_bf<8, 1, 24>(WT + T_B2, Dbo, acc, g, t);
       uint32_t D[4][4];
       relu_mask_pack<4>(acc, AH, D);
-      stage<4, false>(out32, row0, D, g, t);
-      stage<2, true>(in32, row0, A0, g, t);
+      stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
+      stage<2, true>(st32 + (2 * buf) * MATW, row0, A0, g, t);
       __syncthreads();
-      dw_gemm<4, 4>(out_s, in_s, acc_w + A_B1 * 128, bias_acc + B_B1, warp, lane);
-      __syncthreads();
+      dw_gemm<4, 4>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_B1 * 128, bias_acc + B_B1, warp, lane);
+      buf ^= 1;
       float dx[4][4];
       zero_acc<4>(dx);
       layer_bf<4, 4, 72>(WT + T_B1, D, dx, g, t);
