@@ -299,8 +299,13 @@ def run_product(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE JSON line: anything libraries print there meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: the contract is ONE JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
 
@@ -362,6 +367,8 @@ def run_product(args):
                                        "render_rays_per_s": world * m2["Rr"] * m2["n_r"] / m2["t_render"]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sample_rays=4 * args.cpu_rays, steps=2, warmup=1)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

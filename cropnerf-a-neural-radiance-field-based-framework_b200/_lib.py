@@ -155,6 +155,8 @@ class TrainCfg(C.Structure):
         ("grad_scale", C.c_float),
         ("update_proposals", C.c_int32),
         ("want_metrics", C.c_int32),
+        ("phase", C.c_int32),
+        ("_pad", C.c_int32),
     ]
 
 

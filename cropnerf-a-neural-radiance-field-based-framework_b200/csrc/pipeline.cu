@@ -198,12 +198,17 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   float* ws = workspace;
   cudaStream_t st = stream;
   const bool mixed = m->field.precision == CNB_PREC_MIXED;
-  if (cudaMemsetAsync(losses_out, 0, 8 * sizeof(float), stream) != cudaSuccess) return cnb_check_launch("train_step memset");
-  if ((rc = forward_chain(m, rays, L, ws, true, cfg->jitter, cfg->anneal, out, stream))) return rc;
+  CNB_REQUIRE(cfg->phase >= 0 && cfg->phase <= 2, "train_step: phase %d outside 0..2", cfg->phase);
+  const bool first = cfg->phase != 2, second = cfg->phase != 1;
+  if (first) {
+    if (cudaMemsetAsync(losses_out, 0, 8 * sizeof(float), stream) != cudaSuccess) return cnb_check_launch("train_step memset");
+    if ((rc = forward_chain(m, rays, L, ws, true, cfg->jitter, cfg->anneal, out, stream))) return rc;
+  }
   const int lf = L.levels - 1, Sf = L.S[lf];
   const float gs = cfg->grad_scale == 0.0f ? 1.0f : cfg->grad_scale;
   const float* o_rgb = (out && out->rgb) ? out->rgb : ws + L.o_rgb;
   const float* o_sem = (out && out->semantics) ? out->semantics : ws + L.o_sem;
+  if (first) {
   // ---- losses + backward of the final level: MSE / BCE gradients -> renderers -> get_weights, one kernel (fruit_nerf.py:601-608) ----
   STAGE("final_composite_bwd", 1, cnb_final_composite_bwd(ws + L.dens[lf], ws + L.rgb, ws + L.sem, ws + L.eu[lf], ws + L.w[lf], o_rgb, o_sem, cfg->image,
                                                           cfg->fruit_mask, R, Sf, m->bg_mode, m->bg_color, cfg->semantic_loss_weight, gs,
@@ -214,6 +219,8 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
     STAGE("field_bwd", mixed ? 2 : 8, cnb_field_bwd(&m->field, &sm, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, nullptr, ws + L.ctx, stream));
     if (rc) return rc;
   }
+  }
+  if (!second) return CNB_OK;
   // ---- interlevel loss (fruit_nerf.py:610) and, on "updated" steps, its backward into the proposal networks ---------------------
   for (int lv = 0; lv < lf; ++lv) {
     const int S = L.S[lv];

@@ -101,10 +101,20 @@ class _GraphedStep:
         self.batch = {"image": self.static["image"], "fruit_mask": self.static["fruit_mask"]}
         self.update = update
         self.graph = torch.cuda.CUDAGraph()
-        # parameter gradients are accumulated by the captured kernels: snapshot + restore around the capture run
+        self.graph2 = None
         torch.cuda.synchronize()
-        with torch.cuda.graph(self.graph):
-            self.losses, self.outputs = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update)
+        if trainer.world_size > 1:
+            # data parallel: two graphs, so the all-reduce of the field gradients (67 MB) can start after the field backward
+            # and run on NCCL's stream while the proposal networks back-propagate (cnb_train_cfg.phase)
+            with torch.cuda.graph(self.graph):
+                self.losses, self.outputs, state = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, phase=1)
+            self.graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph2, pool=self.graph.pool()):
+                fp.train_step(self.bundle, self.batch, update_proposals=update, phase=2, state=state)
+            self._state = state
+        else:
+            with torch.cuda.graph(self.graph):
+                self.losses, self.outputs = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update)
         for g in trainer.groups.values():  # whatever the capture-time warm-up left in the gradients
             g.zero_grad()
 
@@ -121,6 +131,9 @@ class _GraphedStep:
         self._load(ray_bundle, batch)
         trainer.fused.draw_jitter(self.static["origins"].shape[0], self.static["origins"].device, out=self.jitter)
         self.graph.replay()
+        if self.graph2 is not None:
+            trainer.start_all_reduce("fields")
+            self.graph2.replay()
         return self.losses, self.outputs
 
 
@@ -136,6 +149,7 @@ class Trainer:
         self.cuda_graph = cuda_graph                      # replay one captured graph per step when the step's scalars allow it
         self.force_proposal_update = force_proposal_update  # benchmark aid: every step back-propagates into the proposal networks
         self._graphs: Dict[tuple, _GraphedStep] = {}
+        self._pending: Dict[str, object] = {}
         self.world_size = world_size
         self.optimizers = optimizers or DEFAULT_OPTIMIZERS
         self.groups: Dict[str, FlatGroup] = {name: FlatGroup(params) for name, params in model.get_param_groups().items() if len(params) > 0}
@@ -147,16 +161,37 @@ class Trainer:
             if where in cb.where_to_run and step % cb.update_every_num_iters == 0:
                 cb.func(step)
 
-    def all_reduce_gradients(self) -> None:
+    def start_all_reduce(self, name: str) -> None:
+        """Launch the SUM all-reduce of one flat gradient group asynchronously (NCCL's own stream, ordered after the work
+        already enqueued on the current stream)."""
+        if self.world_size > 1 and name in self.groups and name not in self._pending:
+            self._pending[name] = dist.all_reduce(self.groups[name].grad, op=dist.ReduceOp.SUM, async_op=True)
+
+    def all_reduce_gradients(self, proposals_updated: bool = True, wait: bool = True) -> None:
         """DDP semantics (fruit_pipeline.py:119-121): mean of the per-rank gradients.  The 1/world_size factor is
-        folded into the Adam kernel (``inv_grad_scale``)."""
+        folded into the Adam kernel (``inv_grad_scale``).  On steps where the proposal networks are frozen their gradient
+        is exactly zero on every rank (the schedule is a function of the step), so that group is not communicated --
+        DDP's ``find_unused_parameters=True`` behaviour."""
         if self.world_size > 1:
-            for g in self.groups.values():
-                dist.all_reduce(g.grad, op=dist.ReduceOp.SUM)
+            for name in self.groups:
+                if name == "proposal_networks" and not proposals_updated:
+                    continue
+                self.start_all_reduce(name)
+            if wait:  # train_iteration passes wait=False: optimizer_step then waits group by group
+                for work in self._pending.values():
+                    work.wait()
+                self._pending.clear()
 
     def optimizer_step(self, step: int) -> None:
+        """Adam over every flat group.  Groups whose all-reduce is still in flight are waited for one at a time, largest
+        (launched first) first, so the Adam pass of one group hides the tail of the next group's all-reduce."""
         self.opt_step += 1
-        for name, g in self.groups.items():
+        order = sorted(self.groups, key=lambda n: -self.groups[n].flat.numel())
+        for name in order:
+            g = self.groups[name]
+            work = self._pending.pop(name, None)
+            if work is not None:
+                work.wait()
             spec = self.optimizers[name]
             lr = exponential_decay_lr(step, spec)
             # Adam and the gradient clear of the next step in one pass over the flat group
@@ -195,7 +230,7 @@ class Trainer:
                     sampler._steps_since_update = 0
             else:
                 losses, outputs = fp.train_step(ray_bundle, batch, update_proposals=updated)
-            self.all_reduce_gradients()
+            self.all_reduce_gradients(proposals_updated=updated, wait=False)
             self.optimizer_step(step)
             self._run_callbacks("AFTER_TRAIN_ITERATION", step)
             out = {"rgb_loss": losses[0], "semantics_loss": losses[1], "interlevel_loss": losses[2], "distortion": losses[3],

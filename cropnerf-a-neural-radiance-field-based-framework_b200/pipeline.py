@@ -200,12 +200,22 @@ class FusedPipeline:
         return out.copy_(j) if out is not None else j
 
     def train_step(self, ray_bundle, batch: Dict[str, Tensor], grad_scale: float = 1.0, want_metrics: bool = True,
-                   jitter: Optional[Tensor] = None, update_proposals: Optional[bool] = None):
+                   jitter: Optional[Tensor] = None, update_proposals: Optional[bool] = None, phase: int = 0,
+                   state: Optional[tuple] = None):
         """forward + losses + backward of one batch; gradients are accumulated into ``param.grad``.
         Returns (losses [8] device tensor: rgb, semantics, interlevel, distortion, ...; per-ray outputs)."""
         m = self.model
         dev = ray_bundle.origins.device
         s = m.proposal_sampler
+        if phase == 2:
+            # second half of a split step (cnb_train_cfg.phase): same structs, workspace and outputs as the phase-1 call
+            ms, rays, cfg, out, losses, ws, tensors, updated, keep = state
+            cfg.phase = 2
+            L.check(L.lib().cnb_train_step(C.byref(ms), C.byref(rays), C.byref(cfg), C.byref(out), losses.data_ptr(), ws.data_ptr(), L.stream_ptr(dev)),
+                    "train_step(phase 2)")
+            if updated:
+                s._steps_since_update = 0
+            return losses, tensors
         ms, keep = self._model_struct(dev, training=True, with_grads=True)
         rays, keep2 = self._rays_struct(ray_bundle, training=True)
         R = rays.num_rays
@@ -225,9 +235,12 @@ class FusedPipeline:
         cfg.grad_scale = float(grad_scale)
         cfg.update_proposals = int(bool(updated))
         cfg.want_metrics = int(want_metrics)
+        cfg.phase = int(phase)
         losses = torch.empty((8,), device=dev, dtype=torch.float32)
         L.check(L.lib().cnb_train_step(C.byref(ms), C.byref(rays), C.byref(cfg), C.byref(out), losses.data_ptr(), ws.data_ptr(), L.stream_ptr(dev)),
                 "train_step")
+        if phase == 1:
+            return losses, tensors, (ms, rays, cfg, out, losses, ws, tensors, updated, (keep, keep2, image, mask, jitter))
         if updated:
             s._steps_since_update = 0
         del keep, keep2

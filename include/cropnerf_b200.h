@@ -286,6 +286,10 @@ typedef struct cnb_train_cfg {
   float grad_scale;          /* GradScaler factor applied to every gradient (1 = none) */
   int32_t update_proposals;  /* ProposalNetworkSampler "updated": proposal networks receive gradients this step */
   int32_t want_metrics;      /* distortion metric + psnr inputs (get_metrics_dict) */
+  int32_t phase;             /* 0 = whole step; 1 = forward + final-level/field backward only; 2 = the rest (interlevel loss,
+                                proposal backward, metrics) on the workspace phase 1 left behind -- lets a data-parallel caller
+                                start the all-reduce of the field gradients while the proposal networks back-propagate */
+  int32_t _pad;
 } cnb_train_cfg;
 
 /* forward + losses + backward of one batch; parameter gradients are ACCUMULATED into the d_* pointers of `m`;
