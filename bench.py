@@ -291,6 +291,15 @@ STAGE_BYTES_PER_RAY = {
 }
 
 
+# DRAM traffic per launch of each stage (dram__bytes_read.sum + dram__bytes_write.sum of its kernels, one `ncu --set full`
+# capture of this same command: profiles/r1_mixed_top_kernels_ncu_full.csv).  Far below the algorithmic bytes because the
+# tables live in L2: the forward gathers are bound by the L1TEX data pipe, the backward by L2 atomics / issue.
+NCU_DRAM_BYTES_PER_LAUNCH = {
+    "field_bwd": (19.25 + 0.01 + 73.27 + 1.24) * 1e6, "field_fwd": (47.96 + 4.88) * 1e6, "proposal0_bwd": (14.37 + 0.01) * 1e6,
+    "proposal1_bwd": (6.32 + 0.004) * 1e6, "proposal0_fwd": 7.19e6, "proposal1_fwd": 5.15e6,
+}
+
+
 def run_product(args):
     import torch.distributed as dist
 
@@ -329,7 +338,8 @@ def run_product(args):
         per_launch_ms = tot[dom] / calls
         per_ray = STAGE_BYTES_PER_RAY[dom]
         ach = per_ray * R / (per_launch_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom) if args.precision == "mixed" else None,
                     "peak_source": peak_src, "ms_per_launch": per_launch_ms, "share_of_step": tot[dom] / (sum(tot.values()) + 1e-12),
                     "algorithmic_bytes_per_launch": per_ray * R,
                     "note": "algorithmic bytes = 8-byte corner fetches of SURVEY.md 8d; the 74 MiB of tables are L2-resident, so DRAM traffic is far below this"}
