@@ -186,7 +186,26 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
     # ---- per-stage device times (separate pass so the events do not perturb the timed region) ----------------
     stage, adam_ms, n_prof = {}, 0.0, min(steps, 5)
     nonupdate_ms = None
+    camopt_ms = None
     if full:
+        # the same all-update step with the SO3xR3 camera optimizer on (row a17: nerfacto's default, which fruit_nerf_config.py
+        # keeps): pose deltas with autograd + dLoss/d rays from the kernels (one extra gather pass per network), eager launches
+        from cropnerf_b200.fruit_nerf import CameraOptimizer
+        cmodel = build_model(dev, precision)
+        cmodel.camera_optimizer = CameraOptimizer(NUM_IMAGES, "SO3xR3").to(dev)
+        ctr = engine.Trainer(cmodel, world_size=1, cuda_graph=False, force_proposal_update=True)
+        cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps + 3):
+            rb0, tg0 = resident[(step + i) % nb]
+            l2_flush.fill_(i & 0xFF)
+            if i >= 3:
+                cev[i - 3][0].record()
+            ctr.train_iteration(2000 + i, RayBundle(rb0.origins, rb0.directions, rb0.pixel_area, rb0.camera_indices), tg0)
+            if i >= 3:
+                cev[i - 3][1].record()
+        torch.cuda.synchronize()
+        camopt_ms = sum(a.elapsed_time(b) for a, b in cev) / steps
+        del ctr, cmodel
         # steady-state step kind: proposal networks frozen this step (5 of every 6 steps after proposal_warmup)
         trainer.force_proposal_update = False
         model.proposal_sampler._step = 20000
@@ -277,7 +296,7 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
     del trainer, model, l2_flush
     torch.cuda.empty_cache()
     return {"steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
-            "stage": stage, "n_prof": n_prof, "nonupdate_ms": nonupdate_ms, "adam_ms": adam_ms, "render_stage": render_stage, "loss": loss_host,
+            "stage": stage, "n_prof": n_prof, "nonupdate_ms": nonupdate_ms, "camopt_ms": camopt_ms, "adam_ms": adam_ms, "render_stage": render_stage, "loss": loss_host,
             "h2d_train": bytes_of(host[0]), "h2d_render": bytes_of({k: rhost[k] for k in ("origins", "directions", "pixel_area", "camera_indices")}),
             "d2h_render": int(d2h_render)}
 
@@ -356,6 +375,7 @@ def run_product(args):
                        "includes": "fwd + losses + bwd (all three networks updated EVERY step) + gradient all-reduce + Adam; "
                                    + ("cnb_train_step eager" if args.no_graph else "cnb_train_step replayed as one CUDA graph"),
                        "non_update_step_ms": m["nonupdate_ms"],
+                       "camera_optimizer_step_ms": m["camopt_ms"],
                        "steady_state_rays_per_s": (world * R / ((m["t"] / steps + 5 * m["nonupdate_ms"] * 1e-3) / 6)) if m["nonupdate_ms"] else None},
             "samples_per_s": value * 400,
             "step_roofline": {"algorithmic_bytes_per_ray": TRAIN_BYTES_PER_RAY, "achieved_GBps": step_achieved, "frac": step_achieved / (peak * world),

@@ -129,7 +129,7 @@ class Model(C.Structure):
         ("sampler", Sampler),
         ("bg_mode", C.c_int32),
         ("bg_color", C.c_float * 3),
-        ("_pad", C.c_int32),
+        ("ray_gradients", C.c_int32),
     ]
 
 
@@ -155,6 +155,8 @@ class TrainCfg(C.Structure):
         ("grad_scale", C.c_float),
         ("update_proposals", C.c_int32),
         ("want_metrics", C.c_int32),
+        ("d_origins", C.c_void_p),
+        ("d_directions", C.c_void_p),
         ("phase", C.c_int32),
         ("_pad", C.c_int32),
     ]
@@ -180,6 +182,9 @@ SIGNATURES = {
     "cnb_field_ctx_floats": (_I64, [C.POINTER(Field), _I64, _I32]),
     "cnb_field_fwd": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), _P, _P, _P, _P, _P, _P, _I32, _P]),
     "cnb_field_bwd": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), _P, _P, _P, _P, _P, _P]),
+    "cnb_position_grad_rays": (C.c_int, [C.POINTER(Grid), C.POINTER(Warp), C.POINTER(Samples), _P, _P, _P, _P]),
+    "cnb_density_field_bwd_rays": (C.c_int, [C.POINTER(DensityField), C.POINTER(Samples), _P, _P, _P, _P, _P]),
+    "cnb_field_bwd_rays": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), _P, _P, _P, _P, _P, _P, _P, _P]),
     "cnb_sample_spaced": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I64, _I32, _P, _P, _P]),
     "cnb_sample_pdf": (C.c_int, [_P, _F, _P, _P, _P, _I32, _P, _P, _I32, _I64, _I32, _I32, _F, _F, _P, _P, _P, _P]),
     "cnb_weights_fwd": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P]),

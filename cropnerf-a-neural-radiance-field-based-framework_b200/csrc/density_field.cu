@@ -27,6 +27,7 @@ struct DfArgs {
   float *dW1, *db1, *dW2, *db2;
   int in;  // 2L
   cnb_samples sm;
+  float* d_feat_out;  // optional [N, 2L]: gradient reaching the encoded features (consumed by cnb_position_grad_rays)
 };
 
 template <int LMAX>
@@ -169,6 +170,11 @@ __global__ void __launch_bounds__(BLOCK, (H <= 16 && LMAX <= 8) ? 5 : 1) k_densi
     } else {
       for (int j = 0; j <= H; ++j) U[j * LD + tid] = 0.0f;
       for (int k = 0; k < nv; ++k) V[k * LD + tid] = 0.0f;
+    }
+    if (a.d_feat_out != nullptr && i < total) {
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l)
+        if (l < a.L) reinterpret_cast<float2*>(a.d_feat_out)[i * a.L + l] = make_float2(dfeat[2 * l], dfeat[2 * l + 1]);
     }
     // table gradient: the lanes of a warp are consecutive samples of a ray -> warp-aggregated scatter (all lanes take part)
 #pragma unroll
@@ -335,6 +341,11 @@ __global__ void __launch_bounds__(BLOCK, 5) k_density_bwd_tc(DfArgs a, const flo
 #pragma unroll
         for (int c = 0; c < 4; ++c) row[m * MATQ + c] = zq;
     }
+    if (a.d_feat_out != nullptr && i < total) {
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l)
+        if (l < a.L) reinterpret_cast<float2*>(a.d_feat_out)[i * a.L + l] = make_float2(dfeat[2 * l], dfeat[2 * l + 1]);
+    }
     // table gradient: the lanes of a warp are consecutive samples of a ray -> warp-aggregated scatter (all lanes take part)
 #pragma unroll
     for (int l = 0; l < LMAX; ++l) {
@@ -423,6 +434,7 @@ int make_args(const cnb_density_field* f, const cnb_samples* s, bool bwd, DfArgs
   a.dW1 = m.dW[0]; a.db1 = m.db[0]; a.dW2 = m.dW[1]; a.db2 = m.db[1];
   a.in = m.dims[0];
   a.sm = *s;
+  a.d_feat_out = nullptr;
   return CNB_OK;
 }
 
@@ -490,11 +502,24 @@ extern "C" int cnb_density_field_fwd(const cnb_density_field* f, const cnb_sampl
   DISPATCH(launch_fwd, a, density, positions_out, stream);
 }
 
-extern "C" int cnb_density_field_bwd(const cnb_density_field* f, const cnb_samples* s, const float* d_density, cnb_stream_t stream) {
+static int density_bwd_impl(const cnb_density_field* f, const cnb_samples* s, const float* d_density, float* d_feat_out, cnb_stream_t stream) {
   DfArgs a;
   int rc = make_args(f, s, true, a);
   if (rc) return rc;
   if (a.sm.num_rays == 0) return CNB_OK;
   CNB_REQUIRE(d_density != nullptr, "density_field_bwd: null d_density");
+  a.d_feat_out = d_feat_out;
   DISPATCH(launch_bwd, a, d_density, stream);
+}
+
+extern "C" int cnb_density_field_bwd(const cnb_density_field* f, const cnb_samples* s, const float* d_density, cnb_stream_t stream) {
+  return density_bwd_impl(f, s, d_density, nullptr, stream);
+}
+
+extern "C" int cnb_density_field_bwd_rays(const cnb_density_field* f, const cnb_samples* s, const float* d_density, float* scratch, float* d_origins,
+                                          float* d_directions, cnb_stream_t stream) {
+  CNB_REQUIRE(scratch && d_origins && d_directions, "density_field_bwd_rays: null scratch / ray gradients");
+  int rc = density_bwd_impl(f, s, d_density, scratch, stream);
+  if (rc) return rc;
+  return cnb_position_grad_rays(&f->grid, &f->warp, s, scratch, d_origins, d_directions, stream);
 }

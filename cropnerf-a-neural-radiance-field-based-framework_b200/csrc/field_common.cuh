@@ -36,3 +36,4 @@ int cnb_field_mixed_bwd(const cnb_field* f, const cnb_samples* s, const float* d
                         cudaStream_t stream);
 bool cnb_field_mixed_supported(const cnb_field* f);
 int64_t cnb_field_mixed_ctx_floats(int64_t n, int training);
+float* cnb_field_mixed_dx0(float* ctx, int64_t n);  // d(encoded features) [n,32] written by the mixed backward

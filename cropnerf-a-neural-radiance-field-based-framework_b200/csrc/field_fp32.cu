@@ -235,3 +235,23 @@ extern "C" int cnb_field_bwd(const cnb_field* f, const cnb_samples* s, const flo
   if ((rc = cnb_mlp_bwd(&f->base, x0, c.in0, ctx + c.hb, nullptr, ctx + c.d_bo, N, ctx + c.d_x0, c.in0, stream))) return rc;
   return cnb_hashgrid_bwd(&f->grid, pos, ctx + c.d_x0, N, stream);
 }
+
+// Same as cnb_field_bwd, plus the gradient with respect to the rays (row a17: camera optimizer): the hash-grid input
+// gradient is chained through the position normalisation / contraction and reduced per ray into d_origins / d_directions
+// (accumulated).  Not compiled for the 16-level limit of the mixed d_x0 layout when num_levels > 16.
+extern "C" int cnb_field_bwd_rays(const cnb_field* f, const cnb_samples* s, const float* d_density, const float* d_rgb, const float* d_sem,
+                                  const float* d_geo, float* ctx, float* d_origins, float* d_directions, cnb_stream_t stream) {
+  CNB_REQUIRE(d_origins && d_directions, "field_bwd_rays: null ray gradients");
+  int rc = cnb_field_bwd(f, s, d_density, d_rgb, d_sem, d_geo, ctx, stream);
+  if (rc) return rc;
+  const int64_t N = s->num_rays * s->samples_per_ray;
+  if (N == 0) return CNB_OK;
+  const float* d_x0;
+  if (f->precision == CNB_PREC_MIXED) {
+    CNB_REQUIRE(f->grid.num_levels == 16, "field_bwd_rays: the mixed path stores d(features) as [N,32]; num_levels must be 16");
+    d_x0 = cnb_field_mixed_dx0(ctx, N);
+  } else {
+    d_x0 = ctx + make_layout(f, N, true).d_x0;
+  }
+  return cnb_position_grad_rays(&f->grid, &f->warp, s, d_x0, d_origins, d_directions, stream);
+}

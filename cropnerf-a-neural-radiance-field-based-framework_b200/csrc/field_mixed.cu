@@ -213,6 +213,7 @@ bool cnb_field_mixed_supported(const cnb_field* f) {
 }
 
 int64_t cnb_field_mixed_ctx_floats(int64_t n, int training) { return training ? ctx_total(n) : 0; }
+float* cnb_field_mixed_dx0(float* ctx, int64_t n) { return ctx + ctx_dx0_off(n); }
 
 int cnb_field_mixed_fwd(const cnb_field* f, const cnb_samples* s, float* density, float* rgb, float* sem, float* positions_out, float* ctx,
                         int training, cudaStream_t stream) {

@@ -87,6 +87,102 @@ __global__ void __launch_bounds__(256) k_hashgrid_bwd(const __grid_constant__ Gr
   }
 }
 
+// Row a17 (camera optimizer, fruit_nerf.py:114-116,547): gradient of the loss with respect to the RAYS.  Given the gradient
+// d_feat [N, 2L] that reaches a grid's encoded features, one thread per sample
+//   * re-derives the sample's world position p = o + d (s+e)/2 and its normalised grid position (cnb_sample_position),
+//   * differentiates the trilinear blend of every level w.r.t. the offsets (offset = x*scale - floor(x*scale), so
+//     d offset / d x = scale; floor/ceil carry no gradient, exactly as torch autograd sees HashEncoding.pytorch_fwd),
+//   * applies the selector mask, the (c+2)/4 or AABB normalisation and the Jacobian of SceneContraction(order=inf),
+//   * reduces dL/dp over the ray (d_origins += dL/dp, d_directions += (s+e)/2 * dL/dp): warp shuffle when the 32 lanes
+//     share the ray, atomics otherwise.
+__global__ void __launch_bounds__(128) k_position_grad_rays(const __grid_constant__ GridArgs g, cnb_warp wp, cnb_samples sm, const float* __restrict__ d_feat,
+                                                            float* __restrict__ d_origins, float* __restrict__ d_directions) {
+  const int S = sm.samples_per_ray;
+  const int64_t total = sm.num_rays * S;
+  const int64_t nround = (total + 127) / 128 * 128;
+  const int lane = threadIdx.x & 31;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nround; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool in = i < total;
+    const int64_t ii = in ? i : total - 1;
+    const int64_t r = ii / S;
+    const int s = (int)(ii - r * S);
+    float gx = 0.f, gy = 0.f, gz = 0.f, tt = 0.f;
+    if (in) {
+      const float st = __ldg(sm.starts + r * sm.row_stride + s), en = __ldg(sm.ends + r * sm.row_stride + s);
+      tt = 0.5f * (st + en);
+      const float ox = __ldg(sm.origins + 3 * r), oy = __ldg(sm.origins + 3 * r + 1), oz = __ldg(sm.origins + 3 * r + 2);
+      const float dx = __ldg(sm.directions + 3 * r), dy = __ldg(sm.directions + 3 * r + 1), dz = __ldg(sm.directions + 3 * r + 2);
+      const float px = cnb_axis_position(ox, dx, st, en), py = cnb_axis_position(oy, dy, st, en), pz = cnb_axis_position(oz, dz, st, en);
+      float x = px, y = py, z = pz;
+      const bool sel = cnb_warp_position(wp, x, y, z);
+      if (sel) {
+        float ax = 0.f, ay = 0.f, az = 0.f;  // dL / d(normalised position)
+        for (int l = 0; l < g.L; ++l) {
+          const float2 d = __ldg(reinterpret_cast<const float2*>(d_feat) + i * g.L + l);
+          if (d.x == 0.0f && d.y == 0.0f) continue;
+          const float scale = g.scalings[l];
+          const CnbCell c = cnb_cell(x, y, z, scale);
+          uint32_t h[8];
+          cnb_corner_rows(c, g.mask, (uint32_t)l * g.T, h);
+          float2 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = cnb_ldg2(g.table, h[k]);
+          const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
+          float u[8];  // corner values weighted by the feature gradients
+#pragma unroll
+          for (int k = 0; k < 8; ++k) u[k] = d.x * v[k].x + d.y * v[k].y;
+          const float f03 = u[0] * c.ox + u[3] * mx, f12 = u[1] * c.ox + u[2] * mx, f56 = u[5] * c.ox + u[6] * mx, f47 = u[4] * c.ox + u[7] * mx;
+          const float f0312 = f03 * c.oy + f12 * my, f4756 = f47 * c.oy + f56 * my;
+          const float dox = ((u[0] - u[3]) * c.oy + (u[1] - u[2]) * my) * c.oz + ((u[4] - u[7]) * c.oy + (u[5] - u[6]) * my) * mz;
+          const float doy = (f03 - f12) * c.oz + (f47 - f56) * mz;
+          const float doz = f0312 - f4756;
+          ax = fmaf(scale, dox, ax); ay = fmaf(scale, doy, ay); az = fmaf(scale, doz, az);
+        }
+        if (wp.mode == CNB_WARP_CONTRACT_LINF) {
+          ax *= 0.25f; ay *= 0.25f; az *= 0.25f;
+          const float apx = fabsf(px), apy = fabsf(py), apz = fabsf(pz);
+          const float m = fmaxf(apx, fmaxf(apy, apz));
+          if (!(m < 1.0f)) {
+            // c = f(m) p with f = 2/m - 1/m^2 ; dc_i/dp_j = f delta_ij + p_i f'(m) dm/dp_j ; dm/dp_j = sign(p_k) [j == argmax]
+            const float f = 2.0f / m - 1.0f / (m * m), fp = -2.0f / (m * m) + 2.0f / (m * m * m);
+            const float dot = ax * px + ay * py + az * pz;
+            gx = f * ax; gy = f * ay; gz = f * az;
+            if (apx >= apy && apx >= apz) gx += copysignf(1.0f, px) * fp * dot;
+            else if (apy >= apz) gy += copysignf(1.0f, py) * fp * dot;
+            else gz += copysignf(1.0f, pz) * fp * dot;
+          } else { gx = ax; gy = ay; gz = az; }
+        } else {
+          gx = ax / (wp.aabb_max[0] - wp.aabb_min[0]); gy = ay / (wp.aabb_max[1] - wp.aabb_min[1]); gz = az / (wp.aabb_max[2] - wp.aabb_min[2]);
+        }
+      }
+    }
+    // ---- reduce over the ray ---------------------------------------------------------------------------------------------------
+    const int64_t r0 = __shfl_sync(0xffffffffu, r, 0);
+    const bool uniform = __all_sync(0xffffffffu, r == r0 && in);
+    float vals[6] = {gx, gy, gz, tt * gx, tt * gy, tt * gz};
+    if (uniform) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) vals[q] += __shfl_xor_sync(0xffffffffu, vals[q], off);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          if (vals[q] != 0.0f) atomicAdd(d_origins + 3 * r + q, vals[q]);
+          if (vals[3 + q] != 0.0f) atomicAdd(d_directions + 3 * r + q, vals[3 + q]);
+        }
+      }
+    } else if (in) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        if (vals[q] != 0.0f) atomicAdd(d_origins + 3 * r + q, vals[q]);
+        if (vals[3 + q] != 0.0f) atomicAdd(d_directions + 3 * r + q, vals[3 + q]);
+      }
+    }
+  }
+}
+
 int grid_for(int64_t work_items, int block) {
   int64_t blocks = (work_items + block - 1) / block;
   int64_t cap = (int64_t)cnb_num_sms() * 16;  // multiple of the SM count; grid-stride beyond that
@@ -124,4 +220,17 @@ extern "C" int cnb_hashgrid_bwd(const cnb_grid* g, const float* positions, const
   for (int i = 0; i < a.L; ++i) CNB_REQUIRE(a.scalings[i] < 65535.0f, "hashgrid_bwd: level resolution %g too large for the aggregated scatter", a.scalings[i]);
   k_hashgrid_bwd<<<grid_for(((n + 31) / 32) * 32 * a.L, 256), 256, 0, stream>>>(a, positions, d_out, n);
   return cnb_check_launch("hashgrid_bwd");
+}
+
+extern "C" int cnb_position_grad_rays(const cnb_grid* g, const cnb_warp* warp, const cnb_samples* s, const float* d_feat, float* d_origins,
+                                      float* d_directions, cnb_stream_t stream) {
+  int rc = check_grid(g, false);
+  if (rc) return rc;
+  CNB_REQUIRE(warp && s && d_feat && d_origins && d_directions, "position_grad_rays: null pointer");
+  CNB_REQUIRE(s->origins && s->directions && s->starts && s->ends && s->samples_per_ray >= 1 && s->num_rays >= 0, "position_grad_rays: bad samples");
+  const int64_t total = s->num_rays * s->samples_per_ray;
+  if (total == 0) return CNB_OK;
+  GridArgs a = make_args(g);
+  k_position_grad_rays<<<grid_for(total, 128), 128, 0, stream>>>(a, *warp, *s, d_feat, d_origins, d_directions);
+  return cnb_check_launch("position_grad_rays");
 }

@@ -49,6 +49,7 @@ struct Layout {
   int64_t o_rgb, o_acc, o_sem, o_depth, o_pd[2];
   int64_t g_rgb, g_sem, d_w[MAX_LEVELS_P], d_dens[MAX_LEVELS_P], d_rgb, d_sem;
   int64_t ctx, ctx_floats;
+  int64_t pg_scratch;    // d(features) of one proposal level, for the ray gradients (row a17)
   int64_t total;
 };
 
@@ -73,6 +74,15 @@ int make_layout(const cnb_model* m, int64_t R, bool training, Layout& L) {
     L.g_rgb = take(R * 3); L.g_sem = take(R);
     for (int i = 0; i < L.levels; ++i) { L.d_w[i] = take(R * L.S[i]); L.d_dens[i] = take(R * L.S[i]); }
     L.d_rgb = take(R * Sf * 3); L.d_sem = take(R * Sf);
+  }
+  L.pg_scratch = o;
+  if (training && m->ray_gradients) {
+    int64_t need = 0;
+    for (int i = 0; i + 1 < L.levels; ++i) {
+      const int64_t n = R * L.S[i] * 2 * m->proposal[i].grid.num_levels;
+      if (n > need) need = n;
+    }
+    L.pg_scratch = take(need);
   }
   L.ctx_floats = cnb_field_ctx_floats(&m->field, R * Sf, training ? 1 : 0);
   L.ctx = take(L.ctx_floats);
@@ -199,6 +209,8 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   cudaStream_t st = stream;
   const bool mixed = m->field.precision == CNB_PREC_MIXED;
   CNB_REQUIRE(cfg->phase >= 0 && cfg->phase <= 2, "train_step: phase %d outside 0..2", cfg->phase);
+  const bool rays_grad = cfg->d_origins != nullptr;
+  CNB_REQUIRE(!rays_grad || (cfg->d_directions != nullptr && m->ray_gradients), "train_step: ray gradients need d_directions and cnb_model.ray_gradients (workspace scratch)");
   const bool first = cfg->phase != 2, second = cfg->phase != 1;
   if (first) {
     if (cudaMemsetAsync(losses_out, 0, 8 * sizeof(float), stream) != cudaSuccess) return cnb_check_launch("train_step memset");
@@ -216,7 +228,9 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   if (rc) return rc;
   {
     const cnb_samples sm = make_samples(rays, ws + L.eu[lf], Sf);
-    STAGE("field_bwd", mixed ? 2 : 8, cnb_field_bwd(&m->field, &sm, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, nullptr, ws + L.ctx, stream));
+    if (rays_grad) STAGE("field_bwd", mixed ? 3 : 9, cnb_field_bwd_rays(&m->field, &sm, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, nullptr, ws + L.ctx,
+                                                                        cfg->d_origins, cfg->d_directions, stream));
+    else STAGE("field_bwd", mixed ? 2 : 8, cnb_field_bwd(&m->field, &sm, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, nullptr, ws + L.ctx, stream));
     if (rc) return rc;
   }
   }
@@ -229,7 +243,9 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
     if (rc) return rc;
     if (cfg->update_proposals) {
       const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
-      STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd(&m->proposal[lv], &sm, ws + L.d_dens[lv], stream));
+      if (rays_grad) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 2, cnb_density_field_bwd_rays(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pg_scratch,
+                                                                                                     cfg->d_origins, cfg->d_directions, stream));
+      else STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd(&m->proposal[lv], &sm, ws + L.d_dens[lv], stream));
       if (rc) return rc;
     }
   }

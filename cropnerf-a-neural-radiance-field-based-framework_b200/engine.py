@@ -200,8 +200,7 @@ class Trainer:
         self._grads_clean = True
 
     def _use_fused(self) -> bool:
-        return (self.fused is not None and self.model.camera_optimizer.mode == "off" and self.model.collider is not None
-                and self.fused.eligible())
+        return self.fused is not None and self.model.collider is not None and self.fused.eligible()
 
     def train_iteration(self, step: int, ray_bundle, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
         self.model.train()
@@ -215,7 +214,16 @@ class Trainer:
             fp = self.fused
             updated = True if self.force_proposal_update else fp.proposals_updated()
             sampler = self.model.proposal_sampler
-            if self.cuda_graph and ray_bundle.nears is None:
+            cam_opt = self.model.camera_optimizer
+            if cam_opt.mode != "off":
+                # row a17: pose deltas applied with autograd; cnb_train_step returns dLoss/d(origins, directions) and
+                # pipeline.train_step back-propagates them into pose_adjustment.grad (the "camera_opt" flat group)
+                cam_opt.apply_to_raybundle(ray_bundle)
+                reg: Dict[str, Tensor] = {}
+                cam_opt.get_loss_dict(reg)
+                for v in reg.values():
+                    v.backward()
+            if self.cuda_graph and ray_bundle.nears is None and cam_opt.mode == "off":
                 key = (int(ray_bundle.origins.shape[0]), updated, float(sampler._anneal))
                 gs = self._graphs.get(key)
                 if gs is None:

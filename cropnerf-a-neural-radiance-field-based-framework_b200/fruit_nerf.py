@@ -108,34 +108,65 @@ class NearFarCollider(nn.Module):
         return ray_bundle
 
 
-class CameraOptimizer(nn.Module):
-    """Minimal stand-in for nerfstudio's CameraOptimizer (fruit_nerf.py:114-116,547,614).  mode "off" = identity.
-    "SO3xR3" applies the stored pose deltas in the forward pass; their *gradient* is a "next" row."""
+def exp_map_SO3xR3(tangent_vector: Tensor) -> Tensor:
+    """nerfstudio/cameras/lie_groups.py exp_map_SO3xR3: [N,6] (translation, axis-angle) -> [N,3,4] [R|t] (Rodrigues with
+    the small-angle clamp nerfstudio uses)."""
+    log_rot = tangent_vector[:, 3:]
+    nrms = (log_rot * log_rot).sum(1)
+    rot_angles = torch.clamp(nrms, 1e-4).sqrt()
+    rot_angles_inv = 1.0 / rot_angles
+    fac1 = rot_angles_inv * rot_angles.sin()
+    fac2 = rot_angles_inv * rot_angles_inv * (1.0 - rot_angles.cos())
+    skews = torch.zeros((log_rot.shape[0], 3, 3), dtype=log_rot.dtype, device=log_rot.device)
+    skews[:, 0, 1] = -log_rot[:, 2]
+    skews[:, 0, 2] = log_rot[:, 1]
+    skews[:, 1, 0] = log_rot[:, 2]
+    skews[:, 1, 2] = -log_rot[:, 0]
+    skews[:, 2, 0] = -log_rot[:, 1]
+    skews[:, 2, 1] = log_rot[:, 0]
+    skews_square = torch.bmm(skews, skews)
+    ret = torch.zeros(tangent_vector.shape[0], 3, 4, dtype=tangent_vector.dtype, device=tangent_vector.device)
+    ret[:, :3, :3] = fac1[:, None, None] * skews + fac2[:, None, None] * skews_square + torch.eye(3, dtype=log_rot.dtype, device=log_rot.device)[None]
+    ret[:, :3, 3] = tangent_vector[:, :3]
+    return ret
 
-    def __init__(self, num_cameras: int, mode: str = "off") -> None:
+
+class CameraOptimizer(nn.Module):
+    """nerfstudio/cameras/camera_optimizers.py CameraOptimizer as FruitModel uses it (fruit_nerf.py:114-116,547,614):
+    mode "off" = identity; "SO3xR3" = per-camera pose deltas applied to the ray origins / directions in the forward pass and
+    trained through the ray gradients the kernels return (row a17).  The pose algebra itself is a handful of [R,6] torch
+    ops; the per-sample work (hash-grid input gradient, contraction Jacobian, per-ray reduction) is in the CUDA path."""
+
+    def __init__(self, num_cameras: int, mode: str = "off", trans_l2_penalty: float = 1e-2, rot_l2_penalty: float = 1e-3) -> None:
         super().__init__()
+        if mode not in ("off", "SO3xR3"):
+            raise ValueError(f"camera optimizer mode {mode!r} not compiled (off / SO3xR3)")
         self.mode = mode
         self.num_cameras = num_cameras
+        self.trans_l2_penalty = trans_l2_penalty
+        self.rot_l2_penalty = rot_l2_penalty
         if mode != "off":
             self.pose_adjustment = Parameter(torch.zeros((num_cameras, 6)))
+
+    def forward(self, indices: Tensor) -> Tensor:
+        return exp_map_SO3xR3(self.pose_adjustment[indices.long(), :])
 
     def apply_to_raybundle(self, ray_bundle: RayBundle) -> None:
         if self.mode == "off":
             return
-        adj = self.pose_adjustment.detach()[ray_bundle.camera_indices.squeeze(-1).long()]
-        t, w = adj[:, :3], adj[:, 3:]
-        theta = torch.linalg.norm(w, dim=-1, keepdim=True).clamp_min(1e-12)
-        k = w / theta
-        d = ray_bundle.directions
-        rot = d * torch.cos(theta) + torch.cross(k, d, dim=-1) * torch.sin(theta) + k * (k * d).sum(-1, keepdim=True) * (1 - torch.cos(theta))
-        ray_bundle.origins = ray_bundle.origins + t
-        ray_bundle.directions = torch.where(theta > 1e-11, rot, d)
+        correction = self(ray_bundle.camera_indices.squeeze(-1))
+        ray_bundle.origins = ray_bundle.origins + correction[:, :3, 3]
+        ray_bundle.directions = torch.bmm(correction[:, :3, :3], ray_bundle.directions[..., None]).squeeze(-1)
 
     def get_loss_dict(self, loss_dict: dict) -> None:
-        return
+        if self.mode != "off":
+            loss_dict["camera_opt_regularizer"] = (self.pose_adjustment[:, :3].norm(dim=-1).mean() * self.trans_l2_penalty
+                                                   + self.pose_adjustment[:, 3:].norm(dim=-1).mean() * self.rot_l2_penalty)
 
     def get_metrics_dict(self, metrics_dict: dict) -> None:
-        return
+        if self.mode != "off":
+            metrics_dict["camera_opt_translation"] = self.pose_adjustment[:, :3].detach().norm()
+            metrics_dict["camera_opt_rotation"] = self.pose_adjustment[:, 3:].detach().norm()
 
     def get_param_groups(self, param_groups: dict) -> None:
         params = list(self.parameters())

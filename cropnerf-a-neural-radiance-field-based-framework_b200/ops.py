@@ -146,8 +146,9 @@ class _DensityFieldFn(torch.autograd.Function):
     """(table, W1, b1, W2, b2) -> density [R*S].  ``cfg`` = (sample layout tuple, grid cfg, warp, avg)."""
 
     @staticmethod
-    def forward(ctx, cfg, table: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor):
+    def forward(ctx, cfg, origins_t: Tensor, directions_t: Tensor, table: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor):
         (origins, directions, starts, ends, R, S, row_stride), (num_levels, log2_T, scalings), warp, avg, want_pos = cfg
+        origins, directions = origins.detach(), directions.detach()
         dev = _dev(origins)
         density = torch.empty((R * S,), device=dev, dtype=torch.float32)
         pos_out = torch.empty((R * S, 3), device=dev, dtype=torch.float32) if want_pos else None
@@ -159,6 +160,7 @@ class _DensityFieldFn(torch.autograd.Function):
         sm = make_samples(origins, directions, starts, ends, None, R, S, row_stride)
         L.check(L.lib().cnb_density_field_fwd(C.byref(f), C.byref(sm), density.data_ptr(), _p(pos_out), L.stream_ptr(dev)), "density_field_fwd")
         ctx.cfg = cfg
+        ctx.rays_grad = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         ctx.save_for_backward(table, W1, b1, W2, b2)
         ctx.mark_non_differentiable(*( [pos_out] if pos_out is not None else [] ))
         if want_pos:
@@ -169,6 +171,7 @@ class _DensityFieldFn(torch.autograd.Function):
     def backward(ctx, d_density: Tensor, *unused):
         table, W1, b1, W2, b2 = ctx.saved_tensors
         (origins, directions, starts, ends, R, S, row_stride), (num_levels, log2_T, scalings), warp, avg, _ = ctx.cfg
+        origins, directions = origins.detach(), directions.detach()
         dev = origins.device
         d_table = torch.zeros_like(table)
         dW1, db1, dW2, db2 = (torch.zeros_like(t) for t in (W1, b1, W2, b2))
@@ -179,12 +182,19 @@ class _DensityFieldFn(torch.autograd.Function):
         f.average_init_density = avg
         sm = make_samples(origins, directions, starts, ends, None, R, S, row_stride)
         d = L.f32(d_density).reshape(-1)
-        L.check(L.lib().cnb_density_field_bwd(C.byref(f), C.byref(sm), d.data_ptr(), L.stream_ptr(dev)), "density_field_bwd")
-        return None, d_table, dW1, db1, dW2, db2
+        d_o = d_d = None
+        if ctx.rays_grad:  # row a17: the camera optimizer differentiates through the ray origins / directions
+            d_o, d_d = torch.zeros_like(origins), torch.zeros_like(directions)
+            scratch = torch.empty((R * S * 2 * num_levels,), device=dev, dtype=torch.float32)
+            L.check(L.lib().cnb_density_field_bwd_rays(C.byref(f), C.byref(sm), d.data_ptr(), scratch.data_ptr(), d_o.data_ptr(), d_d.data_ptr(),
+                                                       L.stream_ptr(dev)), "density_field_bwd_rays")
+        else:
+            L.check(L.lib().cnb_density_field_bwd(C.byref(f), C.byref(sm), d.data_ptr(), L.stream_ptr(dev)), "density_field_bwd")
+        return None, d_o, d_d, d_table, dW1, db1, dW2, db2
 
 
 def density_field(cfg, table, W1, b1, W2, b2):
-    return _DensityFieldFn.apply(cfg, table, W1, b1, W2, b2)
+    return _DensityFieldFn.apply(cfg, cfg[0][0], cfg[0][1], table, W1, b1, W2, b2)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -236,11 +246,14 @@ class _FieldFn(torch.autograd.Function):
     """FruitField.forward on one launch chain: -> (density [N], rgb [N,3], sem [N], geo [N,1+geo], positions [N,3])."""
 
     @staticmethod
-    def forward(ctx, cfg: dict, layout, d_geo_hook, *params: Tensor):
+    def forward(ctx, cfg: dict, layout, origins_t: Tensor, directions_t: Tensor, *params: Tensor):
         origins, directions, starts, ends, cam, R, S, row_stride = layout
+        origins, directions = origins.detach(), directions.detach()
+        layout = (origins, directions, starts, ends, cam, R, S, row_stride)
         dev = _dev(origins)
         N = R * S
         training = bool(cfg["training"]) and any(ctx.needs_input_grad)
+        ctx.rays_grad = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         f, keep = _build_field(cfg, params, None)
         sm = make_samples(origins, directions, starts, ends, cam, R, S, row_stride)
         lib = L.lib()
@@ -283,19 +296,21 @@ class _FieldFn(torch.autograd.Function):
         dg = None
         if d_geo is not None and d_geo.numel() > 0 and cfg["precision"] == L.PREC_FP32:
             dg = L.f32(d_geo).reshape(-1, 1 + cfg["geo_feat_dim"])
-        L.check(
-            L.lib().cnb_field_bwd(C.byref(f), C.byref(sm), _p(dd), _p(dr), _p(ds), _p(dg),
-                                  ctx.scratch.data_ptr() if ctx.scratch is not None and ctx.scratch.numel() > 1 else None, L.stream_ptr(dev)),
-            "field_bwd",
-        )
-        if cfg["appearance_mode"] == L.APP_MEAN:
-            pass  # mean-embedding gradient is not propagated (inference-only mode, fruit_field.py:219-221)
+        scratch_ptr = ctx.scratch.data_ptr() if ctx.scratch is not None and ctx.scratch.numel() > 1 else None
+        d_o = d_d = None
+        if ctx.rays_grad:  # row a17: gradient with respect to the rays (camera optimizer)
+            d_o, d_d = torch.zeros_like(origins), torch.zeros_like(directions)
+            L.check(L.lib().cnb_field_bwd_rays(C.byref(f), C.byref(sm), _p(dd), _p(dr), _p(ds), _p(dg), scratch_ptr, d_o.data_ptr(), d_d.data_ptr(),
+                                               L.stream_ptr(dev)), "field_bwd_rays")
+        else:
+            L.check(L.lib().cnb_field_bwd(C.byref(f), C.byref(sm), _p(dd), _p(dr), _p(ds), _p(dg), scratch_ptr, L.stream_ptr(dev)), "field_bwd")
+        # the mean-embedding gradient is not propagated (inference-only mode, fruit_field.py:219-221)
         ctx.scratch = None
-        return (None, None, None, *grads)
+        return (None, None, d_o, d_d, *grads)
 
 
 def fruit_field(cfg: dict, layout, params: Sequence[Tensor]):
-    return _FieldFn.apply(cfg, layout, None, *params)
+    return _FieldFn.apply(cfg, layout, layout[0], layout[1], *params)
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -54,7 +54,7 @@ class FusedPipeline:
             self._tables[key] = t.to(dev)
         return self._tables[key]
 
-    def _model_struct(self, dev, training: bool, with_grads: bool):
+    def _model_struct(self, dev, training: bool, with_grads: bool, ray_gradients: bool = False):
         m = self.model
         keep = []
         field = m.field
@@ -109,6 +109,7 @@ class FusedPipeline:
         ms.bg_mode = mode
         for i in range(3):
             ms.bg_color[i] = float(color[i]) if color is not None else 0.0
+        ms.ray_gradients = int(ray_gradients)
         return ms, keep
 
     def _rays_struct(self, ray_bundle, training: bool):
@@ -122,7 +123,7 @@ class FusedPipeline:
             return t
 
         r = L.Rays()
-        o, d = f32c(ray_bundle.origins.reshape(R, 3)), f32c(ray_bundle.directions.reshape(R, 3))
+        o, d = f32c(ray_bundle.origins.detach().reshape(R, 3)), f32c(ray_bundle.directions.detach().reshape(R, 3))
         r.origins, r.directions = o.data_ptr(), d.data_ptr()
         if ray_bundle.nears is not None and ray_bundle.fars is not None:
             r.nears = f32c(ray_bundle.nears.reshape(R)).data_ptr()
@@ -216,7 +217,9 @@ class FusedPipeline:
             if updated:
                 s._steps_since_update = 0
             return losses, tensors
-        ms, keep = self._model_struct(dev, training=True, with_grads=True)
+        # row a17: when the ray origins / directions carry a graph (camera optimizer), the kernels also return dLoss/d rays
+        ray_grads = bool(ray_bundle.origins.requires_grad or ray_bundle.directions.requires_grad)
+        ms, keep = self._model_struct(dev, training=True, with_grads=True, ray_gradients=ray_grads)
         rays, keep2 = self._rays_struct(ray_bundle, training=True)
         R = rays.num_rays
         ws = self._workspace(ms, R, True, dev)
@@ -236,6 +239,13 @@ class FusedPipeline:
         cfg.update_proposals = int(bool(updated))
         cfg.want_metrics = int(want_metrics)
         cfg.phase = int(phase)
+        d_o = d_d = None
+        if ray_grads:
+            if phase != 0:
+                raise RuntimeError("ray gradients (camera optimizer) are not combined with the split (phase 1/2) train step")
+            d_o = torch.zeros((R, 3), device=dev, dtype=torch.float32)
+            d_d = torch.zeros((R, 3), device=dev, dtype=torch.float32)
+            cfg.d_origins, cfg.d_directions = d_o.data_ptr(), d_d.data_ptr()
         losses = torch.empty((8,), device=dev, dtype=torch.float32)
         L.check(L.lib().cnb_train_step(C.byref(ms), C.byref(rays), C.byref(cfg), C.byref(out), losses.data_ptr(), ws.data_ptr(), L.stream_ptr(dev)),
                 "train_step")
@@ -243,5 +253,9 @@ class FusedPipeline:
             return losses, tensors, (ms, rays, cfg, out, losses, ws, tensors, updated, (keep, keep2, image, mask, jitter))
         if updated:
             s._steps_since_update = 0
+        if ray_grads:  # hand the ray gradients to whatever produced the rays (CameraOptimizer.apply_to_raybundle)
+            roots = [t for t in (ray_bundle.origins, ray_bundle.directions) if t.requires_grad]
+            grads = [g.view_as(t) for t, g in ((ray_bundle.origins, d_o), (ray_bundle.directions, d_d)) if t.requires_grad]
+            torch.autograd.backward(roots, grads)
         del keep, keep2
         return losses, tensors

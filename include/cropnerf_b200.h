@@ -156,6 +156,18 @@ int cnb_field_fwd(const cnb_field* f, const cnb_samples* s, float* density, floa
 int cnb_field_bwd(const cnb_field* f, const cnb_samples* s, const float* d_density, const float* d_rgb, const float* d_sem,
                   const float* d_geo, float* ctx, cnb_stream_t stream);
 
+/* ---- a17: gradient with respect to the rays (camera optimizer, fruit_nerf.py:114-116,547,614) ---------------------- */
+/* d_feat [N, 2L] = gradient reaching a grid's encoded features; accumulates d_origins / d_directions [R,3]:
+ * trilinear-offset derivative of every level -> selector mask -> normalisation / SceneContraction Jacobian -> sum over the ray */
+int cnb_position_grad_rays(const cnb_grid* g, const cnb_warp* warp, const cnb_samples* s, const float* d_feat, float* d_origins,
+                           float* d_directions, cnb_stream_t stream);
+/* cnb_density_field_bwd + ray gradients; scratch: R*S*2L floats */
+int cnb_density_field_bwd_rays(const cnb_density_field* f, const cnb_samples* s, const float* d_density, float* scratch, float* d_origins,
+                               float* d_directions, cnb_stream_t stream);
+/* cnb_field_bwd + ray gradients (the SH direction encoding carries no gradient, as in nerfstudio's torch SHEncoding) */
+int cnb_field_bwd_rays(const cnb_field* f, const cnb_samples* s, const float* d_density, const float* d_rgb, const float* d_sem,
+                       const float* d_geo, float* ctx, float* d_origins, float* d_directions, cnb_stream_t stream);
+
 /* ---- a8/a9: samplers (nerfstudio ray_samplers.py; components/ray_samplers.py:54-104) ----------------------- */
 /* SpacedSampler: lin_bins = torch.linspace(0,1,S+1) supplied by the host (bit-exact u); t_rand NULL (eval) or
  * [R*rand_stride] with rand_stride 1 (single_jitter) or S+1.  Outputs spacing/euclid bin edges [R,S+1]. */
@@ -258,7 +270,7 @@ typedef struct cnb_model {
   cnb_sampler sampler;
   int32_t bg_mode;                 /* CNB_BG_* (renderer_rgb background_color / override context) */
   float bg_color[3];
-  int32_t _pad;
+  int32_t ray_gradients;           /* training workspace also holds the scratch for cnb_train_cfg.d_origins / d_directions */
 } cnb_model;
 
 /* per-ray outputs, each optional (NULL = not wanted) */
@@ -286,6 +298,8 @@ typedef struct cnb_train_cfg {
   float grad_scale;          /* GradScaler factor applied to every gradient (1 = none) */
   int32_t update_proposals;  /* ProposalNetworkSampler "updated": proposal networks receive gradients this step */
   int32_t want_metrics;      /* distortion metric + psnr inputs (get_metrics_dict) */
+  float* d_origins;          /* optional [R,3], ACCUMULATED: dLoss/d origins (camera optimizer, row a17); needs d_directions too */
+  float* d_directions;       /* optional [R,3], ACCUMULATED */
   int32_t phase;             /* 0 = whole step; 1 = forward + final-level/field backward only; 2 = the rest (interlevel loss,
                                 proposal backward, metrics) on the workspace phase 1 left behind -- lets a data-parallel caller
                                 start the all-reduce of the field gradients while the proposal networks back-propagate */

@@ -174,3 +174,34 @@ def test_two_rank_gradient_allreduce_gloo():
             procs.append(subprocess.Popen([sys.executable, path, ROOT], env=env))
         codes = [p.wait(timeout=300) for p in procs]
     assert codes == [0, 0]
+
+
+def test_camera_optimizer_so3xr3_host_math():
+    """exp_map_SO3xR3 (nerfstudio lie_groups.py as used by CameraOptimizer, fruit_nerf.py:114-116): rotation block equals the
+    matrix exponential of the skew matrix, translation passes through, and apply_to_raybundle is differentiable."""
+    import torch
+    from cropnerf_b200.fruit_nerf import CameraOptimizer, exp_map_SO3xR3
+    from cropnerf_b200.rays import RayBundle
+
+    g = torch.Generator().manual_seed(0)
+    tv = torch.randn((7, 6), generator=g) * 0.3
+    m = exp_map_SO3xR3(tv)
+    w = tv[:, 3:]
+    skew = torch.zeros((7, 3, 3))
+    skew[:, 0, 1], skew[:, 0, 2], skew[:, 1, 0], skew[:, 1, 2], skew[:, 2, 0], skew[:, 2, 1] = -w[:, 2], w[:, 1], w[:, 2], -w[:, 0], -w[:, 1], w[:, 0]
+    assert torch.allclose(m[:, :3, :3], torch.matrix_exp(skew), atol=1e-5)
+    assert torch.equal(m[:, :3, 3], tv[:, :3])
+    opt = CameraOptimizer(5, "SO3xR3")
+    with torch.no_grad():
+        opt.pose_adjustment.copy_(torch.randn((5, 6), generator=g) * 0.05)
+    rb = RayBundle(torch.randn((9, 3), generator=g), torch.nn.functional.normalize(torch.randn((9, 3), generator=g), dim=-1), None,
+                   torch.randint(0, 5, (9, 1), generator=g))
+    d0 = rb.directions.clone()
+    opt.apply_to_raybundle(rb)
+    assert torch.allclose(rb.directions.norm(dim=-1), d0.norm(dim=-1), atol=1e-5)  # rotations preserve length
+    (rb.origins.sum() + (rb.directions * d0).sum()).backward()
+    assert opt.pose_adjustment.grad is not None and opt.pose_adjustment.grad.abs().sum() > 0
+    reg = {}
+    opt.get_loss_dict(reg)
+    assert "camera_opt_regularizer" in reg
+    assert CameraOptimizer(5, "off").apply_to_raybundle(rb) is None
