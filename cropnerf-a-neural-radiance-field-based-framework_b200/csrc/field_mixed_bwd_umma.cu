@@ -1,4 +1,11 @@
-// FruitField backward on tensor cores (rows a1/a5/a6 of SURVEY.md section 8, the autograd of fruit_field.py:169-302).
+// FruitField backward, tcgen05 variant (rows a1/a5/a6 of SURVEY.md section 8, the autograd of fruit_field.py:169-302).
+//
+// ALTERNATIVE to field_mixed_bwd.cu, selected with CNB_FIELD_BWD_UMMA=1.  Same numerics contract and tests.  Measured on B200
+// (4096-ray training step): 0.325 ms for the field backward stage versus 0.285 ms for the pure mma.sync kernel, so it is NOT
+// the default: the dW contraction it moves to tcgen05/TMEM was only ~14 % of the instructions, the kernel is bound by the
+// register-chained mma.sync forward-recompute / dX work, and the asynchronous UTCHMMA stream competes with those HMMAs for
+// the same tensor pipe (math-pipe-throttle stalls 0.38 -> 0.86 per issue).  Kept as the working tcgen05 reference for this
+// path (tests/micro/umma_dw_test.cu is the stand-alone descriptor / TMEM-layout test it grew from).
 //
 // One kernel does, per 128-sample batch of a persistent CTA (8 warps, one 16-sample m-tile each):
 //   1. re-run the forward MLPs from the fp16 encoded features the forward kept (no second table gather); the fp16
@@ -7,21 +14,23 @@
 //   2. input gradients layer by layer: dX = dY * W with dY re-packed from the accumulator fragments (bf16 -- the range of
 //      fp32, so no loss scaling is needed for the 1e-7-sized pixel gradients) and W^T read from a transposed bf16 copy
 //      of the weights in shared memory;
-//   3. weight gradients: dW = dY^T * X is a contraction over SAMPLES, so each layer's (X, dY) pair of the 128 samples
-//      is staged once in shared memory and read back with ldmatrix.trans; every warp owns a fixed 1/8 slice of every
-//      dW and accumulates it (fp32) across all batches of the CTA -- no atomics until the one flush per CTA at the end;
-//      bias gradients are the same contraction against a fragment of ones;
+//   3. weight gradients: dW = dY^T * X is a contraction over SAMPLES (K = the 128 samples of the batch) whose operands are
+//      shared-memory resident -- the shape tcgen05 is made for.  Each layer's (dY, X) pair is staged once in the canonical
+//      no-swizzle MN-major UMMA layout, ONE thread issues 8 tcgen05.mma (K = 16 each) per layer, and the eight dW
+//      accumulators (328 of the 512 TMEM columns) live in TENSOR MEMORY across all batches of the persistent CTA: no
+//      ldmatrix, no per-warp accumulator slices, no atomics until the one read-out (tcgen05.ld) + flush per CTA.  The MMAs run
+//      asynchronously behind the warps' mma.sync work of the next layer; a tcgen05.commit -> mbarrier per staging buffer
+//      (4 buffers) tells the warps when a buffer may be overwritten.  Bias gradients come from the same MMAs: a block of
+//      ones sits right behind every staged X matrix, so it is one more 8-column block of the B operand (or 8 more rows of
+//      the A operand for the three narrow layers, which are issued transposed with M = 128 so that N can stay 16);
 //   4. d(encoded features) [N,32] fp32 goes to the scratch the hash-grid scatter (cnb_hashgrid_bwd) reads; the appearance
 //      embedding gradient is reduced over the m-tile (all 16 samples share the ray when S % 16 == 0) before its atomics.
-#include <cstdlib>
-
 #include "field_mixed.cuh"
 
 using namespace cnbmix;
 
 namespace {
 
-constexpr int ST = 72;        // staging row stride (halves)
 constexpr int BATCH = WARPS * 16;
 // transposed bf16 weights, [in][out] with padded rows (half offsets)
 constexpr int T_R3 = 0;                   // [64][24]   out 0..2 of 16 used
@@ -31,12 +40,31 @@ constexpr int T_S2 = T_R1 + 64 * 72;      // [64][72]
 constexpr int T_B2 = T_S2 + 64 * 72;      // [64][24]
 constexpr int T_B1 = T_B2 + 64 * 24;      // [32][72]
 constexpr int T_HALVES = T_B1 + 32 * 72;
-// per-warp dW accumulator tiles (16x8 fp32 each): r3, r2 x4, r1 x4, head, s2 x4, s1, b2, b1 x2
-constexpr int A_R3 = 0, A_R2 = 1, A_R1 = 5, A_H = 9, A_S2 = 10, A_S1 = 14, A_B2 = 15, A_B1 = 16, A_TILES = 18;
-// bias accumulators (floats)
-constexpr int B_R3 = 0, B_R2 = 16, B_R1 = 80, B_H = 144, B_S2 = 160, B_S1 = 224, B_B2 = 288, B_B1 = 304, B_FLOATS = 368;
+// ---- tcgen05 (UMMA) dW contraction: staging buffers in the canonical no-swizzle MN-major layout -----------------------------------
+//   byte(feature f, sample k) = (f/8)*SBO + (k/8)*LBO + (k%8)*16 + (f%8)*2      (cute/atom/mma_traits_sm100.hpp, Major::MN, INTERLEAVE)
+constexpr uint32_t U_LBO = 128;                  // between 8-sample k-blocks
+constexpr uint32_t U_SBO = (BATCH / 8) * 128;    // between 8-feature mn-blocks (2048)
+constexpr uint32_t U_MAT = 8 * U_SBO;            // one 64-feature x 128-sample matrix (16 KB)
+constexpr uint32_t U_BUF = 2 * U_MAT + U_SBO;    // [dY | X | ones block]
+constexpr int NBUF = 4;
+constexpr int BTHREADS = THREADS + 32;  // 8 worker warps + 1 MMA-issuer warp
+// GEMM table: swapped = issued as (dW)^T = [X | ones]^T dY with M = 128 (narrow dY, N = 16); otherwise dW = dY^T [X | ones], M = 64.
+// xblk0 = first 8-feature block of the X region that holds data (narrow X is right-aligned so that the ones block follows it).
+struct GemmSpec { bool swapped; int xblk0; int n; int col; };
+enum { G_R3 = 0, G_R2, G_R1, G_H, G_S2, G_S1, G_B2, G_B1, NGEMM };
+__device__ constexpr GemmSpec GEMMS[NGEMM] = {
+    {true, 0, 16, 0},     // dWr3^T [64(+bias row) x 3]
+    {false, 0, 72, 16},   // dWr2   [64 x 64 | bias]
+    {false, 0, 72, 88},   // dWr1   [64 x 64 | bias]   (column 16 = the cleared dba slot)
+    {true, 0, 16, 160},   // dWh^T  [64(+bias row) x 1]
+    {false, 0, 72, 176},  // dWs2
+    {false, 6, 24, 248},  // dWs1   [64 x 16 | bias]   (X = [0 | geo15] in blocks 6,7)
+    {true, 0, 16, 272},   // dWb2^T [64(+bias row) x 16]
+    {false, 4, 40, 288},  // dWb1   [64 x 32 | bias]   (X = encoded features in blocks 4..7)
+};
+constexpr int TMEM_COLS_USED = 328;
 
-constexpr size_t SMEM_BWD = (size_t)(HALVES + T_HALVES + 4 * BATCH * ST) * 2 + (size_t)(FLOATS + B_FLOATS + WARPS * A_TILES * 128) * 4;  // 228 272 B
+constexpr size_t SMEM_BWD = (size_t)NBUF * U_BUF + (size_t)(HALVES + T_HALVES) * 2 + (size_t)FLOATS * 4 + 128;
 
 struct BwdArgs {
   MixArgs m;
@@ -99,84 +127,37 @@ __device__ __forceinline__ void relu_mask_pack(const float (&acc)[2 * KT][4], co
   }
 }
 
-// write KT k-tiles of an A fragment into the staging matrix [BATCH][ST] (32-bit view, row stride ST/2 words)
+// write KT k-tiles (16 features each) of an A fragment into a staged matrix (canonical UMMA layout), features starting at
+// 8-feature block blk0; this warp's 16 samples are k-blocks 2*warp, 2*warp+1.  Conflict-free 32-bit stores (g*16 + t*4).
 template <int KT, bool CVT>
-__device__ __forceinline__ void stage(uint32_t* st32, int row0, const uint32_t (&A)[KT][4], int g, int t) {
-  uint32_t* r0 = st32 + (row0 + g) * (ST / 2) + t;
-  uint32_t* r1 = r0 + 8 * (ST / 2);
+__device__ __forceinline__ void stage_u(unsigned char* mat, int blk0, int warp, const uint32_t (&A)[KT][4], int g, int t) {
+  unsigned char* p = mat + (uint32_t)blk0 * U_SBO + (uint32_t)(2 * warp) * U_LBO + g * 16 + t * 4;
 #pragma unroll
-  for (int kt = 0; kt < KT; ++kt) {
-    r0[8 * kt] = CVT ? h2_to_bf2(A[kt][0]) : A[kt][0];
-    r1[8 * kt] = CVT ? h2_to_bf2(A[kt][1]) : A[kt][1];
-    r0[8 * kt + 4] = CVT ? h2_to_bf2(A[kt][2]) : A[kt][2];
-    r1[8 * kt + 4] = CVT ? h2_to_bf2(A[kt][3]) : A[kt][3];
-  }
-}
-
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
-}
-
-// dW[16*MT, 8*NTT] += dY^T X over the BATCH staged samples.  Warp w owns m-tile w / WPM and NT consecutive n-tiles.
-template <int MT, int NTT>
-__device__ __forceinline__ void dw_gemm(uint32_t dout_s, uint32_t in_s, float* acc_tiles, float* bias_acc, int warp, int lane) {
-  constexpr int WPM = WARPS / MT;
-  constexpr int NT = NTT / WPM;
-  static_assert(NT == 1 || NT % 2 == 0, "n-tiles per warp");
-  const int mi = warp / WPM, nj0 = (warp % WPM) * NT;
-  const bool do_bias = (warp % WPM) == 0;
-  float c[NT][4], cb[4] = {0.f, 0.f, 0.f, 0.f};
-  zero_acc<NT>(c);
-  const int j = lane >> 3, r = lane & 7;
-  const uint32_t a_addr = dout_s + 2u * (((j >> 1) * 8 + r) * ST + 16 * mi + (j & 1) * 8);
-  const uint32_t b_addr = in_s + 2u * (((j & 1) * 8 + r) * ST + 8 * (nj0 + (j >> 1)));
-  constexpr uint32_t ONES = 0x3F803F80u;  // bf16 (1, 1)
+  for (int kt = 0; kt < KT; ++kt)
 #pragma unroll
-  for (int ks = 0; ks < BATCH / 16; ++ks) {
-    uint32_t A[4];
-    ldsm_x4_t(A, a_addr + 2u * ks * 16 * ST);
-    if constexpr (NT == 1) {
-      uint32_t B[2];
-      ldsm_x2_t(B, b_addr + 2u * ks * 16 * ST);
-      mma_bf16(c[0], A, B[0], B[1]);
-    } else {
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-      for (int p = 0; p < NT / 2; ++p) {
-        uint32_t B[4];
-        ldsm_x4_t(B, b_addr + 2u * (ks * 16 * ST + 16 * p));
-        mma_bf16(c[2 * p], A, B[0], B[1]);
-        mma_bf16(c[2 * p + 1], A, B[2], B[3]);
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t v = A[kt][2 * q + h];
+        *reinterpret_cast<uint32_t*>(p + (uint32_t)(2 * kt + q) * U_SBO + (uint32_t)h * U_LBO) = CVT ? h2_to_bf2(v) : v;
       }
-    }
-    if (do_bias) mma_bf16(cb, A, ONES, ONES);
-  }
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc_tiles[(nt * 4 + q) * 32 + lane] += c[nt][q];
-  if (do_bias && (lane & 3) == 0) {
-    bias_acc[16 * mi + (lane >> 2)] += cb[0];
-    bias_acc[16 * mi + (lane >> 2) + 8] += cb[2];
-  }
 }
 
-// flush one warp-owned group of accumulator tiles: element (n, k) of the padded dW goes through `put`
-template <int MT, int NTT, typename Put>
-__device__ __forceinline__ void flush_tiles(const float* acc_tiles, int warp, int lane, Put put) {
-  constexpr int WPM = WARPS / MT;
-  constexpr int NT = NTT / WPM;
-  const int mi = warp / WPM, nj0 = (warp % WPM) * NT;
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float v = acc_tiles[(nt * 4 + q) * 32 + lane];
-      if (v != 0.f) put(16 * mi + g + (q >> 1) * 8, 8 * (nj0 + nt) + 2 * t + (q & 1), v);
-    }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(U_LBO >> 4) << 16) | ((uint64_t)(U_SBO >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {  // bf16 x bf16 -> f32, both operands MN-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da),
+               "l"(db), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 
 __device__ inline void load_weights_t(const MixArgs& a, __nv_bfloat16* WT) {
@@ -204,31 +185,57 @@ __device__ inline void load_weights_t(const MixArgs& a, __nv_bfloat16* WT) {
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_constant__ BwdArgs b) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(BTHREADS, 1) k_field_mixed_bwd_umma(const __grid_constant__ BwdArgs b) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const MixArgs& a = b.m;
-  __half* Wsm = reinterpret_cast<__half*>(smem_raw);
+  // staging buffers first: the M = 128 operand of the transposed GEMMs reads 7 junk feature blocks past its ones block, which
+  // must stay inside the allocation (they land in the next buffer / the weights and only feed accumulator rows nobody reads)
+  unsigned char* stg = smem_raw;
+  __half* Wsm = reinterpret_cast<__half*>(smem_raw + NBUF * U_BUF);
   __nv_bfloat16* WT = reinterpret_cast<__nv_bfloat16*>(Wsm + HALVES);
-  // two staging buffer pairs (X, dY), used alternately: a warp may stage GEMM k+1 while others still contract GEMM k, so one
-  // block barrier per GEMM suffices (the buffer being overwritten was last read two GEMMs ago, i.e. before the previous barrier)
-  __nv_bfloat16* st_base = WT + T_HALVES;
-  float* Bf = reinterpret_cast<float*>(st_base + 4 * BATCH * ST);
-  float* bias_acc = Bf + FLOATS;
-  float* acc_all = bias_acc + B_FLOATS;
-  load_weights(a, Wsm, Bf);
-  load_weights_t(a, WT);
-  for (int e = threadIdx.x; e < B_FLOATS + WARPS * A_TILES * 128; e += THREADS) bias_acc[e] = 0.f;
-  // the pad columns of the staging rows are never written by `stage`; ldmatrix.x2 never consumes them either
-  __syncthreads();
-
+  float* Bf = reinterpret_cast<float*>(WT + T_HALVES);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(Bf + FLOATS);   // NBUF "empty" (MMAs drained the buffer) + NBUF "full" (all 8 warps staged)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2 * NBUF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  float* acc_w = acc_all + warp * A_TILES * 128;
-  uint32_t* const st32 = reinterpret_cast<uint32_t*>(st_base);
-  const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(st_base);
-  constexpr int MATW = BATCH * ST / 2;  // 32-bit words per staged matrix
-  int buf = 0;
-  const int row0 = warp * 16;
+  load_weights(a, Wsm, Bf);
+  load_weights_t(a, WT);
+  for (int bb = 0; bb < NBUF; ++bb) {  // the ones block behind every X matrix (bias gradients), written once
+    uint32_t* ones = reinterpret_cast<uint32_t*>(stg + bb * U_BUF + 2 * U_MAT);
+    for (int e = threadIdx.x; e < (int)(U_SBO / 4); e += THREADS) ones[e] = 0x3F803F80u;  // bf16 (1, 1)
+  }
+  if (threadIdx.x == 0) {
+    for (int bb = 0; bb < NBUF; ++bb) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar + bb)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar + NBUF + bb)), "r"(WARPS));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (warp == 0) {  // all 512 TMEM columns: the CTA owns the SM (217 KB of shared memory)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t stg_s = (uint32_t)__cvta_generic_to_shared(stg), mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
+  uint32_t buf = 0, used = 0, phase = 0;   // staging buffer ring + per-buffer "empty" phase bits (same sequence in every worker warp)
+  // Workers never meet at a block barrier inside the batch loop.  acquire(): wait until the MMAs of the buffer's previous use
+  // have drained it (tcgen05.commit -> "empty" mbarrier).  publish(): make this warp's rows visible to the async proxy and
+  // arrive on the buffer's "full" mbarrier (8 arrivals); the issuer warp below turns a full buffer into 8 tcgen05.mma.
+  auto acquire = [&]() -> unsigned char* {
+    if (used & (1u << buf)) { mbar_wait(mbar_s + 8 * buf, (phase >> buf) & 1u); phase ^= 1u << buf; }
+    used |= 1u << buf;
+    return stg + buf * U_BUF;
+  };
+  auto launch = [&](int) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_s + 8 * (NBUF + buf)) : "memory");
+    buf = (buf + 1) % NBUF;
+  };
   const int S = a.sm.samples_per_ray;
   const int64_t N = a.sm.num_rays * S;
   const int64_t nbatches = (N + BATCH - 1) / BATCH;
@@ -297,6 +304,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
     load_cam(t0 + tstride, cam2);
   }
 
+  if (warp == WARPS) {
+    // ===== MMA issuer warp: one lane issues the 8 K-steps of every layer's dW GEMM as soon as its buffer is full =====
+    uint32_t fphase = 0, ibuf = 0;
+    bool first_batch = true;
+    for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
+      for (int gi = 0; gi < NGEMM; ++gi) {
+        mbar_wait(mbar_s + 8 * (NBUF + ibuf), (fphase >> ibuf) & 1u);
+        fphase ^= 1u << ibuf;
+        if (lane == 0) {
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const GemmSpec sp = GEMMS[gi];
+          const uint32_t dy_s = stg_s + ibuf * U_BUF, x_s = dy_s + U_MAT;
+          const uint32_t a_s = sp.swapped ? x_s : dy_s;
+          const uint32_t b_s = sp.swapped ? dy_s : x_s + (uint32_t)sp.xblk0 * U_SBO;
+          const uint32_t idesc = umma_idesc(sp.swapped ? 128 : 64, sp.n);
+#pragma unroll
+          for (int ks = 0; ks < BATCH / 16; ++ks)
+            umma_issue(tmem + sp.col, umma_desc(a_s + ks * 2 * U_LBO), umma_desc(b_s + ks * 2 * U_LBO), idesc, (first_batch && ks == 0) ? 0u : 1u);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"l"((uint64_t)(mbar_s + 8 * ibuf)) : "memory");
+        }
+        __syncwarp();
+        ibuf = (ibuf + 1) % NBUF;
+      }
+      first_batch = false;
+    }
+  } else
   for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
     const int64_t tile = batch * WARPS + warp;
     const int64_t row[2] = {tile * 16 + g, tile * 16 + g + 8};
@@ -377,30 +410,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
         }
       }
       // ---- layer 3: dW = D3^T r2 ; d_r2 = D3 W3 -------------------------------------------------------------------------
-      stage<1, false>(st32 + (2 * buf + 1) * MATW, row0, D3, g, t);
-      stage<4, true>(st32 + (2 * buf) * MATW, row0, AR2, g, t);
-      __syncthreads();
-      dw_gemm<1, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_R3 * 128, bias_acc + B_R3, warp, lane);
-      buf ^= 1;
+      {
+        unsigned char* sb = acquire();
+        stage_u<1, false>(sb, 0, warp, D3, g, t);
+        stage_u<4, true>(sb + U_MAT, 0, warp, AR2, g, t);
+        launch(G_R3);
+      }
       uint32_t D[4][4];
       zero_acc<8>(acc);
       layer_bf<8, 1, 24>(WT + T_R3, D3, acc, g, t);
       relu_mask_pack<4>(acc, AR2, D);
       // ---- layer 2 ----------------------------------------------------------------------------------------------------------
-      stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
-      stage<4, true>(st32 + (2 * buf) * MATW, row0, AR1, g, t);
-      __syncthreads();
-      dw_gemm<4, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_R2 * 128, bias_acc + B_R2, warp, lane);
-      buf ^= 1;
+      {
+        unsigned char* sb = acquire();
+        stage_u<4, false>(sb, 0, warp, D, g, t);
+        stage_u<4, true>(sb + U_MAT, 0, warp, AR1, g, t);
+        launch(G_R2);
+      }
       zero_acc<8>(acc);
       layer_bf<8, 4, 72>(WT + T_R2, D, acc, g, t);
       relu_mask_pack<4>(acc, AR1, D);
       // ---- layer 1 ----------------------------------------------------------------------------------------------------------
-      stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
-      stage<4, true>(st32 + (2 * buf) * MATW, row0, Ain, g, t);
-      __syncthreads();
-      dw_gemm<4, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_R1 * 128, bias_acc + B_R1, warp, lane);
-      buf ^= 1;
+      {
+        unsigned char* sb = acquire();
+        stage_u<4, false>(sb, 0, warp, D, g, t);
+        stage_u<4, true>(sb + U_MAT, 0, warp, Ain, g, t);
+        launch(G_R1);
+      }
       float din[6][4];  // d(rgb input) columns 16..63: [0, geo15 | emb32]
       zero_acc<6>(din);
       layer_bf<6, 4, 72>(WT + T_R1 + 16 * 72, D, din, g, t);
@@ -452,11 +488,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
       // ---- head: dWh = d_sem^T s2 ------------------------------------------------------------------------------------------
       uint32_t Dh[1][4] = {{0u, 0u, 0u, 0u}};
       if (t == 0) { Dh[0][0] = pack_bf2(dsem[0], 0.f); Dh[0][1] = pack_bf2(dsem[1], 0.f); }
-      stage<1, false>(st32 + (2 * buf + 1) * MATW, row0, Dh, g, t);
-      stage<4, false>(st32 + (2 * buf) * MATW, row0, S2f, g, t);
-      __syncthreads();
-      dw_gemm<1, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_H * 128, bias_acc + B_H, warp, lane);
-      buf ^= 1;
+      {
+        unsigned char* sb = acquire();
+        stage_u<1, false>(sb, 0, warp, Dh, g, t);
+        stage_u<4, false>(sb + U_MAT, 0, warp, S2f, g, t);
+        launch(G_H);
+      }
       // d_s2 = d_sem * Wh (no activation after the last semantic layer)
 #pragma unroll
       for (int kt = 0; kt < 4; ++kt)
@@ -467,20 +504,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
           D[kt][2 * h + 1] = pack_bf2(dsem[1] * w.x, dsem[1] * w.y);
         }
       // ---- semantic layer 2 ------------------------------------------------------------------------------------------------
-      stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
-      stage<4, true>(st32 + (2 * buf) * MATW, row0, AS1, g, t);
-      __syncthreads();
-      dw_gemm<4, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_S2 * 128, bias_acc + B_S2, warp, lane);
-      buf ^= 1;
+      {
+        unsigned char* sb = acquire();
+        stage_u<4, false>(sb, 0, warp, D, g, t);
+        stage_u<4, true>(sb + U_MAT, 0, warp, AS1, g, t);
+        launch(G_S2);
+      }
       zero_acc<8>(acc);
       layer_bf<8, 4, 72>(WT + T_S2, D, acc, g, t);
       relu_mask_pack<4>(acc, AS1, D);
       // ---- semantic layer 1 (input = [0 | geo15]) -----------------------------------------------------------------------------
-      stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
-      stage<1, true>(st32 + (2 * buf) * MATW, row0, Abo, g, t);
-      __syncthreads();
-      dw_gemm<4, 2>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_S1 * 128, bias_acc + B_S1, warp, lane);
-      buf ^= 1;
+      {
+        unsigned char* sb = acquire();
+        stage_u<4, false>(sb, 0, warp, D, g, t);
+        stage_u<1, true>(sb + U_MAT, 6, warp, Abo, g, t);
+        launch(G_S1);
+      }
     }
 
     // ===================================== base MLP ========================================================================
@@ -496,21 +535,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
       uint32_t Dbo[1][4];
       Dbo[0][0] = pack_bf2(dbo[0][0], dbo[0][1]); Dbo[0][1] = pack_bf2(dbo[0][2], dbo[0][3]);
       Dbo[0][2] = pack_bf2(dbo[1][0], dbo[1][1]); Dbo[0][3] = pack_bf2(dbo[1][2], dbo[1][3]);
-      stage<1, false>(st32 + (2 * buf + 1) * MATW, row0, Dbo, g, t);
-      stage<4, true>(st32 + (2 * buf) * MATW, row0, AH, g, t);
-      __syncthreads();
-      dw_gemm<1, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_B2 * 128, bias_acc + B_B2, warp, lane);
-      buf ^= 1;
+      {
+        unsigned char* sb = acquire();
+        stage_u<1, false>(sb, 0, warp, Dbo, g, t);
+        stage_u<4, true>(sb + U_MAT, 0, warp, AH, g, t);
+        launch(G_B2);
+      }
       float acc[8][4];
       zero_acc<8>(acc);
       layer_bf<8, 1, 24>(WT + T_B2, Dbo, acc, g, t);
       uint32_t D[4][4];
       relu_mask_pack<4>(acc, AH, D);
-      stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
-      stage<2, true>(st32 + (2 * buf) * MATW, row0, A0, g, t);
-      __syncthreads();
-      dw_gemm<4, 4>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_B1 * 128, bias_acc + B_B1, warp, lane);
-      buf ^= 1;
+      {
+        unsigned char* sb = acquire();
+        stage_u<4, false>(sb, 0, warp, D, g, t);
+        stage_u<2, true>(sb + U_MAT, 4, warp, A0, g, t);
+        launch(G_B1);
+      }
       float dx[4][4];
       zero_acc<4>(dx);
       layer_bf<4, 4, 72>(WT + T_B1, D, dx, g, t);
@@ -522,42 +563,104 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
     }
   }
 
-  // ---- one flush per CTA ------------------------------------------------------------------------------------------------------
-  const int in0 = a.in0;
-  if (b.dWr3) flush_tiles<1, 8>(acc_w + A_R3 * 128, warp, lane, [&](int n, int k, float v) { if (n < 3) atomicAdd(b.dWr3 + n * 64 + k, v); });
-  if (b.dWr2) flush_tiles<4, 8>(acc_w + A_R2 * 128, warp, lane, [&](int n, int k, float v) { atomicAdd(b.dWr2 + n * 64 + k, v); });
-  if (b.dWr1) flush_tiles<4, 8>(acc_w + A_R1 * 128, warp, lane, [&](int n, int k, float v) { if (k != 16) atomicAdd(b.dWr1 + n * 63 + (k < 16 ? k : k - 1), v); });
-  if (b.dWh) flush_tiles<1, 8>(acc_w + A_H * 128, warp, lane, [&](int n, int k, float v) { if (n == 0) atomicAdd(b.dWh + k, v); });
-  if (b.dWs2) flush_tiles<4, 8>(acc_w + A_S2 * 128, warp, lane, [&](int n, int k, float v) { atomicAdd(b.dWs2 + n * 64 + k, v); });
-  if (b.dWs1) flush_tiles<4, 2>(acc_w + A_S1 * 128, warp, lane, [&](int n, int k, float v) { if (k >= 1) atomicAdd(b.dWs1 + n * 15 + (k - 1), v); });
-  if (b.dWb2) flush_tiles<1, 8>(acc_w + A_B2 * 128, warp, lane, [&](int n, int k, float v) { atomicAdd(b.dWb2 + n * 64 + k, v); });
-  if (b.dWb1) flush_tiles<4, 4>(acc_w + A_B1 * 128, warp, lane, [&](int n, int k, float v) { if (k < in0) atomicAdd(b.dWb1 + n * in0 + k, v); });
+  // ---- one read-out + flush per CTA: wait for the last MMAs, tcgen05.ld the accumulators, reduce into the global gradients ------
+  if (warp < WARPS)
+    for (int bb = 0; bb < NBUF; ++bb)
+      if (used & (1u << bb)) mbar_wait(mbar_s + 8 * bb, (phase >> bb) & 1u);
   __syncthreads();
-  for (int e = threadIdx.x; e < B_FLOATS; e += THREADS) {
-    const float v = bias_acc[e];
-    if (v == 0.f) continue;
-    float* dst = nullptr;
-    if (e < B_R2) { if (e - B_R3 < 3) dst = b.dbr3 ? b.dbr3 + (e - B_R3) : nullptr; }
-    else if (e < B_R1) dst = b.dbr2 ? b.dbr2 + (e - B_R2) : nullptr;
-    else if (e < B_H) dst = b.dbr1 ? b.dbr1 + (e - B_R1) : nullptr;
-    else if (e < B_S2) { if (e == B_H) dst = b.dbh; }
-    else if (e < B_S1) dst = b.dbs2 ? b.dbs2 + (e - B_S2) : nullptr;
-    else if (e < B_B2) dst = b.dbs1 ? b.dbs1 + (e - B_S1) : nullptr;
-    else if (e < B_B1) dst = b.dbb2 ? b.dbb2 + (e - B_B2) : nullptr;
-    else dst = b.dbb1 ? b.dbb1 + (e - B_B1) : nullptr;
-    if (dst) atomicAdd(dst, v);
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  // Gradient image in shared memory (the staging buffers are free now): every tensor in its GLOBAL element order, so the
+  // flush below is coalesced; straight from the TMEM read-out a warp instruction would scatter over 16-32 rows, and all
+  // 148 CTAs would hit the same addresses in the same order.
+  const int in0 = a.in0;
+  float* img = reinterpret_cast<float*>(stg);
+  constexpr int I_WR3 = 0, I_BR3 = 192, I_WR2 = 196, I_BR2 = I_WR2 + 4096, I_WR1 = I_BR2 + 64, I_BR1 = I_WR1 + 4032, I_WH = I_BR1 + 64, I_BH = I_WH + 64,
+                I_WS2 = I_BH + 4, I_BS2 = I_WS2 + 4096, I_WS1 = I_BS2 + 64, I_BS1 = I_WS1 + 960, I_WB2 = I_BS1 + 64, I_BB2 = I_WB2 + 1024,
+                I_WB1 = I_BB2 + 16, I_BB1 = I_WB1 + 2048, I_END = I_BB1 + 64;
+  static_assert(I_END * 4 <= NBUF * U_BUF, "gradient image must fit the staging buffers");
+  if (warp < 4) {
+    // TMEM lane of this thread: 32*warp + lane.  M = 64 accumulators keep row m in lane (m%16) + 32*(m/16) -> lanes 0..15 of
+    // each warp hold rows 16*warp + lane; M = 128 accumulators (transposed GEMMs) keep row r in lane r.
+    const int m64 = 16 * warp + lane, r128 = 32 * warp + lane;
+    const bool has64 = lane < 16;
+    const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
+    for (int c0 = 0; c0 < TMEM_COLS_USED; c0 += 8) {
+      uint32_t v[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "r"(taddr + c0));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = c0 + j;
+        const float val = __uint_as_float(v[j]);
+        int dst = -1;
+        if (col < 16) {                                   // dWr3^T (M = 128): row = input feature / bias row 64, column = output
+          if (col < 3) { if (r128 < 64) dst = I_WR3 + col * 64 + r128; else if (r128 == 64) dst = I_BR3 + col; }
+        } else if (col < 88) {                            // dWr2 | bias
+          const int k = col - 16;
+          if (has64) dst = k < 64 ? I_WR2 + m64 * 64 + k : (k == 64 ? I_BR2 + m64 : -1);
+        } else if (col < 160) {                           // dWr1 | bias (padded input column 16 = dba slot)
+          const int k = col - 88;
+          if (has64) {
+            if (k < 64) { if (k != 16) dst = I_WR1 + m64 * 63 + (k < 16 ? k : k - 1); }
+            else if (k == 64) dst = I_BR1 + m64;
+          }
+        } else if (col < 176) {                           // dWh^T (M = 128)
+          if (col == 160) { if (r128 < 64) dst = I_WH + r128; else if (r128 == 64) dst = I_BH; }
+        } else if (col < 248) {                           // dWs2 | bias
+          const int k = col - 176;
+          if (has64) dst = k < 64 ? I_WS2 + m64 * 64 + k : (k == 64 ? I_BS2 + m64 : -1);
+        } else if (col < 272) {                           // dWs1 | bias (input column 0 = dba slot)
+          const int k = col - 248;
+          if (has64) {
+            if (k >= 1 && k < 16) dst = I_WS1 + m64 * 15 + (k - 1);
+            else if (k == 16) dst = I_BS1 + m64;
+          }
+        } else if (col < 288) {                           // dWb2^T (M = 128)
+          const int n = col - 272;
+          if (r128 < 64) dst = I_WB2 + n * 64 + r128; else if (r128 == 64) dst = I_BB2 + n;
+        } else {                                          // dWb1 | bias
+          const int k = col - 288;
+          if (has64) {
+            if (k < 32) { if (k < in0) dst = I_WB1 + m64 * in0 + k; }
+            else if (k == 32) dst = I_BB1 + m64;
+          }
+        }
+        if (dst >= 0) img[dst] = val;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  // coalesced flush, CTAs start at staggered offsets so they do not all hammer the same addresses at the same moment
+  {
+    auto flush = [&](float* g, int off, int n) {
+      if (g == nullptr) return;
+      const int rot = (int)((blockIdx.x * 97u) % (unsigned)n);
+      for (int e = threadIdx.x; e < n; e += BTHREADS) {
+        int idx = e + rot;
+        if (idx >= n) idx -= n;
+        const float v = img[off + idx];
+        if (v != 0.f) atomicAdd(g + idx, v);
+      }
+    };
+    flush(b.dWr3, I_WR3, 192); flush(b.dbr3, I_BR3, 3);
+    flush(b.dWr2, I_WR2, 4096); flush(b.dbr2, I_BR2, 64);
+    flush(b.dWr1, I_WR1, 4032); flush(b.dbr1, I_BR1, 64);
+    flush(b.dWh, I_WH, 64); flush(b.dbh, I_BH, 1);
+    flush(b.dWs2, I_WS2, 4096); flush(b.dbs2, I_BS2, 64);
+    flush(b.dWs1, I_WS1, 960); flush(b.dbs1, I_BS1, 64);
+    flush(b.dWb2, I_WB2, 1024); flush(b.dbb2, I_BB2, 16);
+    flush(b.dWb1, I_WB1, 64 * in0); flush(b.dbb1, I_BB1, 64);
   }
 }
 
 }  // namespace
 
 int cnb_field_mixed_bwd_umma(const cnb_field* f, const cnb_samples* s, const float* d_density, const float* d_rgb, const float* d_sem, float* ctx,
-                             cudaStream_t stream);  // field_mixed_bwd_umma.cu: tcgen05 / TMEM variant of the dW contraction
-
-int cnb_field_mixed_bwd(const cnb_field* f, const cnb_samples* s, const float* d_density, const float* d_rgb, const float* d_sem, float* ctx,
                         cudaStream_t stream) {
-  static const bool use_umma = [] { const char* e = getenv("CNB_FIELD_BWD_UMMA"); return e != nullptr && e[0] == '1'; }();
-  if (use_umma) return cnb_field_mixed_bwd_umma(f, s, d_density, d_rgb, d_sem, ctx, stream);
   BwdArgs b;
   fill_args(f, s, b.m);
   const int64_t N = s->num_rays * s->samples_per_ray;
@@ -572,13 +675,13 @@ int cnb_field_mixed_bwd(const cnb_field* f, const cnb_samples* s, const float* d
   b.d_embedding = f->appearance_mode == CNB_APP_PER_CAMERA ? f->d_embedding : nullptr;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(k_field_mixed_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD) != cudaSuccess) return cnb_check_launch("field_mixed_bwd attr");
+    if (cudaFuncSetAttribute(k_field_mixed_bwd_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD) != cudaSuccess) return cnb_check_launch("field_mixed_bwd_umma attr");
     configured = true;
   }
   const int64_t nbatches = (N + BATCH - 1) / BATCH;
   int64_t blocks = nbatches < (int64_t)cnb_num_sms() ? nbatches : (int64_t)cnb_num_sms();
-  k_field_mixed_bwd<<<(int)blocks, THREADS, SMEM_BWD, stream>>>(b);
-  int rc = cnb_check_launch("field_mixed_bwd");
+  k_field_mixed_bwd_umma<<<(int)blocks, BTHREADS, SMEM_BWD, stream>>>(b);
+  int rc = cnb_check_launch("field_mixed_bwd_umma");
   if (rc) return rc;
   return cnb_hashgrid_bwd(&f->grid, b.pos, b.d_x0, N, stream);
 }

@@ -387,3 +387,18 @@ def test_train_step_ray_gradients_and_camera_optimizer(dev, precision):
     tr.train_iteration(3, product_bundle(rays, dev), {k: v.to(dev) for k, v in targets.items()})
     moved = (tr.groups["camera_opt"].flat - before).abs().max().item()
     assert moved > 0, "camera poses did not move"
+
+
+def test_field_backward_tcgen05_variant():
+    """The tcgen05 / TMEM variant of the field backward (CNB_FIELD_BWD_UMMA=1, csrc/field_mixed_bwd_umma.cu) passes the same
+    gradient-parity tests as the default mma.sync kernel.  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, CNB_FIELD_BWD_UMMA="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_model_gpu.py"), "-m", "gpu", "-q", "-x", "-k",
+                          "test_field_backward_mixed_precision or test_train_step_ray_gradients_and_camera_optimizer"],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert "passed" in res.stdout
