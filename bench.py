@@ -419,18 +419,21 @@ def cpu_baseline(sample_rays: int, steps: int, warmup: int):
     rays = synthetic.make_rays(sample_rays, seed=5, num_cameras=NUM_IMAGES)
     tgt = synthetic.make_targets(sample_rays, seed=6)
     times = []
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, eps=1e-15)  # fruit_nerf_config.py:45-60
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        model.zero_grad(set_to_none=True)
+        opt.zero_grad(set_to_none=True)
         out = model(cases.oracle_bundle(rays))
+        metrics = model.get_metrics_dict(out, tgt)  # psnr + distortion, computed every step by the Trainer (fruit_nerf.py:639-645)
         loss = sum(model.get_loss_dict(out, tgt).values())
         loss.backward()
+        opt.step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     t = sum(times) / len(times)
     return {"value": sample_rays / t, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": f"{sample_rays}-ray training step (fwd+bwd, no optimizer) of the same fruit_nerf preset, torch {torch.__version__} CPU, "
+            "sample": f"{sample_rays}-ray training step (fwd + losses/metrics + bwd + Adam) of the same fruit_nerf preset, torch {torch.__version__} CPU, "
                       f"{warmup} warm-up + mean of {steps}", "seconds_per_step": t}
 
 
