@@ -95,6 +95,11 @@ class Field(C.Structure):
     ]
 
 
+class Camera(C.Structure):
+    _fields_ = [("c2w", C.c_float * 12), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("width", C.c_int32), ("height", C.c_int32)]
+
+
 class Rays(C.Structure):
     _fields_ = [
         ("origins", C.c_void_p),
@@ -185,6 +190,7 @@ SIGNATURES = {
     "cnb_position_grad_rays": (C.c_int, [C.POINTER(Grid), C.POINTER(Warp), C.POINTER(Samples), _P, _P, _P, _P]),
     "cnb_density_field_bwd_rays": (C.c_int, [C.POINTER(DensityField), C.POINTER(Samples), _P, _P, _P, _P, _P]),
     "cnb_field_bwd_rays": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cnb_generate_rays": (C.c_int, [C.POINTER(Camera), _P, _I64, C.POINTER(_F), _P, _P, _P, _P, _P, _P, _P]),
     "cnb_sample_spaced": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I64, _I32, _P, _P, _P]),
     "cnb_sample_pdf": (C.c_int, [_P, _F, _P, _P, _P, _I32, _P, _P, _I32, _I64, _I32, _I32, _F, _F, _P, _P, _P, _P]),
     "cnb_weights_fwd": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P]),

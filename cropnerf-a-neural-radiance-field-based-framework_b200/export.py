@@ -10,12 +10,15 @@ collective.
   (``fruit_nerf.py:283-315``): un-occluded semantic render of the rays hitting the box, and the opacity accumulated in
   front of the box (occluded where >= 0.5).
 * :func:`write_ply` -- ``semantics_pc.ply`` in the layout ``segmentation/segmenter.py:210`` reads (float xyz, uchar rgb).
+* :func:`generate_rays` -- device-side ``cam.generate_rays(aabb_box=...)`` (pixel -> ray -> slab test in one kernel).
+* :func:`project_clusters` -- the whole ``get_outputs_for_projections`` loop (``fruit_nerf.py:254-318``) writing the
+  ``super_cluster_k/cam_j/{wo_occ,visible}_cluster_i.png`` tree ``segmentation/merger.py`` reads, sharded over ranks.
 """
 from __future__ import annotations
 
 import struct
 from dataclasses import dataclass
-from typing import Callable, Dict, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -94,6 +97,46 @@ def write_ply(path: str, points: Tensor, rgbs: Tensor) -> None:
         f.write(rec.tobytes())
 
 
+def generate_rays(c2w: Tensor, fx: float, fy: float, cx: float, cy: float, width: int, height: int, device, aabb: Optional[Tensor] = None,
+                  pixel_yx: Optional[Tensor] = None, camera_index: int = 0, count_valid: bool = False):
+    """``cam.generate_rays(camera_indices=0, keep_shape=True, aabb_box=aabb)`` (fruit_nerf.py:283) for one perspective camera
+    on the device: one kernel does pixel -> direction -> normalisation -> pixel_area -> AABB slab test (``cnb_generate_rays``).
+    Returns a flat RayBundle of width*height rays (or of the given integer ``pixel_yx`` [n,2]); with ``aabb`` ([2,3] or [6])
+    ``nears``/``fars`` are set and misses carry 1e10 (``valid = nears < 1e10``, fruit_nerf.py:286).  ``count_valid`` also
+    returns the number of rays that hit the box as a device int32 tensor (no host sync)."""
+    import ctypes as C
+
+    from . import _lib as L
+
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("cropnerf_b200.generate_rays runs on CUDA devices only; there is no CPU fallback")
+    cam = L.Camera()
+    m = c2w.detach().cpu().float().reshape(-1)[:12].tolist()
+    for i in range(12):
+        cam.c2w[i] = m[i]
+    cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height = float(fx), float(fy), float(cx), float(cy), int(width), int(height)
+    pix = None
+    n = int(width) * int(height)
+    if pixel_yx is not None:
+        pix = pixel_yx.to(dev, torch.int32).contiguous()
+        n = pix.shape[0]
+    box = None
+    if aabb is not None:
+        box = (C.c_float * 6)(*[float(v) for v in aabb.detach().cpu().reshape(-1).tolist()])
+    o = torch.empty((n, 3), device=dev, dtype=torch.float32)
+    d = torch.empty((n, 3), device=dev, dtype=torch.float32)
+    area = torch.empty((n, 1), device=dev, dtype=torch.float32)
+    nears = torch.empty((n, 1), device=dev, dtype=torch.float32) if aabb is not None else None
+    fars = torch.empty((n, 1), device=dev, dtype=torch.float32) if aabb is not None else None
+    cnt = torch.zeros((1,), device=dev, dtype=torch.int32) if (count_valid and aabb is not None) else None
+    L.check(L.lib().cnb_generate_rays(C.byref(cam), L.ptr(pix), n, box, o.data_ptr(), d.data_ptr(), area.data_ptr(), L.ptr(nears), L.ptr(fars),
+                                      L.ptr(cnt), L.stream_ptr(dev)), "generate_rays")
+    rb = RayBundle(origins=o, directions=d, pixel_area=area, camera_indices=torch.full((n, 1), int(camera_index), device=dev, dtype=torch.int32),
+                   nears=nears, fars=fars)
+    return (rb, cnt) if count_valid else rb
+
+
 def aabb_near_far(origins: Tensor, directions: Tensor, aabb: Tensor, invalid: float = 1e10) -> Tuple[Tensor, Tensor]:
     """Slab test of rays against an AABB [2,3] (what ``cam.generate_rays(aabb_box=...)`` sets, fruit_nerf.py:283);
     misses get nears = fars = ``invalid``."""
@@ -130,3 +173,101 @@ def render_cluster_projection(model, rays: RayBundle, aabb: Tensor) -> Dict[str,
     visible = sem.clone()
     visible[front >= 0.5] = 0.0
     return {"valid": valid, "semantics": sem, "front_opacity": front, "visible": visible}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# "next" row f3: the files the downstream stages read (segmentation/segmenter.py, segmentation/merger.py)
+
+
+@dataclass
+class PinholeCamera:
+    """What the projection loop needs of one nerfstudio ``Cameras`` entry (perspective, no distortion)."""
+
+    c2w: Tensor  # [3,4]
+    fx: float
+    fy: float
+    cx: float
+    cy: float
+    width: int
+    height: int
+
+
+def load_cluster_info(path: str) -> List[dict]:
+    """``all_super_cluster_info_nsub_*.npy`` written by segmentation/segmenter.py:153-181: a pickled list of
+    ``{'aabb': float[k,2,3] (min,max per sub-cluster), 'pcd': {sub_id: float[n,3]}}`` (read at fruit_nerf.py:265)."""
+    data = np.load(path, allow_pickle=True)
+    out = []
+    for item in list(data):
+        aabb = np.asarray(item["aabb"], dtype=np.float32)
+        if aabb.ndim != 3 or aabb.shape[1:] != (2, 3):
+            raise ValueError(f"{path}: cluster aabb has shape {aabb.shape}, expected [k,2,3]")
+        out.append({"aabb": aabb, "pcd": item.get("pcd", {})})
+    return out
+
+
+def save_cluster_info(path: str, clusters: List[dict]) -> None:
+    np.save(path, np.asarray(clusters, dtype=object), allow_pickle=True)
+
+
+def to_png_bytes(image: Tensor) -> np.ndarray:
+    """torchvision.utils.save_image quantisation (used at fruit_nerf.py:295-315): ``clamp(x*255 + 0.5, 0, 255)`` -> uint8 HxWx3."""
+    img = image.detach().float().cpu()
+    if img.dim() == 2:
+        img = img[..., None].expand(-1, -1, 3)
+    return img.mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8).numpy()
+
+
+def write_png(path: str, image: Tensor) -> None:
+    import cv2
+
+    arr = to_png_bytes(image)
+    if not cv2.imwrite(path, np.ascontiguousarray(arr[..., ::-1])):  # cv2 wants BGR
+        raise IOError(f"could not write {path}")
+
+
+def project_clusters(model, cameras: Sequence[PinholeCamera], clusters: List[dict], out_dir: str, rank: int = 0, world_size: int = 1,
+                     segmentation_files: Optional[Sequence[str]] = None) -> Dict[str, int]:
+    """``FruitModel.get_outputs_for_projections`` (fruit_nerf.py:254-318) with the (super-cluster, camera) pairs sharded over
+    the ranks (no communication): for every sub-cluster AABB of a super-cluster and every camera, rays are generated and clipped
+    on the device, the un-occluded semantic render and the opacity in front of the box are computed on the hit rays only, and
+    ``super_cluster_{k}/cam_{j}/wo_occ_cluster_{i}.png`` / ``visible_cluster_{i}.png`` are written -- the layout
+    segmentation/merger.py:219-333 reads.  Returns counters (pairs, images, rays rendered)."""
+    import os
+    import shutil
+
+    dev = model.device
+    stats = {"pairs": 0, "images": 0, "rays": 0}
+    pair = 0
+    for i_sc, cluster in enumerate(clusters):
+        boxes = torch.as_tensor(cluster["aabb"], dtype=torch.float32)
+        for cam_idx, cam in enumerate(cameras):
+            mine = pair % world_size == rank
+            pair += 1
+            if not mine:
+                continue
+            cam_dir = os.path.join(out_dir, f"super_cluster_{i_sc}", f"cam_{cam_idx}")
+            os.makedirs(cam_dir, exist_ok=True)
+            stats["pairs"] += 1
+            for i in range(boxes.shape[0]):
+                rays, cnt = generate_rays(cam.c2w, cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height, dev, aabb=boxes[i], count_valid=True)
+                n = cam.width * cam.height
+                wo_occ = torch.zeros((n, 3), device=dev)
+                visible = wo_occ
+                if int(cnt.item()) >= 10:  # fruit_nerf.py:293: fewer than 10 hit rays -> black images
+                    valid = rays.nears[:, 0] < 1e10
+                    sub = rays[valid]
+                    stats["rays"] += 2 * int(sub.origins.shape[0])
+                    out = model.get_outputs_for_camera_jagged_ray_bundle(sub)
+                    wo_occ[valid] = out["semantics"].to(dev).expand(-1, 3)
+                    sub.fars = sub.nears
+                    sub.nears = torch.zeros_like(sub.nears)
+                    front = torch.zeros((n,), device=dev)
+                    front[valid] = model.get_density_for_camera_ray_bundle(sub).to(dev)
+                    visible = wo_occ.clone()
+                    visible[front >= 0.5] = 0.0
+                write_png(os.path.join(cam_dir, f"wo_occ_cluster_{i}.png"), wo_occ.view(cam.height, cam.width, 3))
+                write_png(os.path.join(cam_dir, f"visible_cluster_{i}.png"), visible.view(cam.height, cam.width, 3))
+                stats["images"] += 2
+            if segmentation_files is not None:
+                shutil.copy(segmentation_files[cam_idx], cam_dir)
+    return stats

@@ -230,6 +230,20 @@ int cnb_final_composite_bwd(const float* density, const float* rgb, const float*
 int cnb_interlevel_fused(const float* c, const float* w, const float* cp, const float* wp, const float* density_p, const float* euclid_bins_p,
                          int64_t R, int32_t Sc, int32_t Sp, float grad_scale, float* loss_out, float* d_density_p, cnb_stream_t stream);
 
+/* ---- f1 ("next" row): ray generation + AABB clipping on the device (fruit_nerf.py:283-288) ------------------------------ */
+/* nerfstudio Cameras.generate_rays for one perspective camera without distortion */
+typedef struct cnb_camera {
+  float c2w[12];   /* camera-to-world [3,4], row-major (OpenGL axes: +x right, +y up, camera looks down -z) */
+  float fx, fy, cx, cy;
+  int32_t width, height;
+} cnb_camera;
+/* cam / aabb are HOST pointers (aabb = min xyz, max xyz; NULL = no clipping).  pixel_yx (device, optional) [n,2] integer pixel
+ * rows/columns; NULL = every pixel of the image in row-major order (n = width*height).  Outputs (device): origins, directions
+ * [n,3]; pixel_area [n] (optional); nears, fars [n] (with aabb: slab test, misses = 1e10 as nerfstudio's intersect_aabb);
+ * valid_count (optional, device int32, ACCUMULATED) = rays that hit the box. */
+int cnb_generate_rays(const cnb_camera* cam, const int32_t* pixel_yx, int64_t n, const float* aabb, float* origins, float* directions,
+                      float* pixel_area, float* nears, float* fars, int32_t* valid_count, cnb_stream_t stream);
+
 /* ---- f2: optimiser (torch.optim.Adam semantics; fruit_nerf_config.py:45-60) -------------------------------- */
 int cnb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float inv_grad_scale, cnb_stream_t stream);

@@ -841,3 +841,47 @@ def exponential_decay_lr(step: int, lr_init: float, lr_final: float, max_steps: 
     """nerfstudio/engine/schedulers.py ExponentialDecayScheduler without warm-up (fruit_nerf_config.py:45-60)."""
     t = min(max(step / max_steps, 0.0), 1.0)
     return math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
+
+
+# --------------------------------------------------------------------------------------------------------
+# f1 ("next" row of SURVEY.md section 8): ray generation -- nerfstudio/cameras/cameras.py Cameras.generate_rays /
+#     _generate_rays_from_coords (perspective, no distortion) and nerfstudio/utils/math.py intersect_aabb, as used by
+#     cam.generate_rays(camera_indices=0, keep_shape=True, aabb_box=aabb) at fruit_nerf.py:283.  [verify]: restated from the
+#     published nerfstudio 1.1.3 source, not line-checked (nerfstudio is absent here).
+# --------------------------------------------------------------------------------------------------------
+
+
+def generate_pinhole_rays(c2w: Tensor, fx: float, fy: float, cx: float, cy: float, coords_yx: Tensor):
+    """coords_yx [..., 2] pixel coordinates INCLUDING the 0.5 pixel-centre offset -> (origins, directions, pixel_area)."""
+    y, x = coords_yx[..., 0], coords_yx[..., 1]
+    coord = torch.stack([(x - cx) / fx, -(y - cy) / fy], -1)
+    coord_x_offset = torch.stack([(x - cx + 1) / fx, -(y - cy) / fy], -1)
+    coord_y_offset = torch.stack([(x - cx) / fx, -(y - cy + 1) / fy], -1)
+    coord_stack = torch.stack([coord, coord_x_offset, coord_y_offset], dim=0)
+    directions_stack = torch.cat([coord_stack, -torch.ones_like(coord_stack[..., :1])], dim=-1)
+    rotation = c2w[:3, :3]
+    directions_stack = torch.sum(directions_stack[..., None, :] * rotation, dim=-1)
+    norm = torch.linalg.norm(directions_stack, dim=-1, keepdim=True)
+    directions_stack = directions_stack / norm
+    directions = directions_stack[0]
+    dx = torch.sqrt(torch.sum((directions - directions_stack[1]) ** 2, dim=-1))
+    dy = torch.sqrt(torch.sum((directions - directions_stack[2]) ** 2, dim=-1))
+    pixel_area = (dx * dy)[..., None]
+    origins = c2w[:3, 3].expand(directions.shape)
+    return origins, directions, pixel_area
+
+
+def intersect_aabb(origins: Tensor, directions: Tensor, aabb: Tensor, max_bound: float = 1e10, invalid_value: float = 1e10):
+    """aabb [6] = (min xyz, max xyz) -> (t_min, t_max), both `invalid_value` where the ray misses the box."""
+    tx_min = (aabb[:3] - origins) / directions
+    tx_max = (aabb[3:] - origins) / directions
+    t_min = torch.stack((tx_min, tx_max)).amin(dim=0)
+    t_max = torch.stack((tx_min, tx_max)).amax(dim=0)
+    t_min = t_min.amax(dim=-1)
+    t_max = t_max.amin(dim=-1)
+    t_min = torch.clamp(t_min, min=0, max=max_bound)
+    t_max = torch.clamp(t_max, min=0, max=max_bound)
+    cond = t_max <= t_min
+    t_min = torch.where(cond, torch.full_like(t_min, invalid_value), t_min)
+    t_max = torch.where(cond, torch.full_like(t_max, invalid_value), t_max)
+    return t_min, t_max

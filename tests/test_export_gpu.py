@@ -1,0 +1,88 @@
+"""Projection export ("next" rows f1 + f3): ``project_clusters`` (device ray generation + AABB clip -> render of the hit rays ->
+PNG tree for segmentation/merger.py) against the oracle running the reference's loop (fruit_nerf.py:254-318) ray by ray."""
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from helpers import product_model
+
+from cropnerf_b200 import export, synthetic
+from oracle import cases
+from oracle import nerfstudio_torch as ns
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_images(oracle, cam, box):
+    H, W = cam.height, cam.width
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    coords = torch.stack([yy, xx], -1).reshape(-1, 2).float() + 0.5
+    o, d, area = ns.generate_pinhole_rays(cam.c2w, cam.fx, cam.fy, cam.cx, cam.cy, coords)
+    tmin, tmax = ns.intersect_aabb(o, d, torch.as_tensor(box, dtype=torch.float32).reshape(-1))
+    valid = tmin < 1e10
+    wo = torch.zeros((H * W, 3))
+    vis = torch.zeros((H * W, 3))
+    if int(valid.sum()) >= 10:
+        rb = ns.RayBundle(origins=o[valid].contiguous(), directions=d[valid], pixel_area=area[valid], camera_indices=torch.zeros((int(valid.sum()), 1), dtype=torch.long),
+                          nears=tmin[valid][:, None], fars=tmax[valid][:, None])
+        with torch.no_grad():
+            wo[valid] = oracle(rb)["semantics"].expand(-1, 3)
+            rb.fars = rb.nears
+            rb.nears = torch.zeros_like(rb.nears)
+            front = torch.zeros(H * W)
+            front[valid] = oracle.get_density_for_ray_bundle(rb)
+        vis = wo.clone()
+        vis[front >= 0.5] = 0.0
+    return export.to_png_bytes(wo.view(H, W, 3)), export.to_png_bytes(vis.view(H, W, 3)), valid.view(H, W)
+
+
+@pytest.mark.parametrize("world_size", [1, 2])
+def test_project_clusters_png_tree_matches_oracle(dev, tmp_path, world_size):
+    cfg = cases.make_config(dict(log2_hashmap_size=14))
+    oracle, state = cases.build_oracle(cfg, 6, 0, 0.5)
+    oracle.eval()
+    model = product_model(cfg, state, 6, dev, False)
+    c2ws = synthetic.make_cameras(3, seed=7)
+    cams = [export.PinholeCamera(c2w=c2ws[i], fx=60.0, fy=60.0, cx=24.0, cy=18.0, width=48, height=36) for i in range(3)]
+    clusters = [
+        {"aabb": np.array([[[-0.25, -0.2, -0.2], [0.15, 0.2, 0.25]], [[0.1, 0.1, 0.1], [0.4, 0.35, 0.3]]], dtype=np.float32), "pcd": {}},
+        {"aabb": np.array([[[5.0, 5.0, 5.0], [5.1, 5.1, 5.1]]], dtype=np.float32), "pcd": {}},  # off-screen box: black images
+    ]
+    info = str(tmp_path / "all_super_cluster_info_nsub_2.npy")
+    export.save_cluster_info(info, clusters)
+    clusters = export.load_cluster_info(info)
+    seg = []
+    for i in range(3):
+        p = str(tmp_path / f"seg_{i}.png")
+        cv2.imwrite(p, np.full((4, 4), i, np.uint8))
+        seg.append(p)
+    out_dir = str(tmp_path / "projection")
+    total = {"pairs": 0, "images": 0, "rays": 0}
+    for rank in range(world_size):  # ranks write disjoint (super-cluster, camera) directories; no communication
+        st = export.project_clusters(model, cams, clusters, out_dir, rank=rank, world_size=world_size, segmentation_files=seg)
+        for k in total:
+            total[k] += st[k]
+    assert total["pairs"] == 6 and total["images"] == 2 * (2 * 3 + 1 * 3) and total["rays"] > 0
+    n_checked = 0
+    for k, cluster in enumerate(clusters):
+        for j, cam in enumerate(cams):
+            cam_dir = os.path.join(out_dir, f"super_cluster_{k}", f"cam_{j}")
+            assert os.path.exists(os.path.join(cam_dir, f"seg_{j}.png"))
+            for i in range(cluster["aabb"].shape[0]):
+                wo_ref, vis_ref, valid = _oracle_images(oracle, cam, cluster["aabb"][i])
+                wo = cv2.imread(os.path.join(cam_dir, f"wo_occ_cluster_{i}.png"), cv2.IMREAD_COLOR)[..., ::-1]
+                vis = cv2.imread(os.path.join(cam_dir, f"visible_cluster_{i}.png"), cv2.IMREAD_COLOR)[..., ::-1]
+                assert wo.shape == (36, 48, 3)
+                if k == 1:
+                    assert not wo.any() and not vis.any() and not valid.any()
+                    continue
+                assert valid.sum() > 50, "test boxes should be on screen"
+                # 8-bit images: allow one code of rounding, on all but 0.5 % of the pixels (slab-test ties on the box silhouette)
+                assert (np.abs(wo.astype(int) - wo_ref.astype(int)) <= 1).mean() >= 0.995
+                assert (np.abs(vis.astype(int) - vis_ref.astype(int)) <= 1).mean() >= 0.995
+                assert not wo[~valid.numpy()].any()
+                n_checked += 1
+    assert n_checked == 6

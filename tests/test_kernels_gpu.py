@@ -289,3 +289,38 @@ def test_adam_matches_torch(dev):
         opt.step()
         ops.adam_step(p, grad.to(dev), m, v, 1e-2, step)
         assert_close(p, ref.detach(), 1e-5, f"adam step {step}", floor=1e-3)
+
+
+@pytest.mark.parametrize("with_pixels", [False, True])
+def test_generate_rays_and_aabb_clip(dev, with_pixels):
+    """Device ray generation + AABB slab test ("next" row f1) against the restated nerfstudio generate_rays / intersect_aabb."""
+    from cropnerf_b200 import synthetic
+    from cropnerf_b200.export import generate_rays
+
+    W, H = 97, 61
+    c2w = synthetic.make_cameras(5, seed=3)[2]
+    fx, fy, cx, cy = 80.0, 82.0, 48.5, 30.25
+    aabb = torch.tensor([[-0.3, -0.2, -0.25], [0.2, 0.3, 0.15]])
+    if with_pixels:
+        g = torch.Generator().manual_seed(1)
+        pix = torch.stack([torch.randint(0, H, (500,), generator=g), torch.randint(0, W, (500,), generator=g)], -1)
+        coords = pix.float() + 0.5
+    else:
+        pix = None
+        yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+        coords = torch.stack([yy, xx], -1).reshape(-1, 2).float() + 0.5
+    o_ref, d_ref, a_ref = ns.generate_pinhole_rays(c2w, fx, fy, cx, cy, coords)
+    tmin, tmax = ns.intersect_aabb(o_ref, d_ref, aabb.reshape(-1))
+    rb, cnt = generate_rays(c2w, fx, fy, cx, cy, W, H, dev, aabb=aabb, pixel_yx=pix, count_valid=True)
+    assert_close(rb.origins, o_ref, 1e-6, "origins")
+    assert_close(rb.directions, d_ref, 2e-6, "directions", floor=1e-2)
+    assert_close(rb.pixel_area, a_ref, 2e-3, "pixel_area", floor=1e-9)
+    hit_ref = tmin < 1e10
+    hit = rb.nears[:, 0].cpu() < 1e10
+    assert (hit == hit_ref).float().mean().item() >= 0.999
+    both = hit & hit_ref
+    assert both.sum() > 50, "test scene should hit the box"
+    assert_close(rb.nears[:, 0].cpu()[both], tmin[both], 1e-4, "nears", floor=1e-2)
+    assert_close(rb.fars[:, 0].cpu()[both], tmax[both], 1e-4, "fars", floor=1e-2)
+    assert int(cnt.item()) == int(hit.sum().item())
+    assert torch.allclose(rb.directions.norm(dim=-1).cpu(), torch.ones(rb.directions.shape[0]), atol=1e-5)
