@@ -271,3 +271,85 @@ def project_clusters(model, cameras: Sequence[PinholeCamera], clusters: List[dic
             if segmentation_files is not None:
                 shutil.copy(segmentation_files[cam_idx], cam_dir)
     return stats
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# "next" row f4: volumetric export (scripts/exporter.py ExportSemanticPointCloud -> export/exporter_utils.py sample_volume)
+
+
+def aabb_corners(aabb) -> Tensor:
+    """``get_corners_of_aabb`` (data/fruit_datamanager.py:42-68): the 8 corners, x fastest, then y, then z."""
+    lo, hi = [float(v) for v in aabb[0]], [float(v) for v in aabb[1]]
+    return torch.tensor([[(hi if i & 1 else lo)[0], (hi if i & 2 else lo)[1], (hi if i & 4 else lo)[2]] for i in range(8)], dtype=torch.float32)
+
+
+def volume_surface_rays(aabb, num_points_per_side: int) -> Tuple[Tensor, Tensor, float]:
+    """``sample_surface_points`` + ``OrthographicRayGenerator`` (data/fruit_datamanager.py:71-120,
+    components/ray_generators.py:35-64): a regular grid on the z = z_min face of the box (``int(dx/dz*n)`` x ``int(dy/dz*n)``
+    points, ``torch.linspace`` + ij-meshgrid order) and the common ray direction / length.  Returns (origins [M,3],
+    direction [3], far).  The reference's quirks are kept: the ray length is ``sign(z_max)*|z_min| + |z_max|`` (= z_max - z_min
+    only when the box straddles z = 0)."""
+    c = aabb_corners(aabb)
+    c1, c2, c3, c4 = c[0], c[1], c[2], c[-1]
+    ext = (c.max(dim=0).values - c.min(dim=0).values).abs()
+    const_axis = int(torch.argmax(((c1 == c2) & (c2 == c3)).to(torch.int)))
+    ax_x = int(torch.argmax((c1 - c2).abs()))
+    ax_y = int(torch.argmax((c1 - c3).abs()))
+    x = torch.linspace(float(c1[ax_x]), float(c2[ax_x]), int(ext[0] / ext[const_axis] * num_points_per_side), dtype=torch.float32)
+    y = torch.linspace(float(c1[ax_y]), float(c3[ax_y]), int(ext[1] / ext[const_axis] * num_points_per_side), dtype=torch.float32)
+    xx, yy = torch.meshgrid(x, y, indexing="ij")
+    origins = torch.column_stack((xx.flatten(), yy.flatten(), torch.full_like(xx.flatten(), float(c3[const_axis]))))
+    plane = torch.tensor([0.0, 0.0, float(torch.sign(c4[const_axis]) * c1[const_axis].abs() + c4[const_axis].abs())])
+    far = float(torch.linalg.norm(plane))
+    direction = torch.nn.functional.normalize(plane[None])[0]
+    return origins, direction, far
+
+
+def sample_volume(model, aabb, num_points_per_side: int, num_rays_per_batch: int = 512, rank: int = 0, world_size: int = 1,
+                  semantic_threshold: float = 3.0, density_threshold: float = 70.0, colormap_threshold: float = 0.999) -> Dict[str, Dict[str, Tensor]]:
+    """The render loop of ``sample_volume`` (export/exporter_utils.py:88-172) for a model in ``test_mode='export'`` after
+    ``setup_inference`` (uniform sampler, contraction off): orthographic rays from the z_min face, ``num_inference_samples``
+    field evaluations per ray (no compositing), per-SAMPLE thresholds ``semantic >= 3``, ``density >= 70``,
+    ``semantics_colormap >= 0.999``.  The rays of the face are split across ranks by contiguous range, no communication.
+    Thresholding and compaction run on the device; only kept points are copied to the host.  Returns the three clouds of the
+    reference -- ``semantic_colormap``, ``semantic``, ``density`` -- as {'points' [n,3], 'colors' [n,4] = (rgb, sigmoid(.))};
+    the open3d rescaling / PLY writing that follows in the reference is :func:`rescale_to_dataparser` + :func:`write_ply`."""
+    if model.test_mode != "export":
+        raise RuntimeError("sample_volume needs a model built with test_mode='export' and setup_inference() applied (scripts/exporter.py:88-91)")
+    dev = model.device
+    origins, direction, far = volume_surface_rays(aabb, num_points_per_side)
+    lo, hi = shard_range(origins.shape[0], rank, world_size)
+    origins = origins[lo:hi].to(dev)
+    clouds = {k: {"points": [], "colors": []} for k in ("semantic_colormap", "semantic", "density")}
+    n_samples = 0
+    for start in range(0, origins.shape[0], num_rays_per_batch):
+        o = origins[start : start + num_rays_per_batch].contiguous()
+        n = o.shape[0]
+        rb = RayBundle(origins=o, directions=direction.to(dev).repeat(n, 1), pixel_area=torch.zeros((n, 1), device=dev), camera_indices=None,
+                       nears=torch.zeros((n, 1), device=dev), fars=torch.full((n, 1), far, device=dev))
+        with torch.no_grad():
+            out = model(rb)
+        pts = out["point_location"].reshape(-1, 3)
+        sem = out["semantics"].reshape(-1)
+        den = out["density"].reshape(-1)
+        rgb = out["rgb"].reshape(-1, 3)
+        label = out["semantics_colormap"].reshape(-1).to(sem.dtype)
+        n_samples += int(sem.shape[0])
+        m_den = den >= density_threshold
+        m_sem = (sem >= semantic_threshold) & m_den
+        m_cm = (label >= colormap_threshold) & m_den
+        for key, mask, alpha in (("semantic_colormap", m_cm, torch.sigmoid(sem)), ("semantic", m_sem, torch.sigmoid(sem)), ("density", m_den, torch.sigmoid(den))):
+            idx = torch.nonzero(mask)[:, 0]
+            clouds[key]["points"].append(pts[idx].cpu())
+            clouds[key]["colors"].append(torch.cat([rgb[idx], alpha[idx, None]], dim=-1).cpu())
+    result = {}
+    for key, parts in clouds.items():
+        result[key] = {"points": torch.cat(parts["points"]) if parts["points"] else torch.empty((0, 3)),
+                       "colors": torch.cat(parts["colors"]) if parts["colors"] else torch.empty((0, 4))}
+    result["stats"] = {"rays": int(origins.shape[0]), "samples": n_samples}
+    return result
+
+
+def rescale_to_dataparser(points: Tensor, dataparser_scale: float) -> Tensor:
+    """``pcd.scale(1/scale).scale(2)`` about the origin (export/exporter_utils.py:186-193): back to the capture's metric frame."""
+    return points * (2.0 / float(dataparser_scale))

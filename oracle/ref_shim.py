@@ -426,6 +426,49 @@ def run_mode_case(kind: str, which: str, num_images: int = 20, seed: int = 0) ->
     return {k: out[k].detach().numpy() for k in keys if k in out}
 
 
+VOLUME_BOXES = {
+    # scripts/exporter.py:70-73 defaults; a box entirely above z = 0 (exercises the reference's sign()*|z_min| + |z_max| ray length);
+    # an anisotropic one (grid counts int(dx/dz*n), int(dy/dz*n))
+    "exporter_default": ((-1.0, -1.0, -1.0 + 0.318), (1.0, 1.0, 1.0 + 0.318)),
+    "positive_z": ((-0.5, -0.25, 0.125), (0.5, 0.75, 0.625)),
+    "anisotropic": ((-0.3, -0.1, -0.4), (0.6, 0.2, 0.1)),
+}
+
+
+def run_volume_rays_case(n: int = 13, batch: int = 64) -> Dict[str, np.ndarray]:
+    """The reference's volumetric-export ray source executed verbatim: ``get_corners_of_aabb`` + ``sample_surface_points``
+    (data/fruit_datamanager.py:42-120; extracted with ``ast`` because that file imports the nerfstudio data stack) feeding
+    ``OrthographicRayGenerator`` (components/ray_generators.py, imported through the shims), all batches concatenated."""
+    import ast
+
+    if not reference_available():
+        raise RuntimeError("/root/reference is not present on this machine")
+    install_shims()
+    src_path = os.path.join(REFERENCE_ROOT, "fruit_nerf", "data", "fruit_datamanager.py")
+    tree = ast.parse(open(src_path).read())
+    wanted = [node for node in tree.body if isinstance(node, ast.FunctionDef) and node.name in ("get_corners_of_aabb", "sample_surface_points")]
+    ns_exec: Dict[str, object] = {"torch": torch, "np": np}
+    exec(compile(ast.Module(body=wanted, type_ignores=[]), src_path, "exec"), ns_exec)
+    from fruit_nerf.components.ray_generators import OrthographicRayGenerator  # noqa: E402
+
+    out: Dict[str, np.ndarray] = {}
+    for name, box in VOLUME_BOXES.items():
+        corners = ns_exec["get_corners_of_aabb"](aabb=box, device="cpu")
+        pts, plane = ns_exec["sample_surface_points"](corners, n=n, device="cpu", noise=False)
+        gen = OrthographicRayGenerator(surface_points=pts, plane_normal=plane, ray_batch_size=batch, device="cpu", aabb=box)
+        o, d, f, count = [], [], [], 0
+        while sum(x.shape[0] for x in o) < pts.shape[0]:
+            count += 1
+            rb = gen(count)
+            o.append(rb.origins); d.append(rb.directions); f.append(rb.fars)
+        out[name + "_origins"] = torch.cat(o).numpy()
+        out[name + "_directions"] = torch.cat(d).numpy()
+        out[name + "_fars"] = torch.cat(f).numpy()
+        out[name + "_aabb"] = np.asarray(box, dtype=np.float32)
+    out["n"] = np.asarray(n)
+    return out
+
+
 def main() -> None:
     from . import cases
 
@@ -440,6 +483,10 @@ def main() -> None:
         path = os.path.join(out_dir, "ref_mode_" + kind + ".npz")
         np.savez_compressed(path, **res)
         print("reference-executed", kind, "->", path, {k: v.shape for k, v in res.items()})
+    res = run_volume_rays_case()
+    path = os.path.join(out_dir, "ref_volume_rays.npz")
+    np.savez_compressed(path, **res)
+    print("reference-executed volume rays ->", path, {k: v.shape for k, v in res.items()})
 
 
 if __name__ == "__main__":

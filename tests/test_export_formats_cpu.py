@@ -94,3 +94,16 @@ def test_oracle_intersect_aabb_hand_cases():
     tmin, tmax = ns.intersect_aabb(o, d, aabb)
     assert tmin.tolist() == [2.0, 1e10, 0.0, 1e10]  # hit, parallel miss, origin inside (near clamps to 0), offset miss
     assert tmax.tolist() == [4.0, 1e10, 1.0, 1e10]
+
+
+def test_volume_surface_rays_match_reference_executed_fixture():
+    """tests/golden/ref_volume_rays.npz = the reference's get_corners_of_aabb + sample_surface_points +
+    OrthographicRayGenerator executed verbatim (oracle/ref_shim.py:run_volume_rays_case): bit for bit."""
+    ref = np.load(os.path.join(helpers.GOLDEN, "ref_volume_rays.npz"))
+    n = int(ref["n"])
+    for name in ("exporter_default", "positive_z", "anisotropic"):
+        o, d, far = export.volume_surface_rays(ref[name + "_aabb"], n)
+        np.testing.assert_array_equal(o.numpy(), ref[name + "_origins"])
+        np.testing.assert_array_equal(d.numpy()[None].repeat(o.shape[0], 0), ref[name + "_directions"])
+        assert np.all(ref[name + "_fars"] == np.float32(far))
+    assert np.allclose(export.rescale_to_dataparser(torch.ones(2, 3), 0.5).numpy(), 4.0)

@@ -86,3 +86,45 @@ def test_project_clusters_png_tree_matches_oracle(dev, tmp_path, world_size):
                 assert not wo[~valid.numpy()].any()
                 n_checked += 1
     assert n_checked == 6
+
+
+@pytest.mark.parametrize("world_size", [1, 2])
+def test_sample_volume_matches_oracle(dev, world_size):
+    """Volumetric export (row f4): orthographic rays from the box face, per-sample thresholds, device-side compaction."""
+    cfg = cases.make_config(dict(log2_hashmap_size=14))
+    oracle, state = cases.build_oracle(cfg, 6, 0, 0.5)
+    oracle.test_mode = oracle.field.test_mode = "export"
+    oracle.setup_inference(True, 40)
+    oracle.eval()
+    model = product_model(cfg, state, 6, dev, False, test_mode="export")
+    model.field.test_mode = "export"
+    model.setup_inference(True, 40)
+    model.eval()
+    box = ((-0.6, -0.5, -0.4), (0.5, 0.6, 0.7))
+    n_side = 12
+    with pytest.raises(RuntimeError, match="export"):
+        export.sample_volume(product_model(cfg, state, 6, dev, False), box, n_side)
+    o, d, far = export.volume_surface_rays(box, n_side)
+    rb = ns.RayBundle(origins=o, directions=d.repeat(o.shape[0], 1), pixel_area=torch.zeros(o.shape[0], 1), camera_indices=None,
+                      nears=torch.zeros(o.shape[0], 1), fars=torch.full((o.shape[0], 1), far))
+    with torch.no_grad():
+        ref = oracle(rb)
+    den, sem = ref["density"].reshape(-1), ref["semantics"].reshape(-1)
+    thr_d, thr_s = float(den.median()), float(sem[den >= den.median()].median())
+    parts = [export.sample_volume(model, box, n_side, num_rays_per_batch=50, rank=r, world_size=world_size, semantic_threshold=thr_s, density_threshold=thr_d)
+             for r in range(world_size)]
+    assert sum(p["stats"]["rays"] for p in parts) == o.shape[0] and sum(p["stats"]["samples"] for p in parts) == den.numel()
+    masks = {"density": den >= thr_d, "semantic": (sem >= thr_s) & (den >= thr_d), "semantic_colormap": (ref["semantics_colormap"].reshape(-1) >= 0.999) & (den >= thr_d)}
+    for key, mask in masks.items():
+        pts = torch.cat([p[key]["points"] for p in parts])
+        col = torch.cat([p[key]["colors"] for p in parts])
+        n_ref = int(mask.sum())
+        assert abs(pts.shape[0] - n_ref) <= max(2, int(2e-3 * n_ref)), (key, pts.shape[0], n_ref)  # threshold ties at fp32 round-off
+        assert col.shape == (pts.shape[0], 4)
+        if key == "density":
+            assert n_ref > 100
+        if pts.shape[0] == n_ref and n_ref:
+            ref_pts = ref["point_location"].reshape(-1, 3)[mask]
+            if torch.allclose(pts, ref_pts, atol=1e-6):  # same samples kept: colours must agree too
+                ref_rgb = ref["rgb"].reshape(-1, 3)[mask]
+                assert (col[:, :3] - ref_rgb).abs().max() < 2e-4
