@@ -127,6 +127,8 @@ def save_nerfstudio_checkpoint(directory: str, model, step: int, trainer=None) -
         for name, group in trainer.groups.items():
             ckpt["optimizers"][name] = _adam_state_dict(group, trainer.optimizers[name], trainer.opt_step)
             ckpt["schedulers"][name] = {"last_epoch": int(step), "_step_count": int(step) + 1}
+        if getattr(trainer, "grad_scaler", None) is not None:
+            ckpt["scalers"] = trainer.grad_scaler.state_dict()
     path = os.path.join(directory, checkpoint_name(step))
     torch.save(ckpt, path)
     return path
@@ -161,4 +163,6 @@ def resume_trainer(trainer, path_or_state) -> Tuple[int, Optional[int]]:
             opt_step = int(float(st["step"]))
     if opt_step is not None:
         trainer.opt_step = opt_step
+    if getattr(trainer, "grad_scaler", None) is not None:
+        trainer.grad_scaler.load_state_dict(loaded.get("scalers", {}))
     return step, opt_step

@@ -141,8 +141,14 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
 // serialises the LSU -- the pass then runs at 2.0 TB/s instead of 6.3 TB/s on B200 (tests/micro/adam_bench.cu:
 // a_current vs f_late_zero; store cache policy makes no difference).
 __global__ void __launch_bounds__(256) k_adam_zero4(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
-                                                    int64_t n4, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_scale) {
+                                                    int64_t n4, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_scale,
+                                                    const int32_t* __restrict__ skip) {
   const float step_size = lr / bc1;
+  if (skip != nullptr && __ldg(skip) != 0) {
+    // GradScaler.step: a non-finite gradient was found -> the optimizer step is skipped, the gradient is still cleared
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 gi = g[i], mi = m[i], vi = v[i], pi = p[i];
     float* gp = &gi.x; float* mp = &mi.x; float* vp = &vi.x; float* pp = &pi.x;
@@ -158,6 +164,20 @@ __global__ void __launch_bounds__(256) k_adam_zero4(float4* __restrict__ p, floa
     m[i] = mi; v[i] = vi; p[i] = pi;
     g[i] = make_float4(z, z, z, z);
   }
+}
+
+// torch.amp GradScaler's inf check (_amp_foreach_non_finite_check_and_unscale_) over one flat gradient group: found_inf |= any !isfinite
+__global__ void __launch_bounds__(256) k_grad_nonfinite(const float4* __restrict__ g, int64_t n4, const float* __restrict__ tail, int ntail,
+                                                        int32_t* __restrict__ found_inf) {
+  bool bad = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(g + i);
+    // (x - x) is 0 for finite x and NaN for inf / NaN
+    const float t = (v.x - v.x) + (v.y - v.y) + (v.z - v.z) + (v.w - v.w);
+    bad |= !(t == 0.0f);
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) { const float x = tail[threadIdx.x]; bad |= !((x - x) == 0.0f); }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(found_inf, 1);
 }
 
 int ray_grid(int64_t R) {
@@ -236,8 +256,37 @@ extern "C" int cnb_adam_step(float* param, const float* grad, float* exp_avg, fl
   return cnb_check_launch("adam");
 }
 
+extern "C" int cnb_grad_check_finite(const float* grad, int64_t n, int32_t* found_inf, cnb_stream_t stream) {
+  CNB_REQUIRE(n >= 0, "grad_check_finite: bad n");
+  if (n == 0) return CNB_OK;
+  CNB_REQUIRE(grad && found_inf, "grad_check_finite: null pointer");
+  CNB_REQUIRE(((uintptr_t)grad & 15) == 0, "grad_check_finite: gradient buffer must be 16-byte aligned");
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  const int64_t cap = (int64_t)cnb_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_grad_nonfinite<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(grad), n4, grad + 4 * n4, (int)(n - 4 * n4), found_inf);
+  return cnb_check_launch("grad_check_finite");
+}
+
+static int adam_step_zero_impl(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                               float eps, int32_t step, float inv_grad_scale, const int32_t* skip_flag, cnb_stream_t stream);
+
 extern "C" int cnb_adam_step_zero(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
                                   float eps, int32_t step, float inv_grad_scale, cnb_stream_t stream) {
+  return adam_step_zero_impl(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, inv_grad_scale, nullptr, stream);
+}
+
+extern "C" int cnb_adam_step_zero_guarded(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                                          float eps, int32_t step, float inv_grad_scale, const int32_t* skip_flag, cnb_stream_t stream) {
+  CNB_REQUIRE(skip_flag == nullptr || (n % 4 == 0 && ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0)),
+              "adam_step_zero_guarded: the guarded step needs a 16-byte aligned flat group with n % 4 == 0");
+  return adam_step_zero_impl(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, inv_grad_scale, skip_flag, stream);
+}
+
+static int adam_step_zero_impl(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                               float eps, int32_t step, float inv_grad_scale, const int32_t* skip_flag, cnb_stream_t stream) {
   CNB_REQUIRE(n >= 0 && step >= 1, "adam: bad n/step");
   if (n == 0) return CNB_OK;
   CNB_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam: null pointer");
@@ -255,6 +304,6 @@ extern "C" int cnb_adam_step_zero(float* param, float* grad, float* exp_avg, flo
   const int64_t cap = (int64_t)cnb_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   k_adam_zero4<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(param), reinterpret_cast<float4*>(grad), reinterpret_cast<float4*>(exp_avg),
-                                                reinterpret_cast<float4*>(exp_avg_sq), n4, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), inv_grad_scale);
+                                                reinterpret_cast<float4*>(exp_avg_sq), n4, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), inv_grad_scale, skip_flag);
   return cnb_check_launch("adam_zero");
 }

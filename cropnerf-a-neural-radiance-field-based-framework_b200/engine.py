@@ -46,6 +46,54 @@ def exponential_decay_lr(step: int, spec: OptimizerSpec) -> float:
     return math.exp(math.log(spec.lr) * (1 - t) + math.log(spec.lr_final) * t)
 
 
+class GradScaler:
+    """torch.amp.GradScaler semantics for the flat-group optimiser (nerfstudio Trainer: ``grad_scaler.scale(loss).backward()``,
+    ``optimizer_scaler_step_all(grad_scaler)``, ``grad_scaler.update()``; enabled there whenever ``mixed_precision`` is).
+    The scale multiplies the loss-gradient seed of ``cnb_train_step`` (``cnb_train_cfg.grad_scale``), the inf/NaN check over
+    the flat gradients (``cnb_grad_check_finite``) and the decision to skip the Adam update (``cnb_adam_step_zero_guarded``)
+    happen on the device; :meth:`update` reads the 4-byte flag back to grow / back off the scale like ``_amp_update_scale_``."""
+
+    def __init__(self, init_scale: float = 65536.0, growth_factor: float = 2.0, backoff_factor: float = 0.5, growth_interval: int = 2000,
+                 enabled: bool = True):
+        self.scale = float(init_scale) if enabled else 1.0
+        self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, growth_interval
+        self.enabled = enabled
+        self.growth_tracker = 0
+        self.found_inf: Optional[Tensor] = None
+        self.skipped_steps = 0
+
+    def flag(self, device) -> Tensor:
+        if self.found_inf is None or self.found_inf.device != torch.device(device):
+            self.found_inf = torch.zeros((1,), device=device, dtype=torch.int32)
+        return self.found_inf
+
+    def update(self) -> bool:
+        """-> True when the step just taken was skipped.  Resets the flag for the next step."""
+        if not self.enabled or self.found_inf is None:
+            return False
+        skipped = bool(self.found_inf.item())
+        if skipped:
+            self.scale *= self.backoff_factor
+            self.growth_tracker = 0
+            self.skipped_steps += 1
+            self.found_inf.zero_()
+        else:
+            self.growth_tracker += 1
+            if self.growth_tracker == self.growth_interval:
+                self.scale *= self.growth_factor
+                self.growth_tracker = 0
+        return skipped
+
+    def state_dict(self) -> dict:
+        return {"scale": self.scale, "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
+                "growth_interval": self.growth_interval, "_growth_tracker": self.growth_tracker}
+
+    def load_state_dict(self, sd: dict) -> None:
+        if sd:
+            self.scale = float(sd.get("scale", self.scale))
+            self.growth_tracker = int(sd.get("_growth_tracker", 0))
+
+
 class FlatGroup:
     """One param group flattened: ``param.data`` and ``param.grad`` become views of two contiguous buffers."""
 
@@ -107,14 +155,15 @@ class _GraphedStep:
             # data parallel: two graphs, so the all-reduce of the field gradients (67 MB) can start after the field backward
             # and run on NCCL's stream while the proposal networks back-propagate (cnb_train_cfg.phase)
             with torch.cuda.graph(self.graph):
-                self.losses, self.outputs, state = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, phase=1)
+                self.losses, self.outputs, state = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, phase=1,
+                                                                 grad_scale=trainer._loss_scale())
             self.graph2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph2, pool=self.graph.pool()):
                 fp.train_step(self.bundle, self.batch, update_proposals=update, phase=2, state=state)
             self._state = state
         else:
             with torch.cuda.graph(self.graph):
-                self.losses, self.outputs = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update)
+                self.losses, self.outputs = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, grad_scale=trainer._loss_scale())
         for g in trainer.groups.values():  # whatever the capture-time warm-up left in the gradients
             g.zero_grad()
 
@@ -141,7 +190,7 @@ class Trainer:
     """Minimal trainer for FruitModel: callbacks, forward, losses, backward, gradient all-reduce, Adam."""
 
     def __init__(self, model, optimizers: Optional[Dict[str, OptimizerSpec]] = None, world_size: int = 1, fused: bool = True,
-                 cuda_graph: bool = False, force_proposal_update: bool = False):
+                 cuda_graph: bool = False, force_proposal_update: bool = False, grad_scaler: Optional[GradScaler] = None):
         from .pipeline import FusedPipeline
 
         self.model = model
@@ -151,6 +200,7 @@ class Trainer:
         self._graphs: Dict[tuple, _GraphedStep] = {}
         self._pending: Dict[str, object] = {}
         self.world_size = world_size
+        self.grad_scaler = grad_scaler if (grad_scaler is not None and grad_scaler.enabled) else None
         self.optimizers = optimizers or DEFAULT_OPTIMIZERS
         self.groups: Dict[str, FlatGroup] = {name: FlatGroup(params) for name, params in model.get_param_groups().items() if len(params) > 0}
         self.callbacks = model.get_training_callbacks()
@@ -187,6 +237,19 @@ class Trainer:
         (launched first) first, so the Adam pass of one group hides the tail of the next group's all-reduce."""
         self.opt_step += 1
         order = sorted(self.groups, key=lambda n: -self.groups[n].flat.numel())
+        scaler = self.grad_scaler
+        flag = None
+        inv = 1.0 / self.world_size
+        if scaler is not None:
+            # GradScaler.step: one inf/NaN flag over ALL groups (after the all-reduce, so every rank decides alike), then every
+            # group's Adam either runs or is skipped on the device
+            inv /= scaler.scale
+            flag = scaler.flag(self.groups[order[0]].flat.device)
+            for name in order:
+                work = self._pending.pop(name, None)
+                if work is not None:
+                    work.wait()
+                ops.grad_check_finite(self.groups[name].grad, flag)
         for name in order:
             g = self.groups[name]
             work = self._pending.pop(name, None)
@@ -196,8 +259,13 @@ class Trainer:
             lr = exponential_decay_lr(step, spec)
             # Adam and the gradient clear of the next step in one pass over the flat group
             ops.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, lr, self.opt_step, spec.betas[0], spec.betas[1], spec.eps,
-                          inv_grad_scale=1.0 / self.world_size, zero_grad=True)
+                          inv_grad_scale=inv, zero_grad=True, skip_flag=flag)
         self._grads_clean = True
+        if scaler is not None and scaler.update():
+            self.opt_step -= 1  # torch: a skipped optimizer.step() does not advance Adam's step count
+
+    def _loss_scale(self) -> float:
+        return self.grad_scaler.scale if self.grad_scaler is not None else 1.0
 
     def _use_fused(self) -> bool:
         return self.fused is not None and self.model.collider is not None and self.fused.eligible()
@@ -224,7 +292,7 @@ class Trainer:
                 for v in reg.values():
                     v.backward()
             if self.cuda_graph and ray_bundle.nears is None and cam_opt.mode == "off":
-                key = (int(ray_bundle.origins.shape[0]), updated, float(sampler._anneal))
+                key = (int(ray_bundle.origins.shape[0]), updated, float(sampler._anneal), self._loss_scale())
                 gs = self._graphs.get(key)
                 if gs is None:
                     if len(self._graphs) >= 8:  # anneal still moving (first 1000 steps): do not hoard graphs
@@ -237,7 +305,7 @@ class Trainer:
                 if updated:
                     sampler._steps_since_update = 0
             else:
-                losses, outputs = fp.train_step(ray_bundle, batch, update_proposals=updated)
+                losses, outputs = fp.train_step(ray_bundle, batch, update_proposals=updated, grad_scale=self._loss_scale())
             self.all_reduce_gradients(proposals_updated=updated, wait=False)
             self.optimizer_step(step)
             self._run_callbacks("AFTER_TRAIN_ITERATION", step)
@@ -248,7 +316,7 @@ class Trainer:
         metrics = self.model.get_metrics_dict(outputs, batch)
         loss_dict = self.model.get_loss_dict(outputs, batch, metrics)
         loss = sum(loss_dict.values())
-        loss.backward()
+        (loss * self._loss_scale()).backward()
         self.all_reduce_gradients()
         self.optimizer_step(step)
         self._run_callbacks("AFTER_TRAIN_ITERATION", step)

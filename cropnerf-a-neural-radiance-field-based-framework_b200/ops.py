@@ -560,11 +560,21 @@ def pixel_losses(rgb: Tensor, sem: Tensor, image: Tensor, mask: Tensor, sem_weig
 
 
 def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, step: int, beta1: float = 0.9, beta2: float = 0.999,
-              eps: float = 1e-15, inv_grad_scale: float = 1.0, zero_grad: bool = False) -> None:
+              eps: float = 1e-15, inv_grad_scale: float = 1.0, zero_grad: bool = False, skip_flag: Optional[Tensor] = None) -> None:
     dev = _dev(param)
+    if skip_flag is not None:  # GradScaler.step: device-side "skip on inf/NaN" (always clears the gradient)
+        L.check(L.lib().cnb_adam_step_zero_guarded(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(), lr, beta1,
+                                                   beta2, eps, int(step), inv_grad_scale, skip_flag.data_ptr(), L.stream_ptr(dev)), "adam_step_guarded")
+        return
     fn = L.lib().cnb_adam_step_zero if zero_grad else L.lib().cnb_adam_step
     L.check(
         fn(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(), lr, beta1, beta2, eps,
                               int(step), inv_grad_scale, L.stream_ptr(dev)),
         "adam_step",
     )
+
+
+def grad_check_finite(grad: Tensor, found_inf: Tensor) -> None:
+    """found_inf (device int32 [1]) |= any(!isfinite(grad))  -- torch.amp.GradScaler's inf check over one flat gradient group."""
+    dev = _dev(grad)
+    L.check(L.lib().cnb_grad_check_finite(grad.data_ptr(), grad.numel(), found_inf.data_ptr(), L.stream_ptr(dev)), "grad_check_finite")

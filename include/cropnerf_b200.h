@@ -329,6 +329,14 @@ int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cnb_train_cfg
 int cnb_adam_step_zero(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
                        float eps, int32_t step, float inv_grad_scale, cnb_stream_t stream);
 
+/* GradScaler support (nerfstudio Trainer: grad_scaler.scale(loss).backward(); grad_scaler.step(optimizer); grad_scaler.update()).
+ * cnb_grad_check_finite ORs 1 into *found_inf (device int32, caller clears it) when any of the n gradients is inf / NaN;
+ * cnb_adam_step_zero_guarded is cnb_adam_step_zero that, when *skip_flag != 0 (device), leaves param / moments untouched and only
+ * clears the gradient -- GradScaler.step's "skip the optimizer step", decided on the device (no host sync, graph-capturable). */
+int cnb_grad_check_finite(const float* grad, int64_t n, int32_t* found_inf, cnb_stream_t stream);
+int cnb_adam_step_zero_guarded(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                               float eps, int32_t step, float inv_grad_scale, const int32_t* skip_flag, cnb_stream_t stream);
+
 /* ---- measurement aid: per-stage device times of cnb_render_rays / cnb_train_step (CUDA events on the launching stream).
  * cnb_profile_read synchronises, writes "stage:calls:kernels:ms;..." (summed since enable) into buf and clears the log. */
 void cnb_profile_enable(int32_t on);

@@ -154,3 +154,55 @@ def test_cuda_graph_step_equals_eager(dev):
         assert abs(stats[0][k] - stats[1][k]) <= 2e-4 * abs(stats[1][k]) + 1e-7, (k, stats[0][k], stats[1][k])
     for n in params[0]:
         assert (params[0][n] - params[1][n]).abs().max().item() < 5e-2, n
+
+
+def test_grad_scaler_scaled_step_and_skip_on_inf(dev):
+    """GradScaler row of f2: a power-of-two loss scale leaves the update unchanged (the scale is folded out inside Adam); an
+    inf in any gradient skips the whole step on the device (parameters and moments untouched, gradients cleared, Adam's step
+    count not advanced) and halves the scale, like torch.amp.GradScaler.step / update."""
+    from cropnerf_b200 import ops
+
+    R = 256
+    a, b = _models(dev, True, "mixed", small=False)
+    rays = synthetic.make_rays(R, seed=6, num_cameras=20)
+    targets = {k: v.to(dev) for k, v in synthetic.make_targets(R, seed=3).items()}
+    jit = synthetic.make_jitter(R, 3, seed=2)
+    trainers = []
+    for model, scaler in ((a, engine.GradScaler(init_scale=1024.0, growth_interval=2)), (b, None)):
+        feed = synthetic.JitterFeed(jit)
+        model.proposal_sampler.initial_sampler.rand_fn = feed
+        model.proposal_sampler.pdf_sampler.rand_fn = feed
+        tr = engine.Trainer(model, force_proposal_update=True, grad_scaler=scaler)
+        for step in (3000, 3001):
+            feed.reset()
+            tr.train_iteration(step, product_bundle(rays, dev), targets)
+        trainers.append((tr, feed))
+    (ta, fa), (tb, _) = trainers
+    assert ta.opt_step == tb.opt_step == 2
+    assert ta.grad_scaler.scale == 2048.0 and ta.grad_scaler.skipped_steps == 0  # grew after growth_interval clean steps
+    for n in ta.groups:
+        # gradients differ only by the order of the fp32 atomics; Adam normalises them, so compare loosely
+        assert (ta.groups[n].flat - tb.groups[n].flat).abs().max().item() < 5e-2, n
+        assert float(ta.groups[n].grad.abs().max()) == 0.0
+    # ---- poison one gradient element: the next step must be skipped everywhere
+    before = {n: (g.flat.clone(), g.exp_avg.clone(), g.exp_avg_sq.clone()) for n, g in ta.groups.items()}
+    ta.groups["proposal_networks"].grad[12345] = float("inf")
+    ta._grads_clean = True  # keep the poisoned value (train_iteration would otherwise clear a "dirty" gradient first)
+    fa.reset()
+    ta.train_iteration(3002, product_bundle(rays, dev), targets)
+    assert ta.opt_step == 2 and ta.grad_scaler.skipped_steps == 1 and ta.grad_scaler.scale == 1024.0
+    for n, g in ta.groups.items():
+        assert torch.equal(g.flat, before[n][0]) and torch.equal(g.exp_avg, before[n][1]) and torch.equal(g.exp_avg_sq, before[n][2]), n
+        assert float(g.grad.abs().max()) == 0.0
+    # ---- and the step after that runs normally again
+    fa.reset()
+    ta.train_iteration(3003, product_bundle(rays, dev), targets)
+    assert ta.opt_step == 3 and not torch.equal(ta.groups["fields"].flat, before["fields"][0])
+    # the check kernel itself, on a ragged length with the bad value in the tail
+    flag = torch.zeros((1,), device=dev, dtype=torch.int32)
+    gbuf = torch.zeros((1027 + 1,), device=dev)[:1027]
+    ops.grad_check_finite(gbuf, flag)
+    assert int(flag.item()) == 0
+    gbuf[1026] = float("nan")
+    ops.grad_check_finite(gbuf, flag)
+    assert int(flag.item()) == 1
