@@ -129,7 +129,7 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
     model = build_model(dev, precision)
     # every timed step back-propagates into all three networks (the update step SURVEY.md 8d's 485 456 B/ray describes;
     # in steady state only 1 step in 6 does, ProposalNetworkSampler update_sched) and is replayed as one CUDA graph
-    trainer = engine.Trainer(model, world_size=world, cuda_graph=not args.no_graph, force_proposal_update=True)
+    trainer = engine.Trainer(model, world_size=world, cuda_graph=not args.no_graph, force_proposal_update=True, ddp=args.ddp)
     R = RAYS_PER_GPU
     nb = 8  # distinct ray batches cycled through (fresh rays every step, like next_train)
     host = [host_batch(R, seed=100 * rank + i) for i in range(nb)]
@@ -293,9 +293,12 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     t, t_e2e, t_render, t_render_e2e = times.tolist()
+    ddp_mode = trainer.ddp if world > 1 else None
+    if trainer.comm is not None:
+        assert not trainer.comm.timed_out(), "a peer-memory barrier timed out during the benchmark"
     del trainer, model, l2_flush
     torch.cuda.empty_cache()
-    return {"steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
+    return {"ddp": ddp_mode, "steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
             "stage": stage, "n_prof": n_prof, "nonupdate_ms": nonupdate_ms, "camopt_ms": camopt_ms, "adam_ms": adam_ms, "render_stage": render_stage, "loss": loss_host,
             "h2d_train": bytes_of(host[0]), "h2d_render": bytes_of({k: rhost[k] for k in ("origins", "directions", "pixel_area", "camera_indices")}),
             "d2h_render": int(d2h_render)}
@@ -371,7 +374,7 @@ def run_product(args):
             "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: fruit_nerf preset training step, 4096 rays/GPU, proposal 256/96 + 48 NeRF samples, "
                                    "field 16x2^19x2 + 2 proposal 5x2^17x2 fp32 hash tables, 300 synthetic 1080p cameras",
-                       "rays_per_gpu": R, "samples_per_ray": 400, "precision": args.precision, "l2": "flushed between timed iterations (192 MiB fill)",
+                       "rays_per_gpu": R, "samples_per_ray": 400, "precision": args.precision, "l2": "flushed between timed iterations (192 MiB fill)", "data_parallel": m["ddp"],
                        "includes": "fwd + losses + bwd (all three networks updated EVERY step) + gradient all-reduce + Adam; "
                                    + ("cnb_train_step eager" if args.no_graph else "cnb_train_step replayed as one CUDA graph"),
                        "non_update_step_ms": m["nonupdate_ms"],
@@ -469,6 +472,8 @@ def main():
     ap.add_argument("--single-precision", action="store_true", help="skip the short pass in the other precision mode")
     ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per CPU-baseline step (bounded sample of the 4096-ray batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ddp", default=os.environ.get("CNB_DDP", "auto"), choices=["auto", "nccl", "p2p", "p2p_multimem"],
+                    help="N>1: gradient exchange + Adam = NCCL all-reduce then local Adam, or one reduce-scatter+Adam+all-gather kernel over NVLink peer memory")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -167,6 +167,19 @@ class TrainCfg(C.Structure):
     ]
 
 
+MAX_PEERS = 16
+P2P_GRADS_ZERO, P2P_MULTIMEM = 1, 2
+
+
+class P2PComm(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("flags", C.c_void_p * MAX_PEERS), ("state", C.c_void_p), ("timeout_ms", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
+class P2PGroup(C.Structure):
+    _fields_ = [("grad", C.c_void_p * MAX_PEERS), ("param", C.c_void_p * MAX_PEERS), ("mc_grad", C.c_void_p), ("mc_param", C.c_void_p)]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _I32 = C.c_int32
@@ -205,6 +218,9 @@ SIGNATURES = {
     "cnb_adam_step_zero": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P]),
     "cnb_adam_step_zero_guarded": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P, _P]),
     "cnb_grad_check_finite": (C.c_int, [_P, _I64, _P, _P]),
+    "cnb_p2p_owned_range": (None, [_I64, _I32, _I32, C.POINTER(_I64), C.POINTER(_I64)]),
+    "cnb_p2p_barrier": (C.c_int, [C.POINTER(P2PComm), _P]),
+    "cnb_ddp_adam_update": (C.c_int, [C.POINTER(P2PComm), C.POINTER(P2PGroup), _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _I32, _P]),
     "cnb_level_resample": (C.c_int, [_P, _P, _P, _P, _P, _I32, _F, _P, _P, _I32, _I64, _I32, _I32, _F, _F, _P, _P, _P, _P, _P, _P]),
     "cnb_final_composite": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, C.POINTER(_F), _I32, _P, _P, _P, _P, _P, _P]),
     "cnb_final_composite_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, C.POINTER(_F), _F, _F, _I32, _P, _P, _P, _P, _P]),

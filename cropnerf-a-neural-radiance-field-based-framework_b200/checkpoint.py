@@ -124,6 +124,8 @@ def save_nerfstudio_checkpoint(directory: str, model, step: int, trainer=None) -
     pipeline_state = {"_model." + k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     ckpt = {"step": int(step), "pipeline": pipeline_state, "optimizers": {}, "schedulers": {}, "scalers": {}}
     if trainer is not None:
+        if hasattr(trainer, "gather_optimizer_state"):
+            trainer.gather_optimizer_state()  # peer-memory data parallelism shards the moments across ranks (collective call)
         for name, group in trainer.groups.items():
             ckpt["optimizers"][name] = _adam_state_dict(group, trainer.optimizers[name], trainer.opt_step)
             ckpt["schedulers"][name] = {"last_epoch": int(step), "_step_count": int(step) + 1}

@@ -1,0 +1,214 @@
+// Data-parallel optimiser step over NVLink / NVSwitch peer memory (the one collective of the path).
+//
+// The reference's only multi-GPU strategy is DDP (fruit_pipeline.py:119-121): every rank back-propagates its own rays, the
+// gradients are all-reduced (mean) and every rank runs the same Adam step (fruit_nerf_config.py:45-60) on its replica.  Done
+// with NCCL that is: all-reduce (2(N-1)/N x 77.6 MB on the wire per GPU) followed by a dense Adam pass (7 x 4 B x 19.4 M
+// parameters of HBM traffic on EVERY rank).  Here both are ONE kernel over peer-mapped (symmetric) buffers:
+//
+//   rank r owns the slice [r n/N, (r+1) n/N) of every flat parameter group.  For each float4 of its slice it
+//     1. loads the gradient from all N ranks (peer LDG over NVLink, fixed rank order -> every replica gets the same bits),
+//     2. applies Adam with ITS shard of the moments (exp_avg / exp_avg_sq are only maintained for the owned slice:
+//        optimiser HBM traffic and state drop by N, ZeRO-1 style),
+//     3. stores the updated parameters into all N replicas (peer STG).
+//   = reduce-scatter + Adam + all-gather with the same wire bytes as the ring all-reduce, no staging buffers, no second pass;
+//   inbound gradient reads and outbound parameter writes use the two directions of the links concurrently.
+//
+// With NVLS (multicast-mapped buffers) the N loads become one multimem.ld_reduce (the switch adds) and the N stores one
+// multimem.st (the switch replicates): CNB_P2P_MULTIMEM.
+//
+// Cross-GPU ordering: k_p2p_barrier (one warp): every rank publishes a sequence number into its slot of every peer's flag block
+// with a system-scope release and spins (acquire) until all peers published theirs.  barrier -> update kernel(s) -> barrier ->
+// each rank clears its own gradient.  A spin that exceeds the timeout sets state[1] and gives up, so a dead peer cannot hang the GPU.
+#include "cnb_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(32) k_p2p_barrier(cnb_p2p_comm c, uint64_t timeout_ns) {
+  __shared__ uint32_t seq_s;
+  if (threadIdx.x == 0) seq_s = ++c.state[0];  // stream-ordered: only this kernel touches the counter
+  __syncwarp();
+  const uint32_t seq = seq_s;
+  const int k = threadIdx.x;
+  if (k < c.world) {
+    __threadfence_system();
+    st_release_sys(c.flags[k] + c.rank, seq);
+    const uint32_t* mine = c.flags[c.rank] + k;
+    const uint64_t t0 = globaltimer_ns();
+    while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) {
+      if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(c.state + 1, 1u); break; }
+      __nanosleep(64);
+    }
+    __threadfence_system();
+  }
+}
+
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 mm_ld_reduce4(const float4* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void mm_st4(float4* p, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+struct AdamArgs {
+  float lr, b1, b2, eps, bc1, bc2_sqrt, inv_scale;
+};
+
+// MODE 0: peer loads / stores; MODE 1: NVLS multimem.  WORLD > 0: compile-time rank count; 0: run-time (<= CNB_MAX_PEERS).
+// Every thread issues the WORLD peer loads of its element (x U elements) before the first add, then its moments / parameters, updates and scatters
+// the new parameters.  Measured at N=2 (tests/ddp_p2p_check.py): U=1 at 45 registers (5 CTAs/SM) beats U=4 at 128 registers (0.14 vs 0.16 ms for the
+// two flat groups): occupancy, not per-thread unrolling, is what hides the 2-4 us peer latency; the specialised rank counts all use U=1.
+template <int MODE, int WORLD, int U>
+__global__ void __launch_bounds__(256, (U * (WORLD > 0 ? WORLD : CNB_MAX_PEERS) <= 2) ? 5 : ((U * (WORLD > 0 ? WORLD : CNB_MAX_PEERS) <= 4) ? 4 : 2)) k_ddp_adam(cnb_p2p_comm c, cnb_p2p_group g, float4* __restrict__ m, float4* __restrict__ v, int64_t lo4, int64_t hi4,
+                                                  AdamArgs a, int grads_zero) {
+  const float step_size = a.lr / a.bc1;
+  const int world = WORLD > 0 ? WORLD : c.world;
+  constexpr int NP = WORLD > 0 ? WORLD : CNB_MAX_PEERS;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float4* __restrict__ p_own = reinterpret_cast<const float4*>(g.param[c.rank]);
+  for (int64_t base = lo4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < hi4; base += stride * U) {
+    float4 gs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) gs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(grads_zero & 1)) {
+      if (MODE == 1) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t i = base + u * stride;
+          if (i < hi4) gs[u] = mm_ld_reduce4(reinterpret_cast<const float4*>(g.mc_grad) + i);
+        }
+      } else {
+        float4 part[U][NP];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t i = base + u * stride;
+#pragma unroll
+          for (int k = 0; k < NP; ++k)
+            if (k < world && i < hi4) part[u][k] = ld_stream4(reinterpret_cast<const float4*>(g.grad[(grads_zero & 2) ? c.rank : k]) + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t i = base + u * stride;
+#pragma unroll
+          for (int k = 0; k < NP; ++k)  // rank order: the same bits on every replica
+            if (k < world && i < hi4) { gs[u].x += part[u][k].x; gs[u].y += part[u][k].y; gs[u].z += part[u][k].z; gs[u].w += part[u][k].w; }
+        }
+      }
+    }
+    float4 mi[U], vi[U], pi[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * stride;
+      if (i < hi4) { mi[u] = m[i]; vi[u] = v[i]; pi[u] = p_own[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * stride;
+      if (i >= hi4) continue;
+      float* gp = &gs[u].x; float* mp = &mi[u].x; float* vp = &vi[u].x; float* pp = &pi[u].x;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float gk = gp[q] * a.inv_scale;
+        mp[q] = mp[q] + (1.0f - a.b1) * (gk - mp[q]);
+        vp[q] = a.b2 * vp[q] + (1.0f - a.b2) * gk * gk;
+        pp[q] -= step_size * (mp[q] / (sqrtf(vp[q]) / a.bc2_sqrt + a.eps));
+      }
+      m[i] = mi[u]; v[i] = vi[u];
+      if (MODE == 1) {
+        mm_st4(reinterpret_cast<float4*>(g.mc_param) + i, pi[u]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+          if (k < world && (!(grads_zero & 4) || k == c.rank)) reinterpret_cast<float4*>(g.param[k])[i] = pi[u];
+      }
+    }
+  }
+}
+
+template <int MODE, int WORLD, int U>
+int launch_ddp_adam(const cnb_p2p_comm* comm, const cnb_p2p_group* group, float* exp_avg, float* exp_avg_sq, int64_t lo4, int64_t hi4, const AdamArgs& a,
+                    int gz, cudaStream_t stream) {
+  int64_t blocks = (hi4 - lo4 + 256 * U - 1) / (256 * U);
+  const int64_t cap = (int64_t)cnb_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  k_ddp_adam<MODE, WORLD, U><<<(int)blocks, 256, 0, stream>>>(*comm, *group, reinterpret_cast<float4*>(exp_avg), reinterpret_cast<float4*>(exp_avg_sq), lo4,
+                                                                hi4, a, gz);
+  return cnb_check_launch("ddp_adam_update");
+}
+
+int check_comm(const cnb_p2p_comm* c, const char* what) {
+  CNB_REQUIRE(c != nullptr, "%s: null communicator", what);
+  CNB_REQUIRE(c->world >= 1 && c->world <= CNB_MAX_PEERS && c->rank >= 0 && c->rank < c->world, "%s: bad world %d / rank %d", what, c->world, c->rank);
+  CNB_REQUIRE(c->state != nullptr, "%s: null state", what);
+  for (int k = 0; k < c->world; ++k) CNB_REQUIRE(c->flags[k] != nullptr, "%s: null flag block of rank %d", what, k);
+  return CNB_OK;
+}
+
+}  // namespace
+
+extern "C" void cnb_p2p_owned_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi) {
+  // slices are whole float4s: [rank*q, (rank+1)*q) with q = ceil(n/4 / world), clipped
+  const int64_t n4 = n / 4, q = (n4 + world - 1) / world;
+  int64_t a = (int64_t)rank * q, b = a + q;
+  if (a > n4) a = n4;
+  if (b > n4) b = n4;
+  *lo = 4 * a;
+  *hi = 4 * b;
+}
+
+extern "C" int cnb_p2p_barrier(const cnb_p2p_comm* comm, cnb_stream_t stream) {
+  int rc = check_comm(comm, "p2p_barrier");
+  if (rc) return rc;
+  const uint64_t timeout_ns = comm->timeout_ms > 0 ? (uint64_t)comm->timeout_ms * 1000000ull : 10000000000ull;
+  k_p2p_barrier<<<1, 32, 0, stream>>>(*comm, timeout_ns);
+  return cnb_check_launch("p2p_barrier");
+}
+
+extern "C" int cnb_ddp_adam_update(const cnb_p2p_comm* comm, const cnb_p2p_group* group, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                   float beta1, float beta2, float eps, int32_t step, float inv_grad_scale, int32_t flags, cnb_stream_t stream) {
+  int rc = check_comm(comm, "ddp_adam_update");
+  if (rc) return rc;
+  CNB_REQUIRE(group && exp_avg && exp_avg_sq, "ddp_adam_update: null pointer");
+  CNB_REQUIRE(n >= 0 && n % 4 == 0 && step >= 1, "ddp_adam_update: n must be a multiple of 4 (flat groups are), step >= 1");
+  const bool multimem = (flags & CNB_P2P_MULTIMEM) != 0;
+  for (int k = 0; k < comm->world; ++k) {
+    CNB_REQUIRE(group->grad[k] && group->param[k], "ddp_adam_update: null peer buffer of rank %d", k);
+    CNB_REQUIRE((((uintptr_t)group->grad[k] | (uintptr_t)group->param[k]) & 15) == 0, "ddp_adam_update: peer buffers must be 16-byte aligned");
+  }
+  CNB_REQUIRE((((uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0, "ddp_adam_update: moments must be 16-byte aligned");
+  CNB_REQUIRE(!multimem || (group->mc_grad && group->mc_param), "ddp_adam_update: CNB_P2P_MULTIMEM needs the multicast mappings");
+  int64_t lo, hi;
+  cnb_p2p_owned_range(n, comm->rank, comm->world, &lo, &hi);
+  if (hi <= lo) return CNB_OK;
+  AdamArgs a;
+  a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.inv_scale = inv_grad_scale;
+  a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  const int64_t lo4 = lo / 4, hi4 = hi / 4;
+  const int gz = ((flags & CNB_P2P_GRADS_ZERO) ? 1 : 0) | ((flags & 16) ? 2 : 0) | ((flags & 32) ? 4 : 0);  // 16 / 32: timing aids (local loads only / local stores only)
+  if (multimem) return launch_ddp_adam<1, 0, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
+  switch (comm->world) {
+    case 2: return launch_ddp_adam<0, 2, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
+    case 4: return launch_ddp_adam<0, 4, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
+    case 8: return launch_ddp_adam<0, 8, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
+    default: return launch_ddp_adam<0, 0, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
+  }
+}

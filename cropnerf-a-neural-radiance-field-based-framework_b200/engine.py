@@ -99,7 +99,8 @@ class FlatGroup:
 
     ALIGN = 64  # floats
 
-    def __init__(self, params: List[nn.Parameter]):
+    def __init__(self, params: List[nn.Parameter], comm=None):
+        """``comm`` (ddp.PeerComm): allocate the parameter and gradient buffers as symmetric (peer-mapped) memory."""
         uniq, seen = [], set()
         for p in params:
             if id(p) not in seen:
@@ -112,8 +113,16 @@ class FlatGroup:
             offsets.append(n)
             n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         dev = uniq[0].device
-        self.flat = torch.empty((n,), device=dev, dtype=torch.float32)
-        self.grad = torch.zeros((n,), device=dev, dtype=torch.float32)
+        self.peer = None
+        if comm is not None:
+            from .ddp import PeerGroup
+
+            self.flat, p_ptrs, mc_p = comm.alloc_floats(n)
+            self.grad, g_ptrs, mc_g = comm.alloc_floats(n)
+            self.peer = PeerGroup(comm, g_ptrs, p_ptrs, mc_g, mc_p)
+        else:
+            self.flat = torch.empty((n,), device=dev, dtype=torch.float32)
+            self.grad = torch.zeros((n,), device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.flat.zero_()
@@ -151,8 +160,8 @@ class _GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         self.graph2 = None
         torch.cuda.synchronize()
-        if trainer.world_size > 1:
-            # data parallel: two graphs, so the all-reduce of the field gradients (67 MB) can start after the field backward
+        if trainer.world_size > 1 and trainer.comm is None:
+            # data parallel over NCCL: two graphs, so the all-reduce of the field gradients (67 MB) can start after the field backward
             # and run on NCCL's stream while the proposal networks back-propagate (cnb_train_cfg.phase)
             with torch.cuda.graph(self.graph):
                 self.losses, self.outputs, state = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, phase=1,
@@ -190,7 +199,11 @@ class Trainer:
     """Minimal trainer for FruitModel: callbacks, forward, losses, backward, gradient all-reduce, Adam."""
 
     def __init__(self, model, optimizers: Optional[Dict[str, OptimizerSpec]] = None, world_size: int = 1, fused: bool = True,
-                 cuda_graph: bool = False, force_proposal_update: bool = False, grad_scaler: Optional[GradScaler] = None):
+                 cuda_graph: bool = False, force_proposal_update: bool = False, grad_scaler: Optional[GradScaler] = None, ddp: str = "auto"):
+        """``ddp`` (world_size > 1): "nccl" = all-reduce of the flat gradients + local Adam (DDP as the reference does it);
+        "p2p" = one reduce-scatter + Adam + all-gather kernel per group over NVLink peer mappings (csrc/ddp_p2p.cu);
+        "p2p_multimem" = the same through the NVLS multicast mappings; "auto" = p2p when the symmetric-memory rendezvous works
+        (CUDA, peer access), else nccl.  A GradScaler needs the global inf/NaN verdict before any update: it keeps nccl."""
         from .pipeline import FusedPipeline
 
         self.model = model
@@ -202,7 +215,22 @@ class Trainer:
         self.world_size = world_size
         self.grad_scaler = grad_scaler if (grad_scaler is not None and grad_scaler.enabled) else None
         self.optimizers = optimizers or DEFAULT_OPTIMIZERS
-        self.groups: Dict[str, FlatGroup] = {name: FlatGroup(params) for name, params in model.get_param_groups().items() if len(params) > 0}
+        self.comm = None
+        self.ddp = "nccl"
+        if world_size > 1 and ddp != "nccl" and self.grad_scaler is None and next(model.parameters()).is_cuda:
+            try:
+                from .ddp import PeerComm
+
+                self.comm = PeerComm.create(next(model.parameters()).device)
+                self.ddp = "p2p_multimem" if (ddp == "p2p_multimem" and self.comm.multicast) else "p2p"
+            except Exception as e:  # no peer access / symmetric memory unavailable: the NCCL path is the alternative GPU path
+                if ddp != "auto":
+                    raise
+                import warnings
+
+                warnings.warn(f"peer-memory data parallelism unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce path")
+                self.comm = None
+        self.groups: Dict[str, FlatGroup] = {name: FlatGroup(params, self.comm) for name, params in model.get_param_groups().items() if len(params) > 0}
         self.callbacks = model.get_training_callbacks()
         self.opt_step = 0
 
@@ -214,7 +242,7 @@ class Trainer:
     def start_all_reduce(self, name: str) -> None:
         """Launch the SUM all-reduce of one flat gradient group asynchronously (NCCL's own stream, ordered after the work
         already enqueued on the current stream)."""
-        if self.world_size > 1 and name in self.groups and name not in self._pending:
+        if self.world_size > 1 and self.comm is None and name in self.groups and name not in self._pending:
             self._pending[name] = dist.all_reduce(self.groups[name].grad, op=dist.ReduceOp.SUM, async_op=True)
 
     def all_reduce_gradients(self, proposals_updated: bool = True, wait: bool = True) -> None:
@@ -222,7 +250,8 @@ class Trainer:
         folded into the Adam kernel (``inv_grad_scale``).  On steps where the proposal networks are frozen their gradient
         is exactly zero on every rank (the schedule is a function of the step), so that group is not communicated --
         DDP's ``find_unused_parameters=True`` behaviour."""
-        if self.world_size > 1:
+        self._proposals_updated = proposals_updated
+        if self.world_size > 1 and self.comm is None:
             for name in self.groups:
                 if name == "proposal_networks" and not proposals_updated:
                     continue
@@ -237,6 +266,9 @@ class Trainer:
         (launched first) first, so the Adam pass of one group hides the tail of the next group's all-reduce."""
         self.opt_step += 1
         order = sorted(self.groups, key=lambda n: -self.groups[n].flat.numel())
+        if self.comm is not None:
+            self._p2p_optimizer_step(step, order)
+            return
         scaler = self.grad_scaler
         flag = None
         inv = 1.0 / self.world_size
@@ -263,6 +295,41 @@ class Trainer:
         self._grads_clean = True
         if scaler is not None and scaler.update():
             self.opt_step -= 1  # torch: a skipped optimizer.step() does not advance Adam's step count
+
+    def _p2p_optimizer_step(self, step: int, order: List[str]) -> None:
+        """barrier -> one reduce-scatter + Adam + all-gather kernel per flat group over the peer mappings -> barrier -> clear the
+        own gradients.  Every rank owns 1/world of each group's Adam moments (ddp.owned_range); a group whose gradient is zero on
+        every rank this step (frozen proposal networks) skips the peer reads but still takes its (momentum-only) Adam step."""
+        from .ddp import ddp_adam_update
+
+        comm = self.comm
+        comm.barrier()
+        for name in order:
+            g = self.groups[name]
+            spec = self.optimizers[name]
+            lr = exponential_decay_lr(step, spec)
+            zero = name == "proposal_networks" and not getattr(self, "_proposals_updated", True)
+            ddp_adam_update(comm, g.peer, g.exp_avg, g.exp_avg_sq, g.flat.numel(), lr, self.opt_step, spec.betas[0], spec.betas[1], spec.eps,
+                            inv_grad_scale=1.0 / self.world_size, grads_zero=zero, multimem=self.ddp == "p2p_multimem" and g.peer.has_multicast)
+        comm.barrier()
+        for name in order:
+            if not (name == "proposal_networks" and not getattr(self, "_proposals_updated", True)):
+                self.groups[name].grad.zero_()
+        self._grads_clean = True
+
+    def gather_optimizer_state(self) -> None:
+        """Peer-memory mode keeps each group's Adam moments only inside the rank's owned slice: fill in the other ranks' slices
+        (one broadcast per rank and buffer) so that every rank holds the full state, e.g. before writing a checkpoint."""
+        if self.comm is None:
+            return
+        from .ddp import owned_range
+
+        for g in self.groups.values():
+            for r in range(self.world_size):
+                lo, hi = owned_range(g.flat.numel(), r, self.world_size)
+                if hi > lo:
+                    dist.broadcast(g.exp_avg[lo:hi], src=r)
+                    dist.broadcast(g.exp_avg_sq[lo:hi], src=r)
 
     def _loss_scale(self) -> float:
         return self.grad_scaler.scale if self.grad_scaler is not None else 1.0

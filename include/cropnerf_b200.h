@@ -337,6 +337,35 @@ int cnb_grad_check_finite(const float* grad, int64_t n, int32_t* found_inf, cnb_
 int cnb_adam_step_zero_guarded(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
                                float eps, int32_t step, float inv_grad_scale, const int32_t* skip_flag, cnb_stream_t stream);
 
+/* ---- (e) data-parallel optimiser step over NVLink / NVSwitch peer memory: gradient reduce-scatter + Adam + parameter all-gather in ONE
+ * kernel (replaces DDP's all-reduce, fruit_pipeline.py:119-121, followed by torch.optim.Adam, fruit_nerf_config.py:45-60).
+ * Buffers are SYMMETRIC allocations mapped into every rank's address space (torch.distributed._symmetric_memory on the Python
+ * side); rank r owns the float4-aligned slice cnb_p2p_owned_range(n, r, world) of a flat group, reads that slice of the gradient
+ * from every rank, updates it with its shard of the Adam moments (exp_avg / exp_avg_sq are only maintained inside the owned
+ * slice) and writes the new parameters into every replica.  Protocol per step, all on `stream`:
+ *   cnb_p2p_barrier  (all backward passes done)  ->  cnb_ddp_adam_update per group  ->  cnb_p2p_barrier (all replicas written,
+ *   all gradients consumed)  ->  caller clears its own gradient buffers. */
+#define CNB_MAX_PEERS 16
+enum { CNB_P2P_GRADS_ZERO = 1, /* the group's gradient is zero on every rank this step (frozen proposal networks): skip the peer reads */
+       CNB_P2P_MULTIMEM = 2    /* NVLS: one multimem.ld_reduce / multimem.st through the multicast mappings instead of N peer loads / stores */ };
+typedef struct cnb_p2p_comm {
+  int32_t world, rank;
+  uint32_t* flags[CNB_MAX_PEERS]; /* flags[k] = rank k's flag block (>= CNB_MAX_PEERS uint32, zero-initialised), peer-mapped here */
+  uint32_t* state;                /* LOCAL device memory, 2 uint32, zero-initialised: [0] barrier sequence, [1] set to 1 when a barrier timed out */
+  int32_t timeout_ms;             /* spin limit of one barrier (0 = 10 s) */
+  int32_t _pad;
+} cnb_p2p_comm;
+typedef struct cnb_p2p_group {
+  float* grad[CNB_MAX_PEERS];     /* grad[k] = rank k's flat gradient buffer of this group (grad[rank] = own), peer-mapped here */
+  float* param[CNB_MAX_PEERS];    /* likewise the flat parameter buffers */
+  float* mc_grad;                 /* multicast mappings of the same buffers (NULL without NVLS) */
+  float* mc_param;
+} cnb_p2p_group;
+void cnb_p2p_owned_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
+int cnb_p2p_barrier(const cnb_p2p_comm* comm, cnb_stream_t stream);
+int cnb_ddp_adam_update(const cnb_p2p_comm* comm, const cnb_p2p_group* group, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                        float beta1, float beta2, float eps, int32_t step, float inv_grad_scale, int32_t flags, cnb_stream_t stream);
+
 /* ---- measurement aid: per-stage device times of cnb_render_rays / cnb_train_step (CUDA events on the launching stream).
  * cnb_profile_read synchronises, writes "stage:calls:kernels:ms;..." (summed since enable) into buf and clears the log. */
 void cnb_profile_enable(int32_t on);
