@@ -200,6 +200,9 @@ SIGNATURES = {
     "cnb_field_ctx_floats": (_I64, [C.POINTER(Field), _I64, _I32]),
     "cnb_field_fwd": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), _P, _P, _P, _P, _P, _P, _I32, _P]),
     "cnb_field_bwd": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), _P, _P, _P, _P, _P, _P]),
+    "cnb_density_field_fwd_keep": (C.c_int, [C.POINTER(DensityField), C.POINTER(Samples), _P, _P, _P]),
+    "cnb_density_field_bwd_kept": (C.c_int, [C.POINTER(DensityField), C.POINTER(Samples), _P, _P, _P]),
+    "cnb_density_field_kept_supported": (C.c_int, [C.POINTER(DensityField)]),
     "cnb_position_grad_rays": (C.c_int, [C.POINTER(Grid), C.POINTER(Warp), C.POINTER(Samples), _P, _P, _P, _P]),
     "cnb_density_field_bwd_rays": (C.c_int, [C.POINTER(DensityField), C.POINTER(Samples), _P, _P, _P, _P, _P]),
     "cnb_field_bwd_rays": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), _P, _P, _P, _P, _P, _P, _P, _P]),

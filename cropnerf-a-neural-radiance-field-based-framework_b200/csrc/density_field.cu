@@ -28,6 +28,8 @@ struct DfArgs {
   int in;  // 2L
   cnb_samples sm;
   float* d_feat_out;  // optional [N, 2L]: gradient reaching the encoded features (consumed by cnb_position_grad_rays)
+  float* feat_keep;       // forward, optional: encoded features written LEVEL-MAJOR [L][N] float2 (coalesced) for the backward
+  const float* feat_kept; // backward, optional: features kept by the forward -> no re-gather
 };
 
 template <int LMAX>
@@ -100,6 +102,11 @@ __global__ void __launch_bounds__(BLOCK) k_density_fwd(DfArgs a, float* __restri
     if (pos_out) { pos_out[3 * i] = x; pos_out[3 * i + 1] = y; pos_out[3 * i + 2] = z; }
     float feat[INP], hid[H];
     encode<LMAX>(a, x, y, z, feat);
+    if (a.feat_keep != nullptr) {
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l)
+        if (l < a.L) reinterpret_cast<float2*>(a.feat_keep)[(int64_t)l * total + i] = make_float2(feat[2 * l], feat[2 * l + 1]);
+    }
     const float out = mlp_forward<LMAX, H>(Ws, feat, hid);
     density[i] = sel ? a.avg * expf(out) : 0.0f;
   }
@@ -278,7 +285,17 @@ __global__ void __launch_bounds__(BLOCK, 5) k_density_bwd_tc(DfArgs a, const flo
         const int s = (int)(i - r * S);
         const bool sel = cnb_sample_position(a.sm, a.warp, r, s, x, y, z);
         if (sel) {
-          encode<LMAX>(a, x, y, z, feat);
+          if (a.feat_kept != nullptr) {
+            // the forward of this step kept the encoded features (level-major, coalesced): no second gather pass
+#pragma unroll
+            for (int l = 0; l < LMAX; ++l) {
+              float2 fv = make_float2(0.f, 0.f);
+              if (l < a.L) fv = __ldg(reinterpret_cast<const float2*>(a.feat_kept) + (int64_t)l * total + i);
+              feat[2 * l] = fv.x; feat[2 * l + 1] = fv.y;
+            }
+          } else {
+            encode<LMAX>(a, x, y, z, feat);
+          }
           const float out = mlp_forward<LMAX, H>(Ws, feat, hid);
           g = dd * a.avg * cnb_trunc_exp_grad(out);
           active = (g != 0.0f);
@@ -435,6 +452,8 @@ int make_args(const cnb_density_field* f, const cnb_samples* s, bool bwd, DfArgs
   a.in = m.dims[0];
   a.sm = *s;
   a.d_feat_out = nullptr;
+  a.feat_keep = nullptr;
+  a.feat_kept = nullptr;
   return CNB_OK;
 }
 
@@ -493,33 +512,57 @@ int launch_bwd(const DfArgs& a, const float* d_density, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int cnb_density_field_fwd(const cnb_density_field* f, const cnb_samples* s, float* density, float* positions_out, cnb_stream_t stream) {
+static int density_fwd_impl(const cnb_density_field* f, const cnb_samples* s, float* density, float* positions_out, float* feat_keep, cnb_stream_t stream) {
   DfArgs a;
   int rc = make_args(f, s, false, a);
   if (rc) return rc;
   if (a.sm.num_rays == 0) return CNB_OK;
   CNB_REQUIRE(density != nullptr, "density_field_fwd: null output");
+  a.feat_keep = feat_keep;
   DISPATCH(launch_fwd, a, density, positions_out, stream);
 }
 
-static int density_bwd_impl(const cnb_density_field* f, const cnb_samples* s, const float* d_density, float* d_feat_out, cnb_stream_t stream) {
+extern "C" int cnb_density_field_fwd(const cnb_density_field* f, const cnb_samples* s, float* density, float* positions_out, cnb_stream_t stream) {
+  return density_fwd_impl(f, s, density, positions_out, nullptr, stream);
+}
+
+extern "C" int cnb_density_field_fwd_keep(const cnb_density_field* f, const cnb_samples* s, float* density, float* features_keep, cnb_stream_t stream) {
+  CNB_REQUIRE(features_keep != nullptr, "density_field_fwd_keep: null feature buffer");
+  return density_fwd_impl(f, s, density, nullptr, features_keep, stream);
+}
+
+extern "C" int cnb_density_field_kept_supported(const cnb_density_field* f) {
+  // the backward that consumes kept features is the tensor-core kernel of the fruit_nerf proposal architecture
+  return f && f->grid.num_levels <= 7 && f->mlp.num_layers == 2 && f->mlp.dims[1] == 16 && f->mlp.dims[2] == 1;
+}
+
+static int density_bwd_impl(const cnb_density_field* f, const cnb_samples* s, const float* d_density, float* d_feat_out, const float* feat_kept,
+                            cnb_stream_t stream) {
   DfArgs a;
   int rc = make_args(f, s, true, a);
   if (rc) return rc;
   if (a.sm.num_rays == 0) return CNB_OK;
   CNB_REQUIRE(d_density != nullptr, "density_field_bwd: null d_density");
+  CNB_REQUIRE(feat_kept == nullptr || cnb_density_field_kept_supported(f), "density_field_bwd_kept: architecture outside the kept-feature kernel (<= 7 levels, hidden 16)");
   a.d_feat_out = d_feat_out;
+  a.feat_kept = feat_kept;
   DISPATCH(launch_bwd, a, d_density, stream);
 }
 
+extern "C" int cnb_density_field_bwd_kept(const cnb_density_field* f, const cnb_samples* s, const float* d_density, const float* features_kept,
+                                          cnb_stream_t stream) {
+  CNB_REQUIRE(features_kept != nullptr, "density_field_bwd_kept: null feature buffer");
+  return density_bwd_impl(f, s, d_density, nullptr, features_kept, stream);
+}
+
 extern "C" int cnb_density_field_bwd(const cnb_density_field* f, const cnb_samples* s, const float* d_density, cnb_stream_t stream) {
-  return density_bwd_impl(f, s, d_density, nullptr, stream);
+  return density_bwd_impl(f, s, d_density, nullptr, nullptr, stream);
 }
 
 extern "C" int cnb_density_field_bwd_rays(const cnb_density_field* f, const cnb_samples* s, const float* d_density, float* scratch, float* d_origins,
                                           float* d_directions, cnb_stream_t stream) {
   CNB_REQUIRE(scratch && d_origins && d_directions, "density_field_bwd_rays: null scratch / ray gradients");
-  int rc = density_bwd_impl(f, s, d_density, scratch, stream);
+  int rc = density_bwd_impl(f, s, d_density, scratch, nullptr, stream);
   if (rc) return rc;
   return cnb_position_grad_rays(&f->grid, &f->warp, s, scratch, d_origins, d_directions, stream);
 }

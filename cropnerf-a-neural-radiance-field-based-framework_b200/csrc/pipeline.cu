@@ -50,6 +50,7 @@ struct Layout {
   int64_t g_rgb, g_sem, d_w[MAX_LEVELS_P], d_dens[MAX_LEVELS_P], d_rgb, d_sem;
   int64_t ctx, ctx_floats;
   int64_t pg_scratch;    // d(features) of one proposal level, for the ray gradients (row a17)
+  int64_t pfeat[MAX_LEVELS_P];  // (training) encoded features of each proposal level kept by the forward for the backward; -1 = not kept
   int64_t total;
 };
 
@@ -75,6 +76,10 @@ int make_layout(const cnb_model* m, int64_t R, bool training, Layout& L) {
     for (int i = 0; i < L.levels; ++i) { L.d_w[i] = take(R * L.S[i]); L.d_dens[i] = take(R * L.S[i]); }
     L.d_rgb = take(R * Sf * 3); L.d_sem = take(R * Sf);
   }
+  for (int i = 0; i < MAX_LEVELS_P; ++i) L.pfeat[i] = -1;
+  if (training)
+    for (int i = 0; i + 1 < L.levels; ++i)
+      if (cnb_density_field_kept_supported(&m->proposal[i])) L.pfeat[i] = take(R * L.S[i] * 2 * m->proposal[i].grid.num_levels);
   L.pg_scratch = o;
   if (training && m->ray_gradients) {
     int64_t need = 0;
@@ -125,7 +130,7 @@ int check_common(const cnb_model* m, const cnb_rays* rays, const float* ws) {
 
 // sampler + proposal networks + field + compositing.  jitter == nullptr: deterministic (eval) samplers.
 int forward_chain(const cnb_model* m, const cnb_rays* rays, const Layout& L, float* ws, bool training, const float* jitter, float anneal,
-                  const cnb_ray_outputs* out, cudaStream_t st) {
+                  const cnb_ray_outputs* out, cudaStream_t st, bool keep_proposal_features = false) {
   const int64_t R = rays->num_rays;
   const cnb_sampler& sp = m->sampler;
   int rc;
@@ -150,7 +155,10 @@ int forward_chain(const cnb_model* m, const cnb_rays* rays, const Layout& L, flo
     const int S = L.S[lv];
     const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
     if (lv < lf) {
-      STAGE(lv == 0 ? "proposal0_fwd" : "proposal1_fwd", 1, cnb_density_field_fwd(&m->proposal[lv], &sm, ws + L.dens[lv], nullptr, st));
+      if (keep_proposal_features && L.pfeat[lv] >= 0)
+        STAGE(lv == 0 ? "proposal0_fwd" : "proposal1_fwd", 1, cnb_density_field_fwd_keep(&m->proposal[lv], &sm, ws + L.dens[lv], ws + L.pfeat[lv], st));
+      else
+        STAGE(lv == 0 ? "proposal0_fwd" : "proposal1_fwd", 1, cnb_density_field_fwd(&m->proposal[lv], &sm, ws + L.dens[lv], nullptr, st));
       if (rc) return rc;
       // get_weights -> median depth -> PDF resampling of the next level, one kernel
       const int Sn = L.S[lv + 1];
@@ -214,7 +222,8 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   const bool first = cfg->phase != 2, second = cfg->phase != 1;
   if (first) {
     if (cudaMemsetAsync(losses_out, 0, 8 * sizeof(float), stream) != cudaSuccess) return cnb_check_launch("train_step memset");
-    if ((rc = forward_chain(m, rays, L, ws, true, cfg->jitter, cfg->anneal, out, stream))) return rc;
+    // on proposal-update steps the proposal forward keeps its encoded features for the backward (no second gather pass)
+    if ((rc = forward_chain(m, rays, L, ws, true, cfg->jitter, cfg->anneal, out, stream, cfg->update_proposals != 0 && !rays_grad))) return rc;
   }
   const int lf = L.levels - 1, Sf = L.S[lf];
   const float gs = cfg->grad_scale == 0.0f ? 1.0f : cfg->grad_scale;
@@ -245,6 +254,7 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
       const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
       if (rays_grad) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 2, cnb_density_field_bwd_rays(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pg_scratch,
                                                                                                      cfg->d_origins, cfg->d_directions, stream));
+      else if (L.pfeat[lv] >= 0) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd_kept(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pfeat[lv], stream));
       else STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd(&m->proposal[lv], &sm, ws + L.d_dens[lv], stream));
       if (rc) return rc;
     }

@@ -216,6 +216,8 @@ class Trainer:
         self.grad_scaler = grad_scaler if (grad_scaler is not None and grad_scaler.enabled) else None
         self.optimizers = optimizers or DEFAULT_OPTIMIZERS
         self.comm = None
+        self._clear_stream = None
+        self._clear_pending = False
         self.ddp = "nccl"
         if world_size > 1 and ddp != "nccl" and self.grad_scaler is None and next(model.parameters()).is_cuda:
             try:
@@ -312,9 +314,17 @@ class Trainer:
             ddp_adam_update(comm, g.peer, g.exp_avg, g.exp_avg_sq, g.flat.numel(), lr, self.opt_step, spec.betas[0], spec.betas[1], spec.eps,
                             inv_grad_scale=1.0 / self.world_size, grads_zero=zero, multimem=self.ddp == "p2p_multimem" and g.peer.has_multicast)
         comm.barrier()
-        for name in order:
-            if not (name == "proposal_networks" and not getattr(self, "_proposals_updated", True)):
-                self.groups[name].grad.zero_()
+        # every peer has consumed this rank's gradients: clear them OFF the critical path (side stream; the next step's backward waits
+        # for it in train_iteration, its forward does not touch gradients)
+        main = torch.cuda.current_stream(comm.device)
+        if self._clear_stream is None:
+            self._clear_stream = torch.cuda.Stream(device=comm.device)
+        self._clear_stream.wait_stream(main)
+        with torch.cuda.stream(self._clear_stream):
+            for name in order:
+                if not (name == "proposal_networks" and not getattr(self, "_proposals_updated", True)):
+                    self.groups[name].grad.zero_()
+        self._clear_pending = True
         self._grads_clean = True
 
     def gather_optimizer_state(self) -> None:
@@ -340,6 +350,9 @@ class Trainer:
     def train_iteration(self, step: int, ray_bundle, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
         self.model.train()
         self._run_callbacks("BEFORE_TRAIN_ITERATION", step)
+        if self._clear_pending:  # peer-memory mode clears the gradients on a side stream after the optimiser step
+            torch.cuda.current_stream().wait_stream(self._clear_stream)
+            self._clear_pending = False
         if not getattr(self, "_grads_clean", False):
             for g in self.groups.values():
                 g.zero_grad()

@@ -144,6 +144,14 @@ int cnb_mlp_bwd(const cnb_mlp* m, const float* x, int64_t x_stride, const float*
 int cnb_density_field_fwd(const cnb_density_field* f, const cnb_samples* s, float* density, float* positions_out, cnb_stream_t stream);
 /* recomputes the forward per sample; accumulates grid.d_table, mlp.dW/db */
 int cnb_density_field_bwd(const cnb_density_field* f, const cnb_samples* s, const float* d_density, cnb_stream_t stream);
+/* Same pair for callers that run forward and backward of ONE batch back to back (cnb_train_step on proposal-update steps): the
+ * forward also writes the encoded features, level-major [num_levels][N] float2 (N = num_rays * samples_per_ray; 2*num_levels*N
+ * floats), and the backward reads them instead of gathering the table a second time.  Bit-identical gradients.
+ * cnb_density_field_kept_supported: 1 when the architecture has the kept-feature backward (<= 7 levels, MLP 2L->16->1). */
+int cnb_density_field_fwd_keep(const cnb_density_field* f, const cnb_samples* s, float* density, float* features_keep, cnb_stream_t stream);
+int cnb_density_field_bwd_kept(const cnb_density_field* f, const cnb_samples* s, const float* d_density, const float* features_kept,
+                               cnb_stream_t stream);
+int cnb_density_field_kept_supported(const cnb_density_field* f);
 
 /* ---- a1/a5/a6: FruitField.forward (get_density + get_outputs / get_inference_outputs) ---------------------- */
 /* floats of `ctx` scratch per call (activations kept for backward + backward scratch); 0 => ctx may be NULL */
