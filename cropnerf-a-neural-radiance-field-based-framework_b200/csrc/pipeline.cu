@@ -10,6 +10,7 @@
 #include "cnb_common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -106,6 +107,40 @@ __global__ void __launch_bounds__(256) k_fill_near_far(const float* __restrict__
 __global__ void k_scale(float* __restrict__ v, int n, float s) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] *= s;
+}
+
+// Side stream + events for the fork / join inside cnb_train_step (one set per device, created on first use, never destroyed).
+struct ForkState { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool failed = false; };
+ForkState g_fork[64];
+
+bool fork_streams(cudaStream_t main, cudaStream_t* side) {
+  static const bool disabled = [] { const char* e = getenv("CNB_TRAIN_NO_OVERLAP"); return e && e[0] == '1'; }();
+  if (disabled) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  ForkState& f = g_fork[dev];
+  if (f.failed) return false;
+  if (f.side == nullptr) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(main, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return false;  // create outside captures (eager warm-up call)
+    if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) != cudaSuccess) {
+      f.failed = true;
+      (void)cudaGetLastError();
+      return false;
+    }
+  }
+  if (cudaEventRecord(f.fork, main) != cudaSuccess || cudaStreamWaitEvent(f.side, f.fork, 0) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  *side = f.side;
+  return true;
+}
+
+int join_streams(cudaStream_t main, cudaStream_t side) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  ForkState& f = g_fork[dev];
+  if (cudaEventRecord(f.join, side) != cudaSuccess || cudaStreamWaitEvent(main, f.join, 0) != cudaSuccess) return cnb_check_launch("train_step join");
+  return CNB_OK;
 }
 
 cnb_samples make_samples(const cnb_rays* rays, const float* edges, int S) {
@@ -214,7 +249,6 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   Layout L;
   if ((rc = make_layout(m, R, true, L))) return rc;
   float* ws = workspace;
-  cudaStream_t st = stream;
   const bool mixed = m->field.precision == CNB_PREC_MIXED;
   CNB_REQUIRE(cfg->phase >= 0 && cfg->phase <= 2, "train_step: phase %d outside 0..2", cfg->phase);
   const bool rays_grad = cfg->d_origins != nullptr;
@@ -229,45 +263,62 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   const float gs = cfg->grad_scale == 0.0f ? 1.0f : cfg->grad_scale;
   const float* o_rgb = (out && out->rgb) ? out->rgb : ws + L.o_rgb;
   const float* o_sem = (out && out->semantics) ? out->semantics : ws + L.o_sem;
-  if (first) {
-  // ---- losses + backward of the final level: MSE / BCE gradients -> renderers -> get_weights, one kernel (fruit_nerf.py:601-608) ----
-  STAGE("final_composite_bwd", 1, cnb_final_composite_bwd(ws + L.dens[lf], ws + L.rgb, ws + L.sem, ws + L.eu[lf], ws + L.w[lf], o_rgb, o_sem, cfg->image,
-                                                          cfg->fruit_mask, R, Sf, m->bg_mode, m->bg_color, cfg->semantic_loss_weight, gs,
-                                                          m->field.pass_semantic_gradients, losses_out, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, stream));
-  if (rc) return rc;
-  {
+  // The backward splits into two independent chains after the forward: (A) pixel losses -> renderers -> field MLPs -> field table,
+  // (B) interlevel loss -> proposal networks.  They share only read-only inputs (weights / samples of the forward) and write different
+  // gradient tables, so with phase == 0 chain B is forked onto a side stream (event fork / join: still ONE stream-ordered call for the
+  // caller, and capturable as two parallel branches of a CUDA graph).  Neither chain fills the GPU on its own (the field-MLP backward is a
+  // latency-bound persistent kernel at 8 warps/SM, the per-ray kernels are one thin wave at 4096 rays); CNB_TRAIN_NO_OVERLAP=1 keeps them serial.
+  cudaStream_t side = stream;
+  const bool overlap = cfg->phase == 0 && !rays_grad && !g_prof_on && fork_streams(stream, &side);
+  auto chain_field = [&](cudaStream_t st) -> int {
+    int rc;
+    // ---- losses + backward of the final level: MSE / BCE gradients -> renderers -> get_weights, one kernel (fruit_nerf.py:601-608) ----
+    STAGE("final_composite_bwd", 1, cnb_final_composite_bwd(ws + L.dens[lf], ws + L.rgb, ws + L.sem, ws + L.eu[lf], ws + L.w[lf], o_rgb, o_sem, cfg->image,
+                                                            cfg->fruit_mask, R, Sf, m->bg_mode, m->bg_color, cfg->semantic_loss_weight, gs,
+                                                            m->field.pass_semantic_gradients, losses_out, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, st));
+    if (rc) return rc;
     const cnb_samples sm = make_samples(rays, ws + L.eu[lf], Sf);
     if (rays_grad) STAGE("field_bwd", mixed ? 3 : 9, cnb_field_bwd_rays(&m->field, &sm, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, nullptr, ws + L.ctx,
-                                                                        cfg->d_origins, cfg->d_directions, stream));
-    else STAGE("field_bwd", mixed ? 2 : 8, cnb_field_bwd(&m->field, &sm, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, nullptr, ws + L.ctx, stream));
-    if (rc) return rc;
-  }
-  }
-  if (!second) return CNB_OK;
-  // ---- interlevel loss (fruit_nerf.py:610) and, on "updated" steps, its backward into the proposal networks ---------------------
-  for (int lv = 0; lv < lf; ++lv) {
-    const int S = L.S[lv];
-    STAGE("interlevel", 1, cnb_interlevel_fused(ws + L.sp[lf], ws + L.w[lf], ws + L.sp[lv], ws + L.w[lv], ws + L.dens[lv], ws + L.eu[lv], R, Sf, S,
-                                                gs * cfg->interlevel_loss_mult, losses_out + 2, cfg->update_proposals ? ws + L.d_dens[lv] : nullptr, stream));
-    if (rc) return rc;
-    if (cfg->update_proposals) {
-      const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
-      if (rays_grad) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 2, cnb_density_field_bwd_rays(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pg_scratch,
-                                                                                                     cfg->d_origins, cfg->d_directions, stream));
-      else if (L.pfeat[lv] >= 0) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd_kept(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pfeat[lv], stream));
-      else STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd(&m->proposal[lv], &sm, ws + L.d_dens[lv], stream));
+                                                                        cfg->d_origins, cfg->d_directions, st));
+    else STAGE("field_bwd", mixed ? 2 : 8, cnb_field_bwd(&m->field, &sm, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, nullptr, ws + L.ctx, st));
+    return rc;
+  };
+  auto chain_proposals = [&](cudaStream_t st) -> int {
+    int rc = CNB_OK;
+    // ---- interlevel loss (fruit_nerf.py:610) and, on "updated" steps, its backward into the proposal networks ---------------------
+    for (int lv = 0; lv < lf; ++lv) {
+      const int S = L.S[lv];
+      STAGE("interlevel", 1, cnb_interlevel_fused(ws + L.sp[lf], ws + L.w[lf], ws + L.sp[lv], ws + L.w[lv], ws + L.dens[lv], ws + L.eu[lv], R, Sf, S,
+                                                  gs * cfg->interlevel_loss_mult, losses_out + 2, cfg->update_proposals ? ws + L.d_dens[lv] : nullptr, st));
+      if (rc) return rc;
+      if (cfg->update_proposals) {
+        const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
+        if (rays_grad) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 2, cnb_density_field_bwd_rays(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pg_scratch,
+                                                                                                       cfg->d_origins, cfg->d_directions, st));
+        else if (L.pfeat[lv] >= 0) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd_kept(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pfeat[lv], st));
+        else STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd(&m->proposal[lv], &sm, ws + L.d_dens[lv], st));
+        if (rc) return rc;
+      }
+    }
+    if (cfg->interlevel_loss_mult != 1.0f) {
+      k_scale<<<1, 32, 0, st>>>(losses_out + 2, 1, cfg->interlevel_loss_mult);
+      if ((rc = cnb_check_launch("train_step scale"))) return rc;
+    }
+    if (cfg->want_metrics) {
+      STAGE("distortion", 1, cnb_distortion_fwd(ws + L.sp[lf], ws + L.w[lf], R, Sf, losses_out + 3, st));
       if (rc) return rc;
     }
+    return CNB_OK;
+  };
+  if (overlap) {
+    rc = chain_proposals(side);
+    const int rc2 = chain_field(stream);
+    if (join_streams(stream, side) != CNB_OK) return CNB_ERR_CUDA;  // always join, even after a failed launch
+    return rc ? rc : rc2;
   }
-  if (cfg->interlevel_loss_mult != 1.0f) {
-    k_scale<<<1, 32, 0, stream>>>(losses_out + 2, 1, cfg->interlevel_loss_mult);
-    if ((rc = cnb_check_launch("train_step scale"))) return rc;
-  }
-  if (cfg->want_metrics) {
-    STAGE("distortion", 1, cnb_distortion_fwd(ws + L.sp[lf], ws + L.w[lf], R, Sf, losses_out + 3, stream));
-    if (rc) return rc;
-  }
-  return CNB_OK;
+  if (first && (rc = chain_field(stream))) return rc;
+  if (!second) return CNB_OK;
+  return chain_proposals(stream);
 }
 
 // ---- optional stage profiling ---------------------------------------------------------------------------------------------
