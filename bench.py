@@ -168,16 +168,21 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
     t_local = sum(a.elapsed_time(b) for a, b in ev) / 1e3
 
     # ---- timed: end to end through the public API with host buffers ------------------------------------------
-    for i in range(3):  # warm the caching allocator for the per-step H2D buffers
-        rb, tg = to_bundle(host[step % nb], dev)
+    # the public call takes the pinned HOST rays / targets as they are: train_iteration copies them (H2D, async) into the graphed
+    # step's static device buffers, replays the step, runs the optimiser; the loss is read back (D2H + sync) every step
+    def host_bundle(b):
+        return RayBundle(b["origins"], b["directions"], None, b["camera_indices"]), {"image": b["image"], "fruit_mask": b["fruit_mask"]}
+
+    for i in range(3):
+        rb, tg = host_bundle(host[step % nb])
         float(trainer.train_iteration(step, rb, tg)["loss"].item()); step += 1
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     loss_host = 0.0
     for i in range(steps):
-        rb, tg = to_bundle(host[step % nb], dev)       # H2D from pinned memory, every step
-        stats = trainer.train_iteration(step, rb, tg); step += 1
+        rb, tg = host_bundle(host[step % nb])          # pinned host memory in ...
+        stats = trainer.train_iteration(step, rb, tg); step += 1   # ... H2D inside the call, every step
         loss_host = float(stats["loss"].item())        # D2H read of the step's result
     e1.record()
     barrier()
@@ -300,7 +305,7 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
     torch.cuda.empty_cache()
     return {"ddp": ddp_mode, "steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
             "stage": stage, "n_prof": n_prof, "nonupdate_ms": nonupdate_ms, "camopt_ms": camopt_ms, "adam_ms": adam_ms, "render_stage": render_stage, "loss": loss_host,
-            "h2d_train": bytes_of(host[0]), "h2d_render": bytes_of({k: rhost[k] for k in ("origins", "directions", "pixel_area", "camera_indices")}),
+            "h2d_train": bytes_of({k: host[0][k] for k in ("origins", "directions", "camera_indices", "image", "fruit_mask")}), "h2d_render": bytes_of({k: rhost[k] for k in ("origins", "directions", "pixel_area", "camera_indices")}),
             "d2h_render": int(d2h_render)}
 
 

@@ -104,6 +104,15 @@ __global__ void __launch_bounds__(256) k_fill_near_far(const float* __restrict__
   }
 }
 
+// losses[4] = PSNR of the batch (get_metrics_dict, fruit_nerf.py:639-645: 10 log10(1 / mse)), losses[5] = rgb + semantics + interlevel
+// (what the Trainer sums from get_loss_dict): the scalars a training loop logs, so it reads one buffer instead of launching its own kernels
+__global__ void k_finalize_losses(float* __restrict__ l) {
+  if (threadIdx.x == 0) {
+    l[4] = -10.0f * log10f(l[0]);
+    l[5] = l[0] + l[1] + l[2];
+  }
+}
+
 __global__ void k_scale(float* __restrict__ v, int n, float s) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] *= s;
@@ -314,11 +323,14 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
     rc = chain_proposals(side);
     const int rc2 = chain_field(stream);
     if (join_streams(stream, side) != CNB_OK) return CNB_ERR_CUDA;  // always join, even after a failed launch
-    return rc ? rc : rc2;
+    if (rc || rc2) return rc ? rc : rc2;
+  } else {
+    if (first && (rc = chain_field(stream))) return rc;
+    if (!second) return CNB_OK;
+    if ((rc = chain_proposals(stream))) return rc;
   }
-  if (first && (rc = chain_field(stream))) return rc;
-  if (!second) return CNB_OK;
-  return chain_proposals(stream);
+  k_finalize_losses<<<1, 32, 0, stream>>>(losses_out);
+  return cnb_check_launch("train_step finalize");
 }
 
 // ---- optional stage profiling ---------------------------------------------------------------------------------------------

@@ -151,6 +151,10 @@ class _GraphedStep:
             "image": torch.empty((R, 3), device=dev), "fruit_mask": torch.empty((R, 1), device=dev),
         }
         self.jitter = fp.draw_jitter(R, dev).clone()
+        # torch.rand inside a capture is graph-safe (the generator's philox offset advances per replay): the default jitter is drawn by the
+        # graph itself; custom rand_fn feeds (tests) are drawn eagerly into the static buffer before each replay
+        s_ = trainer.model.proposal_sampler
+        self.jitter_in_graph = bool(s_.initial_sampler.single_jitter) and s_.initial_sampler.rand_fn is torch.rand and s_.pdf_sampler.rand_fn is torch.rand
         self._load(ray_bundle, batch)
         from .rays import RayBundle
 
@@ -164,6 +168,8 @@ class _GraphedStep:
             # data parallel over NCCL: two graphs, so the all-reduce of the field gradients (67 MB) can start after the field backward
             # and run on NCCL's stream while the proposal networks back-propagate (cnb_train_cfg.phase)
             with torch.cuda.graph(self.graph):
+                if self.jitter_in_graph:
+                    self.jitter.uniform_()
                 self.losses, self.outputs, state = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, phase=1,
                                                                  grad_scale=trainer._loss_scale())
             self.graph2 = torch.cuda.CUDAGraph()
@@ -172,6 +178,8 @@ class _GraphedStep:
             self._state = state
         else:
             with torch.cuda.graph(self.graph):
+                if self.jitter_in_graph:
+                    self.jitter.uniform_()
                 self.losses, self.outputs = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, grad_scale=trainer._loss_scale())
         for g in trainer.groups.values():  # whatever the capture-time warm-up left in the gradients
             g.zero_grad()
@@ -187,7 +195,8 @@ class _GraphedStep:
 
     def run(self, trainer: "Trainer", ray_bundle, batch):
         self._load(ray_bundle, batch)
-        trainer.fused.draw_jitter(self.static["origins"].shape[0], self.static["origins"].device, out=self.jitter)
+        if not self.jitter_in_graph:
+            trainer.fused.draw_jitter(self.static["origins"].shape[0], self.static["origins"].device, out=self.jitter)
         self.graph.replay()
         if self.graph2 is not None:
             trainer.start_all_reduce("fields")
@@ -371,26 +380,37 @@ class Trainer:
                 cam_opt.get_loss_dict(reg)
                 for v in reg.values():
                     v.backward()
+            # rays / targets may be HOST tensors (pinned): the graphed step copies them straight into its static device buffers
+            host_in = not ray_bundle.origins.is_cuda
+            dev = self.model.device
+
+            def on_device():
+                if not host_in:
+                    return ray_bundle, batch
+                return ray_bundle.to(dev, non_blocking=True), {k: v.to(dev, non_blocking=True) for k, v in batch.items() if isinstance(v, Tensor)}
+
             if self.cuda_graph and ray_bundle.nears is None and cam_opt.mode == "off":
                 key = (int(ray_bundle.origins.shape[0]), updated, float(sampler._anneal), self._loss_scale())
                 gs = self._graphs.get(key)
                 if gs is None:
                     if len(self._graphs) >= 8:  # anneal still moving (first 1000 steps): do not hoard graphs
                         self._graphs.pop(next(iter(self._graphs)))
-                    fp.train_step(ray_bundle, batch, update_proposals=False, want_metrics=True)  # eager warm-up (func attributes, workspace)
+                    rb_d, batch_d = on_device()
+                    fp.train_step(rb_d, batch_d, update_proposals=False, want_metrics=True)  # eager warm-up (func attributes, workspace)
                     for g in self.groups.values():
                         g.zero_grad()
-                    gs = self._graphs[key] = _GraphedStep(self, ray_bundle, batch, updated)
+                    gs = self._graphs[key] = _GraphedStep(self, rb_d, batch_d, updated)
                 losses, outputs = gs.run(self, ray_bundle, batch)
                 if updated:
                     sampler._steps_since_update = 0
             else:
-                losses, outputs = fp.train_step(ray_bundle, batch, update_proposals=updated, grad_scale=self._loss_scale())
+                rb_d, batch_d = on_device()
+                losses, outputs = fp.train_step(rb_d, batch_d, update_proposals=updated, grad_scale=self._loss_scale())
             self.all_reduce_gradients(proposals_updated=updated, wait=False)
             self.optimizer_step(step)
             self._run_callbacks("AFTER_TRAIN_ITERATION", step)
             out = {"rgb_loss": losses[0], "semantics_loss": losses[1], "interlevel_loss": losses[2], "distortion": losses[3],
-                   "psnr": -10.0 * torch.log10(losses[0]), "loss": losses[0] + losses[1] + losses[2]}
+                   "psnr": losses[4], "loss": losses[5]}  # finalised on the device by cnb_train_step: no per-step torch kernels here
             return out
         outputs = self.model(ray_bundle)
         metrics = self.model.get_metrics_dict(outputs, batch)

@@ -329,7 +329,8 @@ typedef struct cnb_train_cfg {
 } cnb_train_cfg;
 
 /* forward + losses + backward of one batch; parameter gradients are ACCUMULATED into the d_* pointers of `m`;
- * losses_out (device, 8 floats, overwritten): [0] rgb mse, [1] weighted semantic bce, [2] interlevel (x mult), [3] distortion */
+ * losses_out (device, 8 floats, overwritten): [0] rgb mse, [1] weighted semantic bce, [2] interlevel (x mult), [3] distortion,
+ * [4] psnr = -10 log10([0]) (get_metrics_dict, fruit_nerf.py:639-645), [5] total = [0] + [1] + [2] (sum of get_loss_dict) */
 int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cnb_train_cfg* cfg, const cnb_ray_outputs* out, float* losses_out,
                    float* workspace, cnb_stream_t stream);
 
