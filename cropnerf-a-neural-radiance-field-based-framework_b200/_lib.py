@@ -149,6 +149,15 @@ class RayOutputs(C.Structure):
     ]
 
 
+MAX_OPT_GROUPS = 4
+CHAIN_FIELD, CHAIN_PROPOSALS = 0, 1
+
+
+class OptGroup(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("n", C.c_int64), ("scalars", C.c_void_p),
+                ("chain", C.c_int32), ("_pad", C.c_int32)]
+
+
 class TrainCfg(C.Structure):
     _fields_ = [
         ("image", C.c_void_p),
@@ -163,7 +172,8 @@ class TrainCfg(C.Structure):
         ("d_origins", C.c_void_p),
         ("d_directions", C.c_void_p),
         ("phase", C.c_int32),
-        ("_pad", C.c_int32),
+        ("num_opt_groups", C.c_int32),
+        ("opt_groups", OptGroup * MAX_OPT_GROUPS),
     ]
 
 
@@ -221,6 +231,7 @@ SIGNATURES = {
     "cnb_adam_step_zero": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P]),
     "cnb_adam_step_zero_guarded": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P, _P]),
     "cnb_grad_check_finite": (C.c_int, [_P, _I64, _P, _P]),
+    "cnb_adam_step_zero_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
     "cnb_p2p_owned_range": (None, [_I64, _I32, _I32, C.POINTER(_I64), C.POINTER(_I64)]),
     "cnb_p2p_barrier": (C.c_int, [C.POINTER(P2PComm), _P]),
     "cnb_ddp_adam_update": (C.c_int, [C.POINTER(P2PComm), C.POINTER(P2PGroup), _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _I32, _P]),

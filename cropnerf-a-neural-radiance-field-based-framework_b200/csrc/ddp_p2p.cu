@@ -204,7 +204,11 @@ extern "C" int cnb_ddp_adam_update(const cnb_p2p_comm* comm, const cnb_p2p_group
   a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   const int64_t lo4 = lo / 4, hi4 = hi / 4;
   const int gz = ((flags & CNB_P2P_GRADS_ZERO) ? 1 : 0) | ((flags & 16) ? 2 : 0) | ((flags & 32) ? 4 : 0);  // 16 / 32: timing aids (local loads only / local stores only)
-  if (multimem) return launch_ddp_adam<1, 0, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
+  if (multimem) {
+    if (flags & 0x100) return launch_ddp_adam<1, 0, 2>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);  // timing aids
+    if (flags & 0x200) return launch_ddp_adam<1, 0, 4>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
+    return launch_ddp_adam<1, 0, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
+  }
   switch (comm->world) {
     case 2: return launch_ddp_adam<0, 2, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
     case 4: return launch_ddp_adam<0, 4, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);

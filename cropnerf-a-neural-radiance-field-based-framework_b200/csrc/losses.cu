@@ -166,6 +166,28 @@ __global__ void __launch_bounds__(256) k_adam_zero4(float4* __restrict__ p, floa
   }
 }
 
+// k_adam_zero4 with the step's scalars in device memory (read once per thread through the constant-like path)
+__global__ void __launch_bounds__(256) k_adam_zero4_dev(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                                                        int64_t n4, const float* __restrict__ sc) {
+  const float lr = __ldg(sc), b1 = __ldg(sc + 1), b2 = __ldg(sc + 2), eps = __ldg(sc + 3), bc1 = __ldg(sc + 4), bc2_sqrt = __ldg(sc + 5), inv_scale = __ldg(sc + 6);
+  const float step_size = lr / bc1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 gi = g[i], mi = m[i], vi = v[i], pi = p[i];
+    float* gp = &gi.x; float* mp = &mi.x; float* vp = &vi.x; float* pp = &pi.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = gp[k] * inv_scale;
+      mp[k] = mp[k] + (1.0f - b1) * (gk - mp[k]);
+      vp[k] = b2 * vp[k] + (1.0f - b2) * gk * gk;
+      pp[k] -= step_size * (mp[k] / (sqrtf(vp[k]) / bc2_sqrt + eps));
+    }
+    float z;
+    asm volatile("mov.f32 %0, 0f00000000;" : "=f"(z) : "f"(pi.w));  // see k_adam_zero4: the clear is issued last
+    m[i] = mi; v[i] = vi; p[i] = pi;
+    g[i] = make_float4(z, z, z, z);
+  }
+}
+
 // torch.amp GradScaler's inf check (_amp_foreach_non_finite_check_and_unscale_) over one flat gradient group: found_inf |= any !isfinite
 __global__ void __launch_bounds__(256) k_grad_nonfinite(const float4* __restrict__ g, int64_t n4, const float* __restrict__ tail, int ntail,
                                                         int32_t* __restrict__ found_inf) {
@@ -254,6 +276,21 @@ extern "C" int cnb_adam_step(float* param, const float* grad, float* exp_avg, fl
   if (blocks > cap) blocks = cap;
   k_adam<<<(int)blocks, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), inv_grad_scale);
   return cnb_check_launch("adam");
+}
+
+extern "C" int cnb_adam_step_zero_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* scalars, cnb_stream_t stream) {
+  CNB_REQUIRE(n >= 0, "adam_dev: bad n");
+  if (n == 0) return CNB_OK;
+  CNB_REQUIRE(param && grad && exp_avg && exp_avg_sq && scalars, "adam_dev: null pointer");
+  CNB_REQUIRE((n % 4 == 0) && ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0),
+              "adam_dev: needs a 16-byte aligned flat group with n % 4 == 0");
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  const int64_t cap = (int64_t)cnb_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  k_adam_zero4_dev<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(param), reinterpret_cast<float4*>(grad), reinterpret_cast<float4*>(exp_avg),
+                                                    reinterpret_cast<float4*>(exp_avg_sq), n4, scalars);
+  return cnb_check_launch("adam_zero_dev");
 }
 
 extern "C" int cnb_grad_check_finite(const float* grad, int64_t n, int32_t* found_inf, cnb_stream_t stream) {

@@ -260,6 +260,7 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   float* ws = workspace;
   const bool mixed = m->field.precision == CNB_PREC_MIXED;
   CNB_REQUIRE(cfg->phase >= 0 && cfg->phase <= 2, "train_step: phase %d outside 0..2", cfg->phase);
+  CNB_REQUIRE(cfg->num_opt_groups >= 0 && cfg->num_opt_groups <= CNB_MAX_OPT_GROUPS, "train_step: num_opt_groups %d outside 0..%d", cfg->num_opt_groups, CNB_MAX_OPT_GROUPS);
   const bool rays_grad = cfg->d_origins != nullptr;
   CNB_REQUIRE(!rays_grad || (cfg->d_directions != nullptr && m->ray_gradients), "train_step: ray gradients need d_directions and cnb_model.ray_gradients (workspace scratch)");
   const bool first = cfg->phase != 2, second = cfg->phase != 1;
@@ -279,6 +280,16 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   // latency-bound persistent kernel at 8 warps/SM, the per-ray kernels are one thin wave at 4096 rays); CNB_TRAIN_NO_OVERLAP=1 keeps them serial.
   cudaStream_t side = stream;
   const bool overlap = cfg->phase == 0 && !rays_grad && !g_prof_on && fork_streams(stream, &side);
+  auto optimise = [&](int chain, cudaStream_t st) -> int {
+    int rc = CNB_OK;
+    for (int i = 0; i < cfg->num_opt_groups; ++i) {
+      const cnb_opt_group& og = cfg->opt_groups[i];
+      if (og.chain != chain) continue;
+      STAGE(chain == CNB_CHAIN_FIELD ? "adam_fields" : "adam_proposals", 1, cnb_adam_step_zero_dev(og.param, og.grad, og.exp_avg, og.exp_avg_sq, og.n, og.scalars, st));
+      if (rc) return rc;
+    }
+    return rc;
+  };
   auto chain_field = [&](cudaStream_t st) -> int {
     int rc;
     // ---- losses + backward of the final level: MSE / BCE gradients -> renderers -> get_weights, one kernel (fruit_nerf.py:601-608) ----
@@ -290,7 +301,8 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
     if (rays_grad) STAGE("field_bwd", mixed ? 3 : 9, cnb_field_bwd_rays(&m->field, &sm, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, nullptr, ws + L.ctx,
                                                                         cfg->d_origins, cfg->d_directions, st));
     else STAGE("field_bwd", mixed ? 2 : 8, cnb_field_bwd(&m->field, &sm, ws + L.d_dens[lf], ws + L.d_rgb, ws + L.d_sem, nullptr, ws + L.ctx, st));
-    return rc;
+    if (rc) return rc;
+    return optimise(CNB_CHAIN_FIELD, st);  // the field gradient is complete: its Adam pass overlaps the proposal chain
   };
   auto chain_proposals = [&](cudaStream_t st) -> int {
     int rc = CNB_OK;
@@ -317,7 +329,7 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
       STAGE("distortion", 1, cnb_distortion_fwd(ws + L.sp[lf], ws + L.w[lf], R, Sf, losses_out + 3, st));
       if (rc) return rc;
     }
-    return CNB_OK;
+    return optimise(CNB_CHAIN_PROPOSALS, st);
   };
   if (overlap) {
     rc = chain_proposals(side);

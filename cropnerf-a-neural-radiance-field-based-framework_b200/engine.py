@@ -141,6 +141,8 @@ class _GraphedStep:
     Inputs are copied into static buffers, jitter is drawn eagerly into a static buffer, then the graph is replayed: the
     ~50 kernels of a step are submitted with one launch."""
 
+    RING = 256
+
     def __init__(self, trainer: "Trainer", ray_bundle, batch, update: bool):
         dev = ray_bundle.origins.device
         R = ray_bundle.origins.shape[0]
@@ -161,6 +163,20 @@ class _GraphedStep:
         self.bundle = RayBundle(self.static["origins"], self.static["directions"], None, self.static["camera_indices"])
         self.batch = {"image": self.static["image"], "fruit_mask": self.static["fruit_mask"]}
         self.update = update
+        # single GPU: the optimiser runs INSIDE the step -- each flat group's fused Adam + gradient clear right behind the backward chain
+        # that completes its gradient, overlapping the other chain (cnb_opt_group); per-step scalars go through a small device buffer
+        self.opt = None
+        if trainer.world_size == 1 and trainer.grad_scaler is None and set(trainer.groups) <= {"fields", "proposal_networks"}:
+            from . import _lib as L_
+
+            names = list(trainer.groups)
+            # ring of pinned rows: the host may run several steps ahead of the stream that executes the copies
+            self.opt_host = torch.zeros((self.RING, len(names), 8), dtype=torch.float32, pin_memory=True)
+            self.opt_np = self.opt_host.numpy()
+            self.opt_dev = torch.zeros((len(names), 8), device=dev, dtype=torch.float32)
+            self.opt = [(trainer.groups[n].flat, trainer.groups[n].grad, trainer.groups[n].exp_avg, trainer.groups[n].exp_avg_sq, self.opt_dev[i],
+                         L_.CHAIN_FIELD if n == "fields" else L_.CHAIN_PROPOSALS) for i, n in enumerate(names)]
+            self.opt_names = names
         self.graph = torch.cuda.CUDAGraph()
         self.graph2 = None
         torch.cuda.synchronize()
@@ -180,7 +196,8 @@ class _GraphedStep:
             with torch.cuda.graph(self.graph):
                 if self.jitter_in_graph:
                     self.jitter.uniform_()
-                self.losses, self.outputs = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, grad_scale=trainer._loss_scale())
+                self.losses, self.outputs = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, grad_scale=trainer._loss_scale(),
+                                                          opt_groups=self.opt)
         for g in trainer.groups.values():  # whatever the capture-time warm-up left in the gradients
             g.zero_grad()
 
@@ -192,6 +209,17 @@ class _GraphedStep:
         st["camera_indices"].copy_(ray_bundle.camera_indices.reshape(R, 1), non_blocking=True)
         st["image"].copy_(batch["image"][:, :3], non_blocking=True)
         st["fruit_mask"].copy_(batch["fruit_mask"].reshape(R, 1), non_blocking=True)
+
+    def set_optimizer_scalars(self, trainer: "Trainer", step: int) -> None:
+        """lr / bias corrections of THIS step for the in-graph Adam passes (one 64-byte async H2D copy)."""
+        trainer.opt_step += 1
+        t = trainer.opt_step
+        slot = t % self.RING
+        for i, name in enumerate(self.opt_names):
+            spec = trainer.optimizers[name]
+            b1, b2 = spec.betas
+            self.opt_np[slot, i, :7] = (exponential_decay_lr(step, spec), b1, b2, spec.eps, 1.0 - b1**t, math.sqrt(1.0 - b2**t), 1.0)
+        self.opt_dev.copy_(self.opt_host[slot], non_blocking=True)
 
     def run(self, trainer: "Trainer", ray_bundle, batch):
         self._load(ray_bundle, batch)
@@ -233,7 +261,11 @@ class Trainer:
                 from .ddp import PeerComm
 
                 self.comm = PeerComm.create(next(model.parameters()).device)
-                self.ddp = "p2p_multimem" if (ddp == "p2p_multimem" and self.comm.multicast) else "p2p"
+                # measured (tests/ddp_p2p_check.py, profiles/): every rank both pulls gradients and pushes parameters, so each link direction
+                # carries 2 (N-1)/N of the flat groups with peer loads / stores but only ~1x with NVLS (the switch reduces and replicates):
+                # multimem wins from N = 4 up (N=8: 0.24 vs 0.30 ms), plain peer access at N = 2 (0.19 vs 0.26 ms)
+                want_mm = ddp == "p2p_multimem" or (ddp == "auto" and world_size >= 4)
+                self.ddp = "p2p_multimem" if (want_mm and self.comm.multicast) else "p2p"
             except Exception as e:  # no peer access / symmetric memory unavailable: the NCCL path is the alternative GPU path
                 if ddp != "auto":
                     raise
@@ -369,6 +401,7 @@ class Trainer:
         if self._use_fused():
             # one C call: samplers + proposal networks + field + renderers + losses + backward (csrc/pipeline.cu)
             fp = self.fused
+            in_graph_opt = False
             updated = True if self.force_proposal_update else fp.proposals_updated()
             sampler = self.model.proposal_sampler
             cam_opt = self.model.camera_optimizer
@@ -400,14 +433,20 @@ class Trainer:
                     for g in self.groups.values():
                         g.zero_grad()
                     gs = self._graphs[key] = _GraphedStep(self, rb_d, batch_d, updated)
+                in_graph_opt = gs.opt is not None
+                if in_graph_opt:
+                    gs.set_optimizer_scalars(self, step)
                 losses, outputs = gs.run(self, ray_bundle, batch)
                 if updated:
                     sampler._steps_since_update = 0
             else:
                 rb_d, batch_d = on_device()
                 losses, outputs = fp.train_step(rb_d, batch_d, update_proposals=updated, grad_scale=self._loss_scale())
-            self.all_reduce_gradients(proposals_updated=updated, wait=False)
-            self.optimizer_step(step)
+            if in_graph_opt:
+                self._grads_clean = True  # the step updated the parameters and cleared the gradients itself
+            else:
+                self.all_reduce_gradients(proposals_updated=updated, wait=False)
+                self.optimizer_step(step)
             self._run_callbacks("AFTER_TRAIN_ITERATION", step)
             out = {"rgb_loss": losses[0], "semantics_loss": losses[1], "interlevel_loss": losses[2], "distortion": losses[3],
                    "psnr": losses[4], "loss": losses[5]}  # finalised on the device by cnb_train_step: no per-step torch kernels here

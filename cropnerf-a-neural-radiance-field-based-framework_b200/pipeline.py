@@ -202,7 +202,7 @@ class FusedPipeline:
 
     def train_step(self, ray_bundle, batch: Dict[str, Tensor], grad_scale: float = 1.0, want_metrics: bool = True,
                    jitter: Optional[Tensor] = None, update_proposals: Optional[bool] = None, phase: int = 0,
-                   state: Optional[tuple] = None):
+                   state: Optional[tuple] = None, opt_groups: Optional[list] = None):
         """forward + losses + backward of one batch; gradients are accumulated into ``param.grad``.
         Returns (losses [8] device tensor: rgb, semantics, interlevel, distortion, ...; per-ray outputs)."""
         m = self.model
@@ -239,6 +239,16 @@ class FusedPipeline:
         cfg.update_proposals = int(bool(updated))
         cfg.want_metrics = int(want_metrics)
         cfg.phase = int(phase)
+        cfg.num_opt_groups = 0
+        if opt_groups:
+            # optimiser stage inside the step (cnb_opt_group): (flat param, grad, exp_avg, exp_avg_sq, device scalars [8], chain)
+            if len(opt_groups) > L.MAX_OPT_GROUPS:
+                raise ValueError(f"at most {L.MAX_OPT_GROUPS} optimiser groups")
+            for i, (p_, g_, m_, v_, sc_, chain) in enumerate(opt_groups):
+                og = cfg.opt_groups[i]
+                og.param, og.grad, og.exp_avg, og.exp_avg_sq = p_.data_ptr(), g_.data_ptr(), m_.data_ptr(), v_.data_ptr()
+                og.n, og.scalars, og.chain = p_.numel(), sc_.data_ptr(), int(chain)
+            cfg.num_opt_groups = len(opt_groups)
         d_o = d_d = None
         if ray_grads:
             if phase != 0:

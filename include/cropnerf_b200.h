@@ -310,6 +310,20 @@ int64_t cnb_render_workspace_floats(const cnb_model* m, int64_t num_rays, int32_
 /* eval-mode render (deterministic samplers, nan_to_num/clamp in the RGB renderer) */
 int cnb_render_rays(const cnb_model* m, const cnb_rays* rays, const cnb_ray_outputs* out, float* workspace, cnb_stream_t stream);
 
+/* Optional optimiser stage of cnb_train_step: one flat param group (engine.FlatGroup) updated by the fused Adam + gradient-clear pass
+ * as soon as the backward chain that produces its gradient has finished -- the "fields" group right after the field backward, while
+ * the proposal networks are still back-propagating on the forked stream, and vice versa.  The per-step scalars live in DEVICE memory
+ * so a captured CUDA graph of the step picks up fresh values on every replay. */
+#define CNB_MAX_OPT_GROUPS 4
+enum { CNB_CHAIN_FIELD = 0, CNB_CHAIN_PROPOSALS = 1 };
+typedef struct cnb_opt_group {
+  float* param; float* grad; float* exp_avg; float* exp_avg_sq;  /* flat, 16-byte aligned, n % 4 == 0 */
+  int64_t n;
+  const float* scalars;      /* device, 8 floats: lr, beta1, beta2, eps, 1 - beta1^t, sqrt(1 - beta2^t), 1 / grad_scale, unused */
+  int32_t chain;             /* CNB_CHAIN_*: which backward chain completes this group's gradient */
+  int32_t _pad;
+} cnb_opt_group;
+
 typedef struct cnb_train_cfg {
   const float* image;        /* [R,3] target colours */
   const float* fruit_mask;   /* [R] 0/1 */
@@ -325,7 +339,8 @@ typedef struct cnb_train_cfg {
   int32_t phase;             /* 0 = whole step; 1 = forward + final-level/field backward only; 2 = the rest (interlevel loss,
                                 proposal backward, metrics) on the workspace phase 1 left behind -- lets a data-parallel caller
                                 start the all-reduce of the field gradients while the proposal networks back-propagate */
-  int32_t _pad;
+  int32_t num_opt_groups;    /* 0 = the caller runs the optimiser itself (cnb_adam_step_zero / cnb_ddp_adam_update) */
+  cnb_opt_group opt_groups[CNB_MAX_OPT_GROUPS];
 } cnb_train_cfg;
 
 /* forward + losses + backward of one batch; parameter gradients are ACCUMULATED into the d_* pointers of `m`;
@@ -337,6 +352,9 @@ int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cnb_train_cfg
 /* ---- f2: fused optimiser over one flat parameter group: Adam update + gradient clear in one pass ----------------- */
 int cnb_adam_step_zero(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
                        float eps, int32_t step, float inv_grad_scale, cnb_stream_t stream);
+
+/* the same pass with its per-step scalars read from device memory (cnb_opt_group.scalars layout): graph-replay safe */
+int cnb_adam_step_zero_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* scalars, cnb_stream_t stream);
 
 /* GradScaler support (nerfstudio Trainer: grad_scaler.scale(loss).backward(); grad_scaler.step(optimizer); grad_scaler.update()).
  * cnb_grad_check_finite ORs 1 into *found_inf (device int32, caller clears it) when any of the n gradients is inf / NaN;

@@ -181,7 +181,7 @@ def time_step(dev, world, comm, multimem_ok):
             w.wait()
 
     variants = {"p2p": lambda: run_p2p(False), "nccl_allreduce_plus_adam": run_nccl, "part_two_barriers": only_barriers, "part_update_kernels": only_update,
-                "part_grad_clear": only_zero, "adam_zero4_symmetric_bufs": adam_symm, "adam_zero4_regular_bufs": adam_regular, "dbg_local_loads": dbg(16), "dbg_local_stores": dbg(32), "dbg_all_local": dbg(48), "dbg_u1": dbg(0x100), "dbg_u2": dbg(0x200), "dbg_u1_all_local": dbg(0x100 | 48), "dbg_u2_all_local": dbg(0x200 | 48), "part_nccl_allreduce": only_allreduce}
+                "part_grad_clear": only_zero, "adam_zero4_symmetric_bufs": adam_symm, "adam_zero4_regular_bufs": adam_regular, "dbg_local_loads": dbg(16), "dbg_local_stores": dbg(32), "dbg_all_local": dbg(48), "mm_u1": dbg(2), "mm_u2": dbg(2 | 0x100), "mm_u4": dbg(2 | 0x200), "mm_u1_grads_zero": dbg(2 | 1), "p2p_grads_zero": dbg(1), "part_nccl_allreduce": only_allreduce}
     if multimem_ok:
         variants["p2p_multimem"] = lambda: run_p2p(True)
     for label, fn in variants.items():
@@ -219,8 +219,10 @@ def main():
             mm_ok = True
         except AssertionError as e:
             summary["kernel_multimem_error"] = str(e)[:200]
-    summary["trainer_p2p_vs_nccl_max_param_diff"] = check_trainer(dev, rank, world, "p2p")
-    if mm_ok:
+    fast = os.environ.get("CNB_CHECK_FAST", "0") == "1"
+    if not fast:
+        summary["trainer_p2p_vs_nccl_max_param_diff"] = check_trainer(dev, rank, world, "p2p")
+    if mm_ok and not fast:
         summary["trainer_multimem_vs_nccl_max_param_diff"] = check_trainer(dev, rank, world, "p2p_multimem")
     summary.update(time_step(dev, world, comm, mm_ok))
     assert not comm.timed_out()
