@@ -319,11 +319,11 @@ STAGE_BYTES_PER_RAY = {
 
 
 # DRAM traffic per launch of each stage (dram__bytes_read.sum + dram__bytes_write.sum of its kernels, one `ncu --set full`
-# capture of this same command: profiles/r1_mixed_top_kernels_ncu_full.csv).  Far below the algorithmic bytes because the
+# capture of this same command: profiles/r1_final_top_kernels_ncu_full.csv).  Far below the algorithmic bytes because the
 # tables live in L2: the forward gathers are bound by the L1TEX data pipe, the backward by L2 atomics / issue.
 NCU_DRAM_BYTES_PER_LAUNCH = {
-    "field_bwd": (19.25 + 0.01 + 73.27 + 1.24) * 1e6, "field_fwd": (47.96 + 4.88) * 1e6, "proposal0_bwd": (14.37 + 0.01) * 1e6,
-    "proposal1_bwd": (6.32 + 0.004) * 1e6, "proposal0_fwd": 7.19e6, "proposal1_fwd": 5.15e6,
+    "field_bwd": (19.25 + 0.004 + 73.28 + 1.38) * 1e6, "field_fwd": (48.02 + 5.74) * 1e6, "proposal0_bwd": (53.61 + 1.30) * 1e6,
+    "proposal1_bwd": (7.25 + 0.04) * 1e6, "proposal0_fwd": (7.19 + 1.61) * 1e6, "proposal1_fwd": 5.16e6,
 }
 
 
@@ -358,7 +358,7 @@ def run_product(args):
         n_prof = m["n_prof"]
         tot = {k: v["ms"] / n_prof for k, v in m["stage"].items()}
         tot["adam (fused Adam + grad clear, 2 flat groups)"] = m["adam_ms"]
-        launches = sum(v["kernels"] for v in m["stage"].values()) / n_prof + 2
+        launches = sum(v["kernels"] for v in m["stage"].values()) / n_prof + 3  # + 2 fused Adam passes + the loss finalisation kernel
         cand = {k: v for k, v in tot.items() if k in STAGE_BYTES_PER_RAY}
         dom = max(cand, key=cand.get)
         calls = m["stage"][dom]["calls"] / n_prof

@@ -86,7 +86,7 @@ __device__ __forceinline__ float mlp_forward(const float* Ws, const float (&feat
   return out;
 }
 
-template <int LMAX, int H>
+template <int LMAX, int H, bool KEEP>
 __global__ void __launch_bounds__(BLOCK) k_density_fwd(DfArgs a, float* __restrict__ density, float* __restrict__ pos_out) {
   constexpr int INP = 2 * LMAX;
   __shared__ __align__(16) float Ws[H * INP + 2 * H + 4];
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(BLOCK) k_density_fwd(DfArgs a, float* __restri
     if (pos_out) { pos_out[3 * i] = x; pos_out[3 * i + 1] = y; pos_out[3 * i + 2] = z; }
     float feat[INP], hid[H];
     encode<LMAX>(a, x, y, z, feat);
-    if (a.feat_keep != nullptr) {
+    if (KEEP) {  // compile-time: the render path keeps its 64-register forward
 #pragma unroll
       for (int l = 0; l < LMAX; ++l)
         if (l < a.L) reinterpret_cast<float2*>(a.feat_keep)[(int64_t)l * total + i] = make_float2(feat[2 * l], feat[2 * l + 1]);
@@ -463,7 +463,8 @@ int launch_fwd(const DfArgs& a, float* density, float* pos_out, cudaStream_t st)
   int64_t blocks = (total + BLOCK - 1) / BLOCK;
   const int64_t cap = (int64_t)cnb_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  k_density_fwd<LMAX, H><<<(int)blocks, BLOCK, 0, st>>>(a, density, pos_out);
+  if (a.feat_keep != nullptr) k_density_fwd<LMAX, H, true><<<(int)blocks, BLOCK, 0, st>>>(a, density, pos_out);
+  else k_density_fwd<LMAX, H, false><<<(int)blocks, BLOCK, 0, st>>>(a, density, pos_out);
   return cnb_check_launch("density_field_fwd");
 }
 

@@ -119,37 +119,36 @@ __global__ void k_scale(float* __restrict__ v, int n, float s) {
 }
 
 // Side stream + events for the fork / join inside cnb_train_step (one set per device, created on first use, never destroyed).
-struct ForkState { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool failed = false; };
+struct ForkState { cudaStream_t side[2] = {nullptr, nullptr}; cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr}, fork2 = nullptr; bool failed = false; };
 ForkState g_fork[64];
 
-bool fork_streams(cudaStream_t main, cudaStream_t* side) {
+ForkState* fork_state(cudaStream_t main) {
   static const bool disabled = [] { const char* e = getenv("CNB_TRAIN_NO_OVERLAP"); return e && e[0] == '1'; }();
-  if (disabled) return false;
+  if (disabled) return nullptr;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   ForkState& f = g_fork[dev];
-  if (f.failed) return false;
-  if (f.side == nullptr) {
+  if (f.failed) return nullptr;
+  if (f.side[0] == nullptr) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(main, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return false;  // create outside captures (eager warm-up call)
-    if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) != cudaSuccess) {
+    if (cudaStreamIsCapturing(main, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;  // create outside captures (eager warm-up call)
+    bool ok = cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&f.fork2, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaStreamCreateWithFlags(&f.side[i], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&f.join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
       f.failed = true;
+      f.side[0] = nullptr;
       (void)cudaGetLastError();
-      return false;
+      return nullptr;
     }
   }
-  if (cudaEventRecord(f.fork, main) != cudaSuccess || cudaStreamWaitEvent(f.side, f.fork, 0) != cudaSuccess) { (void)cudaGetLastError(); return false; }
-  *side = f.side;
-  return true;
+  return &f;
 }
 
-int join_streams(cudaStream_t main, cudaStream_t side) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  ForkState& f = g_fork[dev];
-  if (cudaEventRecord(f.join, side) != cudaSuccess || cudaStreamWaitEvent(main, f.join, 0) != cudaSuccess) return cnb_check_launch("train_step join");
-  return CNB_OK;
+// `to` waits for everything enqueued on `from` so far
+bool stream_after(cudaStream_t to, cudaStream_t from, cudaEvent_t ev) {
+  if (cudaEventRecord(ev, from) != cudaSuccess || cudaStreamWaitEvent(to, ev, 0) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  return true;
 }
 
 cnb_samples make_samples(const cnb_rays* rays, const float* edges, int S) {
@@ -278,8 +277,8 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   // gradient tables, so with phase == 0 chain B is forked onto a side stream (event fork / join: still ONE stream-ordered call for the
   // caller, and capturable as two parallel branches of a CUDA graph).  Neither chain fills the GPU on its own (the field-MLP backward is a
   // latency-bound persistent kernel at 8 warps/SM, the per-ray kernels are one thin wave at 4096 rays); CNB_TRAIN_NO_OVERLAP=1 keeps them serial.
-  cudaStream_t side = stream;
-  const bool overlap = cfg->phase == 0 && !rays_grad && !g_prof_on && fork_streams(stream, &side);
+  ForkState* fk = (cfg->phase == 0 && !rays_grad && !g_prof_on) ? fork_state(stream) : nullptr;
+  const bool overlap = fk != nullptr && stream_after(fk->side[0], stream, fk->fork);
   auto optimise = [&](int chain, cudaStream_t st) -> int {
     int rc = CNB_OK;
     for (int i = 0; i < cfg->num_opt_groups; ++i) {
@@ -304,23 +303,24 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
     if (rc) return rc;
     return optimise(CNB_CHAIN_FIELD, st);  // the field gradient is complete: its Adam pass overlaps the proposal chain
   };
-  auto chain_proposals = [&](cudaStream_t st) -> int {
-    int rc = CNB_OK;
-    // ---- interlevel loss (fruit_nerf.py:610) and, on "updated" steps, its backward into the proposal networks ---------------------
-    for (int lv = 0; lv < lf; ++lv) {
-      const int S = L.S[lv];
-      STAGE("interlevel", 1, cnb_interlevel_fused(ws + L.sp[lf], ws + L.w[lf], ws + L.sp[lv], ws + L.w[lv], ws + L.dens[lv], ws + L.eu[lv], R, Sf, S,
-                                                  gs * cfg->interlevel_loss_mult, losses_out + 2, cfg->update_proposals ? ws + L.d_dens[lv] : nullptr, st));
-      if (rc) return rc;
-      if (cfg->update_proposals) {
-        const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
-        if (rays_grad) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 2, cnb_density_field_bwd_rays(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pg_scratch,
-                                                                                                       cfg->d_origins, cfg->d_directions, st));
-        else if (L.pfeat[lv] >= 0) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd_kept(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pfeat[lv], st));
-        else STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd(&m->proposal[lv], &sm, ws + L.d_dens[lv], st));
-        if (rc) return rc;
-      }
+  // one proposal level: interlevel loss (fruit_nerf.py:610) and, on "updated" steps, its backward into that proposal network
+  auto proposal_level = [&](int lv, cudaStream_t st) -> int {
+    int rc;
+    const int S = L.S[lv];
+    STAGE("interlevel", 1, cnb_interlevel_fused(ws + L.sp[lf], ws + L.w[lf], ws + L.sp[lv], ws + L.w[lv], ws + L.dens[lv], ws + L.eu[lv], R, Sf, S,
+                                                gs * cfg->interlevel_loss_mult, losses_out + 2, cfg->update_proposals ? ws + L.d_dens[lv] : nullptr, st));
+    if (rc) return rc;
+    if (cfg->update_proposals) {
+      const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
+      if (rays_grad) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 2, cnb_density_field_bwd_rays(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pg_scratch,
+                                                                                                     cfg->d_origins, cfg->d_directions, st));
+      else if (L.pfeat[lv] >= 0) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd_kept(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pfeat[lv], st));
+      else STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd(&m->proposal[lv], &sm, ws + L.d_dens[lv], st));
     }
+    return rc;
+  };
+  auto proposals_tail = [&](cudaStream_t st) -> int {
+    int rc = CNB_OK;
     if (cfg->interlevel_loss_mult != 1.0f) {
       k_scale<<<1, 32, 0, st>>>(losses_out + 2, 1, cfg->interlevel_loss_mult);
       if ((rc = cnb_check_launch("train_step scale"))) return rc;
@@ -331,10 +331,26 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
     }
     return optimise(CNB_CHAIN_PROPOSALS, st);
   };
+  auto chain_proposals = [&](cudaStream_t st) -> int {
+    int rc = CNB_OK;
+    for (int lv = 0; lv < lf; ++lv)
+      if ((rc = proposal_level(lv, st))) return rc;
+    return proposals_tail(st);
+  };
   if (overlap) {
-    rc = chain_proposals(side);
+    // three branches: field chain on the caller's stream; proposal level 0 on side[0]; proposal level 1 on side[1] (the two proposal networks
+    // are independent: each only needs its own interlevel gradient; the level-1 backward is a short, latency-bound kernel that fills the gaps
+    // of the level-0 one); side[1] joins side[0] before the proposal group's tail (loss scaling, metrics, Adam), side[0] joins the caller's stream
+    cudaStream_t s0 = fk->side[0], s1 = fk->side[1];
+    bool two = lf >= 2 && cfg->update_proposals && stream_after(s1, stream, fk->fork2);
+    rc = proposal_level(0, s0);
+    if (lf >= 2) { const int r1 = proposal_level(1, two ? s1 : s0); if (!rc) rc = r1; }
+    bool joined = true;
+    if (two) joined = stream_after(s0, s1, fk->join[1]);
+    if (!rc) rc = proposals_tail(s0);
     const int rc2 = chain_field(stream);
-    if (join_streams(stream, side) != CNB_OK) return CNB_ERR_CUDA;  // always join, even after a failed launch
+    joined = stream_after(stream, s0, fk->join[0]) && joined;  // always join, even after a failed launch
+    if (!joined) { cnb_set_error("train_step: stream join failed"); return CNB_ERR_CUDA; }
     if (rc || rc2) return rc ? rc : rc2;
   } else {
     if (first && (rc = chain_field(stream))) return rc;
