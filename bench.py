@@ -166,6 +166,17 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
     barrier()
     clk = clocks.stop() if (rank == 0 and full) else None
     t_local = sum(a.elapsed_time(b) for a, b in ev) / 1e3
+    # the same steps back to back, no flush in between (what a training loop does; a step touches ~400 MB, 3x the L2): one event pair
+    barrier()  # rank 0 has just spent ~0.2 s stopping its clock sampler: line the ranks up again
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for i in range(steps):
+        train_step(step, *resident[step % nb]); step += 1
+    if getattr(trainer, "wait_deferred_update", None) is not None:
+        trainer.wait_deferred_update()
+    b1.record()
+    barrier()
+    t_b2b_local = b0.elapsed_time(b1) / 1e3
 
     # ---- timed: end to end through the public API with host buffers ------------------------------------------
     # the public call takes the pinned HOST rays / targets as they are: train_iteration copies them (H2D, async) into the graphed
@@ -232,9 +243,9 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
         a_ev = []
         orig_opt = trainer.optimizer_step
 
-        def timed_opt(s):
+        def timed_opt(s, **kw):
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record(); orig_opt(s); a1.record()
+            a0.record(); orig_opt(s, **kw); a1.record()
             a_ev.append((a0, a1))
 
         trainer.optimizer_step = timed_opt
@@ -294,16 +305,16 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
     model.train()
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------------------
-    times = torch.tensor([t_local, t_e2e_local, t_render_local, t_render_e2e_local], device=dev, dtype=torch.float64)
+    times = torch.tensor([t_local, t_e2e_local, t_render_local, t_render_e2e_local, t_b2b_local], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t, t_e2e, t_render, t_render_e2e = times.tolist()
+    t, t_e2e, t_render, t_render_e2e, t_b2b = times.tolist()
     ddp_mode = trainer.ddp if world > 1 else None
     if trainer.comm is not None:
         assert not trainer.comm.timed_out(), "a peer-memory barrier timed out during the benchmark"
     del trainer, model, l2_flush
     torch.cuda.empty_cache()
-    return {"ddp": ddp_mode, "steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
+    return {"ddp": ddp_mode, "t_b2b": t_b2b, "steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
             "stage": stage, "n_prof": n_prof, "nonupdate_ms": nonupdate_ms, "camopt_ms": camopt_ms, "adam_ms": adam_ms, "render_stage": render_stage, "loss": loss_host,
             "h2d_train": bytes_of({k: host[0][k] for k in ("origins", "directions", "camera_indices", "image", "fruit_mask")}), "h2d_render": bytes_of({k: rhost[k] for k in ("origins", "directions", "pixel_area", "camera_indices")}),
             "d2h_render": int(d2h_render)}
@@ -379,7 +390,9 @@ def run_product(args):
             "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: fruit_nerf preset training step, 4096 rays/GPU, proposal 256/96 + 48 NeRF samples, "
                                    "field 16x2^19x2 + 2 proposal 5x2^17x2 fp32 hash tables, 300 synthetic 1080p cameras",
-                       "rays_per_gpu": R, "samples_per_ray": 400, "precision": args.precision, "l2": "flushed between timed iterations (192 MiB fill)", "data_parallel": m["ddp"],
+                       "rays_per_gpu": R, "samples_per_ray": 400, "precision": args.precision, "l2": "flushed between timed iterations (192 MiB fill)", "data_parallel": m["ddp"], "ms_per_step_back_to_back_no_flush": 1e3 * m["t_b2b"] / steps,
+                       "note_overlap": ("N>1: the field group's parameter exchange of step i-1 runs on a side stream and overlaps the (untimed, ~30 us) L2 flush and the "
+                                        "proposal forward of step i; ms_per_step_back_to_back_no_flush has no flush window") if world > 1 else None,
                        "includes": "fwd + losses + bwd (all three networks updated EVERY step) + gradient all-reduce + Adam; "
                                    + ("cnb_train_step eager" if args.no_graph else "cnb_train_step replayed as one CUDA graph"),
                        "non_update_step_ms": m["nonupdate_ms"],

@@ -183,7 +183,7 @@ P2P_GRADS_ZERO, P2P_MULTIMEM = 1, 2
 
 class P2PComm(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("flags", C.c_void_p * MAX_PEERS), ("state", C.c_void_p), ("timeout_ms", C.c_int32),
-                ("_pad", C.c_int32)]
+                ("channel", C.c_int32)]
 
 
 class P2PGroup(C.Structure):

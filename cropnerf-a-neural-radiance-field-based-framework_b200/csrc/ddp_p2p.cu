@@ -37,17 +37,18 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 
 __global__ void __launch_bounds__(32) k_p2p_barrier(cnb_p2p_comm c, uint64_t timeout_ns) {
   __shared__ uint32_t seq_s;
-  if (threadIdx.x == 0) seq_s = ++c.state[0];  // stream-ordered: only this kernel touches the counter
+  const int ch = c.channel;
+  if (threadIdx.x == 0) seq_s = ++c.state[2 * ch];  // stream-ordered: only this channel's barriers touch the counter
   __syncwarp();
   const uint32_t seq = seq_s;
   const int k = threadIdx.x;
   if (k < c.world) {
     __threadfence_system();
-    st_release_sys(c.flags[k] + c.rank, seq);
-    const uint32_t* mine = c.flags[c.rank] + k;
+    st_release_sys(c.flags[k] + ch * CNB_MAX_PEERS + c.rank, seq);
+    const uint32_t* mine = c.flags[c.rank] + ch * CNB_MAX_PEERS + k;
     const uint64_t t0 = globaltimer_ns();
     while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) {
-      if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(c.state + 1, 1u); break; }
+      if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(c.state + 2 * ch + 1, 1u); break; }
       __nanosleep(64);
     }
     __threadfence_system();
@@ -158,6 +159,7 @@ int check_comm(const cnb_p2p_comm* c, const char* what) {
   CNB_REQUIRE(c != nullptr, "%s: null communicator", what);
   CNB_REQUIRE(c->world >= 1 && c->world <= CNB_MAX_PEERS && c->rank >= 0 && c->rank < c->world, "%s: bad world %d / rank %d", what, c->world, c->rank);
   CNB_REQUIRE(c->state != nullptr, "%s: null state", what);
+  CNB_REQUIRE(c->channel >= 0 && c->channel < 4, "%s: channel %d outside 0..3", what, c->channel);
   for (int k = 0; k < c->world; ++k) CNB_REQUIRE(c->flags[k] != nullptr, "%s: null flag block of rank %d", what, k);
   return CNB_OK;
 }

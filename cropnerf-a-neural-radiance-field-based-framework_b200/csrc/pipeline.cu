@@ -173,28 +173,28 @@ int check_common(const cnb_model* m, const cnb_rays* rays, const float* ws) {
 
 // sampler + proposal networks + field + compositing.  jitter == nullptr: deterministic (eval) samplers.
 int forward_chain(const cnb_model* m, const cnb_rays* rays, const Layout& L, float* ws, bool training, const float* jitter, float anneal,
-                  const cnb_ray_outputs* out, cudaStream_t st, bool keep_proposal_features = false) {
+                  const cnb_ray_outputs* out, cudaStream_t st, bool keep_proposal_features = false, int part = 0) {
+  // part 0: everything; 1: samplers + proposal networks only (reads no field parameter); 2: field level + compositing on what part 1 left
   const int64_t R = rays->num_rays;
   const cnb_sampler& sp = m->sampler;
-  int rc;
-  int64_t blocks = (R + 255) / 256;
-  if (blocks > 4 * cnb_num_sms()) blocks = 4 * cnb_num_sms();
-  {
-    StageTimer _t("near_far", 1, st);
-    k_fill_near_far<<<(int)blocks, 256, 0, st>>>(rays->nears, rays->fars, rays->near_plane, rays->far_plane, R, ws + L.nears, ws + L.fars);
-  }
-  if ((rc = cnb_check_launch("render near/far"))) return rc;
+  int rc = CNB_OK;
   const bool mixed = m->field.precision == CNB_PREC_MIXED;
   const float* jit = jitter;
   const int lf = L.levels - 1;
   const bool user = out != nullptr;
-  {
+  if (part != 2) {
+    int64_t blocks = (R + 255) / 256;
+    if (blocks > 4 * cnb_num_sms()) blocks = 4 * cnb_num_sms();
+    {
+      StageTimer _t("near_far", 1, st);
+      k_fill_near_far<<<(int)blocks, 256, 0, st>>>(rays->nears, rays->fars, rays->near_plane, rays->far_plane, R, ws + L.nears, ws + L.fars);
+    }
+    if ((rc = cnb_check_launch("render near/far"))) return rc;
     const int rstride = sp.single_jitter ? 1 : L.S[0] + 1;
     STAGE("sample_spaced", 1, cnb_sample_spaced(ws + L.nears, ws + L.fars, sp.lin_bins, jit, rstride, sp.initial_spacing, R, L.S[0], ws + L.sp[0], ws + L.eu[0], st));
     if (rc) return rc;
-    if (jit) jit += R * rstride;
   }
-  for (int lv = 0; lv < L.levels; ++lv) {
+  for (int lv = (part == 2 ? lf : 0); lv < (part == 1 ? lf : L.levels); ++lv) {
     const int S = L.S[lv];
     const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
     if (lv < lf) {
@@ -206,18 +206,22 @@ int forward_chain(const cnb_model* m, const cnb_rays* rays, const Layout& L, flo
       // get_weights -> median depth -> PDF resampling of the next level, one kernel
       const int Sn = L.S[lv + 1];
       const int rstride = sp.single_jitter ? 1 : Sn + 1;
+      if (jitter) {  // draws are laid out in sampler order: the initial sampler's, then one block per PDF resampling
+        jit = jitter + R * (sp.single_jitter ? 1 : L.S[0] + 1);
+        for (int q = 0; q < lv; ++q) jit += R * (sp.single_jitter ? 1 : L.S[q + 1] + 1);
+      }
       STAGE("level_resample", 1, cnb_level_resample(ws + L.dens[lv], ws + L.eu[lv], ws + L.sp[lv], ws + L.nears, ws + L.fars, sp.initial_spacing, anneal,
                                                     sp.u_base[lv], jit, rstride, R, S, Sn, sp.histogram_padding, sp.pdf_eps, training ? ws + L.w[lv] : nullptr,
                                                     user ? out->prop_depth[lv] : nullptr, ws + L.sp[lv + 1], ws + L.eu[lv + 1],
                                                     (lv + 1 == lf && user) ? out->pdf_inds : nullptr, st));
       if (rc) return rc;
-      if (jit) jit += R * rstride;
     } else {
       STAGE("field_fwd", mixed ? 1 : 7, cnb_field_fwd(&m->field, &sm, ws + L.dens[lv], nullptr, ws + L.rgb, ws + L.sem, nullptr,
                                                         L.ctx_floats > 0 ? ws + L.ctx : nullptr, training ? 1 : 0, st));
       if (rc) return rc;
     }
   }
+  if (part == 1) return rc;
   const int Sf = L.S[lf];
   float* o_rgb = (user && out->rgb) ? out->rgb : ws + L.o_rgb;
   float* o_acc = (user && out->accumulation) ? out->accumulation : ws + L.o_acc;
@@ -258,15 +262,17 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   if ((rc = make_layout(m, R, true, L))) return rc;
   float* ws = workspace;
   const bool mixed = m->field.precision == CNB_PREC_MIXED;
-  CNB_REQUIRE(cfg->phase >= 0 && cfg->phase <= 2, "train_step: phase %d outside 0..2", cfg->phase);
+  CNB_REQUIRE(cfg->phase >= 0 && cfg->phase <= 4, "train_step: phase %d outside 0..4", cfg->phase);
   CNB_REQUIRE(cfg->num_opt_groups >= 0 && cfg->num_opt_groups <= CNB_MAX_OPT_GROUPS, "train_step: num_opt_groups %d outside 0..%d", cfg->num_opt_groups, CNB_MAX_OPT_GROUPS);
   const bool rays_grad = cfg->d_origins != nullptr;
   CNB_REQUIRE(!rays_grad || (cfg->d_directions != nullptr && m->ray_gradients), "train_step: ray gradients need d_directions and cnb_model.ray_gradients (workspace scratch)");
   const bool first = cfg->phase != 2, second = cfg->phase != 1;
   if (first) {
-    if (cudaMemsetAsync(losses_out, 0, 8 * sizeof(float), stream) != cudaSuccess) return cnb_check_launch("train_step memset");
+    if (cfg->phase != 4 && cudaMemsetAsync(losses_out, 0, 8 * sizeof(float), stream) != cudaSuccess) return cnb_check_launch("train_step memset");
     // on proposal-update steps the proposal forward keeps its encoded features for the backward (no second gather pass)
-    if ((rc = forward_chain(m, rays, L, ws, true, cfg->jitter, cfg->anneal, out, stream, cfg->update_proposals != 0 && !rays_grad))) return rc;
+    const int part = cfg->phase == 3 ? 1 : (cfg->phase == 4 ? 2 : 0);
+    if ((rc = forward_chain(m, rays, L, ws, true, cfg->jitter, cfg->anneal, out, stream, cfg->update_proposals != 0 && !rays_grad, part))) return rc;
+    if (cfg->phase == 3) return CNB_OK;  // samplers + proposal forward only: the caller continues with phase 4 on the same workspace
   }
   const int lf = L.levels - 1, Sf = L.S[lf];
   const float gs = cfg->grad_scale == 0.0f ? 1.0f : cfg->grad_scale;
@@ -277,7 +283,7 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
   // gradient tables, so with phase == 0 chain B is forked onto a side stream (event fork / join: still ONE stream-ordered call for the
   // caller, and capturable as two parallel branches of a CUDA graph).  Neither chain fills the GPU on its own (the field-MLP backward is a
   // latency-bound persistent kernel at 8 warps/SM, the per-ray kernels are one thin wave at 4096 rays); CNB_TRAIN_NO_OVERLAP=1 keeps them serial.
-  ForkState* fk = (cfg->phase == 0 && !rays_grad && !g_prof_on) ? fork_state(stream) : nullptr;
+  ForkState* fk = ((cfg->phase == 0 || cfg->phase == 4) && !rays_grad && !g_prof_on) ? fork_state(stream) : nullptr;
   const bool overlap = fk != nullptr && stream_after(fk->side[0], stream, fk->fork);
   auto optimise = [&](int chain, cudaStream_t st) -> int {
     int rc = CNB_OK;

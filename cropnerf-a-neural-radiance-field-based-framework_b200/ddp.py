@@ -48,12 +48,13 @@ class PeerComm:
         self._keep: List[object] = []
         flags, hdl = self._alloc((self.FLAG_WORDS,), torch.int32)
         self.flags = flags
-        self.state = torch.zeros((2,), device=self.device, dtype=torch.int32)
+        self.state = torch.zeros((8,), device=self.device, dtype=torch.int32)
         c = L.P2PComm()
         c.world, c.rank, c.timeout_ms = self.world, self.rank, int(timeout_ms)
         for k in range(self.world):
             c.flags[k] = int(hdl.buffer_ptrs[k])
         c.state = self.state.data_ptr()
+        c.channel = 0
         self.struct = c
         self.multicast = bool(int(hdl.multicast_ptr))
 
@@ -78,12 +79,17 @@ class PeerComm:
         mc = int(hdl.multicast_ptr)
         return t, ptrs, (mc + off if mc else 0)
 
-    def barrier(self) -> None:
-        L.check(L.lib().cnb_p2p_barrier(C.byref(self.struct), L.stream_ptr(self.device)), "p2p_barrier")
+    def barrier(self, channel: int = 0) -> None:
+        """Cross-GPU barrier on the current stream.  Barriers on different channels are independent (different streams may run them concurrently)."""
+        c = self.struct
+        if channel != 0:
+            c = L.P2PComm.from_buffer_copy(self.struct)
+            c.channel = int(channel)
+        L.check(L.lib().cnb_p2p_barrier(C.byref(c), L.stream_ptr(self.device)), "p2p_barrier")
 
     def timed_out(self) -> bool:
         """True when a barrier gave up waiting for a peer (synchronises)."""
-        return bool(self.state[1].item())
+        return bool(self.state[1::2].any().item())
 
 
 class PeerGroup:

@@ -208,12 +208,12 @@ class FusedPipeline:
         m = self.model
         dev = ray_bundle.origins.device
         s = m.proposal_sampler
-        if phase == 2:
-            # second half of a split step (cnb_train_cfg.phase): same structs, workspace and outputs as the phase-1 call
+        if phase in (2, 4):
+            # second half of a split step (cnb_train_cfg.phase 1 -> 2, or 3 -> 4): same structs, workspace and outputs as the first call
             ms, rays, cfg, out, losses, ws, tensors, updated, keep = state
-            cfg.phase = 2
+            cfg.phase = phase
             L.check(L.lib().cnb_train_step(C.byref(ms), C.byref(rays), C.byref(cfg), C.byref(out), losses.data_ptr(), ws.data_ptr(), L.stream_ptr(dev)),
-                    "train_step(phase 2)")
+                    f"train_step(phase {phase})")
             if updated:
                 s._steps_since_update = 0
             return losses, tensors
@@ -259,7 +259,7 @@ class FusedPipeline:
         losses = torch.empty((8,), device=dev, dtype=torch.float32)
         L.check(L.lib().cnb_train_step(C.byref(ms), C.byref(rays), C.byref(cfg), C.byref(out), losses.data_ptr(), ws.data_ptr(), L.stream_ptr(dev)),
                 "train_step")
-        if phase == 1:
+        if phase in (1, 3):
             return losses, tensors, (ms, rays, cfg, out, losses, ws, tensors, updated, (keep, keep2, image, mask, jitter))
         if updated:
             s._steps_since_update = 0

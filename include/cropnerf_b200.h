@@ -338,7 +338,10 @@ typedef struct cnb_train_cfg {
   float* d_directions;       /* optional [R,3], ACCUMULATED */
   int32_t phase;             /* 0 = whole step; 1 = forward + final-level/field backward only; 2 = the rest (interlevel loss,
                                 proposal backward, metrics) on the workspace phase 1 left behind -- lets a data-parallel caller
-                                start the all-reduce of the field gradients while the proposal networks back-propagate */
+                                start the all-reduce of the field gradients while the proposal networks back-propagate;
+                                3 = samplers + proposal-network forward only (touches no field parameter); 4 = everything after that
+                                (field forward, compositing, losses, the whole backward) on the workspace phase 3 left behind -- lets a
+                                data-parallel caller begin the next step while the field group's parameter exchange is still in flight */
   int32_t num_opt_groups;    /* 0 = the caller runs the optimiser itself (cnb_adam_step_zero / cnb_ddp_adam_update) */
   cnb_opt_group opt_groups[CNB_MAX_OPT_GROUPS];
 } cnb_train_cfg;
@@ -377,10 +380,10 @@ enum { CNB_P2P_GRADS_ZERO = 1, /* the group's gradient is zero on every rank thi
        CNB_P2P_MULTIMEM = 2    /* NVLS: one multimem.ld_reduce / multimem.st through the multicast mappings instead of N peer loads / stores */ };
 typedef struct cnb_p2p_comm {
   int32_t world, rank;
-  uint32_t* flags[CNB_MAX_PEERS]; /* flags[k] = rank k's flag block (>= CNB_MAX_PEERS uint32, zero-initialised), peer-mapped here */
-  uint32_t* state;                /* LOCAL device memory, 2 uint32, zero-initialised: [0] barrier sequence, [1] set to 1 when a barrier timed out */
+  uint32_t* flags[CNB_MAX_PEERS]; /* flags[k] = rank k's flag block (>= 4 * CNB_MAX_PEERS uint32, zero-initialised), peer-mapped here */
+  uint32_t* state;                /* LOCAL device memory, 8 uint32, zero-initialised: [2c] barrier sequence of channel c, [2c+1] set to 1 when one timed out */
   int32_t timeout_ms;             /* spin limit of one barrier (0 = 10 s) */
-  int32_t _pad;
+  int32_t channel;                /* 0..3: barriers on different channels are independent (may run concurrently on different streams) */
 } cnb_p2p_comm;
 typedef struct cnb_p2p_group {
   float* grad[CNB_MAX_PEERS];     /* grad[k] = rank k's flat gradient buffer of this group (grad[rank] = own), peer-mapped here */
