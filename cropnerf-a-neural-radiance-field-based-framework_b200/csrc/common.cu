@@ -34,3 +34,15 @@ extern "C" int cnb_device_count(void) {
   }
   return n;
 }
+
+// Host -> device staging for the graphed training step (engine._GraphedStep): n async copies on `stream` with one call, no
+// framework dispatch in between.  src[i] should be pinned host memory (otherwise the copy is staged synchronously by the driver).
+extern "C" int cnb_upload(void* const* dst, const void* const* src, const int64_t* bytes, int32_t n, cnb_stream_t stream) {
+  CNB_REQUIRE(n >= 0 && (n == 0 || (dst && src && bytes)), "upload: null arrays");
+  for (int i = 0; i < n; ++i) {
+    if (bytes[i] == 0) continue;
+    CNB_REQUIRE(dst[i] && src[i] && bytes[i] > 0, "upload: null pointer / negative size in entry %d", i);
+    if (cudaMemcpyAsync(dst[i], src[i], (size_t)bytes[i], cudaMemcpyHostToDevice, stream) != cudaSuccess) return cnb_check_launch("upload");
+  }
+  return CNB_OK;
+}

@@ -136,6 +136,11 @@ class FlatGroup:
         self.grad.zero_()
 
 
+def _stats_views(losses: Tensor) -> Dict[str, Tensor]:
+    """names of the loss buffer cnb_train_step fills (psnr / total are finalised on the device: no per-step torch kernels here)"""
+    return {"rgb_loss": losses[0], "semantics_loss": losses[1], "interlevel_loss": losses[2], "distortion": losses[3], "psnr": losses[4], "loss": losses[5]}
+
+
 class _GraphedStep:
     """One captured CUDA graph of ``cnb_train_step`` for a fixed (ray count, proposal-update flag, anneal) combination.
     Inputs are copied into static buffers, jitter is drawn eagerly into a static buffer, then the graph is replayed: the
@@ -152,6 +157,7 @@ class _GraphedStep:
             "camera_indices": torch.empty((R, 1), device=dev, dtype=torch.int32),
             "image": torch.empty((R, 3), device=dev), "fruit_mask": torch.empty((R, 1), device=dev),
         }
+        self.cam64 = torch.zeros((R, 1), device=dev, dtype=torch.int64)
         self.jitter = fp.draw_jitter(R, dev).clone()
         # torch.rand inside a capture is graph-safe (the generator's philox offset advances per replay): the default jitter is drawn by the
         # graph itself; custom rand_fn feeds (tests) are drawn eagerly into the static buffer before each replay
@@ -185,6 +191,7 @@ class _GraphedStep:
             # data parallel over NCCL: two graphs, so the all-reduce of the field gradients (67 MB) can start after the field backward
             # and run on NCCL's stream while the proposal networks back-propagate (cnb_train_cfg.phase)
             with torch.cuda.graph(self.graph):
+                self._narrow_camera_indices()
                 if self.jitter_in_graph:
                     self.jitter.uniform_()
                 self.losses, self.outputs, state = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, phase=1,
@@ -197,6 +204,7 @@ class _GraphedStep:
             # peer-memory data parallelism: graph A = samplers + proposal forward (reads no field parameter), graph B = the rest.  The field
             # group's exchange of the PREVIOUS step runs on a side stream and only has to land before graph B (Trainer._p2p_optimizer_step)
             with torch.cuda.graph(self.graph):
+                self._narrow_camera_indices()
                 if self.jitter_in_graph:
                     self.jitter.uniform_()
                 self.losses, self.outputs, state = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, phase=3,
@@ -207,21 +215,47 @@ class _GraphedStep:
             self._state = state
         else:
             with torch.cuda.graph(self.graph):
+                self._narrow_camera_indices()
                 if self.jitter_in_graph:
                     self.jitter.uniform_()
                 self.losses, self.outputs = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, grad_scale=trainer._loss_scale(),
                                                           opt_groups=self.opt)
+        self.stats = _stats_views(self.losses)
         for g in trainer.groups.values():  # whatever the capture-time warm-up left in the gradients
             g.zero_grad()
 
     def _load(self, ray_bundle, batch) -> None:
         st = self.static
         R = st["origins"].shape[0]
+        cam = ray_bundle.camera_indices
+        srcs = (ray_bundle.origins, ray_bundle.directions, cam, batch["image"], batch["fruit_mask"])
+        if all((not t.is_cuda) and t.is_pinned() and t.is_contiguous() for t in srcs) and cam.dtype == torch.int64 and batch["image"].shape[-1] == 3 \
+                and all(t.dtype == torch.float32 for t in (srcs[0], srcs[1], srcs[3], srcs[4])):
+            # pinned host batch: raw async copies issued by ONE C call (cnb_upload), no framework dispatch per tensor; the int64 camera
+            # indices go up as they are and are narrowed to the kernels' int32 inside the graph
+            import ctypes as C
+
+            from . import _lib as L
+
+            dsts = (st["origins"], st["directions"], self.cam64, st["image"], st["fruit_mask"])
+            n = len(srcs)
+            for d, t in zip(dsts, srcs):
+                if d.numel() * d.element_size() != t.numel() * t.element_size():
+                    raise ValueError("batch tensor sizes do not match the captured step")
+            d_arr = (C.c_void_p * n)(*[d.data_ptr() for d in dsts])
+            s_arr = (C.c_void_p * n)(*[t.data_ptr() for t in srcs])
+            b_arr = (C.c_int64 * n)(*[t.numel() * t.element_size() for t in srcs])
+            L.check(L.lib().cnb_upload(d_arr, s_arr, b_arr, n, L.stream_ptr(st["origins"].device)), "upload")
+            return
         st["origins"].copy_(ray_bundle.origins.reshape(R, 3), non_blocking=True)
         st["directions"].copy_(ray_bundle.directions.reshape(R, 3), non_blocking=True)
-        st["camera_indices"].copy_(ray_bundle.camera_indices.reshape(R, 1), non_blocking=True)
+        self.cam64.copy_(cam.reshape(R, 1), non_blocking=True)
         st["image"].copy_(batch["image"][:, :3], non_blocking=True)
         st["fruit_mask"].copy_(batch["fruit_mask"].reshape(R, 1), non_blocking=True)
+
+    def _narrow_camera_indices(self) -> None:
+        """captured at the head of the graph: the kernels' int32 camera indices from the uploaded int64 ones (one tiny kernel)"""
+        self.static["camera_indices"].copy_(self.cam64)
 
     def set_optimizer_scalars(self, trainer: "Trainer", step: int) -> None:
         """lr / bias corrections of THIS step for the in-graph Adam passes (one 64-byte async H2D copy)."""
@@ -432,7 +466,8 @@ class Trainer:
         return self.fused is not None and self.model.collider is not None and self.fused.eligible()
 
     def train_iteration(self, step: int, ray_bundle, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
-        self.model.train()
+        if not self.model.training:  # nn.Module.train() walks every sub-module: only when the mode actually changes
+            self.model.train()
         self._run_callbacks("BEFORE_TRAIN_ITERATION", step)
         graphed = False
         if not getattr(self, "_grads_clean", False):
@@ -489,11 +524,14 @@ class Trainer:
                 self._grads_clean = True  # the step updated the parameters and cleared the gradients itself
             else:
                 self.all_reduce_gradients(proposals_updated=updated, wait=False)
-                self.optimizer_step(step, pipelined=graphed and self.comm is not None)
+                if graphed and self.comm is not None:
+                    self.optimizer_step(step, pipelined=True)
+                else:
+                    self.optimizer_step(step)
             self._run_callbacks("AFTER_TRAIN_ITERATION", step)
-            out = {"rgb_loss": losses[0], "semantics_loss": losses[1], "interlevel_loss": losses[2], "distortion": losses[3],
-                   "psnr": losses[4], "loss": losses[5]}  # finalised on the device by cnb_train_step: no per-step torch kernels here
-            return out
+            if graphed:  # the graphed step writes the same static loss buffer every replay: its views are made once
+                return gs.stats
+            return _stats_views(losses)
         self.wait_deferred_update()
         outputs = self.model(ray_bundle)
         metrics = self.model.get_metrics_dict(outputs, batch)

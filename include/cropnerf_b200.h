@@ -396,6 +396,10 @@ int cnb_p2p_barrier(const cnb_p2p_comm* comm, cnb_stream_t stream);
 int cnb_ddp_adam_update(const cnb_p2p_comm* comm, const cnb_p2p_group* group, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                         float beta1, float beta2, float eps, int32_t step, float inv_grad_scale, int32_t flags, cnb_stream_t stream);
 
+/* ---- host -> device staging of one batch (rays, targets, optimiser scalars): n cudaMemcpyAsync on `stream` in one call.
+ * dst[i] device, src[i] HOST (pinned for a truly asynchronous copy), bytes[i] sizes; the arrays themselves are host arrays. */
+int cnb_upload(void* const* dst, const void* const* src, const int64_t* bytes, int32_t n, cnb_stream_t stream);
+
 /* ---- measurement aid: per-stage device times of cnb_render_rays / cnb_train_step (CUDA events on the launching stream).
  * cnb_profile_read synchronises, writes "stage:calls:kernels:ms;..." (summed since enable) into buf and clears the log. */
 void cnb_profile_enable(int32_t on);

@@ -88,10 +88,10 @@ def test_fused_train_step_equals_modular(dev, precision):
         grads = {}
         orig = tr.optimizer_step
 
-        def spy(step, tr=tr, grads=grads, orig=orig):
+        def spy(step, tr=tr, grads=grads, orig=orig, **kw):
             for name, g in tr.groups.items():
                 grads[name] = g.grad.clone()
-            orig(step)
+            orig(step, **kw)
 
         tr.optimizer_step = spy
         stats = tr.train_iteration(500, product_bundle(rays, dev), targets)
