@@ -172,10 +172,14 @@ class _GraphedStep:
         # single GPU: the optimiser runs INSIDE the step -- each flat group's fused Adam + gradient clear right behind the backward chain
         # that completes its gradient, overlapping the other chain (cnb_opt_group); per-step scalars go through a small device buffer
         self.opt = None
+        self.defer_fields = False
         if trainer.world_size == 1 and trainer.grad_scaler is None and set(trainer.groups) <= {"fields", "proposal_networks"}:
             from . import _lib as L_
 
-            names = list(trainer.groups)
+            # ... except the big "fields" group when the trainer pipelines it: its Adam pass (HBM bound) then runs on a side stream next to the
+            # NEXT step's samplers + proposal forward (L1 bound, reads no field parameter) and only gates that step's field forward
+            self.defer_fields = trainer.defer_fields and "fields" in trainer.groups
+            names = [n for n in trainer.groups if not (self.defer_fields and n == "fields")]
             # ring of pinned rows: the host may run several steps ahead of the stream that executes the copies
             self.opt_host = torch.zeros((self.RING, len(names), 8), dtype=torch.float32, pin_memory=True)
             self.opt_np = self.opt_host.numpy()
@@ -200,15 +204,16 @@ class _GraphedStep:
             with torch.cuda.graph(self.graph2, pool=self.graph.pool()):
                 fp.train_step(self.bundle, self.batch, update_proposals=update, phase=2, state=state)
             self._state = state
-        elif trainer.comm is not None:
-            # peer-memory data parallelism: graph A = samplers + proposal forward (reads no field parameter), graph B = the rest.  The field
-            # group's exchange of the PREVIOUS step runs on a side stream and only has to land before graph B (Trainer._p2p_optimizer_step)
+        elif trainer.comm is not None or self.defer_fields:
+            # graph A = samplers + proposal forward (reads no field parameter), graph B = the rest.  The field group's update of the PREVIOUS
+            # step (peer-memory exchange, Trainer._p2p_optimizer_step; or plain Adam on one GPU) runs on a side stream and only has to land
+            # before graph B
             with torch.cuda.graph(self.graph):
                 self._narrow_camera_indices()
                 if self.jitter_in_graph:
                     self.jitter.uniform_()
                 self.losses, self.outputs, state = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, phase=3,
-                                                                 grad_scale=trainer._loss_scale())
+                                                                 grad_scale=trainer._loss_scale(), opt_groups=self.opt)
             self.graphB = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graphB, pool=self.graph.pool()):
                 fp.train_step(self.bundle, self.batch, update_proposals=update, phase=4, state=state)
@@ -306,6 +311,9 @@ class Trainer:
         self._side_stream = None
         self._deferred_event = None
         self._deferred_pending = False
+        import os as _os
+
+        self.defer_fields = _os.environ.get("CNB_NO_DEFER", "0") != "1"  # one GPU: pipeline the field group's Adam into the next step (graphed steps)
         self.ddp = "nccl"
         if world_size > 1 and ddp != "nccl" and self.grad_scaler is None and next(model.parameters()).is_cuda:
             try:
@@ -438,6 +446,24 @@ class Trainer:
             self._p2p_clear(name)
         self._grads_clean = True
 
+    def _deferred_fields_adam(self, step: int) -> None:
+        """One GPU, graphed steps: the field group's fused Adam + gradient clear on a side stream, fenced by an event that the next step's
+        field forward (graph B), eval forwards (FruitModel.forward) and every non-graphed path wait for."""
+        dev = self.groups["fields"].flat.device
+        main = torch.cuda.current_stream(dev)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=dev)
+            self._deferred_event = torch.cuda.Event()
+        self._side_stream.wait_stream(main)
+        g = self.groups["fields"]
+        spec = self.optimizers["fields"]
+        with torch.cuda.stream(self._side_stream):
+            ops.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, exponential_decay_lr(step, spec), self.opt_step, spec.betas[0], spec.betas[1], spec.eps,
+                          inv_grad_scale=1.0, zero_grad=True)
+            self._deferred_event.record(self._side_stream)
+        self._deferred_pending = True
+        self.model._param_fence = self._deferred_event
+
     def wait_deferred_update(self) -> None:
         """Make the current stream wait for the field group's deferred exchange (no-op when none is in flight)."""
         if self._deferred_pending:
@@ -522,6 +548,8 @@ class Trainer:
                 losses, outputs = fp.train_step(rb_d, batch_d, update_proposals=updated, grad_scale=self._loss_scale())
             if in_graph_opt:
                 self._grads_clean = True  # the step updated the parameters and cleared the gradients itself
+                if gs.defer_fields:
+                    self._deferred_fields_adam(step)
             else:
                 self.all_reduce_gradients(proposals_updated=updated, wait=False)
                 if graphed and self.comm is not None:
