@@ -155,7 +155,7 @@ CHAIN_FIELD, CHAIN_PROPOSALS = 0, 1
 
 class OptGroup(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("n", C.c_int64), ("scalars", C.c_void_p),
-                ("chain", C.c_int32), ("_pad", C.c_int32)]
+                ("chain", C.c_int32), ("_pad", C.c_int32), ("live", C.c_void_p)]
 
 
 class TrainCfg(C.Structure):
@@ -187,7 +187,7 @@ class P2PComm(C.Structure):
 
 
 class P2PGroup(C.Structure):
-    _fields_ = [("grad", C.c_void_p * MAX_PEERS), ("param", C.c_void_p * MAX_PEERS), ("mc_grad", C.c_void_p), ("mc_param", C.c_void_p)]
+    _fields_ = [("grad", C.c_void_p * MAX_PEERS), ("param", C.c_void_p * MAX_PEERS), ("mc_grad", C.c_void_p), ("mc_param", C.c_void_p), ("live", C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -231,6 +231,10 @@ SIGNATURES = {
     "cnb_adam_step_zero": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P]),
     "cnb_adam_step_zero_guarded": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P, _P]),
     "cnb_grad_check_finite": (C.c_int, [_P, _I64, _P, _P]),
+    "cnb_hashgrid_mark_reachable": (C.c_int, [C.POINTER(Grid), _P, _I64, _P]),
+    "cnb_bitmap_mark_range": (C.c_int, [_P, _I64, _I64, _P]),
+    "cnb_adam_step_zero_live": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P, _P]),
+    "cnb_adam_step_zero_dev_live": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P]),
     "cnb_upload": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _I32, _P]),
     "cnb_adam_step_zero_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
     "cnb_p2p_owned_range": (None, [_I64, _I32, _I32, C.POINTER(_I64), C.POINTER(_I64)]),

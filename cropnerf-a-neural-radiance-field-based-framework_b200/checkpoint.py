@@ -163,6 +163,8 @@ def resume_trainer(trainer, path_or_state) -> Tuple[int, Optional[int]]:
             group.exp_avg[off : off + n].copy_(st["exp_avg"].reshape(-1))
             group.exp_avg_sq[off : off + n].copy_(st["exp_avg_sq"].reshape(-1))
             opt_step = int(float(st["step"]))
+    for group in trainer.groups.values():  # moments that arrived non-zero keep their units live in the optimiser's skip bitmap
+        group.include_nonzero_moments()
     if opt_step is not None:
         trainer.opt_step = opt_step
     if getattr(trainer, "grad_scaler", None) is not None:

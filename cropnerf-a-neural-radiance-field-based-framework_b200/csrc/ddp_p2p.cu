@@ -85,7 +85,11 @@ __global__ void __launch_bounds__(256, (U * (WORLD > 0 ? WORLD : CNB_MAX_PEERS) 
   constexpr int NP = WORLD > 0 ? WORLD : CNB_MAX_PEERS;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const float4* __restrict__ p_own = reinterpret_cast<const float4*>(g.param[c.rank]);
+  const uint32_t* __restrict__ live = g.live;
   for (int64_t base = lo4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < hi4; base += stride * U) {
+    // unreachable hash-table rows (cnb_hashgrid_mark_reachable; the bitmap is the same on every rank): zero gradient and moments on all ranks
+    // forever -> nothing to reduce, update or broadcast
+    if (U == 1 && live != nullptr && !((__ldg(live + (base >> 5)) >> (base & 31)) & 1u)) continue;
     float4 gs[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) gs[u] = make_float4(0.f, 0.f, 0.f, 0.f);

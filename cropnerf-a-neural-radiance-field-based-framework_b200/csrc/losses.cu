@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
 // a_current vs f_late_zero; store cache policy makes no difference).
 __global__ void __launch_bounds__(256) k_adam_zero4(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
                                                     int64_t n4, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_scale,
-                                                    const int32_t* __restrict__ skip) {
+                                                    const int32_t* __restrict__ skip, const uint32_t* __restrict__ live) {
   const float step_size = lr / bc1;
   if (skip != nullptr && __ldg(skip) != 0) {
     // GradScaler.step: a non-finite gradient was found -> the optimizer step is skipped, the gradient is still cleared
@@ -150,6 +150,8 @@ __global__ void __launch_bounds__(256) k_adam_zero4(float4* __restrict__ p, floa
     return;
   }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    // unreachable hash-table rows (cnb_hashgrid_mark_reachable): gradient and moments are exactly 0 forever -> the update is the identity
+    if (live != nullptr && !((__ldg(live + (i >> 5)) >> (i & 31)) & 1u)) continue;
     float4 gi = g[i], mi = m[i], vi = v[i], pi = p[i];
     float* gp = &gi.x; float* mp = &mi.x; float* vp = &vi.x; float* pp = &pi.x;
 #pragma unroll
@@ -168,10 +170,11 @@ __global__ void __launch_bounds__(256) k_adam_zero4(float4* __restrict__ p, floa
 
 // k_adam_zero4 with the step's scalars in device memory (read once per thread through the constant-like path)
 __global__ void __launch_bounds__(256) k_adam_zero4_dev(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
-                                                        int64_t n4, const float* __restrict__ sc) {
+                                                        int64_t n4, const float* __restrict__ sc, const uint32_t* __restrict__ live) {
   const float lr = __ldg(sc), b1 = __ldg(sc + 1), b2 = __ldg(sc + 2), eps = __ldg(sc + 3), bc1 = __ldg(sc + 4), bc2_sqrt = __ldg(sc + 5), inv_scale = __ldg(sc + 6);
   const float step_size = lr / bc1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    if (live != nullptr && !((__ldg(live + (i >> 5)) >> (i & 31)) & 1u)) continue;  // unreachable table rows: identity update
     float4 gi = g[i], mi = m[i], vi = v[i], pi = p[i];
     float* gp = &gi.x; float* mp = &mi.x; float* vp = &vi.x; float* pp = &pi.x;
 #pragma unroll
@@ -278,7 +281,13 @@ extern "C" int cnb_adam_step(float* param, const float* grad, float* exp_avg, fl
   return cnb_check_launch("adam");
 }
 
+extern "C" int cnb_adam_step_zero_dev_live(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* scalars, const uint32_t* live,
+                                           cnb_stream_t stream);
 extern "C" int cnb_adam_step_zero_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* scalars, cnb_stream_t stream) {
+  return cnb_adam_step_zero_dev_live(param, grad, exp_avg, exp_avg_sq, n, scalars, nullptr, stream);
+}
+extern "C" int cnb_adam_step_zero_dev_live(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* scalars, const uint32_t* live,
+                                           cnb_stream_t stream) {
   CNB_REQUIRE(n >= 0, "adam_dev: bad n");
   if (n == 0) return CNB_OK;
   CNB_REQUIRE(param && grad && exp_avg && exp_avg_sq && scalars, "adam_dev: null pointer");
@@ -289,7 +298,7 @@ extern "C" int cnb_adam_step_zero_dev(float* param, float* grad, float* exp_avg,
   const int64_t cap = (int64_t)cnb_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   k_adam_zero4_dev<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(param), reinterpret_cast<float4*>(grad), reinterpret_cast<float4*>(exp_avg),
-                                                    reinterpret_cast<float4*>(exp_avg_sq), n4, scalars);
+                                                    reinterpret_cast<float4*>(exp_avg_sq), n4, scalars, live);
   return cnb_check_launch("adam_zero_dev");
 }
 
@@ -308,7 +317,14 @@ extern "C" int cnb_grad_check_finite(const float* grad, int64_t n, int32_t* foun
 }
 
 static int adam_step_zero_impl(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
-                               float eps, int32_t step, float inv_grad_scale, const int32_t* skip_flag, cnb_stream_t stream);
+                               float eps, int32_t step, float inv_grad_scale, const int32_t* skip_flag, cnb_stream_t stream, const uint32_t* live = nullptr);
+
+extern "C" int cnb_adam_step_zero_live(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                                       float eps, int32_t step, float inv_grad_scale, const uint32_t* live, cnb_stream_t stream) {
+  CNB_REQUIRE(live == nullptr || (n % 4 == 0 && ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0)),
+              "adam_step_zero_live: the masked step needs a 16-byte aligned flat group with n % 4 == 0");
+  return adam_step_zero_impl(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, inv_grad_scale, nullptr, stream, live);
+}
 
 extern "C" int cnb_adam_step_zero(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
                                   float eps, int32_t step, float inv_grad_scale, cnb_stream_t stream) {
@@ -323,7 +339,7 @@ extern "C" int cnb_adam_step_zero_guarded(float* param, float* grad, float* exp_
 }
 
 static int adam_step_zero_impl(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
-                               float eps, int32_t step, float inv_grad_scale, const int32_t* skip_flag, cnb_stream_t stream) {
+                               float eps, int32_t step, float inv_grad_scale, const int32_t* skip_flag, cnb_stream_t stream, const uint32_t* live) {
   CNB_REQUIRE(n >= 0 && step >= 1, "adam: bad n/step");
   if (n == 0) return CNB_OK;
   CNB_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam: null pointer");
@@ -341,6 +357,6 @@ static int adam_step_zero_impl(float* param, float* grad, float* exp_avg, float*
   const int64_t cap = (int64_t)cnb_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   k_adam_zero4<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(param), reinterpret_cast<float4*>(grad), reinterpret_cast<float4*>(exp_avg),
-                                                reinterpret_cast<float4*>(exp_avg_sq), n4, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), inv_grad_scale, skip_flag);
+                                                reinterpret_cast<float4*>(exp_avg_sq), n4, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), inv_grad_scale, skip_flag, live);
   return cnb_check_launch("adam_zero");
 }

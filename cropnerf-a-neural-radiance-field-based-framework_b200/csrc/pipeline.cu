@@ -290,7 +290,7 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
     for (int i = 0; i < cfg->num_opt_groups; ++i) {
       const cnb_opt_group& og = cfg->opt_groups[i];
       if (og.chain != chain) continue;
-      STAGE(chain == CNB_CHAIN_FIELD ? "adam_fields" : "adam_proposals", 1, cnb_adam_step_zero_dev(og.param, og.grad, og.exp_avg, og.exp_avg_sq, og.n, og.scalars, st));
+      STAGE(chain == CNB_CHAIN_FIELD ? "adam_fields" : "adam_proposals", 1, cnb_adam_step_zero_dev_live(og.param, og.grad, og.exp_avg, og.exp_avg_sq, og.n, og.scalars, og.live, st));
       if (rc) return rc;
     }
     return rc;

@@ -114,6 +114,7 @@ class FlatGroup:
             n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         dev = uniq[0].device
         self.peer = None
+        self.live = None
         if comm is not None:
             from .ddp import PeerGroup
 
@@ -134,6 +135,43 @@ class FlatGroup:
 
     def zero_grad(self) -> None:
         self.grad.zero_()
+
+    def build_live(self, model: nn.Module) -> None:
+        """Bitmap of the float4 units the optimiser has to visit (ops.reachable_bitmap): hash-table rows that no lattice corner hashes to
+        have zero gradient and zero Adam moments forever, so skipping them is bit-identical to the dense pass.  Units whose moments are
+        already non-zero (a resumed run of something else) are kept live."""
+        from .field_components import HashEncoding
+
+        mine = {id(p) for p in self.params}
+        tables, table_ids = [], set()
+        for mod in model.modules():
+            if isinstance(mod, HashEncoding) and id(mod.hash_table) in mine and id(mod.hash_table) not in table_ids:
+                table_ids.add(id(mod.hash_table))
+                num_levels, log2_T, scalings = mod.grid_cfg()
+                tables.append((mod.hash_table, num_levels, log2_T, scalings))
+        others = [p for p in self.params if id(p) not in table_ids]
+        self.live = ops.reachable_bitmap(self.flat, tables, others)
+        self.include_nonzero_moments()
+        if self.peer is not None:
+            self.peer.struct.live = self.live.data_ptr()
+
+    def include_nonzero_moments(self) -> None:
+        if self.live is None:
+            return
+        n4 = (self.flat.numel() + 3) // 4
+        nz = ((self.exp_avg != 0) | (self.exp_avg_sq != 0))
+        nz = torch.nn.functional.pad(nz, (0, 4 * n4 - nz.numel())).view(n4, 4).any(dim=1)
+        nz = torch.nn.functional.pad(nz, (0, 32 * self.live.numel() - n4)).view(-1, 32).to(torch.int64)
+        words = (nz << torch.arange(32, device=nz.device, dtype=torch.int64)).sum(dim=1)
+        words = torch.where(words >= 2**31, words - 2**32, words).to(torch.int32)
+        self.live |= words
+
+    def live_fraction(self) -> float:
+        if self.live is None:
+            return 1.0
+        n4 = (self.flat.numel() + 3) // 4
+        bits = sum(int(((self.live >> k) & 1).sum()) for k in range(32))
+        return bits / n4
 
 
 def _stats_views(losses: Tensor) -> Dict[str, Tensor]:
@@ -185,7 +223,7 @@ class _GraphedStep:
             self.opt_np = self.opt_host.numpy()
             self.opt_dev = torch.zeros((len(names), 8), device=dev, dtype=torch.float32)
             self.opt = [(trainer.groups[n].flat, trainer.groups[n].grad, trainer.groups[n].exp_avg, trainer.groups[n].exp_avg_sq, self.opt_dev[i],
-                         L_.CHAIN_FIELD if n == "fields" else L_.CHAIN_PROPOSALS) for i, n in enumerate(names)]
+                         L_.CHAIN_FIELD if n == "fields" else L_.CHAIN_PROPOSALS, trainer.groups[n].live) for i, n in enumerate(names)]
             self.opt_names = names
         self.graph = torch.cuda.CUDAGraph()
         self.graph2 = None
@@ -333,6 +371,9 @@ class Trainer:
                 warnings.warn(f"peer-memory data parallelism unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce path")
                 self.comm = None
         self.groups: Dict[str, FlatGroup] = {name: FlatGroup(params, self.comm) for name, params in model.get_param_groups().items() if len(params) > 0}
+        if _os.environ.get("CNB_NO_LIVE_MASK", "0") != "1" and next(model.parameters()).is_cuda:
+            for g in self.groups.values():
+                g.build_live(model)
         self.callbacks = model.get_training_callbacks()
         self.opt_step = 0
 
@@ -393,7 +434,7 @@ class Trainer:
             lr = exponential_decay_lr(step, spec)
             # Adam and the gradient clear of the next step in one pass over the flat group
             ops.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, lr, self.opt_step, spec.betas[0], spec.betas[1], spec.eps,
-                          inv_grad_scale=inv, zero_grad=True, skip_flag=flag)
+                          inv_grad_scale=inv, zero_grad=True, skip_flag=flag, live=g.live)
         self._grads_clean = True
         if scaler is not None and scaler.update():
             self.opt_step -= 1  # torch: a skipped optimizer.step() does not advance Adam's step count
@@ -459,7 +500,7 @@ class Trainer:
         spec = self.optimizers["fields"]
         with torch.cuda.stream(self._side_stream):
             ops.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, exponential_decay_lr(step, spec), self.opt_step, spec.betas[0], spec.betas[1], spec.eps,
-                          inv_grad_scale=1.0, zero_grad=True)
+                          inv_grad_scale=1.0, zero_grad=True, live=g.live)
             self._deferred_event.record(self._side_stream)
         self._deferred_pending = True
         self.model._param_fence = self._deferred_event

@@ -560,8 +560,13 @@ def pixel_losses(rgb: Tensor, sem: Tensor, image: Tensor, mask: Tensor, sem_weig
 
 
 def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, step: int, beta1: float = 0.9, beta2: float = 0.999,
-              eps: float = 1e-15, inv_grad_scale: float = 1.0, zero_grad: bool = False, skip_flag: Optional[Tensor] = None) -> None:
+              eps: float = 1e-15, inv_grad_scale: float = 1.0, zero_grad: bool = False, skip_flag: Optional[Tensor] = None,
+              live: Optional[Tensor] = None) -> None:
     dev = _dev(param)
+    if live is not None and zero_grad and skip_flag is None:  # skip the units no hash-grid corner can reach (bit-identical, see reachable_bitmap)
+        L.check(L.lib().cnb_adam_step_zero_live(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(), lr, beta1,
+                                                beta2, eps, int(step), inv_grad_scale, live.data_ptr(), L.stream_ptr(dev)), "adam_step_live")
+        return
     if skip_flag is not None:  # GradScaler.step: device-side "skip on inf/NaN" (always clears the gradient)
         L.check(L.lib().cnb_adam_step_zero_guarded(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(), lr, beta1,
                                                    beta2, eps, int(step), inv_grad_scale, skip_flag.data_ptr(), L.stream_ptr(dev)), "adam_step_guarded")
@@ -578,3 +583,24 @@ def grad_check_finite(grad: Tensor, found_inf: Tensor) -> None:
     """found_inf (device int32 [1]) |= any(!isfinite(grad))  -- torch.amp.GradScaler's inf check over one flat gradient group."""
     dev = _dev(grad)
     L.check(L.lib().cnb_grad_check_finite(grad.data_ptr(), grad.numel(), found_inf.data_ptr(), L.stream_ptr(dev)), "grad_check_finite")
+
+
+def reachable_bitmap(flat: Tensor, tables: Sequence[Tuple[Tensor, int, int, Sequence[float]]], others: Sequence[Tensor]) -> Tensor:
+    """One bit per float4 of the flat group ``flat``: 1 where the optimiser has work.  ``tables`` = (hash_table parameter, num_levels,
+    log2_hashmap_size, scalings) of every hash grid living in the group (views of ``flat``): only rows some lattice corner hashes to are
+    marked (``cnb_hashgrid_mark_reachable``); ``others`` = all remaining parameters (marked whole).  Padding between tensors stays 0."""
+    dev = _dev(flat)
+    n4 = (flat.numel() + 3) // 4
+    bitmap = torch.zeros(((n4 + 31) // 32,), device=dev, dtype=torch.int32)
+    base = flat.data_ptr()
+    for table, num_levels, log2_T, scalings in tables:
+        off = (table.data_ptr() - base) // 4
+        if off % 4 != 0:
+            raise ValueError("hash table must start on a 16-byte boundary of its flat group")
+        g = L.make_grid(table.detach(), None, num_levels, log2_T, scalings)
+        L.check(L.lib().cnb_hashgrid_mark_reachable(C.byref(g), bitmap.data_ptr(), off // 4, L.stream_ptr(dev)), "hashgrid_mark_reachable")
+    for t in others:
+        off = (t.data_ptr() - base) // 4
+        first, last = off // 4, (off + t.numel() + 3) // 4
+        L.check(L.lib().cnb_bitmap_mark_range(bitmap.data_ptr(), first, last - first, L.stream_ptr(dev)), "bitmap_mark_range")
+    return bitmap

@@ -244,8 +244,9 @@ class FusedPipeline:
             # optimiser stage inside the step (cnb_opt_group): (flat param, grad, exp_avg, exp_avg_sq, device scalars [8], chain)
             if len(opt_groups) > L.MAX_OPT_GROUPS:
                 raise ValueError(f"at most {L.MAX_OPT_GROUPS} optimiser groups")
-            for i, (p_, g_, m_, v_, sc_, chain) in enumerate(opt_groups):
+            for i, (p_, g_, m_, v_, sc_, chain, live_) in enumerate(opt_groups):
                 og = cfg.opt_groups[i]
+                og.live = live_.data_ptr() if live_ is not None else None
                 og.param, og.grad, og.exp_avg, og.exp_avg_sq = p_.data_ptr(), g_.data_ptr(), m_.data_ptr(), v_.data_ptr()
                 og.n, og.scalars, og.chain = p_.numel(), sc_.data_ptr(), int(chain)
             cfg.num_opt_groups = len(opt_groups)

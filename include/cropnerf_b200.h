@@ -322,6 +322,7 @@ typedef struct cnb_opt_group {
   const float* scalars;      /* device, 8 floats: lr, beta1, beta2, eps, 1 - beta1^t, sqrt(1 - beta2^t), 1 / grad_scale, unused */
   int32_t chain;             /* CNB_CHAIN_*: which backward chain completes this group's gradient */
   int32_t _pad;
+  const uint32_t* live;      /* optional: one bit per float4 of the group (cnb_hashgrid_mark_reachable); 0 = unreachable table rows, skipped */
 } cnb_opt_group;
 
 typedef struct cnb_train_cfg {
@@ -359,6 +360,18 @@ int cnb_adam_step_zero(float* param, float* grad, float* exp_avg, float* exp_avg
 /* the same pass with its per-step scalars read from device memory (cnb_opt_group.scalars layout): graph-replay safe */
 int cnb_adam_step_zero_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* scalars, cnb_stream_t stream);
 
+/* Reachable rows of a hash table.  nerfstudio's torch HashEncoding hashes every level into 2^T slots, also coarse levels whose lattice has
+ * far fewer corners than slots; a row no corner hashes to never receives a gradient, its Adam moments stay exactly 0 and torch.optim.Adam
+ * leaves it exactly unchanged.  cnb_hashgrid_mark_reachable ORs one bit per 16-byte unit (two rows) of the table into `bitmap` (bit index =
+ * first_unit + row / 2; first_unit = float offset of the table inside its flat group / 4); cnb_bitmap_mark_range marks `units` consecutive
+ * units (MLP weights, embeddings: always live).  The *_live optimiser entries skip units whose bit is 0 -- bit-identical to the full pass. */
+int cnb_hashgrid_mark_reachable(const cnb_grid* g, uint32_t* bitmap, int64_t first_unit, cnb_stream_t stream);
+int cnb_bitmap_mark_range(uint32_t* bitmap, int64_t first_unit, int64_t units, cnb_stream_t stream);
+int cnb_adam_step_zero_live(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                            float eps, int32_t step, float inv_grad_scale, const uint32_t* live, cnb_stream_t stream);
+int cnb_adam_step_zero_dev_live(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* scalars, const uint32_t* live,
+                                cnb_stream_t stream);
+
 /* GradScaler support (nerfstudio Trainer: grad_scaler.scale(loss).backward(); grad_scaler.step(optimizer); grad_scaler.update()).
  * cnb_grad_check_finite ORs 1 into *found_inf (device int32, caller clears it) when any of the n gradients is inf / NaN;
  * cnb_adam_step_zero_guarded is cnb_adam_step_zero that, when *skip_flag != 0 (device), leaves param / moments untouched and only
@@ -390,6 +403,7 @@ typedef struct cnb_p2p_group {
   float* param[CNB_MAX_PEERS];    /* likewise the flat parameter buffers */
   float* mc_grad;                 /* multicast mappings of the same buffers (NULL without NVLS) */
   float* mc_param;
+  const uint32_t* live;           /* optional, LOCAL: one bit per float4 of the group (cnb_hashgrid_mark_reachable); 0 = unreachable table rows, skipped */
 } cnb_p2p_group;
 void cnb_p2p_owned_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
 int cnb_p2p_barrier(const cnb_p2p_comm* comm, cnb_stream_t stream);

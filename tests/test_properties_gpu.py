@@ -140,3 +140,34 @@ def test_training_step_is_deterministic_in_outputs_and_finite_at_full_size(dev):
     for n in norms[0]:
         assert np.isfinite(norms[0][n]) and norms[0][n] > 0
         assert abs(norms[0][n] - norms[1][n]) <= 1e-3 * norms[0][n]
+
+
+def test_unreachable_table_rows_never_get_gradient_and_masked_adam_is_bit_identical(dev):
+    """The optimiser's skip bitmap (cnb_hashgrid_mark_reachable): rows of a coarse level that no lattice corner hashes to receive exactly zero
+    gradient from a full-size training batch, so an Adam pass that skips them equals the dense pass bit for bit."""
+    R = 4096
+    model = _full_model(dev, "mixed").train()
+    tr = engine.Trainer(model, force_proposal_update=True)
+    frac = {n: g.live_fraction() for n, g in tr.groups.items()}
+    assert 0.60 < frac["fields"] < 0.85, frac        # ~30 % of the 16-byte units of the 16 x 2^19 field table are unreachable (levels 0-5)
+    assert 0.45 < frac["proposal_networks"] < 0.80, frac
+    rays = synthetic.make_rays(R, seed=31, num_cameras=300)
+    targets = {k: v.to(dev) for k, v in synthetic.make_targets(R, seed=5).items()}
+    tr.fused.train_step(_bundle(rays, dev), targets, update_proposals=True)
+    torch.cuda.synchronize()
+    for name, g in tr.groups.items():
+        n4 = g.flat.numel() // 4
+        bits = torch.stack([(g.live >> k) & 1 for k in range(32)], dim=1).reshape(-1)[:n4].bool()
+        gr = g.grad.view(n4, 4)
+        assert float(gr[~bits].abs().max()) == 0.0, f"{name}: gradient landed in a row marked unreachable"
+        assert float(gr[bits].abs().max()) > 0.0
+        # masked vs dense fused Adam on copies of the real buffers
+        outs = []
+        for live in (g.live, None):
+            p, gg, m, v = g.flat.clone(), g.grad.clone(), g.exp_avg.clone(), g.exp_avg_sq.clone()
+            for step in (1, 2):
+                ops.adam_step(p, gg, m, v, 1e-2, step, zero_grad=True, live=live)
+                gg.copy_(g.grad)
+            outs.append((p, m, v))
+        for a, b in zip(outs[0], outs[1]):
+            assert torch.equal(a, b), f"{name}: masked Adam differs from the dense pass"
