@@ -190,6 +190,12 @@ class P2PGroup(C.Structure):
     _fields_ = [("grad", C.c_void_p * MAX_PEERS), ("param", C.c_void_p * MAX_PEERS), ("mc_grad", C.c_void_p), ("mc_param", C.c_void_p), ("live", C.c_void_p)]
 
 
+class DdpGroupStep(C.Structure):
+    _fields_ = [("group", C.POINTER(P2PGroup)), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("grad_own", C.c_void_p), ("n", C.c_int64),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int32), ("inv_grad_scale", C.c_float),
+                ("flags", C.c_int32), ("deferred", C.c_int32)]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _I32 = C.c_int32
@@ -239,6 +245,8 @@ SIGNATURES = {
     "cnb_adam_step_zero_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
     "cnb_p2p_owned_range": (None, [_I64, _I32, _I32, C.POINTER(_I64), C.POINTER(_I64)]),
     "cnb_p2p_barrier": (C.c_int, [C.POINTER(P2PComm), _P]),
+    "cnb_ddp_optimizer_step": (C.c_int, [C.POINTER(P2PComm), C.POINTER(DdpGroupStep), _I32, _P]),
+    "cnb_ddp_wait_deferred": (C.c_int, [_P]),
     "cnb_ddp_adam_update": (C.c_int, [C.POINTER(P2PComm), C.POINTER(P2PGroup), _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _I32, _P]),
     "cnb_level_resample": (C.c_int, [_P, _P, _P, _P, _P, _I32, _F, _P, _P, _I32, _I64, _I32, _I32, _F, _F, _P, _P, _P, _P, _P, _P]),
     "cnb_final_composite": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, C.POINTER(_F), _I32, _P, _P, _P, _P, _P, _P]),

@@ -222,3 +222,80 @@ extern "C" int cnb_ddp_adam_update(const cnb_p2p_comm* comm, const cnb_p2p_group
     default: return launch_ddp_adam<0, 0, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
   }
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The whole data-parallel optimiser step as ONE host call (what engine.Trainer._p2p_optimizer_step used to sequence from Python: ~0.3 ms of
+// host time per step, which an end-to-end loop that reads the loss every step cannot hide):
+//   stream:  barrier(ch 0)  ->  [groups with deferred == 0: update]  ->  barrier(ch 0)  ->  clear their gradients
+//   side  :  (waits for the first barrier)  [groups with deferred != 0: update]  ->  barrier(ch 1)  ->  clear their gradients  ->  fence event
+// cnb_ddp_wait_deferred(stream) makes a stream wait for the fence of the last step on this device (the consumer of the deferred groups'
+// parameters -- the next step's field forward -- calls it; a no-op when nothing is in flight).
+namespace {
+struct DdpSide { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, fence = nullptr; bool pending = false, failed = false; };
+DdpSide g_ddp[64];
+
+DdpSide* ddp_side() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  DdpSide& d = g_ddp[dev];
+  if (d.failed) return nullptr;
+  if (d.side == nullptr) {
+    if (cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.fence, cudaEventDisableTiming) != cudaSuccess) {
+      d.failed = true; d.side = nullptr;
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+  }
+  return &d;
+}
+
+int ddp_update_one(const cnb_p2p_comm* comm, const cnb_ddp_group_step& g, cudaStream_t st) {
+  return cnb_ddp_adam_update(comm, g.group, g.exp_avg, g.exp_avg_sq, g.n, g.lr, g.beta1, g.beta2, g.eps, g.step, g.inv_grad_scale, g.flags, st);
+}
+int ddp_clear_one(const cnb_ddp_group_step& g, cudaStream_t st) {
+  if ((g.flags & CNB_P2P_GRADS_ZERO) || g.grad_own == nullptr || g.n == 0) return CNB_OK;  // nobody wrote it this step
+  if (cudaMemsetAsync(g.grad_own, 0, sizeof(float) * (size_t)g.n, st) != cudaSuccess) return cnb_check_launch("ddp_optimizer_step clear");
+  return CNB_OK;
+}
+}  // namespace
+
+extern "C" int cnb_ddp_optimizer_step(const cnb_p2p_comm* comm, const cnb_ddp_group_step* groups, int32_t n_groups, cnb_stream_t stream) {
+  int rc = check_comm(comm, "ddp_optimizer_step");
+  if (rc) return rc;
+  CNB_REQUIRE(n_groups >= 0 && (n_groups == 0 || groups != nullptr), "ddp_optimizer_step: null groups");
+  bool any_deferred = false;
+  for (int i = 0; i < n_groups; ++i) any_deferred = any_deferred || groups[i].deferred != 0;
+  cnb_p2p_comm c0 = *comm, c1 = *comm;
+  c0.channel = 0; c1.channel = 1;
+  if ((rc = cnb_p2p_barrier(&c0, stream))) return rc;  // every rank has finished its backward: all gradients are final
+  DdpSide* sd = any_deferred ? ddp_side() : nullptr;
+  if (any_deferred && sd == nullptr) any_deferred = false;  // no side stream: everything on the caller's stream
+  if (any_deferred) {
+    if (cudaEventRecord(sd->fork, stream) != cudaSuccess || cudaStreamWaitEvent(sd->side, sd->fork, 0) != cudaSuccess) return cnb_check_launch("ddp_optimizer_step fork");
+    for (int i = 0; i < n_groups; ++i)
+      if (groups[i].deferred && (rc = ddp_update_one(comm, groups[i], sd->side))) return rc;
+    if ((rc = cnb_p2p_barrier(&c1, sd->side))) return rc;  // every replica of those groups written, every rank's gradient consumed
+    for (int i = 0; i < n_groups; ++i)
+      if (groups[i].deferred && (rc = ddp_clear_one(groups[i], sd->side))) return rc;
+    if (cudaEventRecord(sd->fence, sd->side) != cudaSuccess) return cnb_check_launch("ddp_optimizer_step fence");
+    sd->pending = true;
+  }
+  for (int i = 0; i < n_groups; ++i)
+    if (!(any_deferred && groups[i].deferred) && (rc = ddp_update_one(comm, groups[i], stream))) return rc;
+  if ((rc = cnb_p2p_barrier(&c0, stream))) return rc;
+  for (int i = 0; i < n_groups; ++i)
+    if (!(any_deferred && groups[i].deferred) && (rc = ddp_clear_one(groups[i], stream))) return rc;
+  return CNB_OK;
+}
+
+extern "C" int cnb_ddp_wait_deferred(cnb_stream_t stream) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return CNB_OK;
+  DdpSide& d = g_ddp[dev];
+  if (!d.pending) return CNB_OK;
+  // the flag is not cleared: any number of streams may wait for the same fence; waiting for an already completed event costs nothing
+  if (cudaStreamWaitEvent(stream, d.fence, 0) != cudaSuccess) return cnb_check_launch("ddp_wait_deferred");
+  return CNB_OK;
+}

@@ -363,8 +363,8 @@ class FruitModel(nn.Module):
     # fruit_nerf.py:617-637
     def forward(self, ray_bundle: RayBundle) -> Dict:
         fence = self.__dict__.get("_param_fence")
-        if fence is not None:  # a peer-memory optimiser step may still be writing the field parameters on a side stream (engine.Trainer)
-            torch.cuda.current_stream().wait_event(fence)
+        if fence is not None:  # an optimiser step may still be writing the field parameters on a side stream (engine.Trainer): make this stream wait
+            fence()
         if self.collider is not None:
             ray_bundle = self.collider(ray_bundle)
         if self.test_mode == "inference":

@@ -410,6 +410,22 @@ int cnb_p2p_barrier(const cnb_p2p_comm* comm, cnb_stream_t stream);
 int cnb_ddp_adam_update(const cnb_p2p_comm* comm, const cnb_p2p_group* group, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                         float beta1, float beta2, float eps, int32_t step, float inv_grad_scale, int32_t flags, cnb_stream_t stream);
 
+/* The whole data-parallel optimiser step in one host call.  Groups with deferred != 0 are exchanged on a library-owned side stream with their own
+ * barrier channel and only fence later consumers (cnb_ddp_wait_deferred); the others take barrier -> update -> barrier -> gradient clear on `stream`. */
+typedef struct cnb_ddp_group_step {
+  const cnb_p2p_group* group;
+  float* exp_avg; float* exp_avg_sq;
+  float* grad_own;           /* this rank's gradient buffer of the group (= group->grad[rank]); cleared after the exchange; NULL = leave */
+  int64_t n;
+  float lr, beta1, beta2, eps;
+  int32_t step;              /* Adam step count (bias correction), >= 1 */
+  float inv_grad_scale;      /* 1 / (world * loss scale) */
+  int32_t flags;             /* CNB_P2P_* */
+  int32_t deferred;
+} cnb_ddp_group_step;
+int cnb_ddp_optimizer_step(const cnb_p2p_comm* comm, const cnb_ddp_group_step* groups, int32_t n_groups, cnb_stream_t stream);
+int cnb_ddp_wait_deferred(cnb_stream_t stream);
+
 /* ---- host -> device staging of one batch (rays, targets, optimiser scalars): n cudaMemcpyAsync on `stream` in one call.
  * dst[i] device, src[i] HOST (pinned for a truly asynchronous copy), bytes[i] sizes; the arrays themselves are host arrays. */
 int cnb_upload(void* const* dst, const void* const* src, const int64_t* bytes, int32_t n, cnb_stream_t stream);
