@@ -31,6 +31,27 @@ int ensure_smem(K kernel, size_t smem, size_t& configured, const char* what) {
   return CNB_OK;
 }
 
+// 4-byte asynchronous global -> shared copies: a ray's inputs are all put in flight at once (no register staging, no load->store stall of the
+// in-order warp) and waited for together; the per-ray kernels are bound by the number of dependent global round trips, not by bytes
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// weights of one ray from STAGED inputs: dens_s[0..S) and edges_s[0..S] already in shared memory; wsm may alias dens_s
+__device__ __forceinline__ void ray_weights_staged(const float* dens_s, const float* edges_s, int S, float* dd, float* cs, float* wsm, int lane) {
+  for (int j = lane; j < S; j += 32) dd[j] = __fmul_rn(__fsub_rn(edges_s[j + 1], edges_s[j]), dens_s[j]);
+  __syncwarp();
+  cnb_warp_cumsum(dd, cs, S, lane);
+  __syncwarp();
+  for (int j = lane; j < S; j += 32) {
+    const float alpha = __fsub_rn(1.0f, expf(-dd[j]));
+    const float T = expf(-(j > 0 ? cs[j - 1] : 0.0f));
+    wsm[j] = cnb_nan_to_num(__fmul_rn(alpha, T));
+  }
+  __syncwarp();
+}
+
 // weights of one ray into wsm[0..S): dd/cs are scratch [S] (k_weights_fwd's arithmetic)
 __device__ __forceinline__ void ray_weights(const float* __restrict__ density, const float* __restrict__ edges, int S, float* dd, float* cs, float* wsm, int lane) {
   for (int j = lane; j < S; j += 32) {
@@ -77,11 +98,27 @@ __global__ void __launch_bounds__(WARPS * 32) k_level_resample(const float* __re
   const int nb = S + 1;
   const float inv_nb_half = (float)(1.0 / (2.0 * (double)nb));
   for (int64_t r = blockIdx.x * (int64_t)WARPS + warp; r < R; r += (int64_t)gridDim.x * WARPS) {
-    const float* e = eu_prev + r * (Sp + 1);
-    ray_weights(density + r * Sp, e, Sp, dd, cs, wsm, lane);
+    // every global input of the ray in flight at once: density -> wsm, euclidean edges -> cdf, spacing edges -> bins (async copies), plus the
+    // per-ray scalars; one wait instead of four dependent round trips
+    for (int j = lane; j < Sp; j += 32) cp_async4(wsm + j, density + r * Sp + j);
+    for (int j = lane; j <= Sp; j += 32) { cp_async4(cdf + j, eu_prev + r * (Sp + 1) + j); cp_async4(bins + j, sp_prev + r * (Sp + 1) + j); }
+    const float near_v = __ldg(nears + r), far_v = __ldg(fars + r);
+    const float rand_ray = (rand != nullptr && rand_stride == 1) ? __ldg(rand + r) : 0.0f;
+    cp_async_wait_all();
+    __syncwarp();
+    ray_weights_staged(wsm, cdf, Sp, dd, cs, wsm, lane);
     if (weights_out)
       for (int j = lane; j < Sp; j += 32) weights_out[r * Sp + j] = wsm[j];
-    if (depth_out) ray_median_depth(wsm, e, Sp, cs, depth_out + r, lane);
+    if (depth_out) {  // DepthRenderer "median" on the staged edges (ray_median_depth's arithmetic)
+      cnb_warp_cumsum(wsm, cs, Sp, lane);
+      __syncwarp();
+      if (lane == 0) {
+        int idx = cnb_search_left(cs, Sp, 0.5f);
+        idx = min(max(idx, 0), Sp - 1);
+        depth_out[r] = __fmul_rn(__fadd_rn(cdf[idx], cdf[idx + 1]), 0.5f);
+      }
+      __syncwarp();
+    }
     // ---- PDFSampler (k_sample_pdf's arithmetic) ------------------------------------------------------------------------------
     double part = 0.0;
     for (int j = lane; j < Sp; j += 32) {
@@ -92,7 +129,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_level_resample(const float* __re
       cdf[1 + j] = w;
       part += (double)w;
     }
-    for (int j = lane; j <= Sp; j += 32) bins[j] = __ldg(sp_prev + r * (Sp + 1) + j);
     float wsum = (float)cnb_warp_sum_d(part);
     const float padding = fmaxf(__fsub_rn(eps, wsum), 0.0f);
     const float padj = __fdiv_rn(padding, (float)Sp);
@@ -105,11 +141,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_level_resample(const float* __re
     for (int j = lane; j < Sp; j += 32) cdf[1 + j] = fminf(1.0f, cdf[1 + j]);
     if (lane == 0) cdf[0] = 0.0f;
     __syncwarp();
-    const float s_near = cnb_spacing_fn(kind, __ldg(nears + r));
-    const float s_far = cnb_spacing_fn(kind, __ldg(fars + r));
+    const float s_near = cnb_spacing_fn(kind, near_v);
+    const float s_far = cnb_spacing_fn(kind, far_v);
     for (int k = lane; k < nb; k += 32) {
       float u = __ldg(u_base + k);
-      if (rand != nullptr) u = __fadd_rn(u, __fdiv_rn(__ldg(rand + r * rand_stride + (rand_stride == 1 ? 0 : k)), (float)nb));
+      if (rand != nullptr) u = __fadd_rn(u, __fdiv_rn(rand_stride == 1 ? rand_ray : __ldg(rand + r * rand_stride + k), (float)nb));
       else u = __fadd_rn(u, inv_nb_half);
       const int ind = cnb_search_right(cdf, Sp + 1, u);
       const int below = min(max(ind - 1, 0), Sp);
