@@ -408,8 +408,8 @@ def run_product(args):
                        "ms_per_step_l2_flushed_serialised": 1e3 * m["t_b2b"] / steps, "data_parallel": m["ddp"],
                        "note_overlap": "the big 'fields' group is updated on a side stream (one GPU: fused Adam; N>1: reduce-scatter + Adam + all-gather over NVLink) and only gates the "
                                        "NEXT step's field forward; ms_per_step_l2_flushed_serialised flushes L2 (192 MiB fill) before every step and waits for that update inside the step's timed region",
-                       "includes": "fwd + losses + bwd (all three networks updated EVERY step) + gradient all-reduce + Adam; "
-                                   + ("cnb_train_step eager" if args.no_graph else "cnb_train_step replayed as one CUDA graph"),
+                       "includes": "fwd + losses + bwd (all three networks updated EVERY step) + gradient exchange (N>1) + Adam; "
+                                   + ("cnb_train_step eager" if args.no_graph else "cnb_train_step replayed as two CUDA graphs (samplers + proposal forward | rest)"),
                        "non_update_step_ms": m["nonupdate_ms"],
                        "camera_optimizer_step_ms": m["camopt_ms"],
                        "steady_state_rays_per_s": (world * R / ((m["t"] / steps + 5 * m["nonupdate_ms"] * 1e-3) / 6)) if m["nonupdate_ms"] else None},
