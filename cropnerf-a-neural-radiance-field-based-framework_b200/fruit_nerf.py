@@ -360,6 +360,13 @@ class FruitModel(nn.Module):
         outputs["semantics_colormap"] = torch.heaviside(torch.sigmoid(sem) - 0.9, torch.zeros((), device=sem.device)).to(torch.long)
         return outputs
 
+    def state_dict(self, *args, **kwargs):
+        # a checkpoint writer copies the parameters on ITS stream: make that stream wait for an optimiser step still in flight on a side stream
+        fence = self.__dict__.get("_param_fence")
+        if fence is not None:
+            fence()
+        return super().state_dict(*args, **kwargs)
+
     # fruit_nerf.py:617-637
     def forward(self, ray_bundle: RayBundle) -> Dict:
         fence = self.__dict__.get("_param_fence")
