@@ -72,7 +72,7 @@ class Samples(C.Structure):
 
 
 class DensityField(C.Structure):
-    _fields_ = [("grid", Grid), ("mlp", Mlp), ("warp", Warp), ("average_init_density", C.c_float)]
+    _fields_ = [("grid", Grid), ("mlp", Mlp), ("warp", Warp), ("average_init_density", C.c_float), ("precision", C.c_int32)]
 
 
 class Field(C.Structure):

@@ -30,6 +30,7 @@ struct DfArgs {
   float* d_feat_out;  // optional [N, 2L]: gradient reaching the encoded features (consumed by cnb_position_grad_rays)
   float* feat_keep;       // forward, optional: encoded features written LEVEL-MAJOR [L][N] float2 (coalesced) for the backward
   const float* feat_kept; // backward, optional: features kept by the forward -> no re-gather
+  int mixed;              // CNB_PREC_MIXED: MLP parameter gradients contracted with plain bf16 operands (no hi/lo split)
 };
 
 template <int LMAX>
@@ -254,7 +255,11 @@ __device__ __forceinline__ void tc_split8(const float (&v)[8], uint4& hi, uint4&
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__global__ void __launch_bounds__(BLOCK, 5) k_density_bwd_tc(DfArgs a, const float* __restrict__ d_density) {
+// SPLIT = true: exact mode (bf16 hi + lo operands, three cross products, 42 KB of staging, 5 CTAs/SM).  SPLIT = false: mixed-precision mode --
+// plain bf16 operands like the field's mixed backward (2e-3-class parameter gradients), half the staging and conversions, one product, and
+// with them enough shared memory and registers for 6 CTAs/SM on this latency-bound kernel.
+template <bool SPLIT>
+__global__ void __launch_bounds__(BLOCK, SPLIT ? 5 : 6) k_density_bwd_tc(DfArgs a, const float* __restrict__ d_density) {
   constexpr int LMAX = 8, H = 16, INP = 16;
   extern __shared__ float4 smem4[];
   float* Ws = reinterpret_cast<float*>(smem4);                         // H*INP + 2H + 4 floats (= 292)
@@ -307,6 +312,7 @@ __global__ void __launch_bounds__(BLOCK, 5) k_density_bwd_tc(DfArgs a, const flo
     for (int k = 0; k < INP; ++k) dfeat[k] = 0.0f;
     uint4* row = reinterpret_cast<uint4*>(stg + tid * TC_SW);
     constexpr int MATQ = BLOCK * TC_SW / 8;  // uint4 per matrix
+    constexpr int VQ = SPLIT ? 2 * MATQ : MATQ;  // staged matrices: Uh, (Ul), Vh, (Vl)
     if (active) {
       float dh[H];
 #pragma unroll
@@ -327,14 +333,16 @@ __global__ void __launch_bounds__(BLOCK, 5) k_density_bwd_tc(DfArgs a, const flo
 #pragma unroll
         for (int k = 0; k < 8; ++k) v8[k] = dh[8 * c + k];
         tc_split8(v8, hi, lo);
-        row[c] = hi; row[MATQ + c] = lo;
+        row[c] = hi;
+        if (SPLIT) row[MATQ + c] = lo;
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) v8[k] = 0.0f;
       v8[0] = g;
       tc_split8(v8, hi, lo);
-      row[2] = hi; row[MATQ + 2] = lo;
-      row[3] = make_uint4(0, 0, 0, 0); row[MATQ + 3] = make_uint4(0, 0, 0, 0);
+      row[2] = hi;
+      row[3] = make_uint4(0, 0, 0, 0);
+      if (SPLIT) { row[MATQ + 2] = lo; row[MATQ + 3] = make_uint4(0, 0, 0, 0); }
       // V = [x0..x(in-1) 0.. 1 | h0..15]
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -342,19 +350,21 @@ __global__ void __launch_bounds__(BLOCK, 5) k_density_bwd_tc(DfArgs a, const flo
         for (int k = 0; k < 8; ++k) v8[k] = (8 * c + k < a.in) ? feat[8 * c + k] : 0.0f;
         if (c == 1) v8[7] = 1.0f;
         tc_split8(v8, hi, lo);
-        row[2 * MATQ + c] = hi; row[3 * MATQ + c] = lo;
+        row[VQ + c] = hi;
+        if (SPLIT) row[VQ + MATQ + c] = lo;
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) v8[k] = hid[8 * c + k];
         tc_split8(v8, hi, lo);
-        row[2 * MATQ + 2 + c] = hi; row[3 * MATQ + 2 + c] = lo;
+        row[VQ + 2 + c] = hi;
+        if (SPLIT) row[VQ + MATQ + 2 + c] = lo;
       }
     } else {
       const uint4 zq = make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
+      for (int m = 0; m < (SPLIT ? 4 : 2); ++m)
 #pragma unroll
         for (int c = 0; c < 4; ++c) row[m * MATQ + c] = zq;
     }
@@ -381,8 +391,8 @@ __global__ void __launch_bounds__(BLOCK, 5) k_density_bwd_tc(DfArgs a, const flo
       const int ks = 2 * warp + kk;
       uint32_t A0[2][4], A1[2][4], B01[2][4], B23[2][4];  // [hi/lo]
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const uint32_t ubase = stg_s + p * MAT, vbase = stg_s + (2 + p) * MAT;
+      for (int p = 0; p < (SPLIT ? 2 : 1); ++p) {
+        const uint32_t ubase = stg_s + p * MAT, vbase = stg_s + ((SPLIT ? 2 : 1) + p) * MAT;
         const uint32_t arow = 2u * ((16 * ks + (j >> 1) * 8 + r8) * TC_SW + (j & 1) * 8);
         tc_ldsm_x4_t(A0[p], ubase + arow);
         tc_ldsm_x4_t(A1[p], ubase + arow + 2u * 16);
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(BLOCK, 5) k_density_bwd_tc(DfArgs a, const flo
         tc_ldsm_x4_t(B23[p], vbase + brow + 2u * 16);
       }
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {  // hi*hi, hi*lo, lo*hi
+      for (int c = 0; c < (SPLIT ? 3 : 1); ++c) {  // hi*hi, hi*lo, lo*hi
         const int pa = c == 2 ? 1 : 0, pb = c == 1 ? 1 : 0;
         tc_mma_bf16(acc[0], A0[pa], B01[pb][0], B01[pb][1]);
         tc_mma_bf16(acc[1], A0[pa], B01[pb][2], B01[pb][3]);
@@ -454,6 +464,7 @@ int make_args(const cnb_density_field* f, const cnb_samples* s, bool bwd, DfArgs
   a.d_feat_out = nullptr;
   a.feat_keep = nullptr;
   a.feat_kept = nullptr;
+  a.mixed = f->precision == CNB_PREC_MIXED;
   return CNB_OK;
 }
 
@@ -470,11 +481,13 @@ int launch_fwd(const DfArgs& a, float* density, float* pos_out, cudaStream_t st)
 
 int launch_bwd_tc(const DfArgs& a, const float* d_density, cudaStream_t st) {
   const int64_t total = a.sm.num_rays * a.sm.samples_per_ray;
-  const size_t smem = sizeof(float) * 296 + (size_t)4 * BLOCK * TC_SW * 2;
+  const bool split = !a.mixed;
+  const size_t smem = sizeof(float) * 296 + (size_t)(split ? 4 : 2) * BLOCK * TC_SW * 2;
   int64_t blocks = (total + BLOCK - 1) / BLOCK;
-  const int64_t cap = (int64_t)cnb_num_sms() * 5;
+  const int64_t cap = (int64_t)cnb_num_sms() * (split ? 5 : 6);
   if (blocks > cap) blocks = cap;
-  k_density_bwd_tc<<<(int)blocks, BLOCK, smem, st>>>(a, d_density);
+  if (split) k_density_bwd_tc<true><<<(int)blocks, BLOCK, smem, st>>>(a, d_density);
+  else k_density_bwd_tc<false><<<(int)blocks, BLOCK, smem, st>>>(a, d_density);
   return cnb_check_launch("density_field_bwd");
 }
 

@@ -91,6 +91,7 @@ class FusedPipeline:
                                [b.grad for b in bs] if with_grads else None)
             d.warp = net._warp()
             d.average_init_density = float(net.average_init_density)
+            d.precision = L.PREC_MIXED if getattr(m.config, "precision", "fp32") == "mixed" else L.PREC_FP32
             ms.proposal[i] = d
         sp = ms.sampler
         sp.num_proposal_iterations = n

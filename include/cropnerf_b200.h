@@ -98,6 +98,7 @@ typedef struct cnb_density_field {
   cnb_mlp mlp;               /* 2L -> hidden -> 1 (hidden <= 64), or a single Linear when use_linear */
   cnb_warp warp;
   float average_init_density;
+  int32_t precision;         /* CNB_PREC_FP32 (0): exact gradients; CNB_PREC_MIXED: MLP parameter gradients contracted with bf16 operands */
 } cnb_density_field;
 
 /* FruitField (fruit_field.py:44-302) */
