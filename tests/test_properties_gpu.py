@@ -171,3 +171,26 @@ def test_unreachable_table_rows_never_get_gradient_and_masked_adam_is_bit_identi
             outs.append((p, m, v))
         for a, b in zip(outs[0], outs[1]):
             assert torch.equal(a, b), f"{name}: masked Adam differs from the dense pass"
+
+
+@pytest.mark.parametrize("R", [0, 1, 33])
+def test_empty_single_and_ragged_ray_bundles(dev, R):
+    """Edge sizes of the render loop: an empty bundle, ONE ray (the reference notes its chunk loop cannot handle a size-1 chunk,
+    fruit_nerf.py:289-291 -- here it is just a batch) and a count that is not a multiple of anything; each ray's result equals the same ray
+    rendered inside a larger batch."""
+    model = _full_model(dev)
+    rays = synthetic.make_rays(64, seed=17, num_cameras=300)
+    with torch.no_grad():
+        big = model(_bundle(rays, dev))
+        out = model(_bundle(rays, dev, slice(0, R)))
+        host = model.get_outputs_for_camera_jagged_ray_bundle(_bundle(rays, dev, slice(0, R))) if R > 0 else None
+    for k in ("rgb", "depth", "accumulation", "semantics"):
+        assert out[k].shape[0] == R
+        assert torch.equal(out[k], big[k][:R]), k
+        if host is not None:
+            assert torch.equal(host[k].to(dev), big[k][:R]), k
+    if R > 0:
+        tr = engine.Trainer(_full_model(dev, "mixed").train(), force_proposal_update=True)
+        targets = {k: v[:R].to(dev) for k, v in synthetic.make_targets(64, seed=4).items()}
+        stats = tr.train_iteration(2000, _bundle(rays, dev, slice(0, R)), targets)
+        assert np.isfinite(float(stats["loss"]))
