@@ -533,6 +533,7 @@ class Trainer:
         if not self.model.training:  # nn.Module.train() walks every sub-module: only when the mode actually changes
             self.model.train()
         self._run_callbacks("BEFORE_TRAIN_ITERATION", step)
+        self.model._params_version = getattr(self.model, "_params_version", 0) + 1  # invalidates the eval path's cached descriptors
         graphed = False
         if not getattr(self, "_grads_clean", False):
             for g in self.groups.values():

@@ -360,6 +360,10 @@ class FruitModel(nn.Module):
         outputs["semantics_colormap"] = torch.heaviside(torch.sigmoid(sem) - 0.9, torch.zeros((), device=sem.device)).to(torch.long)
         return outputs
 
+    def load_state_dict(self, *args, **kwargs):
+        self._params_version = getattr(self, "_params_version", 0) + 1  # cached kernel descriptors (mean appearance embedding) are stale now
+        return super().load_state_dict(*args, **kwargs)
+
     def state_dict(self, *args, **kwargs):
         # a checkpoint writer copies the parameters on ITS stream: make that stream wait for an optimiser step still in flight on a side stream
         fence = self.__dict__.get("_param_fence")

@@ -26,6 +26,7 @@ class FusedPipeline:
         self.model = model
         self._ws: Dict[Tuple[int, bool, str], Tensor] = {}
         self._tables: Dict[Tuple, Tensor] = {}
+        self._ms_cache: Dict[str, tuple] = {}
 
     # ------------------------------------------------------------------------------------------------
     def eligible(self) -> bool:
@@ -55,6 +56,24 @@ class FusedPipeline:
         return self._tables[key]
 
     def _model_struct(self, dev, training: bool, with_grads: bool, ray_gradients: bool = False):
+        """The cnb_model descriptor (pointers + hyper-parameters).  Eval / export loops call this once per chunk with unchanged parameters:
+        the no-grad descriptor is cached and rebuilt only when something it depends on changes (parameter storage, a training step or
+        load_state_dict -- ``model._params_version`` --, mode switches, background colour)."""
+        m = self.model
+        if not with_grads:
+            tab = m.field.mlp_base_grid.hash_table
+            key = (str(dev), training, ray_gradients, m.field.test_mode, getattr(m, "_params_version", 0), tab.data_ptr(), m.field.spatial_distortion is None,
+                   str(m.renderer_rgb.background_color), getattr(m.config, "precision", "fp32"), tuple(int(v) for v in m.proposal_sampler.num_proposal_samples_per_ray),
+                   int(m.proposal_sampler.num_nerf_samples_per_ray), id(m.proposal_sampler), tuple(id(fn) for fn in m.density_fns))
+            hit = self._ms_cache.get("eval")
+            if hit is not None and hit[0] == key:
+                return hit[1], hit[2]
+            ms, keep = self._build_model_struct(dev, training, with_grads, ray_gradients)
+            self._ms_cache["eval"] = (key, ms, keep)
+            return ms, keep
+        return self._build_model_struct(dev, training, with_grads, ray_gradients)
+
+    def _build_model_struct(self, dev, training: bool, with_grads: bool, ray_gradients: bool = False):
         m = self.model
         keep = []
         field = m.field
