@@ -67,6 +67,12 @@ __device__ __forceinline__ bool cnb_warp_position(const cnb_warp& w, float& x, f
   return sel;
 }
 
+// flat sample index -> ray index: a 32-bit division whenever the index fits (a 64-bit one is an ~50-instruction subroutine per thread)
+__device__ __forceinline__ int64_t cnb_ray_of(int64_t i, int S) {
+  if (i <= 0x7fffffffLL) return (int64_t)((uint32_t)i / (uint32_t)S);
+  return i / S;
+}
+
 // normalised + masked position of sample i (= r*S + s) of a cnb_samples description
 __device__ __forceinline__ bool cnb_sample_position(const cnb_samples& sm, const cnb_warp& w, int64_t r, int32_t s,
                                                     float& x, float& y, float& z) {

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(BLOCK) k_density_fwd(DfArgs a, float* __restri
   const int S = a.sm.samples_per_ray;
   const int64_t total = a.sm.num_rays * S;
   for (int64_t i = blockIdx.x * (int64_t)BLOCK + threadIdx.x; i < total; i += (int64_t)gridDim.x * BLOCK) {
-    const int64_t r = i / S;
+    const int64_t r = cnb_ray_of(i, S);
     const int s = (int)(i - r * S);
     float x, y, z;
     const bool sel = cnb_sample_position(a.sm, a.warp, r, s, x, y, z);
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(BLOCK, (H <= 16 && LMAX <= 8) ? 5 : 1) k_densi
     if (i < total) {
       const float dd = __ldg(d_density + i);
       if (dd != 0.0f) {
-        const int64_t r = i / S;
+        const int64_t r = cnb_ray_of(i, S);
         const int s = (int)(i - r * S);
         const bool sel = cnb_sample_position(a.sm, a.warp, r, s, x, y, z);
         if (sel) {
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(BLOCK, SPLIT ? 5 : 6) k_density_bwd_tc(DfArgs 
     if (i < total) {
       const float dd = __ldg(d_density + i);
       if (dd != 0.0f) {
-        const int64_t r = i / S;
+        const int64_t r = cnb_ray_of(i, S);
         const int s = (int)(i - r * S);
         const bool sel = cnb_sample_position(a.sm, a.warp, r, s, x, y, z);
         if (sel) {

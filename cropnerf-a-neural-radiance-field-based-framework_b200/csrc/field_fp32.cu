@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_positions(cnb_samples sm, cnb_warp w, f
   const int S = sm.samples_per_ray;
   const int64_t total = sm.num_rays * S;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / S;
+    const int64_t r = cnb_ray_of(i, S);
     float x, y, z;
     const bool s = cnb_sample_position(sm, w, r, (int)(i - r * S), x, y, z);
     pos[3 * i] = x; pos[3 * i + 1] = y; pos[3 * i + 2] = z;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_mid_fwd(cnb_samples sm, const float* __
   const int64_t total = sm.num_rays * S;
   const int geo = ob - 1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / S;
+    const int64_t r = cnb_ray_of(i, S);
     const float* b = bo + i * ob;
     density[i] = sel[i] != 0.0f ? expf(b[0]) : 0.0f;
     if (geo_out) for (int k = 0; k < ob; ++k) geo_out[i * ob + k] = b[k];

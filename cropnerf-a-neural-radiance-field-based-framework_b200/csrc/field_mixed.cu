@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
     {
       const int64_t i = base + sidx;
       if (i < N) {
-        const int64_t r = i / S;
+        const int64_t r = cnb_ray_of(i, S);
         my_sel = cnb_sample_position(a.sm, a.warp, r, (int)(i - r * S), px, py, pz);
         if (a.pos_out && lpar == 0) { a.pos_out[3 * i] = px; a.pos_out[3 * i + 1] = py; a.pos_out[3 * i + 2] = pz; }
       }

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) k_position_grad_rays(const __grid_constan
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nround; i += (int64_t)gridDim.x * blockDim.x) {
     const bool in = i < total;
     const int64_t ii = in ? i : total - 1;
-    const int64_t r = ii / S;
+    const int64_t r = cnb_ray_of(ii, S);
     const int s = (int)(ii - r * S);
     float gx = 0.f, gy = 0.f, gz = 0.f, tt = 0.f;
     if (in) {

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) k_sample_spaced(const float* __restrict__
   const int nb = S + 1;
   const int64_t total = R * nb;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / nb;
+    const int64_t r = cnb_ray_of(i, nb);
     const int j = (int)(i - r * nb);
     float b = __ldg(lin_bins + j);
     if (t_rand != nullptr) {

@@ -205,3 +205,24 @@ def test_camera_optimizer_so3xr3_host_math():
     opt.get_loss_dict(reg)
     assert "camera_opt_regularizer" in reg
     assert CameraOptimizer(5, "off").apply_to_raybundle(rb) is None
+
+
+def test_grad_scaler_grow_and_backoff_host_logic():
+    """torch.amp.GradScaler's update rule on the host side of engine.GradScaler (the flag lives wherever the gradients do; a CPU tensor here)."""
+    from cropnerf_b200 import engine
+
+    sc = engine.GradScaler(init_scale=1024.0, growth_interval=3)
+    flag = sc.flag("cpu")
+    for _ in range(2):
+        assert sc.update() is False
+    assert sc.scale == 1024.0
+    assert sc.update() is False and sc.scale == 2048.0          # third clean step in a row: grow
+    flag.fill_(1)
+    assert sc.update() is True and sc.scale == 1024.0 and sc.skipped_steps == 1 and int(flag.item()) == 0   # inf seen: back off, flag cleared
+    assert sc.update() is False and sc.growth_tracker == 1
+    sd = sc.state_dict()
+    sc2 = engine.GradScaler()
+    sc2.load_state_dict(sd)
+    assert sc2.scale == 1024.0 and sc2.growth_tracker == 1
+    off = engine.GradScaler(enabled=False)
+    assert off.scale == 1.0 and off.update() is False
