@@ -10,7 +10,8 @@
  * Conventions
  *  - plain pointers + sizes only; every pointer is DEVICE memory owned by the caller unless stated; the
  *    library never allocates persistent memory and never frees caller memory;
- *  - all work is enqueued on `stream` (no hidden syncs, graph-capturable); stateless and re-entrant;
+ *  - all work is enqueued on `stream` (no hidden syncs, graph-capturable); stateless and re-entrant (two documented exceptions keep a
+ *    per-device side stream + events: cnb_train_step's forked backward chains and cnb_ddp_optimizer_step's deferred exchange);
  *  - return 0 on success, negative cnb_status otherwise; cnb_last_error() gives the thread-local message;
  *  - tensors are contiguous row-major fp32 unless stated; "[R,S]" sample arrays may carry a row stride so
  *    that bin-edge arrays [R,S+1] can be passed as starts (=edges) and ends (=edges+1) without copies;
@@ -349,6 +350,11 @@ typedef struct cnb_train_cfg {
 } cnb_train_cfg;
 
 /* forward + losses + backward of one batch; parameter gradients are ACCUMULATED into the d_* pointers of `m`;
+ * With phase 0 / 4 the independent backward chains (field | proposal level 0 | proposal level 1) are forked onto two library-owned side
+ * streams per device and joined back with events before the call's last kernel: for the caller it remains ONE stream-ordered call
+ * (and a CUDA graph capture of `stream` records the branches); the side streams are created on the first un-captured call and are the
+ * only state the library keeps (calls from several host threads on one device share them: still correct, merely serialised there).
+ * CNB_TRAIN_NO_OVERLAP=1 in the environment keeps everything on `stream`.
  * losses_out (device, 8 floats, overwritten): [0] rgb mse, [1] weighted semantic bce, [2] interlevel (x mult), [3] distortion,
  * [4] psnr = -10 log10([0]) (get_metrics_dict, fruit_nerf.py:639-645), [5] total = [0] + [1] + [2] (sum of get_loss_dict) */
 int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cnb_train_cfg* cfg, const cnb_ray_outputs* out, float* losses_out,
