@@ -138,15 +138,15 @@ def generate_rays(c2w: Tensor, fx: float, fy: float, cx: float, cy: float, width
 
 
 def aabb_near_far(origins: Tensor, directions: Tensor, aabb: Tensor, invalid: float = 1e10) -> Tuple[Tensor, Tensor]:
-    """Slab test of rays against an AABB [2,3] (what ``cam.generate_rays(aabb_box=...)`` sets, fruit_nerf.py:283);
-    misses get nears = fars = ``invalid``."""
-    inv = 1.0 / directions
-    t0 = (aabb[0].to(origins) - origins) * inv
-    t1 = (aabb[1].to(origins) - origins) * inv
-    tmin = torch.minimum(t0, t1).amax(dim=-1, keepdim=True)
-    tmax = torch.maximum(t0, t1).amin(dim=-1, keepdim=True)
-    tmin = tmin.clamp_min(0.0)
-    miss = tmax < tmin
+    """nerfstudio ``intersect_aabb`` (utils/math.py; what ``cam.generate_rays(aabb_box=...)`` sets, fruit_nerf.py:283) for an arbitrary flat
+    ray bundle, in torch ops (the per-camera path uses the fused kernel, :func:`generate_rays`): slab test against an AABB [2,3], both
+    distances clamped to [0, 1e10], rays with ``t_max <= t_min`` are misses and get nears = fars = ``invalid``."""
+    lo, hi = aabb[0].to(origins), aabb[1].to(origins)
+    t0 = (lo - origins) / directions
+    t1 = (hi - origins) / directions
+    tmin = torch.minimum(t0, t1).amax(dim=-1, keepdim=True).clamp(min=0.0, max=1e10)
+    tmax = torch.maximum(t0, t1).amin(dim=-1, keepdim=True).clamp(min=0.0, max=1e10)
+    miss = tmax <= tmin
     return torch.where(miss, torch.full_like(tmin, invalid), tmin), torch.where(miss, torch.full_like(tmax, invalid), tmax)
 
 

@@ -107,3 +107,17 @@ def test_volume_surface_rays_match_reference_executed_fixture():
         np.testing.assert_array_equal(d.numpy()[None].repeat(o.shape[0], 0), ref[name + "_directions"])
         assert np.all(ref[name + "_fars"] == np.float32(far))
     assert np.allclose(export.rescale_to_dataparser(torch.ones(2, 3), 0.5).numpy(), 4.0)
+
+
+def test_aabb_near_far_equals_oracle_intersect_aabb():
+    g = torch.Generator().manual_seed(4)
+    o = torch.randn((4000, 3), generator=g) * 1.5
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn((4000, 3), generator=g), dim=-1)  # roughly towards the box
+    d[:50, 0] = 0.0  # axis-parallel rays: +-inf slab distances
+    aabb = torch.tensor([[-0.4, -0.3, -0.5], [0.3, 0.5, 0.2]])
+    n, f = export.aabb_near_far(o, d, aabb)
+    tmin, tmax = ns.intersect_aabb(o, d, aabb.reshape(-1))
+    hit = tmin < 1e10
+    assert 200 < int(hit.sum()) < 3800
+    assert torch.equal(n[:, 0] < 1e10, hit)
+    assert torch.equal(n[:, 0], tmin) and torch.equal(f[:, 0], tmax)

@@ -179,3 +179,32 @@ def test_generate_point_cloud_matches_oracle_loop(dev, world_size):
         assert (gc[same] - ref_c[same]).abs().max().item() < 2e-4
         assert bool(obb.within(gp).all())
     assert total == num_points
+
+
+def test_render_cluster_projection_on_arbitrary_rays(dev):
+    """The per-(camera, cluster) step of fruit_nerf.py:283-315 for a flat bundle of arbitrary rays (torch slab test + the two renders)."""
+    cfg = cases.make_config(dict(log2_hashmap_size=14))
+    oracle, state = cases.build_oracle(cfg, 6, 0, 0.5)
+    oracle.eval()
+    model = product_model(cfg, state, 6, dev, False)
+    rays = synthetic.make_rays(1500, seed=9, num_cameras=6)
+    aabb = torch.tensor([[-0.35, -0.3, -0.3], [0.3, 0.35, 0.4]])
+    rb = export.RayBundle(rays["origins"], rays["directions"], rays["pixel_area"], rays["camera_indices"])
+    got = export.render_cluster_projection(model, rb, aabb)
+    tmin, tmax = ns.intersect_aabb(rays["origins"], rays["directions"], aabb.reshape(-1))
+    valid = tmin < 1e10
+    assert torch.equal(got["valid"].cpu(), valid) and int(valid.sum()) > 100
+    ob = ns.RayBundle(origins=rays["origins"][valid], directions=rays["directions"][valid], pixel_area=rays["pixel_area"][valid],
+                      camera_indices=rays["camera_indices"][valid], nears=tmin[valid][:, None], fars=tmax[valid][:, None])
+    with torch.no_grad():
+        sem = oracle(ob)["semantics"]
+        ob.fars = ob.nears
+        ob.nears = torch.zeros_like(ob.nears)
+        front = oracle.get_density_for_ray_bundle(ob)
+    g_sem, g_front = got["semantics"].cpu()[valid][:, :1], got["front_opacity"].cpu()[valid]
+    assert ((g_sem - sem).abs() / (sem.abs() + 1e-2)).max().item() < 2e-3
+    assert (g_front - front).abs().max().item() < 2e-4
+    assert float(got["semantics"].cpu()[~valid].abs().max()) == 0.0
+    occluded = got["front_opacity"] >= 0.5
+    assert float(got["visible"][occluded].abs().max() if bool(occluded.any()) else 0.0) == 0.0
+    assert torch.equal(got["visible"][~occluded], got["semantics"][~occluded])
