@@ -38,7 +38,7 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// weights of one ray from STAGED inputs: dens_s[0..S) and edges_s[0..S] already in shared memory; wsm may alias dens_s
+// weights of one ray (k_weights_fwd's arithmetic) from STAGED inputs: dens_s[0..S) and edges_s[0..S] already in shared memory; wsm may alias dens_s
 __device__ __forceinline__ void ray_weights_staged(const float* dens_s, const float* edges_s, int S, float* dd, float* cs, float* wsm, int lane) {
   for (int j = lane; j < S; j += 32) dd[j] = __fmul_rn(__fsub_rn(edges_s[j + 1], edges_s[j]), dens_s[j]);
   __syncwarp();
@@ -48,35 +48,6 @@ __device__ __forceinline__ void ray_weights_staged(const float* dens_s, const fl
     const float alpha = __fsub_rn(1.0f, expf(-dd[j]));
     const float T = expf(-(j > 0 ? cs[j - 1] : 0.0f));
     wsm[j] = cnb_nan_to_num(__fmul_rn(alpha, T));
-  }
-  __syncwarp();
-}
-
-// weights of one ray into wsm[0..S): dd/cs are scratch [S] (k_weights_fwd's arithmetic)
-__device__ __forceinline__ void ray_weights(const float* __restrict__ density, const float* __restrict__ edges, int S, float* dd, float* cs, float* wsm, int lane) {
-  for (int j = lane; j < S; j += 32) {
-    const float delta = __fsub_rn(__ldg(edges + j + 1), __ldg(edges + j));
-    dd[j] = __fmul_rn(delta, __ldg(density + j));
-  }
-  __syncwarp();
-  cnb_warp_cumsum(dd, cs, S, lane);
-  __syncwarp();
-  for (int j = lane; j < S; j += 32) {
-    const float alpha = __fsub_rn(1.0f, expf(-dd[j]));
-    const float T = expf(-(j > 0 ? cs[j - 1] : 0.0f));
-    wsm[j] = cnb_nan_to_num(__fmul_rn(alpha, T));
-  }
-  __syncwarp();
-}
-
-// median depth (DepthRenderer "median"): cw is scratch [S]
-__device__ __forceinline__ void ray_median_depth(const float* wsm, const float* __restrict__ edges, int S, float* cw, float* depth_out, int lane) {
-  cnb_warp_cumsum(wsm, cw, S, lane);
-  __syncwarp();
-  if (lane == 0) {
-    int idx = cnb_search_left(cw, S, 0.5f);
-    idx = min(max(idx, 0), S - 1);
-    *depth_out = __fmul_rn(__fadd_rn(__ldg(edges + idx), __ldg(edges + idx + 1)), 0.5f);
   }
   __syncwarp();
 }
@@ -164,28 +135,36 @@ __global__ void __launch_bounds__(WARPS * 32) k_level_resample(const float* __re
   }
 }
 
-// smem per warp: dd [S], cs [S], w [S]
+// smem per warp: dd [S], cs [S], w [S], edges [S+1], rgb [3S], sem [S]
 __global__ void __launch_bounds__(WARPS * 32) k_final_composite(const float* __restrict__ density, const float* __restrict__ rgb, const float* __restrict__ sem,
                                                                 const float* __restrict__ eu, int64_t R, int S, int bg_mode, float bg0, float bg1, float bg2,
                                                                 int eval_mode, float* __restrict__ weights_out, float* __restrict__ rgb_out,
                                                                 float* __restrict__ depth_out, float* __restrict__ acc_out, float* __restrict__ sem_out) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* dd = smem + (size_t)warp * 3 * S;
+  float* dd = smem + (size_t)warp * (8 * S + 1);
   float* cs = dd + S;
   float* wsm = cs + S;
+  float* ed = wsm + S;        // [S+1]
+  float* rg = ed + (S + 1);   // [3S]
+  float* se = rg + 3 * S;     // [S]
   for (int64_t r = blockIdx.x * (int64_t)WARPS + warp; r < R; r += (int64_t)gridDim.x * WARPS) {
-    const float* e = eu + r * (S + 1);
-    ray_weights(density + r * S, e, S, dd, cs, wsm, lane);
+    // all global inputs of the ray in flight at once (see k_level_resample)
+    for (int j = lane; j < S; j += 32) { cp_async4(wsm + j, density + r * S + j); cp_async4(se + j, sem + r * S + j); }
+    for (int j = lane; j <= S; j += 32) cp_async4(ed + j, eu + r * (S + 1) + j);
+    for (int j = lane; j < 3 * S; j += 32) cp_async4(rg + j, rgb + r * S * 3 + j);
+    cp_async_wait_all();
+    __syncwarp();
+    ray_weights_staged(wsm, ed, S, dd, cs, wsm, lane);
     float a = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, sm = 0.f;
     for (int j = lane; j < S; j += 32) {  // k_render_fwd's arithmetic
       const float w = wsm[j];
       if (weights_out) weights_out[r * S + j] = w;
       a += w;
-      float x = __ldg(rgb + (r * S + j) * 3), y = __ldg(rgb + (r * S + j) * 3 + 1), z = __ldg(rgb + (r * S + j) * 3 + 2);
+      float x = rg[3 * j], y = rg[3 * j + 1], z = rg[3 * j + 2];
       if (eval_mode) { x = cnb_nan_to_num(x); y = cnb_nan_to_num(y); z = cnb_nan_to_num(z); }
       c0 = fmaf(w, x, c0); c1 = fmaf(w, y, c1); c2 = fmaf(w, z, c2);
-      sm = fmaf(w, __ldg(sem + r * S + j), sm);
+      sm = fmaf(w, se[j], sm);
     }
     a = cnb_warp_sum(a);
     if (acc_out && lane == 0) acc_out[r] = a;
@@ -195,8 +174,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_final_composite(const float* __r
     if (rgb_out && lane == 0) {
       float b0 = bg0, b1 = bg1, b2 = bg2;
       if (bg_mode == CNB_BG_LAST_SAMPLE) {
-        const float* last = rgb + (r * S + S - 1) * 3;
-        b0 = last[0]; b1 = last[1]; b2 = last[2];
+        b0 = rg[3 * (S - 1)]; b1 = rg[3 * (S - 1) + 1]; b2 = rg[3 * (S - 1) + 2];
         if (eval_mode) { b0 = cnb_nan_to_num(b0); b1 = cnb_nan_to_num(b1); b2 = cnb_nan_to_num(b2); }
       }
       if (bg_mode != CNB_BG_NONE) {
@@ -206,7 +184,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_final_composite(const float* __r
       if (eval_mode) { c0 = fminf(fmaxf(c0, 0.f), 1.f); c1 = fminf(fmaxf(c1, 0.f), 1.f); c2 = fminf(fmaxf(c2, 0.f), 1.f); }
       rgb_out[3 * r] = c0; rgb_out[3 * r + 1] = c1; rgb_out[3 * r + 2] = c2;
     }
-    if (depth_out) { __syncwarp(); ray_median_depth(wsm, e, S, cs, depth_out + r, lane); }
+    if (depth_out) {  // DepthRenderer "median" on the staged edges (ray_median_depth's arithmetic)
+      __syncwarp();
+      cnb_warp_cumsum(wsm, cs, S, lane);
+      __syncwarp();
+      if (lane == 0) {
+        int idx = cnb_search_left(cs, S, 0.5f);
+        idx = min(max(idx, 0), S - 1);
+        depth_out[r] = __fmul_rn(__fadd_rn(ed[idx], ed[idx + 1]), 0.5f);
+      }
+    }
     __syncwarp();
   }
 }
@@ -400,7 +387,7 @@ extern "C" int cnb_final_composite(const float* density, const float* rgb, const
   CNB_REQUIRE(bg_mode != CNB_BG_CONSTANT || bg_color != nullptr, "final_composite: constant background needs bg_color (host pointer, 3 floats)");
   float b0 = 0.f, b1 = 0.f, b2 = 0.f;
   if (bg_mode == CNB_BG_CONSTANT) { b0 = bg_color[0]; b1 = bg_color[1]; b2 = bg_color[2]; }
-  const size_t smem = sizeof(float) * WARPS * 3 * (size_t)S;
+  const size_t smem = sizeof(float) * WARPS * (8 * (size_t)S + 1);
   static size_t configured = 48 * 1024;
   int rc = ensure_smem(k_final_composite, smem, configured, "final_composite attr");
   if (rc) return rc;

@@ -96,13 +96,6 @@ int make_layout(const cnb_model* m, int64_t R, bool training, Layout& L) {
   return CNB_OK;
 }
 
-__global__ void __launch_bounds__(256) k_fill_near_far(const float* __restrict__ nears, const float* __restrict__ fars, float near_plane, float far_plane,
-                                                        int64_t R, float* __restrict__ n_out, float* __restrict__ f_out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R; i += (int64_t)gridDim.x * blockDim.x) {
-    n_out[i] = nears ? __ldg(nears + i) : near_plane;
-    f_out[i] = fars ? __ldg(fars + i) : far_plane;
-  }
-}
 
 // losses[4] = PSNR of the batch (get_metrics_dict, fruit_nerf.py:639-645: 10 log10(1 / mse)), losses[5] = rgb + semantics + interlevel
 // (what the Trainer sums from get_loss_dict): the scalars a training loop logs, so it reads one buffer instead of launching its own kernels
@@ -183,15 +176,10 @@ int forward_chain(const cnb_model* m, const cnb_rays* rays, const Layout& L, flo
   const int lf = L.levels - 1;
   const bool user = out != nullptr;
   if (part != 2) {
-    int64_t blocks = (R + 255) / 256;
-    if (blocks > 4 * cnb_num_sms()) blocks = 4 * cnb_num_sms();
-    {
-      StageTimer _t("near_far", 1, st);
-      k_fill_near_far<<<(int)blocks, 256, 0, st>>>(rays->nears, rays->fars, rays->near_plane, rays->far_plane, R, ws + L.nears, ws + L.fars);
-    }
-    if ((rc = cnb_check_launch("render near/far"))) return rc;
+    // NearFarCollider + the initial sampler in one kernel (per-ray near / far land in the workspace for the resampling levels)
     const int rstride = sp.single_jitter ? 1 : L.S[0] + 1;
-    STAGE("sample_spaced", 1, cnb_sample_spaced(ws + L.nears, ws + L.fars, sp.lin_bins, jit, rstride, sp.initial_spacing, R, L.S[0], ws + L.sp[0], ws + L.eu[0], st));
+    STAGE("sample_spaced", 1, cnb_sample_spaced_collide(rays->nears, rays->fars, rays->near_plane, rays->far_plane, sp.lin_bins, jit, rstride, sp.initial_spacing, R,
+                                                        L.S[0], ws + L.nears, ws + L.fars, ws + L.sp[0], ws + L.eu[0], st));
     if (rc) return rc;
   }
   for (int lv = (part == 2 ? lf : 0); lv < (part == 1 ? lf : L.levels); ++lv) {

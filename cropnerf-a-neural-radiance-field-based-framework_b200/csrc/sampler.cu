@@ -14,7 +14,9 @@ namespace {
 
 __global__ void __launch_bounds__(256) k_sample_spaced(const float* __restrict__ nears, const float* __restrict__ fars,
                                                         const float* __restrict__ lin_bins, const float* __restrict__ t_rand, int rand_stride,
-                                                        int kind, int64_t R, int S, float* __restrict__ sp_bins, float* __restrict__ eu_bins) {
+                                                        int kind, int64_t R, int S, float* __restrict__ sp_bins, float* __restrict__ eu_bins,
+                                                        float near_plane, float far_plane, float* __restrict__ nears_out, float* __restrict__ fars_out) {
+  // nears / fars may be NULL: the collider's planes apply (NearFarCollider); nears_out / fars_out (optional) receive the per-ray values
   const int nb = S + 1;
   const int64_t total = R * nb;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -28,8 +30,11 @@ __global__ void __launch_bounds__(256) k_sample_spaced(const float* __restrict__
       const float t = __ldg(t_rand + r * rand_stride + (rand_stride == 1 ? 0 : j));
       b = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t));
     }
-    const float s_near = cnb_spacing_fn(kind, __ldg(nears + r));
-    const float s_far = cnb_spacing_fn(kind, __ldg(fars + r));
+    const float near_v = nears != nullptr ? __ldg(nears + r) : near_plane;
+    const float far_v = fars != nullptr ? __ldg(fars + r) : far_plane;
+    if (j == 0 && nears_out != nullptr) { nears_out[r] = near_v; fars_out[r] = far_v; }
+    const float s_near = cnb_spacing_fn(kind, near_v);
+    const float s_far = cnb_spacing_fn(kind, far_v);
     sp_bins[i] = b;
     eu_bins[i] = cnb_spacing_to_euclid(kind, b, s_near, s_far);
   }
@@ -107,8 +112,28 @@ extern "C" int cnb_sample_spaced(const float* nears, const float* fars, const fl
   int64_t blocks = (R * (S + 1) + 255) / 256;
   const int64_t cap = (int64_t)cnb_num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  k_sample_spaced<<<(int)blocks, 256, 0, stream>>>(nears, fars, lin_bins, t_rand, rand_stride, spacing, R, S, spacing_bins, euclid_bins);
+  k_sample_spaced<<<(int)blocks, 256, 0, stream>>>(nears, fars, lin_bins, t_rand, rand_stride, spacing, R, S, spacing_bins, euclid_bins, 0.0f, 0.0f, nullptr,
+                                                   nullptr);
   return cnb_check_launch("sample_spaced");
+}
+
+// the collider folded in (what cnb_render_rays / cnb_train_step start with): per-ray nears / fars when given, else the planes; the values used
+// are also written to nears_out / fars_out for the PDF resampling levels
+extern "C" int cnb_sample_spaced_collide(const float* ray_nears, const float* ray_fars, float near_plane, float far_plane, const float* lin_bins,
+                                         const float* t_rand, int32_t rand_stride, int32_t spacing, int64_t R, int32_t S, float* nears_out, float* fars_out,
+                                         float* spacing_bins, float* euclid_bins, cnb_stream_t stream) {
+  CNB_REQUIRE(R >= 0 && S >= 1, "sample_spaced_collide: bad sizes R=%lld S=%d", (long long)R, S);
+  if (R == 0) return CNB_OK;
+  CNB_REQUIRE(lin_bins && spacing_bins && euclid_bins && nears_out && fars_out, "sample_spaced_collide: null pointer");
+  CNB_REQUIRE((ray_nears == nullptr) == (ray_fars == nullptr), "sample_spaced_collide: nears and fars come together");
+  CNB_REQUIRE(t_rand == nullptr || rand_stride == 1 || rand_stride == S + 1, "sample_spaced_collide: rand_stride must be 1 or S+1");
+  CNB_REQUIRE(spacing == CNB_SPACING_UNIFORM || spacing == CNB_SPACING_LINDISP_PIECEWISE, "sample_spaced_collide: unknown spacing %d", spacing);
+  int64_t blocks = (R * (S + 1) + 255) / 256;
+  const int64_t cap = (int64_t)cnb_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  k_sample_spaced<<<(int)blocks, 256, 0, stream>>>(ray_nears, ray_fars, lin_bins, t_rand, rand_stride, spacing, R, S, spacing_bins, euclid_bins, near_plane,
+                                                   far_plane, nears_out, fars_out);
+  return cnb_check_launch("sample_spaced_collide");
 }
 
 extern "C" int cnb_sample_pdf(const float* weights, float anneal, const float* prev_spacing_bins, const float* nears, const float* fars,

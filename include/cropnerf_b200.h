@@ -183,6 +183,11 @@ int cnb_field_bwd_rays(const cnb_field* f, const cnb_samples* s, const float* d_
  * [R*rand_stride] with rand_stride 1 (single_jitter) or S+1.  Outputs spacing/euclid bin edges [R,S+1]. */
 int cnb_sample_spaced(const float* nears, const float* fars, const float* lin_bins, const float* t_rand, int32_t rand_stride,
                       int32_t spacing, int64_t R, int32_t S, float* spacing_bins, float* euclid_bins, cnb_stream_t stream);
+/* the same with nerfstudio's NearFarCollider folded in (fruit_nerf.py:167): ray_nears / ray_fars [R] when the bundle carries them (AABB-clipped
+ * projection rays), else the two planes; the values used are written to nears_out / fars_out [R] for the PDF resampling levels */
+int cnb_sample_spaced_collide(const float* ray_nears, const float* ray_fars, float near_plane, float far_plane, const float* lin_bins,
+                              const float* t_rand, int32_t rand_stride, int32_t spacing, int64_t R, int32_t S, float* nears_out, float* fars_out,
+                              float* spacing_bins, float* euclid_bins, cnb_stream_t stream);
 /* PDFSampler(include_original=False): weights [R,Sp] (raised to `anneal` in-kernel), prev spacing bins [R,Sp+1];
  * u_base = torch.linspace(0, 1-1/(S+1), S+1) from the host; rand NULL (eval: + 1/(2(S+1))) or [R*rand_stride];
  * inds (optional) [R,S+1] int32 = searchsorted(cdf,u,right). */
