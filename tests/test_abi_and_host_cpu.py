@@ -226,3 +226,24 @@ def test_grad_scaler_grow_and_backoff_host_logic():
     assert sc2.scale == 1024.0 and sc2.growth_tracker == 1
     off = engine.GradScaler(enabled=False)
     assert off.scale == 1.0 and off.update() is False
+
+
+def test_live_bitmap_bit_packing_of_nonzero_moments():
+    """FlatGroup.include_nonzero_moments: units (float4s) whose Adam moments are non-zero are OR-ed into the skip bitmap, bit i of word w
+    = unit 32 w + i, including bit 31 (the sign bit of the int32 word)."""
+    from cropnerf_b200 import engine
+
+    p = torch.nn.Parameter(torch.zeros(64 * 5))  # 320 floats = 80 units = 2.5 words
+    g = engine.FlatGroup([p])
+    n4 = g.flat.numel() // 4
+    g.live = torch.zeros(((n4 + 31) // 32,), dtype=torch.int32)
+    for unit in (0, 31, 32, 63, 79):
+        g.exp_avg[4 * unit + 2] = 1.0
+    g.exp_avg_sq[4 * 5] = 2.0
+    g.include_nonzero_moments()
+    bits = torch.stack([(g.live >> k) & 1 for k in range(32)], dim=1).reshape(-1)[:n4]
+    assert sorted(torch.nonzero(bits)[:, 0].tolist()) == [0, 5, 31, 32, 63, 79]
+    assert abs(g.live_fraction() - 6 / 80) < 1e-9
+    g.live[0] |= 2  # bits already set stay set
+    g.include_nonzero_moments()
+    assert int((g.live[0] >> 1) & 1) == 1
