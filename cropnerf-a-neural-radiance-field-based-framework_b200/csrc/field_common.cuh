@@ -36,4 +36,10 @@ int cnb_field_mixed_bwd(const cnb_field* f, const cnb_samples* s, const float* d
                         cudaStream_t stream);
 bool cnb_field_mixed_supported(const cnb_field* f);
 int64_t cnb_field_mixed_ctx_floats(int64_t n, int training);
-float* cnb_field_mixed_dx0(float* ctx, int64_t n);  // d(encoded features) [n,32] written by the mixed backward
+float* cnb_field_mixed_dx0(float* ctx, int64_t n);  // d(encoded features), LEVEL-MAJOR [16][n][2], written by the mixed backward
+
+// hashgrid.cu, library-internal variants reading d(features) level-major [L][n][2]: the fused field backward's accumulator pair of a
+// thread IS one level's two features, and the level-major scatter warps then read one contiguous 256-byte run per request.
+int cnb_hashgrid_bwd_level_major(const cnb_grid* g, const float* positions, const float* d_out, int64_t n, cudaStream_t stream);
+int cnb_position_grad_rays_level_major(const cnb_grid* g, const cnb_warp* warp, const cnb_samples* s, const float* d_feat, float* d_origins,
+                                       float* d_directions, cudaStream_t stream);

@@ -246,12 +246,9 @@ extern "C" int cnb_field_bwd_rays(const cnb_field* f, const cnb_samples* s, cons
   if (rc) return rc;
   const int64_t N = s->num_rays * s->samples_per_ray;
   if (N == 0) return CNB_OK;
-  const float* d_x0;
   if (f->precision == CNB_PREC_MIXED) {
-    CNB_REQUIRE(f->grid.num_levels == 16, "field_bwd_rays: the mixed path stores d(features) as [N,32]; num_levels must be 16");
-    d_x0 = cnb_field_mixed_dx0(ctx, N);
-  } else {
-    d_x0 = ctx + make_layout(f, N, true).d_x0;
+    CNB_REQUIRE(f->grid.num_levels == 16, "field_bwd_rays: the mixed path stores d(features) as [16][N][2]; num_levels must be 16");
+    return cnb_position_grad_rays_level_major(&f->grid, &f->warp, s, cnb_field_mixed_dx0(ctx, N), d_origins, d_directions, stream);
   }
-  return cnb_position_grad_rays(&f->grid, &f->warp, s, d_x0, d_origins, d_directions, stream);
+  return cnb_position_grad_rays(&f->grid, &f->warp, s, ctx + make_layout(f, N, true).d_x0, d_origins, d_directions, stream);
 }

@@ -120,7 +120,7 @@ __device__ inline void load_weights(const MixArgs& a, __half* Wh_, float* Bf) {
   if (tid < 4) Bf[F_BH + tid] = tid == 0 ? __ldg(a.bh) : 0.f;
 }
 
-// ctx (mixed, training): [x0: N*32 fp16][positions: N*3 floats][d_x0: N*32 floats], every block 16-byte aligned
+// ctx (mixed, training): [x0: N*32 fp16][positions: N*3 floats][d_x0: 16 levels x N x 2 floats, level-major], every block 16-byte aligned
 inline int64_t ctx_pos_off(int64_t n) { return n * 16; }
 inline int64_t ctx_dx0_off(int64_t n) { return (n * 19 + 3) & ~(int64_t)3; }
 inline int64_t ctx_total(int64_t n) { return ctx_dx0_off(n) + n * 32 + 16; }

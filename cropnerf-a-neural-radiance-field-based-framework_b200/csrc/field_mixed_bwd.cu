@@ -11,7 +11,7 @@
 //      is staged once in shared memory and read back with ldmatrix.trans; every warp owns a fixed 1/8 slice of every
 //      dW and accumulates it (fp32) across all batches of the CTA -- no atomics until the one flush per CTA at the end;
 //      bias gradients are the same contraction against a fragment of ones;
-//   4. d(encoded features) [N,32] fp32 goes to the scratch the hash-grid scatter (cnb_hashgrid_bwd) reads; the appearance
+//   4. d(encoded features), level-major [16][N][2] fp32, goes to the scratch the hash-grid scatter (cnb_hashgrid_bwd_level_major) reads; the appearance
 //      embedding gradient is reduced over the m-tile (all 16 samples share the ray when S % 16 == 0) before its atomics.
 #include <cstdlib>
 
@@ -516,8 +516,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
       layer_bf<4, 4, 72>(WT + T_B1, D, dx, g, t);
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        if (valid[0]) *reinterpret_cast<float2*>(b.d_x0 + row[0] * 32 + 8 * nt + 2 * t) = make_float2(dx[nt][0], dx[nt][1]);
-        if (valid[1]) *reinterpret_cast<float2*>(b.d_x0 + row[1] * 32 + 8 * nt + 2 * t) = make_float2(dx[nt][2], dx[nt][3]);
+        // level-major [16][N][2]: this thread's accumulator pair is level 4 nt + t of its two rows
+        float2* const dlev = reinterpret_cast<float2*>(b.d_x0) + (int64_t)(4 * nt + t) * N;
+        if (valid[0]) dlev[row[0]] = make_float2(dx[nt][0], dx[nt][1]);
+        if (valid[1]) dlev[row[1]] = make_float2(dx[nt][2], dx[nt][3]);
       }
     }
   }
@@ -580,5 +582,5 @@ int cnb_field_mixed_bwd(const cnb_field* f, const cnb_samples* s, const float* d
   k_field_mixed_bwd<<<(int)blocks, THREADS, SMEM_BWD, stream>>>(b);
   int rc = cnb_check_launch("field_mixed_bwd");
   if (rc) return rc;
-  return cnb_hashgrid_bwd(&f->grid, b.pos, b.d_x0, N, stream);
+  return cnb_hashgrid_bwd_level_major(&f->grid, b.pos, b.d_x0, N, stream);
 }

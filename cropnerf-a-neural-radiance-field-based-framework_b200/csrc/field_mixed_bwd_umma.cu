@@ -23,7 +23,7 @@
 //      (4 buffers) tells the warps when a buffer may be overwritten.  Bias gradients come from the same MMAs: a block of
 //      ones sits right behind every staged X matrix, so it is one more 8-column block of the B operand (or 8 more rows of
 //      the A operand for the three narrow layers, which are issued transposed with M = 128 so that N can stay 16);
-//   4. d(encoded features) [N,32] fp32 goes to the scratch the hash-grid scatter (cnb_hashgrid_bwd) reads; the appearance
+//   4. d(encoded features), level-major [16][N][2] fp32, goes to the scratch the hash-grid scatter (cnb_hashgrid_bwd_level_major) reads; the appearance
 //      embedding gradient is reduced over the m-tile (all 16 samples share the ray when S % 16 == 0) before its atomics.
 #include "field_mixed.cuh"
 
@@ -557,8 +557,10 @@ __global__ void __launch_bounds__(BTHREADS, 1) k_field_mixed_bwd_umma(const __gr
       layer_bf<4, 4, 72>(WT + T_B1, D, dx, g, t);
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        if (valid[0]) *reinterpret_cast<float2*>(b.d_x0 + row[0] * 32 + 8 * nt + 2 * t) = make_float2(dx[nt][0], dx[nt][1]);
-        if (valid[1]) *reinterpret_cast<float2*>(b.d_x0 + row[1] * 32 + 8 * nt + 2 * t) = make_float2(dx[nt][2], dx[nt][3]);
+        // level-major [16][N][2]: this thread's accumulator pair is level 4 nt + t of its two rows
+        float2* const dlev = reinterpret_cast<float2*>(b.d_x0) + (int64_t)(4 * nt + t) * N;
+        if (valid[0]) dlev[row[0]] = make_float2(dx[nt][0], dx[nt][1]);
+        if (valid[1]) dlev[row[1]] = make_float2(dx[nt][2], dx[nt][3]);
       }
     }
   }
@@ -683,5 +685,5 @@ int cnb_field_mixed_bwd_umma(const cnb_field* f, const cnb_samples* s, const flo
   k_field_mixed_bwd_umma<<<(int)blocks, BTHREADS, SMEM_BWD, stream>>>(b);
   int rc = cnb_check_launch("field_mixed_bwd_umma");
   if (rc) return rc;
-  return cnb_hashgrid_bwd(&f->grid, b.pos, b.d_x0, N, stream);
+  return cnb_hashgrid_bwd_level_major(&f->grid, b.pos, b.d_x0, N, stream);
 }

@@ -66,6 +66,9 @@ __global__ void __launch_bounds__(256) k_hashgrid_fwd(const __grid_constant__ Gr
 
 // Backward: a warp owns 32 CONSECUTIVE samples of one level (samples are ray-major, so neighbouring lanes are
 // neighbouring samples of a ray and often share a cell): cnb_scatter_cell aggregates those runs before the reductions.
+// LM = d_out is level-major [L][n][2] (what the fused field backward writes: a warp's 32 loads are one 256-byte run
+// instead of 32 sectors of a [n, 2L] row-major matrix).
+template <bool LM>
 __global__ void __launch_bounds__(256) k_hashgrid_bwd(const __grid_constant__ GridArgs g, const float* __restrict__ pos, const float* __restrict__ d_out, int64_t n) {
   const int lane = threadIdx.x & 31;
   const int64_t nblk = (n + 31) >> 5;
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(256) k_hashgrid_bwd(const __grid_constant__ Gr
     bool active = s < n;
     float2 d = make_float2(0.f, 0.f);
     if (active) {
-      d = __ldg(reinterpret_cast<const float2*>(d_out) + s * g.L + l);
+      d = __ldg(reinterpret_cast<const float2*>(d_out) + (LM ? (int64_t)l * n + s : s * g.L + l));
       active = d.x != 0.0f || d.y != 0.0f;  // zero gradients add nothing (masked samples, App. B-3)
     }
     CnbCell c = {};
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(256) k_hashgrid_bwd(const __grid_constant__ Gr
 //   * applies the selector mask, the (c+2)/4 or AABB normalisation and the Jacobian of SceneContraction(order=inf),
 //   * reduces dL/dp over the ray (d_origins += dL/dp, d_directions += (s+e)/2 * dL/dp): warp shuffle when the 32 lanes
 //     share the ray, atomics otherwise.
+template <bool LM>  // LM: d_feat is level-major [L][total][2]
 __global__ void __launch_bounds__(128) k_position_grad_rays(const __grid_constant__ GridArgs g, cnb_warp wp, cnb_samples sm, const float* __restrict__ d_feat,
                                                             float* __restrict__ d_origins, float* __restrict__ d_directions) {
   const int S = sm.samples_per_ray;
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(128) k_position_grad_rays(const __grid_constan
       if (sel) {
         float ax = 0.f, ay = 0.f, az = 0.f;  // dL / d(normalised position)
         for (int l = 0; l < g.L; ++l) {
-          const float2 d = __ldg(reinterpret_cast<const float2*>(d_feat) + i * g.L + l);
+          const float2 d = __ldg(reinterpret_cast<const float2*>(d_feat) + (LM ? (int64_t)l * total + i : i * g.L + l));
           if (d.x == 0.0f && d.y == 0.0f) continue;
           const float scale = g.scalings[l];
           const CnbCell c = cnb_cell(x, y, z, scale);
@@ -211,19 +215,30 @@ extern "C" int cnb_hashgrid_fwd(const cnb_grid* g, const float* positions, int64
   return cnb_check_launch("hashgrid_fwd");
 }
 
-extern "C" int cnb_hashgrid_bwd(const cnb_grid* g, const float* positions, const float* d_out, int64_t n, cnb_stream_t stream) {
+static int hashgrid_bwd_impl(const cnb_grid* g, const float* positions, const float* d_out, int64_t n, bool level_major, cnb_stream_t stream) {
   int rc = check_grid(g, true);
   if (rc) return rc;
   CNB_REQUIRE(n >= 0 && (n == 0 || (positions && d_out)), "hashgrid_bwd: null positions/d_out");
   if (n == 0) return CNB_OK;
   GridArgs a = make_args(g);
   for (int i = 0; i < a.L; ++i) CNB_REQUIRE(a.scalings[i] < 65535.0f, "hashgrid_bwd: level resolution %g too large for the aggregated scatter", a.scalings[i]);
-  k_hashgrid_bwd<<<grid_for(((n + 31) / 32) * 32 * a.L, 256), 256, 0, stream>>>(a, positions, d_out, n);
+  const int blocks = grid_for(((n + 31) / 32) * 32 * a.L, 256);
+  if (level_major) k_hashgrid_bwd<true><<<blocks, 256, 0, stream>>>(a, positions, d_out, n);
+  else k_hashgrid_bwd<false><<<blocks, 256, 0, stream>>>(a, positions, d_out, n);
   return cnb_check_launch("hashgrid_bwd");
 }
 
-extern "C" int cnb_position_grad_rays(const cnb_grid* g, const cnb_warp* warp, const cnb_samples* s, const float* d_feat, float* d_origins,
-                                      float* d_directions, cnb_stream_t stream) {
+extern "C" int cnb_hashgrid_bwd(const cnb_grid* g, const float* positions, const float* d_out, int64_t n, cnb_stream_t stream) {
+  return hashgrid_bwd_impl(g, positions, d_out, n, false, stream);
+}
+
+// library-internal: d_out level-major [L][n][2] (scratch of the fused field backward)
+int cnb_hashgrid_bwd_level_major(const cnb_grid* g, const float* positions, const float* d_out, int64_t n, cudaStream_t stream) {
+  return hashgrid_bwd_impl(g, positions, d_out, n, true, stream);
+}
+
+static int position_grad_rays_impl(const cnb_grid* g, const cnb_warp* warp, const cnb_samples* s, const float* d_feat, float* d_origins,
+                                   float* d_directions, bool level_major, cnb_stream_t stream) {
   int rc = check_grid(g, false);
   if (rc) return rc;
   CNB_REQUIRE(warp && s && d_feat && d_origins && d_directions, "position_grad_rays: null pointer");
@@ -231,10 +246,21 @@ extern "C" int cnb_position_grad_rays(const cnb_grid* g, const cnb_warp* warp, c
   const int64_t total = s->num_rays * s->samples_per_ray;
   if (total == 0) return CNB_OK;
   GridArgs a = make_args(g);
-  k_position_grad_rays<<<grid_for(total, 128), 128, 0, stream>>>(a, *warp, *s, d_feat, d_origins, d_directions);
+  if (level_major) k_position_grad_rays<true><<<grid_for(total, 128), 128, 0, stream>>>(a, *warp, *s, d_feat, d_origins, d_directions);
+  else k_position_grad_rays<false><<<grid_for(total, 128), 128, 0, stream>>>(a, *warp, *s, d_feat, d_origins, d_directions);
   return cnb_check_launch("position_grad_rays");
 }
 
+extern "C" int cnb_position_grad_rays(const cnb_grid* g, const cnb_warp* warp, const cnb_samples* s, const float* d_feat, float* d_origins,
+                                      float* d_directions, cnb_stream_t stream) {
+  return position_grad_rays_impl(g, warp, s, d_feat, d_origins, d_directions, false, stream);
+}
+
+// library-internal: d_feat level-major [L][total][2]
+int cnb_position_grad_rays_level_major(const cnb_grid* g, const cnb_warp* warp, const cnb_samples* s, const float* d_feat, float* d_origins,
+                                       float* d_directions, cudaStream_t stream) {
+  return position_grad_rays_impl(g, warp, s, d_feat, d_origins, d_directions, true, stream);
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Reachable rows.  nerfstudio's torch HashEncoding hashes EVERY level into its 2^T slots, also the coarse ones whose lattice has far fewer
