@@ -132,3 +132,104 @@ def test_oracle_field_gradcheck_fp64():
             with torch.no_grad():
                 num = (fn(tp) - fn(tm)) / 2e-6
             assert abs(num.item() - analytic[r, c].item()) <= 1e-5 * max(1.0, abs(num.item()))
+
+
+def test_sh_components_equal_scipy_real_spherical_harmonics():
+    """Independent pin of the SH basis (App. A.4): the 16 hard-coded polynomials of components_from_spherical_harmonics are the
+    orthonormal REAL spherical harmonics of degree <= 3 without the Condon-Shortley phase, ordered l^2 + l + m -- checked against
+    scipy.special.sph_harm_y on random unit vectors (an external implementation, not a restatement)."""
+    from scipy import special
+
+    rng = np.random.default_rng(0)
+    d = rng.normal(size=(2000, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    theta, phi = np.arccos(np.clip(d[:, 2], -1.0, 1.0)), np.arctan2(d[:, 1], d[:, 0])
+    out = ns.components_from_spherical_harmonics(3, torch.tensor(d, dtype=torch.float64)).numpy()
+    for l in range(4):
+        for m in range(-l, l + 1):
+            Y = special.sph_harm_y(l, abs(m), theta, phi)
+            want = Y.real if m == 0 else np.sqrt(2.0) * (-1) ** m * (Y.real if m > 0 else Y.imag)
+            assert np.abs(want - out[:, l * l + l + m]).max() < 1e-13, (l, m)
+    # orthonormality on the sphere (Monte-Carlo: 2000 points -> a few percent)
+    gram = 4.0 * np.pi * (out.T @ out) / out.shape[0]
+    assert np.abs(gram - np.eye(16)).max() < 0.15
+
+
+def _ray_samples_from_edges(edges: torch.Tensor, far: float):
+    R, S = edges.shape[0], edges.shape[1] - 1
+    fr = ns.Frustums(torch.zeros(R, S, 3, dtype=edges.dtype), torch.ones(R, S, 3, dtype=edges.dtype), edges[:, :-1, None], edges[:, 1:, None],
+                     torch.ones(R, S, 1, dtype=edges.dtype))
+    return ns.RaySamples(fr, deltas=edges[:, 1:, None] - edges[:, :-1, None], spacing_starts=edges[:, :-1, None] / far,
+                         spacing_ends=edges[:, 1:, None] / far, spacing_to_euclidean_fn=lambda x: x * far)
+
+
+def test_weights_equal_the_transmittance_integral_of_a_piecewise_constant_medium():
+    """get_weights (App. A.5) against the volume-rendering integral it discretises: for sigma constant on each bin,
+    w_i = T(t_i) - T(t_{i+1}) with T(t) = exp(-int_0^t sigma), evaluated independently in numpy float64."""
+    rng = np.random.default_rng(3)
+    R, S = 20, 48
+    edges = np.sort(rng.random((R, S + 1)) * 4.0, -1)
+    sigma = rng.random((R, S)) * 5.0
+    rs = _ray_samples_from_edges(torch.tensor(edges), 4.0)
+    w = rs.get_weights(torch.tensor(sigma)[..., None])[..., 0].numpy()
+    tau = np.concatenate([np.zeros((R, 1)), np.cumsum(sigma * np.diff(edges, axis=-1), -1)], -1)  # optical depth at every edge
+    T = np.exp(-tau)
+    assert np.abs(w - (T[:, :-1] - T[:, 1:])).max() < 1e-12
+
+
+def test_pdf_sampler_is_the_inverse_cdf_of_the_padded_histogram():
+    """PDFSampler (App. A.6) in eval mode against numpy's own piecewise-linear interpolation: the new bin edges are
+    F^-1(u) at the bin-centre quantiles u_k = (k + 1/2) / (n + 1), F = cdf of (weights + 0.01) over the existing edges."""
+    rng = np.random.default_rng(4)
+    R, S, n = 16, 64, 32
+    edges = np.sort(rng.random((R, S + 1)), -1)
+    edges[:, 0], edges[:, -1] = 0.0, 1.0
+    wts = rng.random((R, S)) ** 4
+    rs = _ray_samples_from_edges(torch.tensor(edges), 1.0)
+    rb = ns.RayBundle(torch.zeros(R, 3, dtype=torch.float64), torch.ones(R, 3, dtype=torch.float64), torch.ones(R, 1, dtype=torch.float64),
+                      torch.zeros(R, 1, dtype=torch.long), torch.zeros(R, 1, dtype=torch.float64), torch.ones(R, 1, dtype=torch.float64))
+    out = ns.PDFSampler(include_original=False).eval()(rb, rs, torch.tensor(wts)[..., None], num_samples=n)
+    got = torch.cat([out.spacing_starts[..., 0], out.spacing_ends[..., -1:, 0]], -1).numpy()
+    u = (np.arange(n + 1) + 0.5) / (n + 1)
+    for r in range(R):
+        p = wts[r] + 0.01
+        cdf = np.concatenate([[0.0], np.cumsum(p / p.sum())])
+        assert np.abs(np.interp(u, cdf, edges[r]) - got[r]).max() < 1e-9
+    # and the samples are distributed like the histogram: mass of every original bin ~ number of new edges inside it
+    hist = np.stack([np.histogram(got[r], bins=edges[r])[0] for r in range(R)])
+    p = (wts + 0.01) / (wts + 0.01).sum(-1, keepdims=True)
+    assert np.abs(hist / (n + 1) - p).max() < 1.0 / (n + 1) + 1e-9
+
+
+def test_distortion_loss_equals_the_double_integral():
+    """lossfun_distortion (App. A.8, mip-NeRF 360 eq. 15) against the quantity it is the closed form of: the double integral of
+    w(u) w(v) |u - v| for the piecewise-constant density w_i / delta_i, integrated numerically on a fine grid."""
+    rng = np.random.default_rng(5)
+    S = 6
+    t = np.array([0, 3, 11, 12, 30, 41, 50]) / 50.0  # edges on the integration grid: the midpoint rule is then exact up to O(1/G^2)
+    w = rng.random(S)
+    closed = ns.lossfun_distortion(torch.tensor(t)[None], torch.tensor(w)[None]).item()
+    G = 4000
+    x = (np.arange(G) + 0.5) / G
+    dens = (w / np.diff(t))[np.clip(np.searchsorted(t, x, side="right") - 1, 0, S - 1)]
+    numeric = (dens[:, None] * dens[None, :] * np.abs(x[:, None] - x[None, :])).sum() / G**2
+    assert abs(closed - numeric) < 1e-5 * closed
+
+
+def test_interlevel_outer_measure_bounds_the_overlap_by_brute_force():
+    """`outer` (App. A.8, mip-NeRF 360 eq. 13): for every fine interval, the summed weight of ALL proposal bins that touch it --
+    checked against an explicit double loop, and it must upper-bound the exactly overlapping proposal mass."""
+    rng = np.random.default_rng(6)
+    for _ in range(5):
+        tf = np.sort(rng.random(13)); tf[0], tf[-1] = 0.0, 1.0
+        tp = np.sort(rng.random(9)); tp[0], tp[-1] = 0.0, 1.0
+        wp = rng.random(8)
+        got = ns.outer(torch.tensor(tf[:-1])[None], torch.tensor(tf[1:])[None], torch.tensor(tp[:-1])[None], torch.tensor(tp[1:])[None],
+                       torch.tensor(wp)[None])[0].numpy()
+        for i in range(12):
+            a, b = tf[i], tf[i + 1]
+            touching = sum(wp[j] for j in range(8) if tp[j + 1] > a and tp[j] < b)          # open-interval intersection
+            overlap = sum(wp[j] * max(0.0, min(b, tp[j + 1]) - max(a, tp[j])) / (tp[j + 1] - tp[j]) for j in range(8))
+            assert got[i] >= touching - 1e-12 and got[i] >= overlap - 1e-12
+            closed_touching = sum(wp[j] for j in range(8) if tp[j + 1] >= a and tp[j] <= b)  # closed intervals: at most one bin more per side
+            assert got[i] <= closed_touching + 1e-12
