@@ -53,7 +53,7 @@ __device__ __forceinline__ void ray_weights_staged(const float* dens_s, const fl
 }
 
 // smem per warp: dd [Sp], cs [Sp], w [Sp], cdf [Sp+1], bins [Sp+1]
-__global__ void __launch_bounds__(WARPS * 32) k_level_resample(const float* __restrict__ density, const float* __restrict__ eu_prev, const float* __restrict__ sp_prev,
+__global__ void __launch_bounds__(WARPS * 32, 8) k_level_resample(const float* __restrict__ density, const float* __restrict__ eu_prev, const float* __restrict__ sp_prev,
                                                                const float* __restrict__ nears, const float* __restrict__ fars, int kind, float anneal,
                                                                const float* __restrict__ u_base, const float* __restrict__ rand, int rand_stride, int64_t R,
                                                                int Sp, int S, float hist_pad, float eps, float* __restrict__ weights_out,
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_level_resample(const float* __re
 }
 
 // smem per warp: dd [S], cs [S], w [S], edges [S+1], rgb [3S], sem [S]
-__global__ void __launch_bounds__(WARPS * 32) k_final_composite(const float* __restrict__ density, const float* __restrict__ rgb, const float* __restrict__ sem,
+__global__ void __launch_bounds__(WARPS * 32, 7) k_final_composite(const float* __restrict__ density, const float* __restrict__ rgb, const float* __restrict__ sem,
                                                                 const float* __restrict__ eu, int64_t R, int S, int bg_mode, float bg0, float bg1, float bg2,
                                                                 int eval_mode, float* __restrict__ weights_out, float* __restrict__ rgb_out,
                                                                 float* __restrict__ depth_out, float* __restrict__ acc_out, float* __restrict__ sem_out) {
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_final_composite_bwd(const float*
 
 // interlevel loss of one proposal level, forward (+ backward through get_weights when d_density != nullptr).
 // smem per warp: cps [Sp+1], cy1 [Sp+1], dcy [Sp+1], dd [Sp], cs [Sp]
-__global__ void __launch_bounds__(WARPS * 32) k_interlevel_fused(const float* __restrict__ c, const float* __restrict__ w, const float* __restrict__ cp,
+__global__ void __launch_bounds__(WARPS * 32, 8) k_interlevel_fused(const float* __restrict__ c, const float* __restrict__ w, const float* __restrict__ cp,
                                                                  const float* __restrict__ wp, const float* __restrict__ density_p,
                                                                  const float* __restrict__ eu_p, int64_t R, int Sc, int Sp, float grad_scale,
                                                                  float* __restrict__ loss_out, float* __restrict__ d_density_p) {

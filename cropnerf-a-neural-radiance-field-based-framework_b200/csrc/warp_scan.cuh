@@ -8,9 +8,84 @@
 
 #define CNB_FULL 0xffffffffu
 
+// ---- 8 elements per lane (n in 225..256: the 256-sample proposal level) -------------------------------------------------------
+// A lane's chunk in[8 lane .. 8 lane + 8) starts in bank 8 (lane % 4): walking the chunks in step makes the eight lanes with equal
+// lane % 4 hit the same bank (8-way conflict on every access, three passes per scan).  Here every lane starts its walk at element
+// q = lane / 4 of its chunk (bank 8 (lane % 4) + (k + q) % 8: all 32 distinct), keeps the chunk in registers, and a 3-stage barrel
+// rotation puts the values back into element order, so the additions happen in exactly the order of the generic code below.
+__device__ __forceinline__ void cnb_rot8_right(float (&v)[8], int q) {  // v[j] <- v[(j - q) mod 8]
+#pragma unroll
+  for (int bit = 1; bit < 8; bit <<= 1) {
+    const bool on = (q & bit) != 0;
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = v[(j - bit) & 7];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = on ? t[j] : v[j];
+  }
+}
+__device__ __forceinline__ void cnb_chunk8_load(const float* in, int n, int lane, float (&v)[8]) {
+  const int b = lane * 8, q = lane >> 2;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int idx = b + ((k + q) & 7);
+    v[k] = idx < n ? in[idx] : 0.0f;  // v[k] = element (k + q) mod 8
+  }
+  cnb_rot8_right(v, q);               // v[j] = element j
+}
+__device__ __forceinline__ void cnb_chunk8_store(float* out, int n, int lane, float (&r)[8]) {
+  const int b = lane * 8, q = lane >> 2;
+  cnb_rot8_right(r, (8 - q) & 7);     // r[k] = result of element (k + q) mod 8
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int idx = b + ((k + q) & 7);
+    if (idx < n) out[idx] = r[k];
+  }
+}
+static __device__ __noinline__ double cnb_warp_cumsum8(const float* in, float* out, int n, int lane) {
+  float v[8];
+  cnb_chunk8_load(in, n, lane, v);
+  const int cnt = min(8, max(0, n - lane * 8));  // elements this lane owns (adding the zero padding would be exact too; keep the op count equal)
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) if (j < cnt) s += (double)v[j];
+  double incl = s;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double t = __shfl_up_sync(CNB_FULL, incl, off);
+    if (lane >= off) incl += t;
+  }
+  double run = incl - s;
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { if (j < cnt) run += (double)v[j]; r[j] = (float)run; }
+  cnb_chunk8_store(out, n, lane, r);
+  return __shfl_sync(CNB_FULL, incl, 31);
+}
+static __device__ __noinline__ void cnb_warp_suffix_excl8(const float* in, float* out, int n, int lane) {
+  float v[8];
+  cnb_chunk8_load(in, n, lane, v);
+  const int cnt = min(8, max(0, n - lane * 8));
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) if (j < cnt) s += (double)v[j];
+  double incl = s;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double t = __shfl_down_sync(CNB_FULL, incl, off);
+    if (lane + off < 32) incl += t;
+  }
+  double run = incl - s;
+  float r[8];
+#pragma unroll
+  for (int j = 7; j >= 0; --j) { r[j] = (float)run; if (j < cnt) run += (double)v[j]; }
+  cnb_chunk8_store(out, n, lane, r);
+}
+
 // inclusive cumsum of in[0..n) -> out[0..n) (out may alias in). Lane owns a contiguous chunk.
 __device__ __forceinline__ double cnb_warp_cumsum(const float* in, float* out, int n, int lane) {
   const int per = (n + 31) >> 5;
+  if (per == 8) return cnb_warp_cumsum8(in, out, n, lane);
   const int b = min(n, lane * per), e = min(n, b + per);
   double s = 0.0;
   for (int j = b; j < e; ++j) s += (double)in[j];
@@ -28,6 +103,7 @@ __device__ __forceinline__ double cnb_warp_cumsum(const float* in, float* out, i
 // suffix sums: out[j] = sum_{k > j} in[k]  (exclusive reverse cumsum), double partials
 __device__ __forceinline__ void cnb_warp_suffix_excl(const float* in, float* out, int n, int lane) {
   const int per = (n + 31) >> 5;
+  if (per == 8) { cnb_warp_suffix_excl8(in, out, n, lane); return; }
   const int b = min(n, lane * per), e = min(n, b + per);
   double s = 0.0;
   for (int j = b; j < e; ++j) s += (double)in[j];
