@@ -400,10 +400,11 @@ STAGE_BYTES_PER_RAY = {
 
 
 # DRAM traffic per launch of each stage (dram__bytes_read.sum + dram__bytes_write.sum of its kernels, one `ncu --set full`
-# capture of this same command: profiles/r1_final_top_kernels_ncu_full.csv).  Far below the algorithmic bytes because the
+# capture of this same command: profiles/r1_final_changed_kernels_ncu_full.csv for field_bwd, r1_final_top_kernels_ncu_full.csv for the
+# rest).  Far below the algorithmic bytes because the
 # tables live in L2: the forward gathers are bound by the L1TEX data pipe, the backward by L2 atomics / issue.
 NCU_DRAM_BYTES_PER_LAUNCH = {
-    "field_bwd": (19.25 + 0.004 + 73.28 + 1.38) * 1e6, "field_fwd": (48.02 + 5.74) * 1e6, "proposal0_bwd": (53.61 + 1.30) * 1e6,
+    "field_bwd": (19.25 + 0.002 + 73.36 + 0.90) * 1e6, "field_fwd": (48.02 + 5.74) * 1e6, "proposal0_bwd": (53.61 + 1.30) * 1e6,
     "proposal1_bwd": (7.25 + 0.04) * 1e6, "proposal0_fwd": (7.19 + 1.61) * 1e6, "proposal1_fwd": 5.16e6,
 }
 
