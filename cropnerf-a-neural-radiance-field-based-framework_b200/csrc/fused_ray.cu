@@ -39,10 +39,13 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // weights of one ray (k_weights_fwd's arithmetic) from STAGED inputs: dens_s[0..S) and edges_s[0..S] already in shared memory; wsm may alias dens_s
+// WIDE: the caller sees the 256-sample proposal level (conflict-free 8-per-lane scan, warp_scan.cuh); the field-level kernels pass false
+template <bool WIDE>
 __device__ __forceinline__ void ray_weights_staged(const float* dens_s, const float* edges_s, int S, float* dd, float* cs, float* wsm, int lane) {
   for (int j = lane; j < S; j += 32) dd[j] = __fmul_rn(__fsub_rn(edges_s[j + 1], edges_s[j]), dens_s[j]);
   __syncwarp();
-  cnb_warp_cumsum(dd, cs, S, lane);
+  if (WIDE) cnb_warp_cumsum(dd, cs, S, lane);
+  else cnb_warp_cumsum_chunked(dd, cs, S, lane);
   __syncwarp();
   for (int j = lane; j < S; j += 32) {
     const float alpha = __fsub_rn(1.0f, expf(-dd[j]));
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_level_resample(const float* _
     const float rand_ray = (rand != nullptr && rand_stride == 1) ? __ldg(rand + r) : 0.0f;
     cp_async_wait_all();
     __syncwarp();
-    ray_weights_staged(wsm, cdf, Sp, dd, cs, wsm, lane);
+    ray_weights_staged<true>(wsm, cdf, Sp, dd, cs, wsm, lane);
     if (weights_out)
       for (int j = lane; j < Sp; j += 32) weights_out[r * Sp + j] = wsm[j];
     if (depth_out) {  // DepthRenderer "median" on the staged edges (ray_median_depth's arithmetic)
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_level_resample(const float* _
 }
 
 // smem per warp: dd [S], cs [S], w [S], edges [S+1], rgb [3S], sem [S]
-__global__ void __launch_bounds__(WARPS * 32, 7) k_final_composite(const float* __restrict__ density, const float* __restrict__ rgb, const float* __restrict__ sem,
+__global__ void __launch_bounds__(WARPS * 32) k_final_composite(const float* __restrict__ density, const float* __restrict__ rgb, const float* __restrict__ sem,
                                                                 const float* __restrict__ eu, int64_t R, int S, int bg_mode, float bg0, float bg1, float bg2,
                                                                 int eval_mode, float* __restrict__ weights_out, float* __restrict__ rgb_out,
                                                                 float* __restrict__ depth_out, float* __restrict__ acc_out, float* __restrict__ sem_out) {
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(WARPS * 32, 7) k_final_composite(const float* 
     for (int j = lane; j < 3 * S; j += 32) cp_async4(rg + j, rgb + r * S * 3 + j);
     cp_async_wait_all();
     __syncwarp();
-    ray_weights_staged(wsm, ed, S, dd, cs, wsm, lane);
+    ray_weights_staged<false>(wsm, ed, S, dd, cs, wsm, lane);
     float a = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, sm = 0.f;
     for (int j = lane; j < S; j += 32) {  // k_render_fwd's arithmetic
       const float w = wsm[j];
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(WARPS * 32, 7) k_final_composite(const float* 
     }
     if (depth_out) {  // DepthRenderer "median" on the staged edges (ray_median_depth's arithmetic)
       __syncwarp();
-      cnb_warp_cumsum(wsm, cs, S, lane);
+      cnb_warp_cumsum_chunked(wsm, cs, S, lane);
       __syncwarp();
       if (lane == 0) {
         int idx = cnb_search_left(cs, S, 0.5f);
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_final_composite_bwd(const float*
     }
     __syncwarp();
     // ---- k_weights_bwd ------------------------------------------------------------------------------------------------------------
-    cnb_warp_cumsum(dd, cs, S, lane);
+    cnb_warp_cumsum_chunked(dd, cs, S, lane);
     __syncwarp();
     for (int j = lane; j < S; j += 32) {
       const float T = expf(-(j > 0 ? cs[j - 1] : 0.0f));
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_final_composite_bwd(const float*
       gw[j] = isfinite(w) ? gd[j] * w : 0.0f;
     }
     __syncwarp();
-    cnb_warp_suffix_excl(gw, gw, S, lane);
+    cnb_warp_suffix_excl_chunked(gw, gw, S, lane);
     __syncwarp();
     for (int j = lane; j < S; j += 32) {
       const float T = expf(-(j > 0 ? cs[j - 1] : 0.0f));

@@ -83,9 +83,12 @@ static __device__ __noinline__ void cnb_warp_suffix_excl8(const float* in, float
 }
 
 // inclusive cumsum of in[0..n) -> out[0..n) (out may alias in). Lane owns a contiguous chunk.
-__device__ __forceinline__ double cnb_warp_cumsum(const float* in, float* out, int n, int lane) {
+// WIDE = the caller may see the 256-sample proposal level: take the conflict-free 8-per-lane path there (same results either way; kernels
+// that only ever scan the field's 48 samples instantiate WIDE = false and keep the callee out of their register allocation).
+template <bool WIDE>
+__device__ __forceinline__ double cnb_warp_cumsum_t(const float* in, float* out, int n, int lane) {
   const int per = (n + 31) >> 5;
-  if (per == 8) return cnb_warp_cumsum8(in, out, n, lane);
+  if (WIDE && per == 8) return cnb_warp_cumsum8(in, out, n, lane);
   const int b = min(n, lane * per), e = min(n, b + per);
   double s = 0.0;
   for (int j = b; j < e; ++j) s += (double)in[j];
@@ -101,9 +104,10 @@ __device__ __forceinline__ double cnb_warp_cumsum(const float* in, float* out, i
 }
 
 // suffix sums: out[j] = sum_{k > j} in[k]  (exclusive reverse cumsum), double partials
-__device__ __forceinline__ void cnb_warp_suffix_excl(const float* in, float* out, int n, int lane) {
+template <bool WIDE>
+__device__ __forceinline__ void cnb_warp_suffix_excl_t(const float* in, float* out, int n, int lane) {
   const int per = (n + 31) >> 5;
-  if (per == 8) { cnb_warp_suffix_excl8(in, out, n, lane); return; }
+  if (WIDE && per == 8) { cnb_warp_suffix_excl8(in, out, n, lane); return; }
   const int b = min(n, lane * per), e = min(n, b + per);
   double s = 0.0;
   for (int j = b; j < e; ++j) s += (double)in[j];
@@ -116,6 +120,11 @@ __device__ __forceinline__ void cnb_warp_suffix_excl(const float* in, float* out
   double run = incl - s;  // sum of all chunks above this lane
   for (int j = e - 1; j >= b; --j) { const float v = in[j]; out[j] = (float)run; run += (double)v; }
 }
+
+__device__ __forceinline__ double cnb_warp_cumsum(const float* in, float* out, int n, int lane) { return cnb_warp_cumsum_t<true>(in, out, n, lane); }
+__device__ __forceinline__ double cnb_warp_cumsum_chunked(const float* in, float* out, int n, int lane) { return cnb_warp_cumsum_t<false>(in, out, n, lane); }
+__device__ __forceinline__ void cnb_warp_suffix_excl(const float* in, float* out, int n, int lane) { cnb_warp_suffix_excl_t<true>(in, out, n, lane); }
+__device__ __forceinline__ void cnb_warp_suffix_excl_chunked(const float* in, float* out, int n, int lane) { cnb_warp_suffix_excl_t<false>(in, out, n, lane); }
 
 __device__ __forceinline__ float cnb_warp_sum(float v) {
 #pragma unroll
