@@ -19,6 +19,9 @@ lines it follows.
   for bit (train / eval / aabb / inference / export modes).
 * Primitives (``oracle/nerfstudio_torch.py``: HashEncoding, MLP, SH, samplers, renderers, losses): parity unpinned --
   nerfstudio 1.1.3 is absent, so they are a restatement of its published torch algorithms checked only against
-  hand-computed cases and torch autograd (``tests/test_oracle_cpu.py``).  ``tests/golden/tiny_*.npz``
-  (``oracle/make_golden.py``) pin them against regressions, not against nerfstudio itself.
+  hand-computed cases, torch autograd and -- where one exists in this image -- an implementation that is not ours or the
+  integral the primitive is the closed form of (scipy's real spherical harmonics, the transmittance integral, numpy's
+  piecewise-linear inverse cdf, the mip-NeRF 360 distortion double integral, a brute-force outer measure:
+  ``tests/test_oracle_cpu.py``).  ``tests/golden/tiny_*.npz`` (``oracle/make_golden.py``) pin them against regressions,
+  not against nerfstudio itself.
 """
