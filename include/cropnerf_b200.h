@@ -126,13 +126,15 @@ const char* cnb_last_error(void);
 /* number of CUDA devices visible, or a negative status; never throws */
 int cnb_device_count(void);
 
-/* ---- a2: HashEncoding.pytorch_fwd / its autograd (nerfstudio encodings.py) -------------------------------- */
+/* ---- a2: HashEncoding.pytorch_fwd / its autograd (nerfstudio encodings.py; constructed fruit_field.py:125-132, and inside
+ *      HashMLPDensityField fruit_nerf.py:124-141; called fruit_field.py:181-182) ------------------------------------------------ */
 /* positions [n,3] in [0,1]; out [n, 2*L]; indices (optional) [n, L, 8] int32 table rows in h0..h7 order */
 int cnb_hashgrid_fwd(const cnb_grid* g, const float* positions, int64_t n, float* out, int32_t* indices, cnb_stream_t stream);
 /* accumulates g->d_table from d_out [n, 2*L] */
 int cnb_hashgrid_bwd(const cnb_grid* g, const float* positions, const float* d_out, int64_t n, cnb_stream_t stream);
 
-/* ---- a3/a4: MLP / FieldHead ------------------------------------------------------------------------------- */
+/* ---- a3/a4: MLP / FieldHead (nerfstudio mlp.py, field_heads.py; fruit_field.py:133-141,146-154,159-167;
+ *      SemanticFieldHead components/field_heads.py:29-40, used fruit_field.py:155-157,207,269) ---------------------------------- */
 /* floats of `hidden` needed per sample when training (sum of hidden widths) */
 int64_t cnb_mlp_hidden_floats(const cnb_mlp* m);
 /* x: element (i,k) at x[i*x_stride+k]; y [n, out] dense; hidden (optional, for bwd) [sum_l n*width_l] */
@@ -141,7 +143,8 @@ int cnb_mlp_fwd(const cnb_mlp* m, const float* x, int64_t x_stride, int64_t n, f
 int cnb_mlp_bwd(const cnb_mlp* m, const float* x, int64_t x_stride, const float* hidden, const float* y, const float* dy,
                 int64_t n, float* dx, int64_t dx_stride, cnb_stream_t stream);
 
-/* ---- a7: HashMLPDensityField.get_density / density_fn ------------------------------------------------------ */
+/* ---- a7: HashMLPDensityField.get_density / density_fn (nerfstudio density_fields.py; built fruit_nerf.py:118-142,
+ *      handed to the sampler as density_fns fruit_nerf.py:143-145,549) ----------------------------------------------------------- */
 /* density [R*S]; positions_out (optional) [R*S,3] normalised+masked positions */
 int cnb_density_field_fwd(const cnb_density_field* f, const cnb_samples* s, float* density, float* positions_out, cnb_stream_t stream);
 /* recomputes the forward per sample; accumulates grid.d_table, mlp.dW/db */
@@ -155,7 +158,8 @@ int cnb_density_field_bwd_kept(const cnb_density_field* f, const cnb_samples* s,
                                cnb_stream_t stream);
 int cnb_density_field_kept_supported(const cnb_density_field* f);
 
-/* ---- a1/a5/a6: FruitField.forward (get_density + get_outputs / get_inference_outputs) ---------------------- */
+/* ---- a1/a5/a6: FruitField.forward (fruit_field.py:284-302) = get_density (:169-194) + get_outputs (:235-282) /
+ *      get_inference_outputs (:196-233); called fruit_nerf.py:340,431,480,503,551 ---------------------------------------------- */
 /* floats of `ctx` scratch per call (activations kept for backward + backward scratch); 0 => ctx may be NULL */
 int64_t cnb_field_ctx_floats(const cnb_field* f, int64_t n, int32_t training);
 /* outputs (each optional except density): density [N], geo [N,1+geo] (col 0 = pre-activation density),
@@ -195,13 +199,14 @@ int cnb_sample_pdf(const float* weights, float anneal, const float* prev_spacing
                    int32_t spacing, const float* u_base, const float* rand, int32_t rand_stride, int64_t R, int32_t Sp, int32_t S,
                    float histogram_padding, float eps, float* spacing_bins, float* euclid_bins, int32_t* inds, cnb_stream_t stream);
 
-/* ---- a10: RaySamples.get_weights -------------------------------------------------------------------------- */
+/* ---- a10: RaySamples.get_weights (nerfstudio rays.py; called fruit_nerf.py:556,508,442,341 and inside the proposal sampler) */
 int cnb_weights_fwd(const float* density, const float* starts, const float* ends, int64_t row_stride, int64_t R, int32_t S,
                     float* weights, cnb_stream_t stream);
 int cnb_weights_bwd(const float* density, const float* starts, const float* ends, int64_t row_stride, int64_t R, int32_t S,
                     const float* d_weights, float* d_density, cnb_stream_t stream);
 
-/* ---- a11-a14: RGB / Depth(median) / Accumulation / Semantic renderers -------------------------------------- */
+/* ---- a11-a14: RGB / Depth(median) / Accumulation / Semantic renderers (nerfstudio renderers.py; built fruit_nerf.py:170-174,
+ *      called :560-591, :512-520, :446-452; background_color_override_context scripts/semantic_projection.py:51,169) ------------ */
 /* Any of rgb/sem inputs and outputs may be NULL (that renderer is skipped).  eval_mode: nan_to_num(rgb) in, clamp out.
  * median_index (optional) [R] int32. */
 int cnb_render_fwd(const float* weights, const float* rgb, const float* sem, const float* starts, const float* ends,
