@@ -100,6 +100,11 @@ class Camera(C.Structure):
                 ("width", C.c_int32), ("height", C.c_int32)]
 
 
+class ImageSet(C.Structure):
+    _fields_ = [("images_u8", C.c_void_p), ("images_f32", C.c_void_p), ("masks_u8", C.c_void_p), ("cameras", C.c_void_p),
+                ("num_images", C.c_int32), ("height", C.c_int32), ("width", C.c_int32)]
+
+
 class Rays(C.Structure):
     _fields_ = [
         ("origins", C.c_void_p),
@@ -223,6 +228,7 @@ SIGNATURES = {
     "cnb_density_field_bwd_rays": (C.c_int, [C.POINTER(DensityField), C.POINTER(Samples), _P, _P, _P, _P, _P]),
     "cnb_field_bwd_rays": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), _P, _P, _P, _P, _P, _P, _P, _P]),
     "cnb_generate_rays": (C.c_int, [C.POINTER(Camera), _P, _I64, C.POINTER(_F), _P, _P, _P, _P, _P, _P, _P]),
+    "cnb_sample_train_batch": (C.c_int, [C.POINTER(ImageSet), _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cnb_sample_spaced": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I64, _I32, _P, _P, _P]),
     "cnb_sample_spaced_collide": (C.c_int, [_P, _P, _F, _F, _P, _P, _I32, _I32, _I64, _I32, _P, _P, _P, _P, _P]),
     "cnb_sample_pdf": (C.c_int, [_P, _F, _P, _P, _P, _I32, _P, _P, _I32, _I64, _I32, _I32, _F, _F, _P, _P, _P, _P]),

@@ -264,6 +264,22 @@ typedef struct cnb_camera {
 int cnb_generate_rays(const cnb_camera* cam, const int32_t* pixel_yx, int64_t n, const float* aabb, float* origins, float* directions,
                       float* pixel_area, float* nears, float* fars, int32_t* valid_count, cnb_stream_t stream);
 
+/* ---- f1, training side: FruitDataManager.next_train (data/fruit_datamanager.py:188-197) on the device ---------------------
+ * = nerfstudio PixelSampler.sample (indices = (rand[R,3] * [N,H,W]).long(); value[c,y,x] of every per-pixel tensor) followed by
+ * RayGenerator (image_coords[y,x] = pixel centre -> Cameras.generate_rays(camera_indices=c)).  All images of the split are resident
+ * in device memory with one size (nerfstudio's PixelSampler assumes that too). */
+typedef struct cnb_image_set {
+  const uint8_t* images_u8;  /* device [N,H,W,3] uint8 (value / 255 = the float image of cotton_dataset.py), or NULL */
+  const float* images_f32;   /* device [N,H,W,3] float32, or NULL; exactly one of the two when the image output is requested */
+  const uint8_t* masks_u8;   /* device [N,H,W] fruit masks, non-zero = fruit (binary, cotton_dataset.py:34-39); NULL = all zero */
+  const cnb_camera* cameras; /* device array [N] (width / height fields unused here) */
+  int32_t num_images, height, width;
+} cnb_image_set;
+/* rand3 (device) [R,3] uniform in [0,1) (torch.rand).  Outputs (device): indices [R,3] int32 (camera, y, x) optional; origins,
+ * directions [R,3]; pixel_area [R] optional; camera_indices [R] int32 optional; image [R,3] and fruit_mask [R] optional. */
+int cnb_sample_train_batch(const cnb_image_set* set, const float* rand3, int64_t R, int32_t* indices, float* origins, float* directions,
+                           float* pixel_area, int32_t* camera_indices, float* image, float* fruit_mask, cnb_stream_t stream);
+
 /* ---- f2: optimiser (torch.optim.Adam semantics; fruit_nerf_config.py:45-60) -------------------------------- */
 int cnb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float inv_grad_scale, cnb_stream_t stream);

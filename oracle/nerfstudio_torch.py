@@ -885,3 +885,41 @@ def intersect_aabb(origins: Tensor, directions: Tensor, aabb: Tensor, max_bound:
     t_min = torch.where(cond, torch.full_like(t_min, invalid_value), t_min)
     t_max = torch.where(cond, torch.full_like(t_max, invalid_value), t_max)
     return t_min, t_max
+
+
+# --------------------------------------------------------------------------------------------------------
+# A.10 training batch -- FruitDataManager.next_train (data/fruit_datamanager.py:188-197): nerfstudio
+#      data/pixel_samplers.py PixelSampler.sample_method / collate_image_dataset_batch followed by
+#      model_components/ray_generators.py RayGenerator.forward.  Published nerfstudio 1.1.3 source restated,
+#      not line-checked (nerfstudio is absent here).
+# --------------------------------------------------------------------------------------------------------
+
+
+def pixel_sampler_indices(rand3: Tensor, num_images: int, height: int, width: int) -> Tensor:
+    """PixelSampler.sample_method, mask=None branch: ``(torch.rand((R, 3)) * tensor([N, H, W])).long()`` -> [R,3] (camera, y, x)."""
+    return (rand3 * torch.tensor([num_images, height, width], dtype=rand3.dtype)).long()
+
+
+def next_train_batch(rand3: Tensor, images: Tensor, masks: Optional[Tensor], c2w: Tensor, fx: Tensor, fy: Tensor, cx: Tensor, cy: Tensor):
+    """``batch = pixel_sampler.sample(image_batch); ray_bundle = ray_generator(batch["indices"])`` for images [N,H,W,3] float32,
+    fruit masks [N,H,W] (0/1) and per-camera c2w [N,3,4] / intrinsics [N].  Returns (indices, origins, directions, pixel_area, image, mask)."""
+    n, h, w = images.shape[:3]
+    idx = pixel_sampler_indices(rand3, n, h, w)
+    c, y, x = idx[:, 0], idx[:, 1], idx[:, 2]
+    image = images[c, y, x]                                     # collate_image_dataset_batch: value[c, y, x]
+    mask = masks[c, y, x][:, None].to(images.dtype) if masks is not None else torch.zeros((idx.shape[0], 1), dtype=images.dtype)
+    coords = torch.stack([y.to(rand3.dtype) + 0.5, x.to(rand3.dtype) + 0.5], -1)   # Cameras.get_image_coords()[y, x]: pixel centres
+    yy, xx = coords[:, 0], coords[:, 1]
+    fxc, fyc, cxc, cyc = fx[c], fy[c], cx[c], cy[c]
+    coord = torch.stack([(xx - cxc) / fxc, -(yy - cyc) / fyc], -1)
+    coord_x_offset = torch.stack([(xx - cxc + 1) / fxc, -(yy - cyc) / fyc], -1)
+    coord_y_offset = torch.stack([(xx - cxc) / fxc, -(yy - cyc + 1) / fyc], -1)
+    coord_stack = torch.stack([coord, coord_x_offset, coord_y_offset], dim=0)
+    directions_stack = torch.cat([coord_stack, -torch.ones_like(coord_stack[..., :1])], dim=-1)
+    rotation = c2w[c][:, :3, :3]
+    directions_stack = torch.sum(directions_stack[..., None, :] * rotation, dim=-1)
+    directions_stack = directions_stack / torch.linalg.norm(directions_stack, dim=-1, keepdim=True)
+    directions = directions_stack[0]
+    dx = torch.sqrt(torch.sum((directions - directions_stack[1]) ** 2, dim=-1))
+    dy = torch.sqrt(torch.sum((directions - directions_stack[2]) ** 2, dim=-1))
+    return idx, c2w[c][:, :3, 3], directions, (dx * dy)[..., None], image, mask

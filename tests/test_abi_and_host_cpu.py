@@ -41,7 +41,7 @@ def test_struct_sizes_match_c_compiler():
     prog = r"""
 #include <stdio.h>
 #include "cropnerf_b200.h"
-int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(cnb_grid), sizeof(cnb_mlp), sizeof(cnb_warp), sizeof(cnb_samples), sizeof(cnb_density_field), sizeof(cnb_field), sizeof(cnb_camera), sizeof(cnb_train_cfg), sizeof(cnb_opt_group), sizeof(cnb_p2p_comm), sizeof(cnb_p2p_group), sizeof(cnb_ddp_group_step)); return 0; }
+int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(cnb_grid), sizeof(cnb_mlp), sizeof(cnb_warp), sizeof(cnb_samples), sizeof(cnb_density_field), sizeof(cnb_field), sizeof(cnb_camera), sizeof(cnb_train_cfg), sizeof(cnb_opt_group), sizeof(cnb_p2p_comm), sizeof(cnb_p2p_group), sizeof(cnb_ddp_group_step), sizeof(cnb_image_set)); return 0; }
 """
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "s.c")
@@ -49,7 +49,7 @@ int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", size
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
-    mine = [C.sizeof(t) for t in (L.Grid, L.Mlp, L.Warp, L.Samples, L.DensityField, L.Field, L.Camera, L.TrainCfg, L.OptGroup, L.P2PComm, L.P2PGroup, L.DdpGroupStep)]
+    mine = [C.sizeof(t) for t in (L.Grid, L.Mlp, L.Warp, L.Samples, L.DensityField, L.Field, L.Camera, L.TrainCfg, L.OptGroup, L.P2PComm, L.P2PGroup, L.DdpGroupStep, L.ImageSet)]
     assert sizes == mine
 
 
