@@ -525,9 +525,22 @@ def cpu_baseline(sample_rays: int, steps: int, warmup: int):
         if i >= warmup:
             times.append(dt)
     t = sum(times) / len(times)
+    # BASELINE configs[0]: the reference's own CPU-runnable case -- field forward + volume render (eval mode, no gradients) of the same rays;
+    # the denominator for the `render` numbers of the product line
+    model.eval()
+    rtimes = []
+    with torch.no_grad():
+        for i in range(1 + max(1, min(steps, 3))):
+            t0 = time.perf_counter()
+            model(cases.oracle_bundle(rays))
+            if i >= 1:
+                rtimes.append(time.perf_counter() - t0)
+    tr = sum(rtimes) / len(rtimes)
     return {"value": sample_rays / t, "unit": "rays/s", "cores": cores, "kind": "port",
             "sample": f"{sample_rays}-ray training step (fwd + losses/metrics + bwd + Adam) of the same fruit_nerf preset, torch {torch.__version__} CPU, "
-                      f"{warmup} warm-up + mean of {steps}", "seconds_per_step": t}
+                      f"{warmup} warm-up + mean of {steps}", "seconds_per_step": t,
+            "render": {"value": sample_rays / tr, "unit": "rays/s", "seconds_per_call": tr,
+                       "sample": f"eval forward + volume render of the same {sample_rays} rays (BASELINE configs[0]), 1 warm-up + mean of {len(rtimes)}"}}
 
 
 def run_reference(args):
