@@ -439,14 +439,21 @@ class HashMLPDensityField(nn.Module):
         else:
             self.linear = nn.Linear(self.encoding.get_out_dim(), 1)
 
-    def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, None]:
+    def normalised_positions(self, positions: Tensor) -> Tuple[Tensor, Tensor]:
+        """Contraction / AABB normalisation + selector mask of density_fields.py get_density.  The reference tree restates the same
+        steps itself ("according to density_feild.py in nerfstudio", bayesrays/utils.py:6-16); tests/test_reference_pin_cpu.py
+        executes that function and requires this one to agree bit for bit."""
         if self.spatial_distortion is not None:
-            positions = self.spatial_distortion(ray_samples.frustums.get_positions())
+            positions = self.spatial_distortion(positions)
             positions = (positions + 2.0) / 4.0
         else:
-            positions = get_normalized_positions(ray_samples.frustums.get_positions(), self.aabb)
+            positions = get_normalized_positions(positions, self.aabb)
         selector = ((positions > 0.0) & (positions < 1.0)).all(dim=-1)
         positions = positions * selector[..., None]
+        return positions, selector
+
+    def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, None]:
+        positions, selector = self.normalised_positions(ray_samples.frustums.get_positions())
         positions_flat = positions.view(-1, 3)
         if not self.use_linear:
             dba = self.mlp_base(positions_flat).view(*ray_samples.frustums.shape, -1).to(positions)

@@ -469,6 +469,39 @@ def run_volume_rays_case(n: int = 13, batch: int = 64) -> Dict[str, np.ndarray]:
     return out
 
 
+def density_normalisation_inputs() -> Dict[str, torch.Tensor]:
+    """Points inside, on the faces of, and far outside the scene box (contracted and AABB-normalised variants)."""
+    g = torch.Generator().manual_seed(7)
+    pts = torch.cat([torch.rand((64, 3), generator=g) * 2 - 1, (torch.rand((64, 3), generator=g) * 2 - 1) * 6,
+                     torch.tensor([[1.0, 0.0, 0.0], [-1.0, -1.0, -1.0], [0.0, 0.0, 0.0], [2.0, 2.0, 2.0], [1e3, -5.0, 0.5], [0.999999, 0.5, -0.25]])])
+    return {"points": pts, "aabb": torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]])}
+
+
+def run_density_normalisation_case() -> Dict[str, np.ndarray]:
+    """``normalize_point_coords`` of the reference (bayesrays/utils.py:6-16: "coordinate normalization process according to
+    density_feild.py in nerfstudio") executed verbatim -- extracted with ``ast`` because the file imports nerfstudio.utils.math --
+    with the scene contraction / SceneBox of the shims.  Pins the normalisation + selector wiring of the restated HashMLPDensityField."""
+    import ast
+
+    if not reference_available():
+        raise RuntimeError("/root/reference is not present on this machine")
+    install_shims()
+    from . import nerfstudio_torch as ns
+
+    src_path = os.path.join(REFERENCE_ROOT, "fruit_nerf", "bayesrays", "utils.py")
+    tree = ast.parse(open(src_path).read())
+    wanted = [node for node in tree.body if isinstance(node, ast.FunctionDef) and node.name == "normalize_point_coords"]
+    ns_exec: Dict[str, object] = {"torch": torch, "SceneBox": sys.modules["nerfstudio.data.scene_box"].SceneBox}
+    exec(compile(ast.Module(body=wanted, type_ignores=[]), src_path, "exec"), ns_exec)
+    inp = density_normalisation_inputs()
+    out: Dict[str, np.ndarray] = {"points": inp["points"].numpy(), "aabb": inp["aabb"].numpy()}
+    for name, distortion in (("contract", ns.SceneContraction()), ("aabb", None)):
+        pos, sel = ns_exec["normalize_point_coords"](inp["points"], inp["aabb"], distortion)
+        out[name + "_pos"] = pos.numpy()
+        out[name + "_selector"] = sel.numpy()
+    return out
+
+
 def main() -> None:
     from . import cases
 
@@ -487,6 +520,10 @@ def main() -> None:
     path = os.path.join(out_dir, "ref_volume_rays.npz")
     np.savez_compressed(path, **res)
     print("reference-executed volume rays ->", path, {k: v.shape for k, v in res.items()})
+    res = run_density_normalisation_case()
+    path = os.path.join(out_dir, "ref_density_normalisation.npz")
+    np.savez_compressed(path, **res)
+    print("reference-executed density-field normalisation ->", path, {k: v.shape for k, v in res.items()})
 
 
 if __name__ == "__main__":

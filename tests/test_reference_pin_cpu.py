@@ -58,3 +58,36 @@ def test_live_reference_code_matches_fixtures():
     fix = dict(np.load(os.path.join(GOLDEN, "ref_mode_export.npz")))
     for k, v in fix.items():
         assert np.array_equal(live[k], v), k
+
+
+def _oracle_density_normalisation():
+    from oracle import nerfstudio_torch as ns
+
+    inp = ref_shim.density_normalisation_inputs()
+    out = {}
+    for name, distortion in (("contract", ns.SceneContraction()), ("aabb", None)):
+        f = ns.HashMLPDensityField(inp["aabb"], spatial_distortion=distortion, num_levels=2, max_res=32, log2_hashmap_size=8, hidden_dim=16)
+        pos, sel = f.normalised_positions(inp["points"])
+        out[name + "_pos"], out[name + "_selector"] = pos.numpy(), sel.numpy()
+    return inp, out
+
+
+def test_density_field_normalisation_matches_the_reference_trees_own_restatement():
+    """bayesrays/utils.py:6-16 (``normalize_point_coords``: "coordinate normalization process according to density_feild.py in
+    nerfstudio") is the reference authors' own statement of what HashMLPDensityField does before the hash grid: contraction,
+    (x + 2) / 4 (or AABB normalisation), selector = all(0 < x < 1), masked positions.  Executed verbatim -> fixture; the restated
+    HashMLPDensityField (oracle, SURVEY.md App. A.3 [verify]) must agree bit for bit."""
+    fix = dict(np.load(os.path.join(GOLDEN, "ref_density_normalisation.npz")))
+    inp, got = _oracle_density_normalisation()
+    assert np.array_equal(fix["points"], inp["points"].numpy())
+    for k, v in got.items():
+        assert np.array_equal(v, fix[k]), k
+    assert fix["contract_selector"].all() and 0 < fix["aabb_selector"].sum() < fix["aabb_selector"].size
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present (GPU box): fixtures only")
+def test_live_reference_normalisation_matches_fixture():
+    live = ref_shim.run_density_normalisation_case()
+    fix = dict(np.load(os.path.join(GOLDEN, "ref_density_normalisation.npz")))
+    for k, v in fix.items():
+        assert np.array_equal(live[k], v), k
