@@ -168,9 +168,14 @@ def test_two_rank_gradient_allreduce_gloo():
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, "w.py")
         open(path, "w").write(_WORKER)
+        import socket
+
+        with socket.socket() as sock:   # a free port: a fixed one can collide with another rendezvous on the same machine
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
         procs = []
         for rank in range(2):
-            env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29617")
+            env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
             procs.append(subprocess.Popen([sys.executable, path, ROOT], env=env))
         codes = [p.wait(timeout=300) for p in procs]
     assert codes == [0, 0]
