@@ -37,6 +37,16 @@ RENDER_BYTES_PER_RAY = sum(FETCH_BYTES.values()) + 40 + 24                    # 
 TRAIN_BYTES_PER_RAY = 3 * sum(FETCH_BYTES.values()) + 64 + 16                 # 485 456 (update step: gather + scatter RMW)
 
 
+WORKLOAD = ("BASELINE configs[1]: fruit_nerf preset training step, 4096 rays/GPU, proposal 256/96 + 48 NeRF samples, "
+            "field 16x2^19x2 + 2 proposal 5x2^17x2 fp32 hash tables, 300 synthetic 1080p cameras")
+
+
+def workload_config():
+    """`config` of the JSON line -- the SAME dict in the product arm and in `--impl reference` (the driver compares them)."""
+    return {"workload": WORKLOAD, "rays_per_gpu": RAYS_PER_GPU, "samples_per_ray": sum(PROPOSAL_SAMPLES) + NERF_SAMPLES,
+            "l2": "inputs larger than L2: one step streams ~0.4 GB (parameters, gradients, Adam moments, workspace) through the 126 MB L2; steps timed back to back"}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -263,6 +273,48 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
     barrier()
     t_e2e_local = e0.elapsed_time(e1) / 1e3
 
+    # ---- replicas: after all those steps every rank must hold bit-identical parameters (each element is computed once, by its
+    # owner, and broadcast; or all-reduced in a fixed order) -- a checksum of every flat group, all-gathered and compared ----------
+    replicas_identical = None
+    if world > 1:
+        settle()
+        torch.cuda.synchronize()
+        sums = torch.stack([g.flat.view(torch.int32).to(torch.int64).sum() for g in trainer.groups.values()])
+        allsums = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(allsums, sums)
+        replicas_identical = all(bool(torch.equal(a, allsums[0])) for a in allsums)
+        assert replicas_identical, f"rank {rank}: parameter checksums differ across replicas: {[a.tolist() for a in allsums]}"
+
+    # ---- end to end from DEVICE-resident images (row f1: FruitDataManager.next_train as one kernel, datamanager.DeviceTrainBatches):
+    # the pixel sampler + ray generator run on the GPU over uint8 images held in HBM, so no ray / target bytes cross PCIe at all;
+    # the loss is still read back every step -----------------------------------------------------------------------------------
+    t_dev_batches = None
+    if full and not args.no_device_batches:
+        from cropnerf_b200 import synthetic
+        from cropnerf_b200.datamanager import DeviceTrainBatches
+        from cropnerf_b200.export import PinholeCamera
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        imgs = torch.randint(0, 256, (NUM_IMAGES, synthetic.IMAGE_H, synthetic.IMAGE_W, 3), device=dev, dtype=torch.uint8, generator=gen)
+        msk = (torch.rand((NUM_IMAGES, synthetic.IMAGE_H, synthetic.IMAGE_W), device=dev, generator=gen) < 0.1).to(torch.uint8)
+        c2w = synthetic.make_cameras(NUM_IMAGES, seed=1)
+        cams = [PinholeCamera(c2w[i], synthetic.FOCAL, synthetic.FOCAL, synthetic.IMAGE_W / 2, synthetic.IMAGE_H / 2, synthetic.IMAGE_W, synthetic.IMAGE_H)
+                for i in range(NUM_IMAGES)]
+        dm = DeviceTrainBatches(imgs, msk, cams, num_rays_per_batch=R, device=dev, seed=rank)
+        for i in range(3):
+            rb, tg = dm.next_train(step)
+            float(trainer.train_iteration(step, rb, tg)["loss"].item()); step += 1
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for i in range(steps):
+            rb, tg = dm.next_train(step)
+            stats = trainer.train_iteration(step, rb, tg); step += 1
+            float(stats["loss"].item())
+        d1.record()
+        barrier()
+        t_dev_batches = d0.elapsed_time(d1) / 1e3
+        del dm, imgs, msk
+
     # ---- per-stage device times (separate pass so the events do not perturb the timed region) ----------------
     stage, adam_ms, n_prof = {}, 0.0, min(steps, 5)
     nonupdate_ms = None
@@ -384,18 +436,18 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
         assert not trainer.comm.timed_out(), "a peer-memory barrier timed out during the benchmark"
     del trainer, model, l2_flush
     torch.cuda.empty_cache()
-    return {"ddp": ddp_mode, "t_b2b": t_b2b, "steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
+    return {"ddp": ddp_mode, "replicas_identical": replicas_identical, "t_dev_batches": t_dev_batches, "t_b2b": t_b2b, "steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
             "stage": stage, "n_prof": n_prof, "nonupdate_ms": nonupdate_ms, "camopt_ms": camopt_ms, "adam_ms": adam_ms, "render_stage": render_stage, "loss": loss_host,
             "h2d_train": bytes_of({k: host[0][k] for k in ("origins", "directions", "camera_indices", "image", "fruit_mask")}), "h2d_render": bytes_of({k: rhost[k] for k in ("origins", "directions", "pixel_area", "camera_indices")}),
             "d2h_render": int(d2h_render)}
 
 
 # algorithmic bytes per ray of each pipeline stage (fp32 tables, 8 corners x 8 B per (sample, level)):
-# forward = one gather; proposal backward = re-gather + scatter read-modify-write; field backward = scatter RMW only
-# (the encoded features are kept by the forward)
+# forward = one gather; backward (proposals and field alike) = scatter read-modify-write only: the encoded features are kept by
+# the forward on update steps (cnb_density_field_fwd_keep / the field ctx), so no backward kernel re-gathers the tables
 STAGE_BYTES_PER_RAY = {
     "proposal0_fwd": FETCH_BYTES["prop0"], "proposal1_fwd": FETCH_BYTES["prop1"], "field_fwd": FETCH_BYTES["field"],
-    "proposal0_bwd": 3 * FETCH_BYTES["prop0"], "proposal1_bwd": 3 * FETCH_BYTES["prop1"], "field_bwd": 2 * FETCH_BYTES["field"],
+    "proposal0_bwd": 2 * FETCH_BYTES["prop0"], "proposal1_bwd": 2 * FETCH_BYTES["prop1"], "field_bwd": 2 * FETCH_BYTES["field"],
 }
 
 
@@ -403,6 +455,7 @@ STAGE_BYTES_PER_RAY = {
 # capture of this same command: profiles/r1_final_changed_kernels_ncu_full.csv for field_bwd, r1_final_top_kernels_ncu_full.csv for the
 # rest).  Far below the algorithmic bytes because the
 # tables live in L2: the forward gathers are bound by the L1TEX data pipe, the backward by L2 atomics / issue.
+NCU_DRAM_SOURCE = "profiles/r1_final_changed_kernels_ncu_full.csv (field_bwd) / profiles/r1_final_top_kernels_ncu_full.csv (others): ncu --set full, round-1 final code state"
 NCU_DRAM_BYTES_PER_LAUNCH = {
     "field_bwd": (19.25 + 0.002 + 73.36 + 0.90) * 1e6, "field_fwd": (48.02 + 5.74) * 1e6, "proposal0_bwd": (53.61 + 1.30) * 1e6,
     "proposal1_bwd": (7.25 + 0.04) * 1e6, "proposal0_fwd": (7.19 + 1.61) * 1e6, "proposal1_fwd": 5.16e6,
@@ -423,7 +476,8 @@ def run_product(args):
     os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: the contract is ONE JSON line
+        # NCCL_DEBUG is left as the launcher set it (the driver reads the communicator lines); fd 1 already points at stderr here,
+        # so whatever NCCL prints cannot land on the JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
 
@@ -449,6 +503,7 @@ def run_product(args):
         ach = per_ray * R / (per_launch_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom) if args.precision == "mixed" else None,
+                    "traffic_source": NCU_DRAM_SOURCE if (args.precision == "mixed" and dom in NCU_DRAM_BYTES_PER_LAUNCH) else None,
                     "peak_source": peak_src, "ms_per_launch": per_launch_ms, "share_of_step": tot[dom] / (sum(tot.values()) + 1e-12),
                     "algorithmic_bytes_per_launch": per_ray * R,
                     "note": "algorithmic bytes = 8-byte corner fetches of SURVEY.md 8d; the 74 MiB of tables are L2-resident, so DRAM traffic is far below this"}
@@ -459,10 +514,9 @@ def run_product(args):
             "ms_per_step": 1e3 * m["t"] / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "f16 tensor-core MLPs (bf16 gradients), f32 hash tables / accumulation / compositing",
             "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: fruit_nerf preset training step, 4096 rays/GPU, proposal 256/96 + 48 NeRF samples, "
-                                   "field 16x2^19x2 + 2 proposal 5x2^17x2 fp32 hash tables, 300 synthetic 1080p cameras",
-                       "rays_per_gpu": R, "samples_per_ray": 400, "precision": args.precision, "l2": "inputs larger than L2: one step streams ~0.4 GB (parameters, gradients, Adam moments, workspace) through the 126 MB L2; steps timed back to back",
-                       "ms_per_step_l2_flushed_serialised": 1e3 * m["t_b2b"] / steps, "data_parallel": m["ddp"],
+            "config": workload_config(),
+            "detail": {"precision": args.precision,
+                       "ms_per_step_l2_flushed_serialised": 1e3 * m["t_b2b"] / steps, "data_parallel": m["ddp"], "replicas_identical": m["replicas_identical"],
                        "note_overlap": "the big 'fields' group is updated on a side stream (one GPU: fused Adam; N>1: reduce-scatter + Adam + all-gather over NVLink) and only gates the "
                                        "NEXT step's field forward; ms_per_step_l2_flushed_serialised flushes L2 (192 MiB fill) before every step and waits for that update inside the step's timed region",
                        "includes": "fwd + losses + bwd (all three networks updated EVERY step) + gradient exchange (N>1) + Adam; "
@@ -475,6 +529,9 @@ def run_product(args):
                               "roofline_rays_per_s_per_gpu": peak * 1e9 / TRAIN_BYTES_PER_RAY},
             "e2e": {"value": total_rays / m["t_e2e"], "unit": "rays/s", "h2d_bytes_per_step": m["h2d_train"], "d2h_bytes_per_step": 4,
                     "last_loss": m["loss"]},
+            "e2e_device_batches": ({"value": total_rays / m["t_dev_batches"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
+                                    "what": "same step fed by DeviceTrainBatches.next_train (cnb_sample_train_batch over 300 uint8 1080p images + masks resident in HBM)"}
+                                   if m["t_dev_batches"] else None),
             "render": {"value": world * Rr * n_r / m["t_render"], "unit": "rays/s", "rays_per_call": Rr, "l2": "flushed between calls",
                        "e2e": {"value": world * Rr * n_r / m["t_render_e2e"], "unit": "rays/s", "h2d_bytes_per_step": m["h2d_render"],
                                "d2h_bytes_per_step": m["d2h_render"]},
@@ -489,7 +546,7 @@ def run_product(args):
             line["other_precision"] = {"precision": other, "train_rays_per_s": world * R * m2["steps"] / m2["t"], "ms_per_step": 1e3 * m2["t"] / m2["steps"],
                                        "render_rays_per_s": world * m2["Rr"] * m2["n_r"] / m2["t_render"]}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(sample_rays=4 * args.cpu_rays, steps=2, warmup=1)
+            line["cpu_baseline"] = cpu_baseline(sample_rays=args.cpu_rays, steps=2, warmup=1)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -550,13 +607,13 @@ def run_reference(args):
     if rank != 0:
         return
     sample = args.cpu_rays
-    res = cpu_baseline(sample_rays=sample, steps=max(1, min(args.steps, 50)), warmup=max(1, min(args.warmup, 5)))
+    res = cpu_baseline(sample_rays=sample, steps=max(1, min(args.steps, 50)), warmup=max(1, min(args.warmup, 3)))
     line = {
         "impl": "reference", "metric": "train_rays_per_s", "value": res["value"], "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: fruit_nerf preset training step (bounded sample of the 4096-ray batch)", "rays_per_step": sample,
-                   "samples_per_ray": 400},
+        "config": workload_config(),
+        "detail": {"rays_per_step": sample, "precision": "fp32", "cores": res["cores"]},
         "cpu_baseline": res,
         "e2e": {"value": res["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -573,7 +630,8 @@ def main():
                     help="mixed = fp16 tensor-core MLPs like the reference's autocast training (fruit_nerf_config.py:35); fp32 = exact mode")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--single-precision", action="store_true", help="skip the short pass in the other precision mode")
-    ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per CPU-baseline step (bounded sample of the 4096-ray batch)")
+    ap.add_argument("--cpu-rays", type=int, default=RAYS_PER_GPU, help="rays per CPU-baseline step (default: the full 4096-ray batch of the workload, ~1.1 s per step on 16 cores)")
+    ap.add_argument("--no-device-batches", action="store_true", help="skip the leg that trains from DeviceTrainBatches (2.5 GB of synthetic images in HBM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ddp", default=os.environ.get("CNB_DDP", "auto"), choices=["auto", "nccl", "p2p", "p2p_multimem"],
                     help="N>1: gradient exchange + Adam = NCCL all-reduce then local Adam, or one reduce-scatter+Adam+all-gather kernel over NVLink peer memory")

@@ -66,7 +66,23 @@ def _refuse_tcnn(state: Dict[str, Tensor]) -> None:
             "nerfstudio's torch implementation that this library reproduces; retrain / export with implementation='torch'")
 
 
-def load_nerfstudio_checkpoint(model, path_or_state, strict: bool = True) -> int:
+# state-dict prefixes of modules the reference model owns that are NOT part of the ray-render path (fruit_nerf.py:181-183 builds
+# psnr / ssim / LearnedPerceptualImagePatchSimilarity metric modules; torchmetrics' LPIPS carries its VGG/Alex weights in the state dict)
+_NON_PRODUCT_PREFIXES = ("lpips.", "psnr.", "ssim.", "rgb_loss.", "binary_cross_entropy_loss.", "cross_entropy_loss.")
+
+
+def _load_file(path: str, allow_pickle: bool):
+    """nerfstudio checkpoints hold dicts, tensors and scalars only: load with ``weights_only=True``; full unpickling (arbitrary code
+    from the file) only on the caller's explicit ``allow_pickle=True``."""
+    try:
+        return torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as e:  # pickle.UnpicklingError and friends
+        if not allow_pickle:
+            raise RuntimeError(f"{path}: not loadable with weights_only=True ({type(e).__name__}: {e}); pass allow_pickle=True only for files you trust") from e
+        return torch.load(path, map_location="cpu", weights_only=False)
+
+
+def load_nerfstudio_checkpoint(model, path_or_state, strict: bool = True, allow_pickle: bool = False) -> int:
     """Load a nerfstudio ``step-*.ckpt`` (path, directory holding them, or the already loaded dict) into a B200 ``FruitModel``.
     Returns the training step stored in the file.  Shapes must match exactly (``num_train_data`` / ``log2_hashmap_size`` of
     the model must be the checkpoint's); with ``strict`` every learnable tensor of the model must be present."""
@@ -74,12 +90,13 @@ def load_nerfstudio_checkpoint(model, path_or_state, strict: bool = True) -> int
         path = str(path_or_state)
         if os.path.isdir(path):
             path = latest_checkpoint(path)
-        loaded = torch.load(path, map_location="cpu", weights_only=False)
+        loaded = _load_file(path, allow_pickle)
     else:
         loaded = path_or_state
     pipeline_state = loaded["pipeline"] if "pipeline" in loaded else loaded
     state = model_state_from_pipeline_state(pipeline_state) if any(k.startswith(_MODEL_PREFIXES) for k in pipeline_state) else dict(pipeline_state)
     _refuse_tcnn(state)
+    state = {k: v for k, v in state.items() if not k.startswith(_NON_PRODUCT_PREFIXES)}  # metric modules of the reference model
     own = model.state_dict()
     for key, value in state.items():
         if key in own and tuple(own[key].shape) != tuple(value.shape):
@@ -117,8 +134,9 @@ def _adam_state_dict(group, spec, opt_step: int) -> dict:
 
 
 def save_nerfstudio_checkpoint(directory: str, model, step: int, trainer=None) -> str:
-    """Write ``step-{step:09d}.ckpt`` in the nerfstudio layout (readable by ``eval_setup`` of a torch-implementation
-    reference install and by :func:`load_nerfstudio_checkpoint`).  With a :class:`engine.Trainer` the Adam moments of every
+    """Write ``step-{step:09d}.ckpt`` in the nerfstudio layout (same nesting and key names as the reference trainer's files; read back by
+    :func:`load_nerfstudio_checkpoint`.  The reference model's metric modules -- ``lpips.net.*`` etc. -- are not written, so a reference
+    install has to load it with ``strict=False``).  With a :class:`engine.Trainer` the Adam moments of every
     flat group are stored in ``torch.optim.Adam.state_dict()`` form so training can resume."""
     os.makedirs(directory, exist_ok=True)
     pipeline_state = {"_model." + k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
@@ -136,13 +154,13 @@ def save_nerfstudio_checkpoint(directory: str, model, step: int, trainer=None) -
     return path
 
 
-def resume_trainer(trainer, path_or_state) -> Tuple[int, Optional[int]]:
+def resume_trainer(trainer, path_or_state, allow_pickle: bool = False) -> Tuple[int, Optional[int]]:
     """Load model weights AND Adam moments back into a :class:`engine.Trainer` (flat groups).  Returns (step, opt_step)."""
     if isinstance(path_or_state, (str, os.PathLike)):
         path = str(path_or_state)
         if os.path.isdir(path):
             path = latest_checkpoint(path)
-        loaded = torch.load(path, map_location="cpu", weights_only=False)
+        loaded = _load_file(path, allow_pickle)
     else:
         loaded = path_or_state
     step = load_nerfstudio_checkpoint(trainer.model, loaded, strict=True)  # param.data are views of the flat buffers: copied in place

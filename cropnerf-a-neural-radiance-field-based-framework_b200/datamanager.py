@@ -7,9 +7,8 @@ Here the images of the split stay in HBM (uint8 RGB: 300 x 1080p = 1.9 GB, masks
 (``csrc/train_batch.cu``) does index -> pixel gather -> per-camera pinhole ray -> pixel area, one thread per ray, writing exactly
 the tensors the training step reads.  SURVEY.md section 8, "next" row f1 (pixel sampler).
 
-STATUS: built and checked against the oracle on CPU-testable pieces (index arithmetic, ABI); the kernel itself has not yet run on a
-GPU (written after this round's GPU budget was spent) -- its parity test is ``tests/test_train_batch_gpu.py`` and is skipped unless
-``CNB_RUN_UNVERIFIED=1``.  Nothing else in the package calls this module yet.
+Parity: ``tests/test_train_batch_gpu.py`` (indices and gathered pixels bit-exact against the oracle, uint8 and float32 storage);
+``bench.py``'s end-to-end leg ``e2e_device_batches`` trains from it (images resident in HBM, no host ray traffic at all).
 """
 from __future__ import annotations
 

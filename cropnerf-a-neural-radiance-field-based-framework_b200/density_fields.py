@@ -19,8 +19,10 @@ from .rays import Frustums, RaySamples, ray_layout
 class HashMLPDensityField(nn.Module):
     def __init__(self, aabb: Tensor, num_layers: int = 2, hidden_dim: int = 64, spatial_distortion: Optional[nn.Module] = None,
                  use_linear: bool = False, num_levels: int = 8, max_res: int = 1024, base_res: int = 16, log2_hashmap_size: int = 18,
-                 features_per_level: int = 2, average_init_density: float = 1.0, implementation: str = "b200") -> None:
+                 features_per_level: int = 2, average_init_density: float = 1.0, implementation: str = "b200",
+                 precision: str = "fp32") -> None:
         super().__init__()
+        self.precision = precision  # "mixed": bf16 operands in the backward's MLP parameter-gradient contraction (k_density_bwd_tc<0>)
         self.register_buffer("aabb", aabb)
         self._aabb_host = aabb.detach().cpu().tolist()
         self.spatial_distortion = spatial_distortion
@@ -50,7 +52,8 @@ class HashMLPDensityField(nn.Module):
         if self.use_linear:
             raise NotImplementedError("use_linear proposal fields: compose HashEncoding + Linear (not on the fruit_nerf presets)")
         net = self.mlp_base[1]
-        cfg = ((origins, directions, starts, ends, R, S, row_stride), self.encoding.grid_cfg(), self._warp(), float(self.average_init_density), want_positions)
+        cfg = ((origins, directions, starts, ends, R, S, row_stride), self.encoding.grid_cfg(), self._warp(), float(self.average_init_density), want_positions,
+               L.PREC_MIXED if self.precision == "mixed" else L.PREC_FP32)
         return ops.density_field(cfg, self.encoding.hash_table, net.layers[0].weight, net.layers[0].bias, net.layers[1].weight, net.layers[1].bias)
 
     def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, None]:

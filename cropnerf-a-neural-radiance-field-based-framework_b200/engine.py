@@ -353,6 +353,8 @@ class Trainer:
         import os as _os
 
         self.defer_fields = _os.environ.get("CNB_NO_DEFER", "0") != "1"  # one GPU: pipeline the field group's Adam into the next step (graphed steps)
+        self.graph_during_anneal = False  # True: capture a graph per distinct anneal value as well (tests)
+        self.check_peers_every = 64       # peer-memory mode: read the barrier time-out flag every N steps (and before checkpoints)
         self.ddp = "nccl"
         if world_size > 1 and ddp != "nccl" and self.grad_scaler is None and next(model.parameters()).is_cuda:
             try:
@@ -476,6 +478,16 @@ class Trainer:
             self._deferred_pending = True
             self.model._param_fence = self.wait_deferred_update  # eval / export forwards on any stream wait for it (FruitModel.forward)
         self._grads_clean = True
+        if self.check_peers_every and self.opt_step % self.check_peers_every == 0:
+            self.check_peers()
+
+    def check_peers(self) -> None:
+        """Peer-memory mode: a barrier that timed out (stalled or dead peer) only sets a flag on the device and lets the stream carry on,
+        so the update that followed may have used stale peer gradients.  Read the flag (one 4-byte D2H read) and fail loudly instead of
+        letting replicas diverge silently; called every ``check_peers_every`` steps, by ``gather_optimizer_state`` and before checkpoints."""
+        if self.comm is not None and self.comm.timed_out():
+            raise RuntimeError("cropnerf_b200: a peer-memory barrier timed out (stalled or dead peer): replicas may have diverged; "
+                               "restart from the last checkpoint (or train with ddp='nccl')")
 
     def _deferred_fields_adam(self, step: int) -> None:
         """One GPU, graphed steps: the field group's fused Adam + gradient clear on a side stream, fenced by an event that the next step's
@@ -514,6 +526,7 @@ class Trainer:
         if self.comm is None:
             return
         self.wait_deferred_update()
+        self.check_peers()
         from .ddp import owned_range
 
         for g in self.groups.values():
@@ -563,12 +576,22 @@ class Trainer:
                     return ray_bundle, batch
                 return ray_bundle.to(dev, non_blocking=True), {k: v.to(dev, non_blocking=True) for k, v in batch.items() if isinstance(v, Tensor)}
 
-            if self.cuda_graph and ray_bundle.nears is None and cam_opt.mode == "off":
-                key = (int(ray_bundle.origins.shape[0]), updated, float(sampler._anneal), self._loss_scale())
+            # anneal is a kernel argument baked into the captured graph and moves every step for the first
+            # proposal_weights_anneal_max_num_iters (1000) iterations: those steps run the same C call eagerly instead of
+            # capturing (and throwing away) one graph per step; from then on anneal == 1 and one graph per (R, updated) is replayed
+            anneal = float(sampler._anneal)
+            graphable = self.cuda_graph and ray_bundle.nears is None and cam_opt.mode == "off"
+            if graphable and anneal != 1.0 and (int(ray_bundle.origins.shape[0]), updated, anneal, self._loss_scale()) not in self._graphs:
+                graphable = self.graph_during_anneal
+            if graphable:
+                key = (int(ray_bundle.origins.shape[0]), updated, anneal, self._loss_scale())
                 gs = self._graphs.get(key)
                 if gs is None:
-                    if len(self._graphs) >= 8:  # anneal still moving (first 1000 steps): do not hoard graphs
+                    if len(self._graphs) >= 8:
                         self._graphs.pop(next(iter(self._graphs)))
+                    # a deferred `fields` update (side-stream Adam / peer-memory exchange) of the previous step may still be reading and
+                    # clearing the gradient buffer this warm-up accumulates into, and writing the parameters it reads
+                    self.wait_deferred_update()
                     rb_d, batch_d = on_device()
                     fp.train_step(rb_d, batch_d, update_proposals=False, want_metrics=True)  # eager warm-up (func attributes, workspace)
                     for g in self.groups.values():

@@ -228,13 +228,13 @@ class FruitModel(nn.Module):
         self.proposal_networks = nn.ModuleList()
         if cfg.use_same_proposal_network:
             assert len(cfg.proposal_net_args_list) == 1, "Only one proposal network is allowed."
-            network = HashMLPDensityField(self.aabb, spatial_distortion=scene_contraction, **cfg.proposal_net_args_list[0])
+            network = HashMLPDensityField(self.aabb, spatial_distortion=scene_contraction, precision=cfg.precision, **cfg.proposal_net_args_list[0])
             self.proposal_networks.append(network)
             self.density_fns.extend([network.density_fn for _ in range(num_prop_nets)])
         else:
             for i in range(num_prop_nets):
                 args = cfg.proposal_net_args_list[min(i, len(cfg.proposal_net_args_list) - 1)]
-                self.proposal_networks.append(HashMLPDensityField(self.aabb, spatial_distortion=scene_contraction, **args))
+                self.proposal_networks.append(HashMLPDensityField(self.aabb, spatial_distortion=scene_contraction, precision=cfg.precision, **args))
             self.density_fns.extend([network.density_fn for network in self.proposal_networks])
 
         def update_schedule(step):

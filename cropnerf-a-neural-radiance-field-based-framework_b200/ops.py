@@ -147,7 +147,7 @@ class _DensityFieldFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, origins_t: Tensor, directions_t: Tensor, table: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor):
-        (origins, directions, starts, ends, R, S, row_stride), (num_levels, log2_T, scalings), warp, avg, want_pos = cfg
+        (origins, directions, starts, ends, R, S, row_stride), (num_levels, log2_T, scalings), warp, avg, want_pos = cfg[:5]
         origins, directions = origins.detach(), directions.detach()
         dev = _dev(origins)
         density = torch.empty((R * S,), device=dev, dtype=torch.float32)
@@ -170,7 +170,8 @@ class _DensityFieldFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_density: Tensor, *unused):
         table, W1, b1, W2, b2 = ctx.saved_tensors
-        (origins, directions, starts, ends, R, S, row_stride), (num_levels, log2_T, scalings), warp, avg, _ = ctx.cfg
+        (origins, directions, starts, ends, R, S, row_stride), (num_levels, log2_T, scalings), warp, avg, _ = ctx.cfg[:5]
+        precision = ctx.cfg[5] if len(ctx.cfg) > 5 else L.PREC_FP32  # mixed: plain-bf16 operands in the MLP parameter-gradient contraction
         origins, directions = origins.detach(), directions.detach()
         dev = origins.device
         d_table = torch.zeros_like(table)
@@ -180,6 +181,7 @@ class _DensityFieldFn(torch.autograd.Function):
         f.mlp = L.make_mlp([W1.detach(), W2.detach()], [b1.detach(), b2.detach()], L.ACT_NONE, [dW1, dW2], [db1, db2])
         f.warp = warp
         f.average_init_density = avg
+        f.precision = precision
         sm = make_samples(origins, directions, starts, ends, None, R, S, row_stride)
         d = L.f32(d_density).reshape(-1)
         d_o = d_d = None

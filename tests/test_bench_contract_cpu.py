@@ -24,8 +24,21 @@ def test_reference_arm_prints_one_contract_line_on_cpu():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["render"]["value"] > 0 and d["cpu_baseline"]["render"]["unit"] == "rays/s"
-    assert abs(d["value"] - d["config"]["rays_per_step"] / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"]
+    assert abs(d["value"] - d["detail"]["rays_per_step"] / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the reference arm names the product arm's workload: the very same `config` dict (the driver's same_config check)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config()
+
+
+def test_reference_arm_defaults_to_the_full_batch_of_the_workload():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.RAYS_PER_GPU == 4096 and bench.workload_config()["rays_per_gpu"] == 4096
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert '"--cpu-rays", type=int, default=RAYS_PER_GPU' in src
+    assert 'os.environ["NCCL_DEBUG"]' not in src   # the driver reads NCCL's communicator lines
 
 
 def test_reference_arm_non_zero_ranks_exit_quietly():
@@ -36,7 +49,9 @@ def test_reference_arm_non_zero_ranks_exit_quietly():
 
 
 def test_committed_product_line_has_every_contract_key_and_consistent_arithmetic():
-    path = os.path.join(ROOT, "profiles", "r1_final_bench_1gpu.json")
+    path = os.path.join(ROOT, "profiles", "r2_bench_1gpu.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1_final_bench_1gpu.json")
     if not os.path.exists(path):
         pytest.skip("no committed bench line")
     d = json.loads(open(path).read().strip().splitlines()[-1])

@@ -86,3 +86,35 @@ def test_save_and_resume_restores_weights_and_adam_moments(tmp_path):
             assert torch.equal(grp2.exp_avg_sq[off : off + p2.numel()], grp.exp_avg_sq[off1 : off1 + p.numel()])
         # parameters are still views of the flat buffer after loading (load_state_dict copies in place)
         assert all(p2.data_ptr() >= grp2.flat.data_ptr() and p2.data_ptr() < grp2.flat.data_ptr() + 4 * grp2.flat.numel() for p2 in grp2.params)
+
+
+def test_metric_module_entries_of_a_reference_checkpoint_do_not_break_strict_loading(tmp_path):
+    """The reference model owns metric modules (fruit_nerf.py:181-183: psnr, ssim, LearnedPerceptualImagePatchSimilarity); torchmetrics'
+    LPIPS keeps its backbone in the state dict, so a checkpoint written by the reference trainer carries `_model.lpips.net.*` entries the
+    ray-render path has no module for.  They are dropped before the strict check; unknown keys elsewhere still fail."""
+    cfg, model = _model()
+    _, state = cases.build_oracle(cfg, 6, seed=3, table_scale=0.5)
+    pipe = {"_model." + k: v for k, v in state.items()}
+    pipe["_model.lpips.net.net.slice1.0.weight"] = torch.zeros(64, 3, 11, 11)
+    pipe["_model.lpips.net.lin0.model.1.weight"] = torch.zeros(1, 64, 1, 1)
+    pipe["_model.psnr.dummy"] = torch.zeros(1)
+    path = str(tmp_path / checkpoint.checkpoint_name(7))
+    torch.save({"step": 7, "pipeline": pipe, "optimizers": {}, "schedulers": {}, "scalers": {}}, path)
+    assert checkpoint.load_nerfstudio_checkpoint(model, path, strict=True) == 7        # loaded with weights_only=True
+    assert torch.equal(model.field.mlp_base_grid.hash_table, state["field.mlp_base_grid.hash_table"])
+    pipe["_model.field.some_new_head.weight"] = torch.zeros(3)
+    with pytest.raises(KeyError, match="does not know"):
+        checkpoint.load_nerfstudio_checkpoint(model, {"step": 7, "pipeline": pipe})
+
+
+class _Evil:
+    def __reduce__(self):
+        return (print, ("pickled code ran",))
+
+
+def test_checkpoint_files_are_loaded_without_unpickling_code(tmp_path):
+    path = str(tmp_path / checkpoint.checkpoint_name(1))
+    torch.save({"step": 1, "pipeline": {}, "evil": _Evil()}, path)
+    _, model = _model()
+    with pytest.raises(RuntimeError, match="weights_only"):
+        checkpoint.load_nerfstudio_checkpoint(model, path, strict=False)

@@ -64,11 +64,14 @@ def test_field_forward_backward(dev, contraction, training):
         assert err < 5e-4, f"field grad {name}: {err:.3e}"
 
 
-def test_density_field_forward_backward(dev):
+@pytest.mark.parametrize("precision", ["fp32", "mixed"])
+def test_density_field_forward_backward(dev, precision):
+    """mixed: the forward and the table scatter are the fp32 kernels' (same tolerances); only the MLP parameter gradients are contracted
+    with plain bf16 operands on the tensor cores (k_density_bwd_tc<0>): relative L2 <= 2e-2 (8 mantissa bits, fp32 accumulation)."""
     R, S, num_images = 200, 64, 20
     cfg = cases.make_config(dict(log2_hashmap_size=14))
     oracle, state = cases.build_oracle(cfg, num_images, seed=0, table_scale=0.5)
-    model = product_model(cfg, state, num_images, dev, True)
+    model = product_model(cfg, state, num_images, dev, True, precision=precision)
     rays, edges = _field_samples(R, S, 4)
     rs = cases.oracle_bundle(rays).get_ray_samples(edges[:, :-1, None], edges[:, 1:, None])
     e = edges.to(dev)
@@ -91,7 +94,11 @@ def test_density_field_forward_backward(dev):
             gr_ = ref_params[name].grad
             scale = gr_.abs().max().item() + 1e-20
             err = (p.grad.cpu() - gr_).abs().max().item() / scale
-            assert err < 5e-4, f"proposal {i} grad {name}: {err:.3e}"
+            if precision == "mixed" and "hash_table" not in name:
+                l2 = (p.grad.cpu().double() - gr_.double()).norm().item() / (gr_.double().norm().item() + 1e-30)
+                assert l2 < 2e-2, f"mixed proposal {i} grad {name}: relative L2 {l2:.3e}"
+            else:
+                assert err < 5e-4, f"proposal {i} grad {name}: {err:.3e}"
 
 
 def _run_product(name, dev, spec=None, num_images=20, seed=0):
@@ -118,9 +125,10 @@ def _check_outputs(outputs, ref, tag):
     # sample, so a last-ulp difference in the cumulative weights may move a few rays by one sample
     assert_close(outputs["rgb"], ref["rgb"], RTOL_FP32, tag + " rgb")
     assert_close(outputs["accumulation"], ref["accumulation"], RTOL_FP32, tag + " accumulation")
-    assert_close(outputs["depth"], ref["depth"], RTOL_FP32, tag + " depth", frac=0.98)
-    assert_close(outputs["prop_depth_0"], ref["prop_depth_0"], RTOL_FP32, tag + " prop_depth_0", frac=0.98)
-    assert_close(outputs["prop_depth_1"], ref["prop_depth_1"], RTOL_FP32, tag + " prop_depth_1", frac=0.98)
+    # (measured on the B200: 100 % of the rays, 99.9 % for prop_depth_0 at 1024 rays -- profiles/r1_parity_report_fp32.json)
+    assert_close(outputs["depth"], ref["depth"], RTOL_FP32, tag + " depth", frac=0.999)
+    assert_close(outputs["prop_depth_0"], ref["prop_depth_0"], RTOL_FP32, tag + " prop_depth_0", frac=0.998)
+    assert_close(outputs["prop_depth_1"], ref["prop_depth_1"], RTOL_FP32, tag + " prop_depth_1", frac=0.999)
     assert_close(outputs["semantics"], ref["semantics"], 5e-4, tag + " semantics", floor=1e-2)
     agree = (outputs["semantics_colormap"].cpu().numpy() == ref["semantics_colormap"]).mean()
     assert agree >= 0.999, f"{tag}: semantic label agreement {agree}"
@@ -133,7 +141,9 @@ def test_model_against_golden(dev, name):
     _check_outputs(outputs, ref, name)
     inds = model.proposal_sampler.pdf_sampler.last_inds.cpu().numpy()
     same = (inds == ref["pdf_inds_last"]).mean()
-    assert same >= 0.995, f"{name}: resampling bins agree on {same*100:.2f}%"
+    # bit-exact GIVEN an identical cdf (test_pdf_sampler_bit_exact_given_identical_cdf); end to end the cdf may differ in the last ulp (fp32 sum
+    # order of the histogram, powf), which can move a tie: at most 2 of the ~4700 bin indices of these cases
+    assert same >= 0.9995, f"{name}: resampling bins agree on {same*100:.3f}%"
     assert inds.shape == ref["pdf_inds_last"].shape  # proposal sample counts
 
 

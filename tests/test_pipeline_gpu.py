@@ -48,10 +48,10 @@ def test_fused_render_against_golden(dev):
         out = model(product_bundle(rays, dev))
     assert_close(out["rgb"], ref["rgb"], 1e-4, "rgb")
     assert_close(out["accumulation"], ref["accumulation"], 1e-4, "accumulation")
-    assert_close(out["depth"], ref["depth"], 1e-4, "depth", frac=0.98)
+    assert_close(out["depth"], ref["depth"], 1e-4, "depth", frac=0.999)
     inds = model.proposal_sampler.pdf_sampler.last_inds.cpu().numpy()
     assert inds.shape == ref["pdf_inds_last"].shape
-    assert (inds == ref["pdf_inds_last"]).mean() >= 0.995
+    assert (inds == ref["pdf_inds_last"]).mean() >= 0.9995
     assert (out["semantics_colormap"].cpu().numpy() == ref["semantics_colormap"]).mean() >= 0.999
 
 

@@ -2,17 +2,13 @@
 data/fruit_datamanager.py:188-197) against the oracle: indices and gathered pixels bit-exact, ray directions to 2e-6 and pixel areas to
 2e-3 relative (fused multiply-adds in the norm / pixel-area expressions; the bounds of test_generate_rays_and_aabb_clip).
 
-The kernel was written after round 1's GPU budget was spent and has not run on a GPU yet: the test is skipped unless
-CNB_RUN_UNVERIFIED=1 so that an unverified kernel cannot fail the suite; drop the gate once it has passed on a B200."""
-import os
-
+First run on a B200 in round 2 (gpurun_out/r2_trainbatch.log: 2 passed); the round-1 gate is gone."""
 import pytest
 import torch
 
 from oracle import nerfstudio_torch as ns
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("CNB_RUN_UNVERIFIED", "0") != "1",
-                                                  reason="kernel not yet verified on a GPU (set CNB_RUN_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("storage", ["uint8", "float32"])
