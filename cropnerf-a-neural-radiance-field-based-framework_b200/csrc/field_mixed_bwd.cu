@@ -11,8 +11,15 @@
 //      is staged once in shared memory and read back with ldmatrix.trans; every warp owns a fixed 1/8 slice of every
 //      dW and accumulates it (fp32) across all batches of the CTA -- no atomics until the one flush per CTA at the end;
 //      bias gradients are the same contraction against a fragment of ones;
-//   4. d(encoded features), level-major [16][N][2] fp32, goes to the scratch the hash-grid scatter (cnb_hashgrid_bwd_level_major) reads; the appearance
-//      embedding gradient is reduced over the m-tile (all 16 samples share the ray when S % 16 == 0) before its atomics.
+//   4. d(encoded features), level-major [16][N][2] fp32, goes to a scratch array; the appearance embedding gradient is reduced over the
+//      m-tile (all 16 samples share the ray when S % 16 == 0) before its atomics;
+//   5. (FUSED, the default) the hash-table scatter of those d(features) runs INSIDE this kernel on four extra "scatter" warps: the MLP
+//      part is a latency chain on the tensor pipe at 8 warps/SM (1 CTA/SM: 228 KB of shared memory), the scatter is bound by the L2
+//      reduction rate and needs no shared memory -- run back to back as two kernels they cost 0.164 + 0.104 ms, but no second kernel can
+//      co-reside with a 228 KB CTA, so the overlap has to happen inside the CTA.  The MLP warps publish each finished 128-sample batch
+//      through a ring of full/empty mbarriers; scatter warp w takes samples [32 w, 32 w + 32) of the batch, reads its 16 levels'
+//      d(features) back (L2-resident, written microseconds earlier by the same SM) and issues the aggregated vector reductions of
+//      cnb_scatter_cell.  Registers are re-split with setmaxnreg (MLP warpgroups 224, scatter warpgroup 56; 384 threads x 168 at launch).
 #include <cstdlib>
 
 #include "field_mixed.cuh"
@@ -37,9 +44,17 @@ constexpr int A_R3 = 0, A_R2 = 1, A_R1 = 5, A_H = 9, A_S2 = 10, A_S1 = 14, A_B2 
 constexpr int B_R3 = 0, B_R2 = 16, B_R1 = 80, B_H = 144, B_S2 = 160, B_S1 = 224, B_B2 = 288, B_B1 = 304, B_FLOATS = 368;
 
 constexpr size_t SMEM_BWD = (size_t)(HALVES + T_HALVES + 4 * BATCH * ST) * 2 + (size_t)(FLOATS + B_FLOATS + WARPS * A_TILES * 128) * 4;  // 228 272 B
+// fused scatter: 4 scatter warps behind the 8 MLP warps, NSLOT-deep full/empty mbarrier ring (after SMEM_BWD)
+constexpr int SC_WARPS = 4;
+constexpr int THREADS_FUSED = THREADS + SC_WARPS * 32;
+constexpr int NSLOT = 4;
+constexpr size_t SMEM_BWD_FUSED = SMEM_BWD + 2 * NSLOT * sizeof(uint64_t);
+static_assert(BATCH == SC_WARPS * 32, "one scatter warp per 32 samples of a batch");
+static_assert(SMEM_BWD_FUSED <= 232448, "227 KB of dynamic shared memory per CTA");
 
 struct BwdArgs {
   MixArgs m;
+  float* d_table;               // FUSED: gradient table of the hash grid
   const __half* x0;
   const float* pos;
   const float *d_density, *d_rgb, *d_sem;
@@ -179,6 +194,53 @@ __device__ __forceinline__ void flush_tiles(const float* acc_tiles, int warp, in
     }
 }
 
+// block barrier over the 8 MLP warps only (the scatter warps of the fused kernel never take part)
+__device__ __forceinline__ void bar_mlp() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+
+// Scatter role of the fused kernel: warp sw owns samples [32 sw, 32 sw + 32) of every batch of this CTA.
+__device__ __forceinline__ void scatter_role(const MixArgs& a, float* __restrict__ d_table, const float* __restrict__ pos, const float* __restrict__ d_x0,
+                                             uint32_t mbar_s, int sw, int lane, int64_t N, int64_t nbatches) {
+  int j = 0;
+  for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x, ++j) {
+    const int slot = j % NSLOT;
+    const uint32_t par = (uint32_t)(j / NSLOT) & 1u;
+    const int64_t s = batch * BATCH + sw * 32 + lane;
+    const bool in = s < N;
+    // the positions come from the forward: requested before the wait
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (in) { px = __ldg(pos + 3 * s); py = __ldg(pos + 3 * s + 1); pz = __ldg(pos + 3 * s + 2); }
+    mbar_wait(mbar_s + 8 * slot, par);  // "full": all 256 MLP threads have stored this batch's d(features)
+#pragma unroll 1
+    for (int l0 = 0; l0 < a.L; l0 += 4) {
+      float2 d[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        d[q] = make_float2(0.f, 0.f);
+        if (in && l0 + q < a.L) d[q] = __ldcg(reinterpret_cast<const float2*>(d_x0) + (int64_t)(l0 + q) * N + s);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int l = l0 + q;
+        if (l < a.L) {  // warp-uniform
+          const bool active = d[q].x != 0.0f || d[q].y != 0.0f;  // zero gradients add nothing (masked samples, App. B-3)
+          CnbCell c = {};
+          if (active) c = cnb_cell(px, py, pz, a.scalings[l]);
+          cnb_scatter_cell(d_table, c, a.mask, (uint32_t)l * a.T, d[q].x, d[q].y, active);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(mbar_s + 8 * (NSLOT + slot));  // "empty"
+  }
+}
+
 __device__ inline void load_weights_t(const MixArgs& a, __nv_bfloat16* WT) {
   const int tid = threadIdx.x;
   for (int e = tid; e < 64 * 24; e += THREADS) {
@@ -204,7 +266,8 @@ __device__ inline void load_weights_t(const MixArgs& a, __nv_bfloat16* WT) {
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_constant__ BwdArgs b) {
+template <bool FUSED>
+__global__ void __launch_bounds__(FUSED ? THREADS_FUSED : THREADS, 1) k_field_mixed_bwd(const __grid_constant__ BwdArgs b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const MixArgs& a = b.m;
   __half* Wsm = reinterpret_cast<__half*>(smem_raw);
@@ -215,13 +278,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
   float* Bf = reinterpret_cast<float*>(st_base + 4 * BATCH * ST);
   float* bias_acc = Bf + FLOATS;
   float* acc_all = bias_acc + B_FLOATS;
-  load_weights(a, Wsm, Bf);
-  load_weights_t(a, WT);
-  for (int e = threadIdx.x; e < B_FLOATS + WARPS * A_TILES * 128; e += THREADS) bias_acc[e] = 0.f;
+  const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(smem_raw + SMEM_BWD);  // FUSED: NSLOT "full" then NSLOT "empty" barriers
+  if (!FUSED || threadIdx.x < THREADS) {
+    load_weights(a, Wsm, Bf);
+    load_weights_t(a, WT);
+    for (int e = threadIdx.x; e < B_FLOATS + WARPS * A_TILES * 128; e += THREADS) bias_acc[e] = 0.f;
+  } else if (threadIdx.x == THREADS) {
+    for (int i = 0; i < NSLOT; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_s + 8 * i), "r"(THREADS));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_s + 8 * (NSLOT + i)), "r"(SC_WARPS));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   // the pad columns of the staging rows are never written by `stage`; ldmatrix.x2 never consumes them either
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (FUSED) {
+    const int64_t N_ = a.sm.num_rays * a.sm.samples_per_ray;
+    if (warp >= WARPS) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      scatter_role(a, b.d_table, b.pos, b.d_x0, mbar_s, warp - WARPS, lane, N_, (N_ + BATCH - 1) / BATCH);
+      return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+  }
   const int g = lane >> 2, t = lane & 3;
   float* acc_w = acc_all + warp * A_TILES * 128;
   uint32_t* const st32 = reinterpret_cast<uint32_t*>(st_base);
@@ -297,7 +378,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
     load_cam(t0 + tstride, cam2);
   }
 
-  for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
+  int jb = 0;  // FUSED: index of this CTA's batch in the full / empty barrier ring
+  for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x, ++jb) {
     const int64_t tile = batch * WARPS + warp;
     const int64_t row[2] = {tile * 16 + g, tile * 16 + g + 8};
     bool valid[2];
@@ -379,7 +461,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
       // ---- layer 3: dW = D3^T r2 ; d_r2 = D3 W3 -------------------------------------------------------------------------
       stage<1, false>(st32 + (2 * buf + 1) * MATW, row0, D3, g, t);
       stage<4, true>(st32 + (2 * buf) * MATW, row0, AR2, g, t);
-      __syncthreads();
+      bar_mlp();
       dw_gemm<1, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_R3 * 128, bias_acc + B_R3, warp, lane);
       buf ^= 1;
       uint32_t D[4][4];
@@ -389,7 +471,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
       // ---- layer 2 ----------------------------------------------------------------------------------------------------------
       stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
       stage<4, true>(st32 + (2 * buf) * MATW, row0, AR1, g, t);
-      __syncthreads();
+      bar_mlp();
       dw_gemm<4, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_R2 * 128, bias_acc + B_R2, warp, lane);
       buf ^= 1;
       zero_acc<8>(acc);
@@ -398,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
       // ---- layer 1 ----------------------------------------------------------------------------------------------------------
       stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
       stage<4, true>(st32 + (2 * buf) * MATW, row0, Ain, g, t);
-      __syncthreads();
+      bar_mlp();
       dw_gemm<4, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_R1 * 128, bias_acc + B_R1, warp, lane);
       buf ^= 1;
       float din[6][4];  // d(rgb input) columns 16..63: [0, geo15 | emb32]
@@ -454,7 +536,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
       if (t == 0) { Dh[0][0] = pack_bf2(dsem[0], 0.f); Dh[0][1] = pack_bf2(dsem[1], 0.f); }
       stage<1, false>(st32 + (2 * buf + 1) * MATW, row0, Dh, g, t);
       stage<4, false>(st32 + (2 * buf) * MATW, row0, S2f, g, t);
-      __syncthreads();
+      bar_mlp();
       dw_gemm<1, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_H * 128, bias_acc + B_H, warp, lane);
       buf ^= 1;
       // d_s2 = d_sem * Wh (no activation after the last semantic layer)
@@ -469,7 +551,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
       // ---- semantic layer 2 ------------------------------------------------------------------------------------------------
       stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
       stage<4, true>(st32 + (2 * buf) * MATW, row0, AS1, g, t);
-      __syncthreads();
+      bar_mlp();
       dw_gemm<4, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_S2 * 128, bias_acc + B_S2, warp, lane);
       buf ^= 1;
       zero_acc<8>(acc);
@@ -478,7 +560,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
       // ---- semantic layer 1 (input = [0 | geo15]) -----------------------------------------------------------------------------
       stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
       stage<1, true>(st32 + (2 * buf) * MATW, row0, Abo, g, t);
-      __syncthreads();
+      bar_mlp();
       dw_gemm<4, 2>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_S1 * 128, bias_acc + B_S1, warp, lane);
       buf ^= 1;
     }
@@ -498,7 +580,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
       Dbo[0][2] = pack_bf2(dbo[1][0], dbo[1][1]); Dbo[0][3] = pack_bf2(dbo[1][2], dbo[1][3]);
       stage<1, false>(st32 + (2 * buf + 1) * MATW, row0, Dbo, g, t);
       stage<4, true>(st32 + (2 * buf) * MATW, row0, AH, g, t);
-      __syncthreads();
+      bar_mlp();
       dw_gemm<1, 8>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_B2 * 128, bias_acc + B_B2, warp, lane);
       buf ^= 1;
       float acc[8][4];
@@ -508,7 +590,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
       relu_mask_pack<4>(acc, AH, D);
       stage<4, false>(st32 + (2 * buf + 1) * MATW, row0, D, g, t);
       stage<2, true>(st32 + (2 * buf) * MATW, row0, A0, g, t);
-      __syncthreads();
+      bar_mlp();
       dw_gemm<4, 4>(st_s + (2 * buf + 1) * MATW * 4, st_s + (2 * buf) * MATW * 4, acc_w + A_B1 * 128, bias_acc + B_B1, warp, lane);
       buf ^= 1;
       float dx[4][4];
@@ -520,6 +602,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
         float2* const dlev = reinterpret_cast<float2*>(b.d_x0) + (int64_t)(4 * nt + t) * N;
         if (valid[0]) dlev[row[0]] = make_float2(dx[nt][0], dx[nt][1]);
         if (valid[1]) dlev[row[1]] = make_float2(dx[nt][2], dx[nt][3]);
+      }
+      if (FUSED) {
+        // publish the batch to the scatter warps.  The slot's previous phase (batch jb - NSLOT) must have been consumed before the
+        // barrier may complete again; the data itself is never overwritten (every batch has its own rows of d_x0)
+        const int slot = jb % NSLOT;
+        if (jb >= NSLOT) mbar_wait(mbar_s + 8 * (NSLOT + slot), (uint32_t)(jb / NSLOT - 1) & 1u);
+        mbar_arrive(mbar_s + 8 * slot);  // release at CTA scope: orders this thread's d_x0 stores before the scatter warps' loads
       }
     }
   }
@@ -534,7 +623,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_field_mixed_bwd(const __grid_con
   if (b.dWs1) flush_tiles<4, 2>(acc_w + A_S1 * 128, warp, lane, [&](int n, int k, float v) { if (k >= 1) atomicAdd(b.dWs1 + n * 15 + (k - 1), v); });
   if (b.dWb2) flush_tiles<1, 8>(acc_w + A_B2 * 128, warp, lane, [&](int n, int k, float v) { atomicAdd(b.dWb2 + n * 64 + k, v); });
   if (b.dWb1) flush_tiles<4, 4>(acc_w + A_B1 * 128, warp, lane, [&](int n, int k, float v) { if (k < in0) atomicAdd(b.dWb1 + n * in0 + k, v); });
-  __syncthreads();
+  bar_mlp();
   for (int e = threadIdx.x; e < B_FLOATS; e += THREADS) {
     const float v = bias_acc[e];
     if (v == 0.f) continue;
@@ -572,14 +661,28 @@ int cnb_field_mixed_bwd(const cnb_field* f, const cnb_samples* s, const float* d
   b.dWh = f->sem_head.dW[0]; b.dbh = f->sem_head.db[0];
   b.dWr1 = f->rgb.dW[0]; b.dbr1 = f->rgb.db[0]; b.dWr2 = f->rgb.dW[1]; b.dbr2 = f->rgb.db[1]; b.dWr3 = f->rgb.dW[2]; b.dbr3 = f->rgb.db[2];
   b.d_embedding = f->appearance_mode == CNB_APP_PER_CAMERA ? f->d_embedding : nullptr;
+  b.d_table = f->grid.d_table;
+  // CNB_FIELD_BWD_FUSED=1: the table scatter on four extra warps of this kernel instead of a second kernel (same arithmetic).  Measured on
+  // B200 (4096-ray step): 0.298 ms fused vs 0.270 ms as two kernels -- the reductions occupy the SM's LSU for ~1.6 cycles per lane-red
+  // (tests/micro/table_access_bench: the red ceiling is an SM-side rate), and the MLP warps' shared-memory fragment loads queue behind
+  // them, so the latency chain gets longer than the overlap saves.  Not the default.
+  static const bool want_fused = [] { const char* e = getenv("CNB_FIELD_BWD_FUSED"); return e != nullptr && e[0] == '1'; }();
+  bool fused = want_fused && b.d_table != nullptr;
+  for (int i = 0; i < f->grid.num_levels && fused; ++i) fused = f->grid.scalings[i] < 65535.0f;  // cnb_scatter_cell's 16-bit cell keys
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(k_field_mixed_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD) != cudaSuccess) return cnb_check_launch("field_mixed_bwd attr");
+    if (cudaFuncSetAttribute(k_field_mixed_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD) != cudaSuccess ||
+        cudaFuncSetAttribute(k_field_mixed_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD_FUSED) != cudaSuccess)
+      return cnb_check_launch("field_mixed_bwd attr");
     configured = true;
   }
   const int64_t nbatches = (N + BATCH - 1) / BATCH;
   int64_t blocks = nbatches < (int64_t)cnb_num_sms() ? nbatches : (int64_t)cnb_num_sms();
-  k_field_mixed_bwd<<<(int)blocks, THREADS, SMEM_BWD, stream>>>(b);
+  if (fused) {
+    k_field_mixed_bwd<true><<<(int)blocks, THREADS_FUSED, SMEM_BWD_FUSED, stream>>>(b);
+    return cnb_check_launch("field_mixed_bwd (fused scatter)");
+  }
+  k_field_mixed_bwd<false><<<(int)blocks, THREADS, SMEM_BWD, stream>>>(b);
   int rc = cnb_check_launch("field_mixed_bwd");
   if (rc) return rc;
   return cnb_hashgrid_bwd_level_major(&f->grid, b.pos, b.d_x0, N, stream);

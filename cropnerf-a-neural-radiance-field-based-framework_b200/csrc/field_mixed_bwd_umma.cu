@@ -47,7 +47,10 @@ constexpr uint32_t U_SBO = (BATCH / 8) * 128;    // between 8-feature mn-blocks 
 constexpr uint32_t U_MAT = 8 * U_SBO;            // one 64-feature x 128-sample matrix (16 KB)
 constexpr uint32_t U_BUF = 2 * U_MAT + U_SBO;    // [dY | X | ones block]
 constexpr int NBUF = 4;
-constexpr int BTHREADS = THREADS + 32;  // 8 worker warps + 1 MMA-issuer warp
+// 8 worker warps (warpgroups 0, 1) + one more warpgroup whose first warp is the MMA issuer.  A 9-warp CTA would cap every thread at 168
+// registers (three warps on one SM sub-partition) and spill the workers' fragment chains; with a full third warpgroup the registers are
+// re-split after launch (setmaxnreg: workers 224, issuer warpgroup 56; 3 x 168 = 224 + 224 + 56 per sub-partition lane).
+constexpr int BTHREADS = THREADS + 128;
 // GEMM table: swapped = issued as (dW)^T = [X | ones]^T dY with M = 128 (narrow dY, N = 16); otherwise dW = dY^T [X | ones], M = 64.
 // xblk0 = first 8-feature block of the X region that holds data (narrow X is right-aligned so that the ones block follows it).
 struct GemmSpec { bool swapped; int xblk0; int n; int col; };
@@ -240,6 +243,37 @@ __global__ void __launch_bounds__(BTHREADS, 1) k_field_mixed_bwd_umma(const __gr
   const int64_t N = a.sm.num_rays * S;
   const int64_t nbatches = (N + BATCH - 1) / BATCH;
 
+  if (warp >= WARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp > WARPS) return;  // the rest of the third warpgroup only donates its registers
+    // ===== MMA issuer warp: one lane issues the 8 K-steps of every layer's dW GEMM as soon as its buffer is full =====
+    uint32_t fphase = 0, ibuf = 0;
+    bool first_batch = true;
+    for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
+      for (int gi = 0; gi < NGEMM; ++gi) {
+        mbar_wait(mbar_s + 8 * (NBUF + ibuf), (fphase >> ibuf) & 1u);
+        fphase ^= 1u << ibuf;
+        if (lane == 0) {
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const GemmSpec sp = GEMMS[gi];
+          const uint32_t dy_s = stg_s + ibuf * U_BUF, x_s = dy_s + U_MAT;
+          const uint32_t a_s = sp.swapped ? x_s : dy_s;
+          const uint32_t b_s = sp.swapped ? dy_s : x_s + (uint32_t)sp.xblk0 * U_SBO;
+          const uint32_t idesc = umma_idesc(sp.swapped ? 128 : 64, sp.n);
+#pragma unroll
+          for (int ks = 0; ks < BATCH / 16; ++ks)
+            umma_issue(tmem + sp.col, umma_desc(a_s + ks * 2 * U_LBO), umma_desc(b_s + ks * 2 * U_LBO), idesc, (first_batch && ks == 0) ? 0u : 1u);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"l"((uint64_t)(mbar_s + 8 * ibuf)) : "memory");
+        }
+        __syncwarp();
+        ibuf = (ibuf + 1) % NBUF;
+      }
+      first_batch = false;
+    }
+    return;
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+
   // Software pipeline over the batches of this CTA: the encoded features and camera indices of the NEXT tile are requested
   // while the current one is processed, and every other global input of the current tile (directions, embedding row,
   // incoming gradients) is requested at the top of the iteration, long before its first use -- with one CTA (2 warps per
@@ -304,32 +338,6 @@ __global__ void __launch_bounds__(BTHREADS, 1) k_field_mixed_bwd_umma(const __gr
     load_cam(t0 + tstride, cam2);
   }
 
-  if (warp == WARPS) {
-    // ===== MMA issuer warp: one lane issues the 8 K-steps of every layer's dW GEMM as soon as its buffer is full =====
-    uint32_t fphase = 0, ibuf = 0;
-    bool first_batch = true;
-    for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
-      for (int gi = 0; gi < NGEMM; ++gi) {
-        mbar_wait(mbar_s + 8 * (NBUF + ibuf), (fphase >> ibuf) & 1u);
-        fphase ^= 1u << ibuf;
-        if (lane == 0) {
-          asm volatile("tcgen05.fence::after_thread_sync;");
-          const GemmSpec sp = GEMMS[gi];
-          const uint32_t dy_s = stg_s + ibuf * U_BUF, x_s = dy_s + U_MAT;
-          const uint32_t a_s = sp.swapped ? x_s : dy_s;
-          const uint32_t b_s = sp.swapped ? dy_s : x_s + (uint32_t)sp.xblk0 * U_SBO;
-          const uint32_t idesc = umma_idesc(sp.swapped ? 128 : 64, sp.n);
-#pragma unroll
-          for (int ks = 0; ks < BATCH / 16; ++ks)
-            umma_issue(tmem + sp.col, umma_desc(a_s + ks * 2 * U_LBO), umma_desc(b_s + ks * 2 * U_LBO), idesc, (first_batch && ks == 0) ? 0u : 1u);
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"l"((uint64_t)(mbar_s + 8 * ibuf)) : "memory");
-        }
-        __syncwarp();
-        ibuf = (ibuf + 1) % NBUF;
-      }
-      first_batch = false;
-    }
-  } else
   for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
     const int64_t tile = batch * WARPS + warp;
     const int64_t row[2] = {tile * 16 + g, tile * 16 + g + 8};
@@ -566,10 +574,9 @@ __global__ void __launch_bounds__(BTHREADS, 1) k_field_mixed_bwd_umma(const __gr
   }
 
   // ---- one read-out + flush per CTA: wait for the last MMAs, tcgen05.ld the accumulators, reduce into the global gradients ------
-  if (warp < WARPS)
-    for (int bb = 0; bb < NBUF; ++bb)
-      if (used & (1u << bb)) mbar_wait(mbar_s + 8 * bb, (phase >> bb) & 1u);
-  __syncthreads();
+  for (int bb = 0; bb < NBUF; ++bb)
+    if (used & (1u << bb)) mbar_wait(mbar_s + 8 * bb, (phase >> bb) & 1u);
+  asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");  // the 8 worker warps (the issuer warpgroup has left)
   asm volatile("tcgen05.fence::after_thread_sync;");
   // Gradient image in shared memory (the staging buffers are free now): every tensor in its GLOBAL element order, so the
   // flush below is coalesced; straight from the TMEM read-out a warp instruction would scatter over 16-32 rows, and all
@@ -634,14 +641,14 @@ __global__ void __launch_bounds__(BTHREADS, 1) k_field_mixed_bwd_umma(const __gr
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
-  __syncthreads();
+  asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
   // coalesced flush, CTAs start at staggered offsets so they do not all hammer the same addresses at the same moment
   {
     auto flush = [&](float* g, int off, int n) {
       if (g == nullptr) return;
       const int rot = (int)((blockIdx.x * 97u) % (unsigned)n);
-      for (int e = threadIdx.x; e < n; e += BTHREADS) {
+      for (int e = threadIdx.x; e < n; e += THREADS) {
         int idx = e + rot;
         if (idx >= n) idx -= n;
         const float v = img[off + idx];
