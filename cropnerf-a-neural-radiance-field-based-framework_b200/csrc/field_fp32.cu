@@ -164,9 +164,9 @@ extern "C" int cnb_field_fwd(const cnb_field* f, const cnb_samples* s, float* de
       cnb_set_error("field_fwd: mixed precision is compiled for the base fruit_nerf architecture only (L<=16, widths 64, geo 15, app 32)");
       return CNB_ERR_UNSUPPORTED;
     }
-    CNB_REQUIRE(geo == nullptr, "field_fwd: mixed precision path does not export the geo embedding");
+    CNB_REQUIRE(geo == nullptr || f->geo_feat_dim == 15, "field_fwd: the mixed path exports geo as [N,16]");
     CNB_REQUIRE(!training || ctx != nullptr, "field_fwd: mixed training forward needs ctx scratch (cnb_field_ctx_floats)");
-    return cnb_field_mixed_fwd(f, s, density, rgb, sem, positions_out, ctx, training, stream);
+    return cnb_field_mixed_fwd(f, s, density, geo, rgb, sem, positions_out, ctx, training, stream);
   }
   CNB_REQUIRE(ctx != nullptr, "field_fwd: fp32 path needs ctx scratch (cnb_field_ctx_floats)");
   const CtxLayout c = make_layout(f, N, training != 0);

@@ -126,6 +126,13 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
       float acc2[2][4];
       init_bias<2>(acc2, Bf + F_BB2, t);
       layer<2, 4, S64>(Wsm + O_WB2, AH, acc2, g, t);
+      if (a.geo_out) {  // get_density's (density_before_activation, embedding) pair, fp32 accumulators as they are (fruit_field.py:183-187)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          if (valid[0]) *reinterpret_cast<float2*>(a.geo_out + row[0] * 16 + 8 * nt + 2 * t) = make_float2(acc2[nt][0], acc2[nt][1]);
+          if (valid[1]) *reinterpret_cast<float2*>(a.geo_out + row[1] * 16 + 8 * nt + 2 * t) = make_float2(acc2[nt][2], acc2[nt][3]);
+        }
+      }
       if (t == 0) {  // column 0 = density before activation (fruit_field.py:185-193: trunc_exp in fp32, times the selector)
         if (valid[0]) a.density[row[0]] = sel[0] ? expf(acc2[0][0]) : 0.f;
         if (valid[1]) a.density[row[1]] = sel[1] ? expf(acc2[0][2]) : 0.f;
@@ -215,12 +222,12 @@ bool cnb_field_mixed_supported(const cnb_field* f) {
 int64_t cnb_field_mixed_ctx_floats(int64_t n, int training) { return training ? ctx_total(n) : 0; }
 float* cnb_field_mixed_dx0(float* ctx, int64_t n) { return ctx + ctx_dx0_off(n); }
 
-int cnb_field_mixed_fwd(const cnb_field* f, const cnb_samples* s, float* density, float* rgb, float* sem, float* positions_out, float* ctx,
+int cnb_field_mixed_fwd(const cnb_field* f, const cnb_samples* s, float* density, float* geo, float* rgb, float* sem, float* positions_out, float* ctx,
                         int training, cudaStream_t stream) {
   MixArgs a;
   fill_args(f, s, a);
   const int64_t N = s->num_rays * s->samples_per_ray;
-  a.density = density; a.rgb = rgb; a.sem = sem; a.pos_out = positions_out; a.x0_out = nullptr;
+  a.density = density; a.rgb = rgb; a.sem = sem; a.pos_out = positions_out; a.x0_out = nullptr; a.geo_out = geo;
   if (training) {
     a.x0_out = reinterpret_cast<__half*>(ctx);
     a.pos_out = ctx + ctx_pos_off(N);

@@ -41,6 +41,7 @@ struct MixArgs {
   int app_mode;
   int in0;                      // 2L
   float* density; float* rgb; float* sem; float* pos_out;
+  float* geo_out;               // optional [N][16] fp32: base-MLP output [density before activation | geo15] (FruitField.get_density's embedding)
   __half* x0_out;               // optional [N][32] fp16 copy of the encoded features (kept for the backward)
 };
 
@@ -140,6 +141,7 @@ inline int fill_args(const cnb_field* f, const cnb_samples* s, MixArgs& a) {
   a.app_mode = f->appearance_mode;
   a.embedding = f->appearance_mode == CNB_APP_PER_CAMERA ? f->embedding : (f->appearance_mode == CNB_APP_MEAN ? f->mean_embedding : nullptr);
   a.in0 = f->base.dims[0];
+  a.geo_out = nullptr;
   return CNB_OK;
 }
 

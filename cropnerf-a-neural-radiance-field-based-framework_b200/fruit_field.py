@@ -119,9 +119,10 @@ class FruitField(nn.Module):
             "want_positions": True,
         }
 
-    def _run(self, ray_samples: RaySamples, inference: bool):
+    def _run(self, ray_samples: RaySamples, inference: bool, want_geo: bool = False):
         layout = ray_layout(ray_samples)
         cfg = self._cfg(inference)
+        cfg["want_geo"] = want_geo
         if cfg["appearance_mode"] == L.APP_PER_CAMERA and layout[4] is None:
             raise AttributeError("Camera indices are not provided.")
         density, rgb, sem, geo, pos = ops.fruit_field(cfg, layout, self.kernel_params())
@@ -139,10 +140,11 @@ class FruitField(nn.Module):
 
     # fruit_field.py:169-194
     def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, Tensor]:
-        if self.precision == "mixed":
-            raise RuntimeError("get_density/get_outputs split needs precision='fp32'; the mixed path exposes forward() only")
+        # mixed precision: the tensor-core kernel also writes the base MLP's fp32 output row [density before activation | geo15]; the
+        # embedding is returned for the caller to hand back to get_outputs (fruit_nerf.py:340,431,480,503; bayesrays/uncertainty.py:109)
+        # and carries no gradient of its own there (the heads' gradients flow through the fused operator)
         inference = self.test_mode in ("inference", "export")
-        out = self._run(ray_samples, inference)
+        out = self._run(ray_samples, inference, want_geo=True)
         embedding = out["geo"][..., 1:]
         self._cache = (ray_samples, embedding, out, inference)
         return out["density"], embedding

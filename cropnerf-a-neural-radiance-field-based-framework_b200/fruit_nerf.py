@@ -174,6 +174,21 @@ class CameraOptimizer(nn.Module):
             param_groups["camera_opt"] = params
 
 
+@dataclass
+class CameraOptimizerConfig:
+    """nerfstudio ``CameraOptimizerConfig`` as FruitModel uses it (``self.config.camera_optimizer.setup(num_cameras=, device=)``,
+    fruit_nerf.py:114-116)."""
+
+    mode: str = "off"
+    trans_l2_penalty: float = 1e-2
+    rot_l2_penalty: float = 1e-3
+
+    def setup(self, num_cameras: int, device=None, **kwargs) -> "CameraOptimizer":
+        opt = CameraOptimizer(num_cameras, self.mode, self.trans_l2_penalty, self.rot_l2_penalty)
+        opt.config = self
+        return opt
+
+
 class FruitModel(nn.Module):
     config: FruitNerfModelConfig
 

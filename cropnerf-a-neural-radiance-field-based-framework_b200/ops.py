@@ -264,7 +264,8 @@ class _FieldFn(torch.autograd.Function):
         density = torch.empty((N,), device=dev, dtype=torch.float32)
         rgb = torch.empty((N, 3), device=dev, dtype=torch.float32)
         sem = torch.empty((N,), device=dev, dtype=torch.float32)
-        want_geo = cfg["precision"] == L.PREC_FP32
+        # fp32: always (its gradient is accepted); mixed: only for the get_density / get_outputs split, as a non-differentiable output
+        want_geo = cfg["precision"] == L.PREC_FP32 or bool(cfg.get("want_geo", False))
         geo = torch.empty((N, 1 + cfg["geo_feat_dim"]), device=dev, dtype=torch.float32) if want_geo else None
         pos = torch.empty((N, 3), device=dev, dtype=torch.float32) if cfg.get("want_positions", True) else None
         L.check(
@@ -277,6 +278,8 @@ class _FieldFn(torch.autograd.Function):
         ctx.save_for_backward(*params)
         outs = [density, rgb, sem, geo if geo is not None else torch.empty(0, device=dev), pos if pos is not None else torch.empty(0, device=dev)]
         ctx.mark_non_differentiable(outs[4])
+        if cfg["precision"] != L.PREC_FP32:
+            ctx.mark_non_differentiable(outs[3])
         return tuple(outs)
 
     @staticmethod

@@ -49,6 +49,10 @@ class SpacedSampler(nn.Module):
         self.num_samples = num_samples
         self.train_stratified = train_stratified
         self.single_jitter = single_jitter
+        # kept for subclasses that override generate_ray_samples with their own torch code (the reference's
+        # components/ray_samplers.py:31-104 UniformSamplerWithNoise does); the kernels use spacing_kind
+        self.spacing_fn = spacing_fn if spacing_fn is not None else (lambda x: x)
+        self.spacing_fn_inv = spacing_fn_inv if spacing_fn_inv is not None else (lambda x: x)
         self.rand_fn = torch.rand
         self._lin = {}
 

@@ -64,11 +64,20 @@ class _Inert:
         return self
 
 
-def install_shims() -> None:
+def install_shims(backend: str = "oracle") -> None:
+    """``backend="oracle"``: nerfstudio's names are bound to the restated primitives (pins the oracle's wiring to the reference's code).
+    ``backend="product"``: the SAME names are bound to the cropnerf_b200 classes and ``fruit_nerf.fruit_field`` to the product's FruitField
+    -- the drop-in demonstration: the reference's unmodified ``fruit_nerf.py`` builds and drives the B200 modules
+    (``tests/ref_dropin.py``; one backend per process)."""
     global _installed
     if _installed:
+        if _installed != backend:
+            raise RuntimeError(f"shims already installed for backend {_installed!r}; run the other backend in a fresh process")
         return
-    _installed = True
+    _installed = backend
+    if backend == "product":
+        _install_product_shims()
+        return
 
     # ---- hot-path primitives = the oracle's restatement, with nerfstudio's constructor signatures ------------------
     class HashEncoding(ns.HashEncoding):
@@ -293,6 +302,135 @@ def install_shims() -> None:
         sys.path.insert(0, REFERENCE_ROOT)
 
 
+def _install_product_shims() -> None:
+    """nerfstudio's module names -> cropnerf_b200 classes (what a nerfstudio install would provide is replaced class for class by the
+    product; INTEGRATION.md lists the same table).  Off-path names stay inert stubs."""
+    from cropnerf_b200 import density_fields as p_df
+    from cropnerf_b200 import field_components as p_fc
+    from cropnerf_b200 import fruit_field as p_ff
+    from cropnerf_b200 import fruit_nerf as p_fn
+    from cropnerf_b200 import ray_samplers as p_rs
+    from cropnerf_b200 import rays as p_rays
+    from cropnerf_b200 import renderers as p_rd
+
+    class SceneBox:
+        def __init__(self, aabb):
+            self.aabb = aabb
+
+    @dataclass
+    class Semantics:
+        filenames: list
+        classes: list
+        colors: torch.Tensor
+        mask_classes: list = field(default_factory=list)
+
+    class Model(nn.Module):  # nerfstudio/models/base_model.py Model.__init__
+        def __init__(self, config, scene_box, num_train_data, **kwargs):
+            super().__init__()
+            self.config, self.scene_box, self.render_aabb, self.num_train_data, self.kwargs = config, scene_box, None, num_train_data, kwargs
+            self.collider = None
+            self.populate_modules()
+            self.device_indicator_param = nn.Parameter(torch.empty(0))
+
+        @property
+        def device(self):
+            return self.device_indicator_param.device
+
+        def populate_modules(self):
+            return None
+
+    @dataclass
+    class NerfactoModelConfig:  # nerfacto.py defaults FruitModel reads (SURVEY.md section 8 preamble)
+        _target: type = None
+        near_plane: float = 0.05
+        far_plane: float = 1000.0
+        background_color: str = "last_sample"
+        hidden_dim: int = 64
+        hidden_dim_color: int = 64
+        hidden_dim_transient: int = 64
+        num_levels: int = 16
+        base_res: int = 16
+        max_res: int = 2048
+        log2_hashmap_size: int = 19
+        features_per_level: int = 2
+        num_proposal_samples_per_ray: tuple = (256, 96)
+        num_nerf_samples_per_ray: int = 48
+        proposal_update_every: int = 5
+        proposal_warmup: int = 5000
+        num_proposal_iterations: int = 2
+        use_same_proposal_network: bool = False
+        proposal_net_args_list: list = field(default_factory=lambda: [
+            {"hidden_dim": 16, "log2_hashmap_size": 17, "num_levels": 5, "max_res": 128, "use_linear": False},
+            {"hidden_dim": 16, "log2_hashmap_size": 17, "num_levels": 5, "max_res": 256, "use_linear": False},
+        ])
+        proposal_initial_sampler: str = "piecewise"
+        interlevel_loss_mult: float = 1.0
+        distortion_loss_mult: float = 0.002
+        use_proposal_weight_anneal: bool = True
+        use_average_appearance_embedding: bool = True
+        proposal_weights_anneal_slope: float = 10.0
+        proposal_weights_anneal_max_num_iters: int = 1000
+        use_single_jitter: bool = True
+        predict_normals: bool = False
+        disable_scene_contraction: bool = False
+        use_gradient_scaling: bool = False
+        implementation: str = "torch"
+        appearance_embed_dim: int = 32
+        camera_optimizer: object = field(default_factory=p_fn.CameraOptimizerConfig)
+        eval_num_rays_per_chunk: int = 1 << 15
+
+    _module("nerfstudio")
+    _module("nerfstudio.cameras.rays", RaySamples=p_rays.RaySamples, Frustums=p_rays.Frustums, RayBundle=p_rays.RayBundle)
+    _module("nerfstudio.cameras.cameras", Cameras=_Inert)
+    _module("nerfstudio.cameras.camera_optimizers", CameraOptimizer=p_fn.CameraOptimizer, CameraOptimizerConfig=p_fn.CameraOptimizerConfig)
+    _module("nerfstudio.data.scene_box", SceneBox=SceneBox, OrientedBox=_Inert)
+    _module("nerfstudio.data.dataparsers.base_dataparser", Semantics=Semantics)
+    _module("nerfstudio.engine.callbacks", TrainingCallback=_Callback, TrainingCallbackAttributes=_Inert, TrainingCallbackLocation=_Loc)
+    _module("nerfstudio.field_components.activations", trunc_exp=None)
+    _module("nerfstudio.field_components.base_field_component", FieldComponent=nn.Module)
+    _module("nerfstudio.field_components.encodings", Encoding=nn.Module, Identity=nn.Identity, HashEncoding=p_fc.HashEncoding, NeRFEncoding=_InertModule,
+            SHEncoding=p_fc.SHEncoding)
+    _module("nerfstudio.field_components.embedding", Embedding=p_fc.Embedding)
+    _module("nerfstudio.field_components.field_heads", FieldHeadNames=p_fc.FieldHeadNames, FieldHead=p_fc.FieldHead, DensityFieldHead=_Inert,
+            SemanticFieldHead=p_fc.SemanticFieldHead, RGBFieldHead=_Inert)
+    _module("nerfstudio.field_components.mlp", MLP=p_fc.MLP)
+    _module("nerfstudio.field_components.spatial_distortions", SpatialDistortion=nn.Module, SceneContraction=p_fc.SceneContraction)
+    _module("nerfstudio.fields.base_field", Field=nn.Module, get_normalized_directions=None)
+    _module("nerfstudio.fields.density_fields", HashMLPDensityField=p_df.HashMLPDensityField)
+    _module("nerfstudio.fields.semantic_nerf_field", SemanticNerfField=_Inert)
+    _module("nerfstudio.model_components.losses", MSELoss=nn.MSELoss, distortion_loss=p_rd.distortion_loss, interlevel_loss=p_rd.interlevel_loss,
+            scale_gradients_by_distance_squared=None)
+    _module("nerfstudio.model_components.renderers", AccumulationRenderer=p_rd.AccumulationRenderer, DepthRenderer=p_rd.DepthRenderer,
+            RGBRenderer=p_rd.RGBRenderer, SemanticRenderer=p_rd.SemanticRenderer, UncertaintyRenderer=_InertModule)
+    _module("nerfstudio.model_components.ray_samplers", ProposalNetworkSampler=p_rs.ProposalNetworkSampler, UniformSampler=p_rs.UniformSampler,
+            SpacedSampler=p_rs.SpacedSampler)
+    _module("nerfstudio.model_components.scene_colliders", NearFarCollider=p_fn.NearFarCollider)
+    _module("nerfstudio.models.base_model", Model=Model)
+    _module("nerfstudio.models.nerfacto", NerfactoModelConfig=NerfactoModelConfig)
+    _module("nerfstudio.utils.colormaps")
+    _module("nerfstudio.utils", colormaps=sys.modules["nerfstudio.utils.colormaps"])
+    if "torchmetrics" not in sys.modules:
+        try:
+            import torchmetrics  # noqa: F401
+        except ImportError:
+            _module("torchmetrics", PeakSignalNoiseRatio=_Psnr, JaccardIndex=_Inert)
+            _module("torchmetrics.functional", structural_similarity_index_measure=None)
+            _module("torchmetrics.image.lpip", LearnedPerceptualImagePatchSimilarity=_Inert)
+    try:
+        import nerfacc  # noqa: F401
+    except ImportError:
+        _module("nerfacc", OccGridEstimator=_Inert)
+    if "segmentation" not in sys.modules:
+        _module("segmentation.segmenter")
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    # the Field itself is replaced as a module (north_star: "the FruitField field ... replaced behind the same nerfstudio Field interface"):
+    # `from fruit_nerf.fruit_field import FruitField, SemanticNeRFField` in the reference's fruit_nerf.py resolves to the product's class
+    import fruit_nerf  # noqa: F401  (the reference's package, empty __init__)
+
+    _module("fruit_nerf.fruit_field", FruitField=p_ff.FruitField, SemanticNeRFField=_Inert)
+
+
 class _InertModule(nn.Module):
     def __init__(self, *a, **k):
         super().__init__()
@@ -322,21 +460,21 @@ class _Loc(enum.Enum):
 
 
 # -------------------------------------------------------------------------------------------------------------------
-def load_reference():
+def load_reference(backend: str = "oracle"):
     """-> (reference fruit_field module, reference fruit_nerf module), imported from /root/reference."""
     if not reference_available():
         raise RuntimeError("/root/reference is not present on this machine (GPU box): use the committed tests/golden/ref_*.npz")
-    install_shims()
+    install_shims(backend)
     import fruit_nerf.fruit_field as ref_field  # noqa: E402
     import fruit_nerf.fruit_nerf as ref_model  # noqa: E402
 
     return ref_field, ref_model
 
 
-def build_reference_model(cfg, num_images: int, state: Dict[str, torch.Tensor], test_mode: str = "val"):
+def build_reference_model(cfg, num_images: int, state: Dict[str, torch.Tensor], test_mode: str = "val", backend: str = "oracle"):
     """The reference's FruitModel configured like the oracle's ``cfg`` (oracle/fruit_torch.FruitNerfModelConfig) and
     loaded with the same state dict."""
-    _, ref_model = load_reference()
+    _, ref_model = load_reference(backend)
     sem_cls = sys.modules["nerfstudio.data.dataparsers.base_dataparser"].Semantics
     rc = ref_model.FruitNerfModelConfig()
     for k in cfg.__dataclass_fields__:

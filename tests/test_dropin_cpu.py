@@ -1,0 +1,44 @@
+"""Row (b) of SURVEY.md section 8, the drop-in boundary: the reference's own model file runs on the product classes.
+
+``tests/ref_dropin.py`` imports the UNMODIFIED ``/root/reference/crop_nerf/fruit_nerf/fruit_nerf.py`` with the nerfstudio names bound to
+cropnerf_b200 (and ``fruit_nerf.fruit_field`` to the product's FruitField) and lets the reference's ``populate_modules`` /
+``get_param_groups`` / ``get_training_callbacks`` / ``setup_inference`` / ``forward`` drive them.  Needs the reference tree (this
+container); skipped where it is absent.  The numerical side of the same wiring is covered on the GPU by the product FruitModel against the
+reference-executed fixtures (tests/golden/ref_*.npz, test_model_gpu.py) -- the GPU boxes have no /root/reference."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from oracle import ref_shim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
+def test_reference_model_file_drives_the_product_classes():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_dropin.py")], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    rep = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert rep["ok"] and rep["model_class"] == "fruit_nerf.fruit_nerf.FruitModel" and rep["model_file"].startswith("/root/reference/")
+    assert rep["parameters"] >= 25 and ("cpu_forward" in rep or "gpu_forward" in rep)
+
+
+def test_one_backend_per_process():
+    """the oracle-bound and the product-bound shims cannot be mixed in one interpreter (sys.modules is global)"""
+    code = ("import sys; sys.path.insert(0, %r)\nfrom oracle import ref_shim\nref_shim.install_shims('oracle')\n"
+            "try:\n    ref_shim.install_shims('product')\nexcept RuntimeError as e:\n    print('refused')\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert "refused" in out.stdout, out.stderr[-2000:]
+
+
+def test_method_plugin_module_is_import_guarded():
+    """`cropnerf_b200.method_config` (the fruit_nerf_config.py-shaped MethodSpecification) never raises on import: without nerfstudio it
+    says why it is unavailable."""
+    from cropnerf_b200 import method_config
+
+    assert (method_config.fruit_nerf_b200_method is None) == (method_config.UNAVAILABLE is not None)
+    if method_config.fruit_nerf_b200_method is None:
+        assert "nerfstudio" in method_config.UNAVAILABLE or "fruit_nerf" in method_config.UNAVAILABLE

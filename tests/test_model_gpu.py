@@ -247,6 +247,54 @@ def test_field_forward_mixed_precision(dev, training):
     assert torch.equal(model.field._sample_locations.cpu(), oracle.field._sample_locations.detach())
 
 
+@pytest.mark.parametrize("precision", ["fp32", "mixed"])
+@pytest.mark.parametrize("training", [False, True])
+def test_get_density_get_outputs_split(dev, precision, training):
+    """The Field interface the reference and BayesRays call as a PAIR (fruit_nerf.py:340,431,480,503; bayesrays/uncertainty.py:109):
+    ``density, embedding = field.get_density(rs); heads = field.get_outputs(rs, density_embedding=embedding)`` -- in BOTH precisions.
+    The pair must return exactly what ``forward`` returns (same fused operator), the embedding must be the base MLP's geo features
+    (oracle, 1e-4 fp32 / 2e-2 absolute for the fp16 tensor-core MLP), and gradients must flow through the pair as through forward."""
+    R, S, num_images = 96, 48, 20
+    cfg = cases.make_config(dict(log2_hashmap_size=14))
+    oracle, state = cases.build_oracle(cfg, num_images, seed=0, table_scale=0.5)
+    oracle.train(training)
+    model = product_model(cfg, state, num_images, dev, training, precision=precision)
+    rays, edges = _field_samples(R, S, 5)
+    rs_o = cases.oracle_bundle(rays).get_ray_samples(edges[:, :-1, None], edges[:, 1:, None])
+    e = edges.to(dev)
+    rs = product_bundle(rays, dev).get_ray_samples(e[:, :-1, None], e[:, 1:, None])
+    with torch.set_grad_enabled(training):
+        d_ref, emb_ref = oracle.field.get_density(rs_o)
+        density, emb = model.field.get_density(rs)
+        heads = model.field.get_outputs(rs, density_embedding=emb)
+        full = model.field(rs)
+    assert emb.shape == (R, S, 15) and density.shape == (R, S, 1)
+    assert torch.equal(density, full[FieldHeadNames.DENSITY]) and torch.equal(heads[FieldHeadNames.RGB], full[FieldHeadNames.RGB])
+    assert torch.equal(heads[FieldHeadNames.SEMANTICS], full[FieldHeadNames.SEMANTICS])
+    if precision == "fp32":
+        assert_close(emb, emb_ref, RTOL_FP32, "geo embedding", floor=1e-2)
+    else:
+        assert (emb.detach().cpu() - emb_ref.detach()).abs().max().item() <= 2e-2 * max(1.0, emb_ref.detach().abs().max().item())
+    assert model.field._density_before_activation.shape == (R, S, 1)   # side effect of fruit_field.py:181-187
+    with pytest.raises(RuntimeError, match="get_density"):
+        model.field.get_outputs(rs, density_embedding=emb.clone())   # not the pair's embedding: the field is one fused operator
+    if training:
+        g = torch.Generator().manual_seed(3)
+        gd, gr = torch.randn((R, S, 1), generator=g).to(dev) * 0.01, torch.randn((R, S, 3), generator=g).to(dev)
+        for p in model.field.parameters():
+            p.grad = None
+        ((density * gd).sum() + (heads[FieldHeadNames.RGB] * gr).sum()).backward()
+        g_pair = {n: p.grad.clone() for n, p in model.field.named_parameters() if p.grad is not None}
+        for p in model.field.parameters():
+            p.grad = None
+        ((full[FieldHeadNames.DENSITY] * gd).sum() + (full[FieldHeadNames.RGB] * gr).sum()).backward()
+        assert g_pair and all(float(v.abs().max()) > 0 for k, v in g_pair.items() if "semantic" not in k)
+        for n, p in model.field.named_parameters():
+            if p.grad is not None:
+                scale = float(p.grad.abs().max()) + 1e-20
+                assert float((g_pair[n] - p.grad).abs().max()) <= 1e-4 * scale, n   # same kernels; fp32 atomics order only
+
+
 def test_model_eval_mixed_precision(dev):
     spec = dict(num_rays=512, training=False, cfg=dict(), table_scale=0.5)
     cfg = cases.make_config(spec["cfg"], small=False)
