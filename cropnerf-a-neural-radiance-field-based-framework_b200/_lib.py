@@ -228,6 +228,11 @@ SIGNATURES = {
     "cnb_density_field_bwd_rays": (C.c_int, [C.POINTER(DensityField), C.POINTER(Samples), _P, _P, _P, _P, _P]),
     "cnb_field_bwd_rays": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), _P, _P, _P, _P, _P, _P, _P, _P]),
     "cnb_generate_rays": (C.c_int, [C.POINTER(Camera), _P, _I64, C.POINTER(_F), _P, _P, _P, _P, _P, _P, _P]),
+    "cnb_extract_points_scratch_ints": (_I64, [_I64]),
+    "cnb_extract_points": (C.c_int, [_P, _P, _P, _P, _P, _I64, C.POINTER(_F), C.c_int32, _F, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "cnb_generate_rays_boxes": (C.c_int, [C.POINTER(Camera), _P, C.c_int32, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cnb_projection_scatter": (C.c_int, [_P, _P, _P, _I64, _F, _P, _P, _P]),
+    "cnb_volume_face_rays": (C.c_int, [_F, _F, C.c_int32, _F, _F, C.c_int32, _F, C.POINTER(_F), _F, _I64, _I64, _P, _P, _P, _P, _P]),
     "cnb_sample_train_batch": (C.c_int, [C.POINTER(ImageSet), _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cnb_sample_spaced": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I64, _I32, _P, _P, _P]),
     "cnb_sample_spaced_collide": (C.c_int, [_P, _P, _F, _F, _P, _P, _I32, _I32, _I64, _I32, _P, _P, _P, _P, _P]),

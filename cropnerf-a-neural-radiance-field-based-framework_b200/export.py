@@ -55,32 +55,81 @@ class OrientedBox:
         return ((local > -S / 2) & (local < S / 2)).all(dim=-1)
 
 
+def _obb_array(crop_obb: Optional["OrientedBox"]):
+    import ctypes as C
+
+    if crop_obb is None:
+        return None
+    vals = [float(v) for v in crop_obb.R.detach().cpu().reshape(-1).tolist()] + [float(v) for v in crop_obb.T.detach().cpu().tolist()] \
+        + [float(v) for v in crop_obb.S.detach().cpu().tolist()]
+    return (C.c_float * 15)(*vals)
+
+
 def generate_point_cloud(model, next_rays: Callable[[int], RayBundle], num_points: int, crop_obb: Optional[OrientedBox] = None,
-                         only_semantics: bool = True, rank: int = 0, world_size: int = 1, max_batches: int = 1 << 30) -> Dict[str, Tensor]:
-    """Rank-local share of the export: collects ``num_points / world_size`` kept points (over-produces at most one batch
-    and trims).  ``next_rays(i)`` returns the i-th ray batch of this rank (ranks draw disjoint ray streams)."""
+                         only_semantics: bool = True, rank: int = 0, world_size: int = 1, max_batches: int = 1 << 30, lag: int = 2) -> Dict[str, Tensor]:
+    """Rank-local share of the export (export/exporter_utils_nerfacto.py:126-183): collects ``num_points / world_size`` kept points.
+    ``next_rays(i)`` returns the i-th ray batch of this rank (ranks draw disjoint ray streams).
+
+    Per batch: the fused render, then ONE C call (``cnb_extract_points``) does depth -> point -> semantic mask -> OBB test ->
+    order-preserving append into the output arrays, with the running count kept in device memory.  The host never waits for a batch it has
+    just launched: the count of batch ``i - lag`` (an asynchronous 4-byte copy into pinned memory) decides whether batch ``i`` is still
+    needed, so at most ``lag`` batches are rendered beyond the one that completes the cloud -- their points fall past ``num_points`` and are
+    dropped, so the result is exactly the first ``num_points / world_size`` kept points of the ray stream, in stream order, as in the
+    reference's loop.  ``rays_needed`` counts the rays up to the completing batch (what the reference renders), ``rays_rendered`` all of them."""
+    import ctypes as C
+
+    from . import _lib as L
+
+    dev = model.device
+    if dev.type != "cuda":
+        raise RuntimeError("cropnerf_b200.generate_point_cloud runs on CUDA devices only; there is no CPU fallback")
     lo, hi = shard_range(num_points, rank, world_size)
     want = hi - lo
-    points, rgbs, dirs = [], [], []
-    have = 0
-    rays_rendered = 0
+    points = torch.empty((want, 3), device=dev, dtype=torch.float32)
+    rgbs = torch.empty((want, 3), device=dev, dtype=torch.float32)
+    dirs = torch.empty((want, 3), device=dev, dtype=torch.float32)
+    counters = torch.zeros((2,), device=dev, dtype=torch.int32)
+    ring = lag + 2
+    host_counts = torch.zeros((ring,), dtype=torch.int32, pin_memory=True)
+    events = [torch.cuda.Event() for _ in range(ring)]
+    obb = _obb_array(crop_obb)
+    lib = L.lib()
+    scratch = None
+    cum: List[int] = []      # kept points after batch j (filled as the counts arrive)
+    sizes: List[int] = []
     i = 0
-    while have < want and i < max_batches:
+
+    def collect(j: int) -> int:
+        events[j % ring].synchronize()
+        cum.append(int(host_counts[j % ring]))
+        return cum[-1]
+
+    stream = torch.cuda.current_stream(dev)
+    while want > 0 and i < max_batches:
+        if i >= lag and collect(i - lag) >= want:
+            break
         with torch.no_grad():
             ray_bundle = next_rays(i)
             outputs = model(ray_bundle)
-        rays_rendered += len(ray_bundle)
-        point = ray_bundle.origins + ray_bundle.directions * outputs["depth"]
-        mask = outputs["semantics_colormap"][:, 0] > 0 if only_semantics else torch.ones_like(outputs["depth"][:, 0], dtype=torch.bool)
-        if crop_obb is not None:
-            mask = mask & crop_obb.within(point)
-        points.append(point[mask])
-        rgbs.append(outputs["rgb"][mask])
-        dirs.append(ray_bundle.directions[mask])
-        have += int(mask.sum().item())
+        n = len(ray_bundle)
+        sizes.append(n)
+        need = int(lib.cnb_extract_points_scratch_ints(n))
+        if scratch is None or scratch.numel() < need:
+            scratch = torch.empty((max(need, 1),), device=dev, dtype=torch.int32)
+        o, d = L.f32(ray_bundle.origins.reshape(n, 3)), L.f32(ray_bundle.directions.reshape(n, 3))
+        depth, sem, rgb = L.f32(outputs["depth"].reshape(n)), L.f32(outputs["semantics"].reshape(n)), L.f32(outputs["rgb"].reshape(n, 3))
+        L.check(lib.cnb_extract_points(o.data_ptr(), d.data_ptr(), depth.data_ptr(), sem.data_ptr(), rgb.data_ptr(), n, obb, int(only_semantics), 0.9,
+                                       scratch.data_ptr(), counters[i & 1 :].data_ptr(), counters[(i + 1) & 1 :].data_ptr(), want, points.data_ptr(),
+                                       rgbs.data_ptr(), dirs.data_ptr(), L.stream_ptr(dev)), "extract_points")
+        host_counts[i % ring : i % ring + 1].copy_(counters[(i + 1) & 1 : ((i + 1) & 1) + 1], non_blocking=True)
+        events[i % ring].record(stream)
         i += 1
-    cat = lambda xs, c: torch.cat(xs, dim=0)[:want] if xs else torch.empty((0, c))  # noqa: E731
-    return {"points": cat(points, 3), "rgbs": cat(rgbs, 3), "view_directions": cat(dirs, 3), "rays_rendered": rays_rendered}
+    for j in range(len(cum), i):
+        collect(j)
+    have = min(cum[-1], want) if cum else 0
+    needed = next((k + 1 for k, c in enumerate(cum) if c >= want), len(cum))
+    return {"points": points[:have], "rgbs": rgbs[:have], "view_directions": dirs[:have], "rays_rendered": int(sum(sizes)),
+            "rays_needed": int(sum(sizes[:needed])), "batches": i}
 
 
 def write_ply(path: str, points: Tensor, rgbs: Tensor) -> None:
@@ -225,17 +274,105 @@ def write_png(path: str, image: Tensor) -> None:
         raise IOError(f"could not write {path}")
 
 
-def project_clusters(model, cameras: Sequence[PinholeCamera], clusters: List[dict], out_dir: str, rank: int = 0, world_size: int = 1,
+def _camera_struct(cam: "PinholeCamera"):
+    from . import _lib as L
+
+    c = L.Camera()
+    m = torch.as_tensor(cam.c2w).detach().cpu().float().reshape(-1)[:12].tolist()
+    for i in range(12):
+        c.c2w[i] = m[i]
+    c.fx, c.fy, c.cx, c.cy, c.width, c.height = float(cam.fx), float(cam.fy), float(cam.cx), float(cam.cy), int(cam.width), int(cam.height)
+    return c
+
+
+def _render_on_device(model, bundle: RayBundle, keys: Sequence[str]) -> Dict[str, Tensor]:
+    """Chunked no-grad render of a flat DEVICE bundle; the requested outputs stay on the device (no pinned-host round trip)."""
+    n = len(bundle)
+    step = int(model.config.eval_num_rays_per_chunk)
+    parts: Dict[str, List[Tensor]] = {k: [] for k in keys}
+    with torch.no_grad():
+        for i in range(0, n, step):
+            out = model(bundle._map(lambda t: t[i : i + step]))
+            for k in keys:
+                parts[k].append(out[k])
+    return {k: (torch.cat(v, dim=0) if len(v) != 1 else v[0]) for k, v in parts.items()}
+
+
+def project_camera_boxes(model, cam: "PinholeCamera", boxes: Tensor, min_valid_rays: int = 10, occlusion_threshold: float = 0.5,
+                         capacity: Optional[int] = None) -> Dict[str, Tensor]:
+    """One (super-cluster, camera) pair of ``get_outputs_for_projections`` (fruit_nerf.py:276-315) with ALL ``k`` sub-cluster boxes in
+    one pass: ``cnb_generate_rays_boxes`` builds the compacted list of (pixel, box) hits, two fused renders over that list give the
+    un-occluded semantics (between each box's near / far) and the opacity in front of the box (0 .. near), and
+    ``cnb_projection_scatter`` writes the quantised pixels into the k ``wo_occ`` / ``visible`` images.  One host read-back (the hit
+    count) per pair; images are returned as device uint8 ``[k, H, W]`` (single channel: the reference's three channels are equal)."""
+    import ctypes as C
+
+    from . import _lib as L
+
+    dev = model.device
+    if dev.type != "cuda":
+        raise RuntimeError("cropnerf_b200.project_camera_boxes runs on CUDA devices only; there is no CPU fallback")
+    boxes_d = L.f32(torch.as_tensor(boxes, dtype=torch.float32).reshape(-1, 6).to(dev))
+    k = int(boxes_d.shape[0])
+    npix = int(cam.width) * int(cam.height)
+    cap = int(capacity) if capacity is not None else min(k * npix, max(npix, 1 << 21))
+    cs = _camera_struct(cam)
+    lib = L.lib()
+    while True:
+        o = torch.empty((cap, 3), device=dev)
+        d = torch.empty((cap, 3), device=dev)
+        area = torch.empty((cap, 1), device=dev)
+        nears = torch.empty((cap, 1), device=dev)
+        fars = torch.empty((cap, 1), device=dev)
+        tags = torch.empty((cap,), device=dev, dtype=torch.int32)
+        count = torch.zeros((1,), device=dev, dtype=torch.int32)
+        L.check(lib.cnb_generate_rays_boxes(C.byref(cs), boxes_d.data_ptr(), k, cap, o.data_ptr(), d.data_ptr(), area.data_ptr(), nears.data_ptr(),
+                                            fars.data_ptr(), tags.data_ptr(), count.data_ptr(), L.stream_ptr(dev)), "generate_rays_boxes")
+        n = int(count.item())  # the one host read-back of the pair
+        if n <= cap:
+            break
+        cap = n                # more overlapping boxes than the first guess: once more with room for every hit
+    wo_occ = torch.zeros((k, int(cam.height), int(cam.width)), device=dev, dtype=torch.uint8)
+    visible = torch.zeros_like(wo_occ)
+    rays = 0
+    if n > 0:
+        o, d, area, nears, fars, tags = o[:n], d[:n], area[:n], nears[:n], fars[:n], tags[:n]
+        box_of = torch.div(tags, npix, rounding_mode="floor")
+        per_box = torch.bincount(box_of, minlength=k)
+        if bool((per_box < min_valid_rays).any()):  # fruit_nerf.py:293: fewer than 10 hit rays -> that box's images stay black
+            keep = per_box[box_of.long()] >= min_valid_rays
+            o, d, area, nears, fars, tags = o[keep], d[keep], area[keep], nears[keep], fars[keep], tags[keep]
+            n = int(tags.shape[0])
+    if n > 0:
+        cam_idx = torch.zeros((n, 1), device=dev, dtype=torch.int32)
+        bundle = RayBundle(origins=o, directions=d, pixel_area=area, camera_indices=cam_idx, nears=nears, fars=fars)
+        sem = _render_on_device(model, bundle, ("semantics",))["semantics"]
+        front_bundle = RayBundle(origins=o, directions=d, pixel_area=area, camera_indices=cam_idx, nears=torch.zeros_like(nears), fars=nears)
+        front = _render_on_device(model, front_bundle, ("accumulation",))["accumulation"]
+        L.check(lib.cnb_projection_scatter(tags.contiguous().data_ptr(), L.f32(sem.reshape(n)).data_ptr(), L.f32(front.reshape(n)).data_ptr(), n,
+                                           float(occlusion_threshold), wo_occ.data_ptr(), visible.data_ptr(), L.stream_ptr(dev)), "projection_scatter")
+        rays = 2 * n
+    return {"wo_occ": wo_occ, "visible": visible, "rays": rays, "hits": n}
+
+
+def write_png_u8(path: str, image_u8: np.ndarray) -> None:
+    """uint8 [H,W] -> the 3-channel PNG ``save_image`` writes for a gray [3,H,W] tensor."""
+    import cv2
+
+    if not cv2.imwrite(path, np.ascontiguousarray(np.repeat(image_u8[..., None], 3, axis=-1))):
+        raise IOError(f"could not write {path}")
+
+
+def project_clusters(model, cameras: Sequence[PinholeCamera], clusters: List[dict], out_dir: Optional[str], rank: int = 0, world_size: int = 1,
                      segmentation_files: Optional[Sequence[str]] = None) -> Dict[str, int]:
     """``FruitModel.get_outputs_for_projections`` (fruit_nerf.py:254-318) with the (super-cluster, camera) pairs sharded over
-    the ranks (no communication): for every sub-cluster AABB of a super-cluster and every camera, rays are generated and clipped
-    on the device, the un-occluded semantic render and the opacity in front of the box are computed on the hit rays only, and
-    ``super_cluster_{k}/cam_{j}/wo_occ_cluster_{i}.png`` / ``visible_cluster_{i}.png`` are written -- the layout
-    segmentation/merger.py:219-333 reads.  Returns counters (pairs, images, rays rendered)."""
+    the ranks (no communication).  Every pair is one :func:`project_camera_boxes` call (all sub-cluster boxes of the super-cluster in one
+    ray-generation pass and two batched renders); the uint8 images come down in one copy per pair and are written as
+    ``super_cluster_{k}/cam_{j}/wo_occ_cluster_{i}.png`` / ``visible_cluster_{i}.png`` -- the layout segmentation/merger.py:219-333 reads.
+    ``out_dir=None`` renders without writing files (benchmarks).  Returns counters (pairs, images, rays rendered)."""
     import os
     import shutil
 
-    dev = model.device
     stats = {"pairs": 0, "images": 0, "rays": 0}
     pair = 0
     for i_sc, cluster in enumerate(clusters):
@@ -245,29 +382,18 @@ def project_clusters(model, cameras: Sequence[PinholeCamera], clusters: List[dic
             pair += 1
             if not mine:
                 continue
+            res = project_camera_boxes(model, cam, boxes)
+            stats["pairs"] += 1
+            stats["rays"] += int(res["rays"])
+            stats["images"] += 2 * int(boxes.shape[0])
+            if out_dir is None:
+                continue
             cam_dir = os.path.join(out_dir, f"super_cluster_{i_sc}", f"cam_{cam_idx}")
             os.makedirs(cam_dir, exist_ok=True)
-            stats["pairs"] += 1
+            wo, vis = res["wo_occ"].cpu().numpy(), res["visible"].cpu().numpy()
             for i in range(boxes.shape[0]):
-                rays, cnt = generate_rays(cam.c2w, cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height, dev, aabb=boxes[i], count_valid=True)
-                n = cam.width * cam.height
-                wo_occ = torch.zeros((n, 3), device=dev)
-                visible = wo_occ
-                if int(cnt.item()) >= 10:  # fruit_nerf.py:293: fewer than 10 hit rays -> black images
-                    valid = rays.nears[:, 0] < 1e10
-                    sub = rays[valid]
-                    stats["rays"] += 2 * int(sub.origins.shape[0])
-                    out = model.get_outputs_for_camera_jagged_ray_bundle(sub)
-                    wo_occ[valid] = out["semantics"].to(dev).expand(-1, 3)
-                    sub.fars = sub.nears
-                    sub.nears = torch.zeros_like(sub.nears)
-                    front = torch.zeros((n,), device=dev)
-                    front[valid] = model.get_density_for_camera_ray_bundle(sub).to(dev)
-                    visible = wo_occ.clone()
-                    visible[front >= 0.5] = 0.0
-                write_png(os.path.join(cam_dir, f"wo_occ_cluster_{i}.png"), wo_occ.view(cam.height, cam.width, 3))
-                write_png(os.path.join(cam_dir, f"visible_cluster_{i}.png"), visible.view(cam.height, cam.width, 3))
-                stats["images"] += 2
+                write_png_u8(os.path.join(cam_dir, f"wo_occ_cluster_{i}.png"), wo[i])
+                write_png_u8(os.path.join(cam_dir, f"visible_cluster_{i}.png"), vis[i])
             if segmentation_files is not None:
                 shutil.copy(segmentation_files[cam_idx], cam_dir)
     return stats
@@ -305,6 +431,42 @@ def volume_surface_rays(aabb, num_points_per_side: int) -> Tuple[Tensor, Tensor,
     return origins, direction, far
 
 
+def volume_face_grid(aabb, num_points_per_side: int) -> Dict[str, float]:
+    """The parameters of :func:`volume_surface_rays`'s grid (same quirks), for the device generator ``cnb_volume_face_rays``."""
+    c = aabb_corners(aabb)
+    c1, c2, c3, c4 = c[0], c[1], c[2], c[-1]
+    ext = (c.max(dim=0).values - c.min(dim=0).values).abs()
+    const_axis = int(torch.argmax(((c1 == c2) & (c2 == c3)).to(torch.int)))
+    ax_x = int(torch.argmax((c1 - c2).abs()))
+    ax_y = int(torch.argmax((c1 - c3).abs()))
+    plane = torch.tensor([0.0, 0.0, float(torch.sign(c4[const_axis]) * c1[const_axis].abs() + c4[const_axis].abs())])
+    direction = torch.nn.functional.normalize(plane[None])[0]
+    return {"x0": float(c1[ax_x]), "x1": float(c2[ax_x]), "nx": int(ext[0] / ext[const_axis] * num_points_per_side),
+            "y0": float(c1[ax_y]), "y1": float(c3[ax_y]), "ny": int(ext[1] / ext[const_axis] * num_points_per_side),
+            "z": float(c3[const_axis]), "direction": [float(v) for v in direction.tolist()], "far": float(torch.linalg.norm(plane))}
+
+
+def volume_face_rays_device(grid: Dict[str, float], first: int, n: int, device) -> RayBundle:
+    """Rays ``first .. first + n`` of the export face (``OrthographicRayGenerator``, components/ray_generators.py:46-66) written by one
+    kernel: origins on the grid (bit-equal to ``torch.linspace`` + ij-meshgrid), the common direction, nears = 0, fars = ray length."""
+    import ctypes as C
+
+    from . import _lib as L
+
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("cropnerf_b200.volume_face_rays_device runs on CUDA devices only; there is no CPU fallback")
+    o = torch.empty((n, 3), device=dev)
+    d = torch.empty((n, 3), device=dev)
+    nears = torch.empty((n, 1), device=dev)
+    fars = torch.empty((n, 1), device=dev)
+    direction = (C.c_float * 3)(*grid["direction"])
+    L.check(L.lib().cnb_volume_face_rays(grid["x0"], grid["x1"], grid["nx"], grid["y0"], grid["y1"], grid["ny"], grid["z"], direction, grid["far"],
+                                         int(first), int(n), o.data_ptr(), d.data_ptr(), nears.data_ptr(), fars.data_ptr(), L.stream_ptr(dev)),
+            "volume_face_rays")
+    return RayBundle(origins=o, directions=d, pixel_area=torch.zeros((n, 1), device=dev), camera_indices=None, nears=nears, fars=fars)
+
+
 def sample_volume(model, aabb, num_points_per_side: int, num_rays_per_batch: int = 512, rank: int = 0, world_size: int = 1,
                   semantic_threshold: float = 3.0, density_threshold: float = 70.0, colormap_threshold: float = 0.999) -> Dict[str, Dict[str, Tensor]]:
     """The render loop of ``sample_volume`` (export/exporter_utils.py:88-172) for a model in ``test_mode='export'`` after
@@ -317,16 +479,14 @@ def sample_volume(model, aabb, num_points_per_side: int, num_rays_per_batch: int
     if model.test_mode != "export":
         raise RuntimeError("sample_volume needs a model built with test_mode='export' and setup_inference() applied (scripts/exporter.py:88-91)")
     dev = model.device
-    origins, direction, far = volume_surface_rays(aabb, num_points_per_side)
-    lo, hi = shard_range(origins.shape[0], rank, world_size)
-    origins = origins[lo:hi].to(dev)
+    grid = volume_face_grid(aabb, num_points_per_side)
+    total = grid["nx"] * grid["ny"]
+    lo, hi = shard_range(total, rank, world_size)
     clouds = {k: {"points": [], "colors": []} for k in ("semantic_colormap", "semantic", "density")}
     n_samples = 0
-    for start in range(0, origins.shape[0], num_rays_per_batch):
-        o = origins[start : start + num_rays_per_batch].contiguous()
-        n = o.shape[0]
-        rb = RayBundle(origins=o, directions=direction.to(dev).repeat(n, 1), pixel_area=torch.zeros((n, 1), device=dev), camera_indices=None,
-                       nears=torch.zeros((n, 1), device=dev), fars=torch.full((n, 1), far, device=dev))
+    for start in range(lo, hi, num_rays_per_batch):
+        n = min(num_rays_per_batch, hi - start)
+        rb = volume_face_rays_device(grid, start, n, dev)   # OrthographicRayGenerator batch, generated on the device
         with torch.no_grad():
             out = model(rb)
         pts = out["point_location"].reshape(-1, 3)
@@ -346,7 +506,7 @@ def sample_volume(model, aabb, num_points_per_side: int, num_rays_per_batch: int
     for key, parts in clouds.items():
         result[key] = {"points": torch.cat(parts["points"]) if parts["points"] else torch.empty((0, 3)),
                        "colors": torch.cat(parts["colors"]) if parts["colors"] else torch.empty((0, 4))}
-    result["stats"] = {"rays": int(origins.shape[0]), "samples": n_samples}
+    result["stats"] = {"rays": int(hi - lo), "samples": n_samples}
     return result
 
 

@@ -264,6 +264,32 @@ typedef struct cnb_camera {
 int cnb_generate_rays(const cnb_camera* cam, const int32_t* pixel_yx, int64_t n, const float* aabb, float* origins, float* directions,
                       float* pixel_area, float* nears, float* fars, int32_t* valid_count, cnb_stream_t stream);
 
+/* ---- e2 / e3 / f1: the loop bodies of the two export workloads around the render call -------------------------------------- */
+/* `ns-export pointcloud` (export/exporter_utils_nerfacto.py:153-176): point = origin + direction * depth; keep = (only_semantics ?
+ * sigmoid(semantics) - threshold > 0 : true) && (obb ? OrientedBox.within(point) : true); kept points / colours / view directions are
+ * appended IN RAY ORDER at out_*[*count_in ...]; *count_out = *count_in + kept (two distinct device counters, so the export loop chains
+ * batches without a host round trip; entries past `capacity` are counted but not written).  obb: HOST pointer to 15 floats (R row-major
+ * [3,3], T [3], S [3]) or NULL.  block_counts: device scratch of cnb_extract_points_scratch_ints(n) int32.  All other pointers device. */
+int64_t cnb_extract_points_scratch_ints(int64_t n);
+int cnb_extract_points(const float* origins, const float* directions, const float* depth, const float* semantics, const float* rgb, int64_t n,
+                       const float* obb, int32_t only_semantics, float threshold, int32_t* block_counts, const int32_t* count_in,
+                       int32_t* count_out, int64_t capacity, float* out_points, float* out_rgbs, float* out_dirs, cnb_stream_t stream);
+/* fruit_nerf.py:281-288 for all `num_boxes` sub-cluster AABBs of a super-cluster in one pass over the camera's pixels: every (pixel, box)
+ * hit of nerfstudio's intersect_aabb is appended (any order) to a compacted ray list -- origins, directions [cap,3], pixel_area, nears,
+ * fars [cap], tags [cap] = box * width*height + pixel -- and counted in *count (device int32, ACCUMULATED; hits past `capacity` are counted,
+ * not written).  cam: HOST pointer; boxes: DEVICE [num_boxes,6] (min xyz, max xyz). */
+int cnb_generate_rays_boxes(const cnb_camera* cam, const float* boxes, int32_t num_boxes, int64_t capacity, float* origins, float* directions,
+                            float* pixel_area, float* nears, float* fars, int32_t* tags, int32_t* count, cnb_stream_t stream);
+/* fruit_nerf.py:296-315: wo_occ[tag] = q(semantics), visible[tag] = front_opacity >= occlusion_threshold ? 0 : q(semantics), with
+ * q(x) = uint8(clamp(x * 255 + 0.5, 0, 255)) (torchvision save_image); the two uint8 images [num_boxes, H*W] are cleared by the caller. */
+int cnb_projection_scatter(const int32_t* tags, const float* semantics, const float* front_opacity, int64_t n, float occlusion_threshold,
+                           uint8_t* wo_occ, uint8_t* visible, cnb_stream_t stream);
+/* Volumetric export ray source (data/fruit_datamanager.py:71-120 sample_surface_points + components/ray_generators.py:46-66
+ * OrthographicRayGenerator): rays first .. first+n of the nx x ny grid meshgrid(linspace(x0,x1,nx), linspace(y0,y1,ny), indexing="ij") on
+ * the plane z, common direction (HOST pointer, 3 floats), nears = 0, fars = far.  Bit-equal to torch.linspace on the host. */
+int cnb_volume_face_rays(float x0, float x1, int32_t nx, float y0, float y1, int32_t ny, float z, const float* direction, float far,
+                         int64_t first, int64_t n, float* origins, float* directions, float* nears, float* fars, cnb_stream_t stream);
+
 /* ---- f1, training side: FruitDataManager.next_train (data/fruit_datamanager.py:188-197) on the device ---------------------
  * = nerfstudio PixelSampler.sample (indices = (rand[R,3] * [N,H,W]).long(); value[c,y,x] of every per-pixel tensor) followed by
  * RayGenerator (image_coords[y,x] = pixel centre -> Cameras.generate_rays(camera_indices=c)).  All images of the split are resident
