@@ -28,15 +28,22 @@ constexpr int TILE = WARPS * 16;   // samples per CTA tile
 constexpr int XS = 40;             // row stride (halves) of the staged feature tile: conflict-free A-fragment reads
 constexpr size_t SMEM_FWD2 = SMEM_FWD + (size_t)TILE * XS * sizeof(__half);
 
-// gather + trilinear blend of one (sample, level) -> packed fp16 feature pair.  When floor(x) is even the two x-neighbours
-// of each corner pair are adjacent table rows (hash prime of x is 1): one 16-byte load instead of two 8-byte loads.
-__device__ __forceinline__ uint32_t gather_level(const float* __restrict__ table, uint32_t mask, uint32_t level_offset, float scale, float x, float y,
-                                                 float z) {
-  const CnbCell c = cnb_cell(x, y, z, scale);
+// gather + trilinear blend of one (sample, level) -> packed fp16 feature pair, in two halves so that the loads of TWO levels can be issued
+// before the first blend consumes one.  When floor(x) is even the two x-neighbours of each corner pair are adjacent table rows (hash prime
+// of x is 1): one 16-byte load instead of two 8-byte loads.
+struct LevelLoads { CnbCell c; float2 v[8]; };
+
+__device__ __forceinline__ void gather_issue(const float* __restrict__ table, uint32_t mask, uint32_t level_offset, float scale, float x, float y, float z,
+                                             LevelLoads& o) {
+  o.c = cnb_cell(x, y, z, scale);
   uint32_t h[8];
-  cnb_corner_rows(c, mask, level_offset, h);
-  float2 v[8];
-  cnb_gather8(table, c, h, v);
+  cnb_corner_rows(o.c, mask, level_offset, h);
+  cnb_gather8(table, o.c, h, o.v);
+}
+
+__device__ __forceinline__ uint32_t gather_blend(const LevelLoads& o) {
+  const CnbCell& c = o.c;
+  const float2 (&v)[8] = o.v;
   const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
   // same pairing as the reference blend (f03,f12,f56,f47 -> f0312,f4756), FMA-contracted
   float2 f03, f12, f56, f47;
@@ -84,12 +91,17 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
       }
     }
     __syncwarp();  // the previous tile's fragment reads of X0 are complete
-#pragma unroll 2
-    for (int it = 0; it < 8; ++it) {
-      const int l = 2 * it + lpar;
-      uint32_t f = 0u;
-      if (l < a.L) f = gather_level(a.table, a.mask, (uint32_t)l * a.T, a.scalings[l], px, py, pz);
-      X32[sidx * (XS / 2) + l] = f;
+    // two levels per lane in flight: 16 corner loads issued, THEN blended (the warp barrier keeps ptxas from sinking the second level's
+    // loads behind the first level's blend; tests/micro/gather_ilp_bench: two levels in flight is the optimum)
+#pragma unroll 1
+    for (int it = 0; it < 8; it += 2) {
+      const int l0 = 2 * it + lpar, l1 = l0 + 2;
+      LevelLoads g0, g1;
+      if (l0 < a.L) gather_issue(a.table, a.mask, (uint32_t)l0 * a.T, a.scalings[l0], px, py, pz, g0);
+      if (l1 < a.L) gather_issue(a.table, a.mask, (uint32_t)l1 * a.T, a.scalings[l1], px, py, pz, g1);
+      __syncwarp();
+      X32[sidx * (XS / 2) + l0] = l0 < a.L ? gather_blend(g0) : 0u;
+      X32[sidx * (XS / 2) + l1] = l1 < a.L ? gather_blend(g1) : 0u;
     }
     __syncwarp();
     int64_t row[2] = {base + g, base + g + 8};

@@ -104,10 +104,10 @@ int main() {
   const size_t tab_floats = (size_t)LEVELS * g.T * 2;
   std::vector<float> tab(tab_floats);
   for (auto& v : tab) v = frand() - 0.5f;
-  float *d_pos, *d_tab, *d_out[3];
+  float *d_pos, *d_tab, *d_out[5];
   char* flush;
   cudaMalloc(&d_pos, pos.size() * 4); cudaMalloc(&d_tab, tab_floats * 4); cudaMalloc(&flush, 256u << 20);
-  for (int k = 0; k < 3; ++k) cudaMalloc(&d_out[k], (size_t)nmax * LEVELS * 2 * 4);
+  for (int k = 0; k < 5; ++k) cudaMalloc(&d_out[k], (size_t)nmax * LEVELS * 2 * 4);
   cudaMemcpy(d_pos, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(d_tab, tab.data(), tab_floats * 4, cudaMemcpyHostToDevice);
   g.table = d_tab;
@@ -123,17 +123,20 @@ int main() {
       cudaEventRecord(e0);
       if (which == 0) k_gather<1, false><<<(int)blocks, 128>>>(g, d_pos, n, d_out[0]);
       else if (which == 1) k_gather<1, true><<<(int)blocks, 128>>>(g, d_pos, n, d_out[1]);
-      else k_gather<2, false><<<(int)blocks, 128>>>(g, d_pos, n, d_out[2]);
+      else if (which == 2) k_gather<2, false><<<(int)blocks, 128>>>(g, d_pos, n, d_out[2]);
+      else if (which == 3) k_gather<3, false><<<(int)blocks, 128>>>(g, d_pos, n, d_out[3]);
+      else k_gather<5, false><<<(int)blocks, 128>>>(g, d_pos, n, d_out[4]);
       cudaEventRecord(e1); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       if (rep > 0 && ms < best) best = ms;
     }
     return best;
   };
-  const char* names[3] = {"0 library order (8 loads)", "1 + 40 L1 prefetches up front", "2 two levels pinned (16 loads)"};
+  const char* names[5] = {"0 library order (8 loads)", "1 + 40 L1 prefetches up front", "2 two levels pinned (16 loads)", "3 three levels pinned (24 loads)",
+                          "4 five levels pinned (40 loads)"};
   for (int s = 0; s < 2; ++s) {
     printf("---- %lld samples (%lld rays x %d) ----\n", (long long)sizes[s], (long long)(sizes[s] / S), S);
-    for (int w = 0; w < 3; ++w) {
+    for (int w = 0; w < 5; ++w) {
       const float ms = run(w, sizes[s]);
       printf("%-32s %8.4f ms   %7.2f G corner fetches/s\n", names[w], ms, sizes[s] * 40.0 / (ms * 1e-3) / 1e9);
     }
@@ -143,7 +146,7 @@ int main() {
   std::vector<float> h0(bytes / 4), hk(bytes / 4);
   cudaMemcpy(h0.data(), d_out[0], bytes, cudaMemcpyDeviceToHost);
   int bad = 0;
-  for (int k = 1; k < 3; ++k) {
+  for (int k = 1; k < 5; ++k) {
     cudaMemcpy(hk.data(), d_out[k], bytes, cudaMemcpyDeviceToHost);
     if (memcmp(h0.data(), hk.data(), bytes) != 0) { printf("variant %d differs from variant 0\n", k); bad = 1; }
   }
