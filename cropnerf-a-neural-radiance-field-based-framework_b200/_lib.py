@@ -160,7 +160,8 @@ CHAIN_FIELD, CHAIN_PROPOSALS = 0, 1
 
 class OptGroup(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("n", C.c_int64), ("scalars", C.c_void_p),
-                ("chain", C.c_int32), ("_pad", C.c_int32), ("live", C.c_void_p)]
+                ("chain", C.c_int32), ("_pad", C.c_int32), ("live", C.c_void_p), ("peer_comm", C.c_void_p), ("peer_group", C.c_void_p),
+                ("peer_flags", C.c_int32), ("peer_channel", C.c_int32)]
 
 
 class TrainCfg(C.Structure):
@@ -257,6 +258,7 @@ SIGNATURES = {
     "cnb_adam_step_zero_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
     "cnb_p2p_owned_range": (None, [_I64, _I32, _I32, C.POINTER(_I64), C.POINTER(_I64)]),
     "cnb_p2p_barrier": (C.c_int, [C.POINTER(P2PComm), _P]),
+    "cnb_ddp_exchange_dev": (C.c_int, [C.POINTER(P2PComm), C.POINTER(P2PGroup), _P, _P, _P, _I64, _P, _I32, _I32, _P]),
     "cnb_ddp_optimizer_step": (C.c_int, [C.POINTER(P2PComm), C.POINTER(DdpGroupStep), _I32, _P]),
     "cnb_ddp_wait_deferred": (C.c_int, [_P]),
     "cnb_ddp_adam_update": (C.c_int, [C.POINTER(P2PComm), C.POINTER(P2PGroup), _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _I32, _P]),

@@ -79,7 +79,11 @@ struct AdamArgs {
 // two flat groups): occupancy, not per-thread unrolling, is what hides the 2-4 us peer latency; the specialised rank counts all use U=1.
 template <int MODE, int WORLD, int U>
 __global__ void __launch_bounds__(256, (U * (WORLD > 0 ? WORLD : CNB_MAX_PEERS) <= 2) ? 5 : ((U * (WORLD > 0 ? WORLD : CNB_MAX_PEERS) <= 4) ? 4 : 2)) k_ddp_adam(cnb_p2p_comm c, cnb_p2p_group g, float4* __restrict__ m, float4* __restrict__ v, int64_t lo4, int64_t hi4,
-                                                  AdamArgs a, int grads_zero) {
+                                                  AdamArgs a, int grads_zero, const float* __restrict__ dev_scalars) {
+  if (dev_scalars != nullptr) {  // graph-replayed step: this step's scalars live in device memory (cnb_opt_group.scalars layout)
+    a.lr = __ldg(dev_scalars); a.b1 = __ldg(dev_scalars + 1); a.b2 = __ldg(dev_scalars + 2); a.eps = __ldg(dev_scalars + 3);
+    a.bc1 = __ldg(dev_scalars + 4); a.bc2_sqrt = __ldg(dev_scalars + 5); a.inv_scale = __ldg(dev_scalars + 6);
+  }
   const float step_size = a.lr / a.bc1;
   const int world = WORLD > 0 ? WORLD : c.world;
   constexpr int NP = WORLD > 0 ? WORLD : CNB_MAX_PEERS;
@@ -150,12 +154,12 @@ __global__ void __launch_bounds__(256, (U * (WORLD > 0 ? WORLD : CNB_MAX_PEERS) 
 
 template <int MODE, int WORLD, int U>
 int launch_ddp_adam(const cnb_p2p_comm* comm, const cnb_p2p_group* group, float* exp_avg, float* exp_avg_sq, int64_t lo4, int64_t hi4, const AdamArgs& a,
-                    int gz, cudaStream_t stream) {
+                    int gz, cudaStream_t stream, const float* dev_scalars = nullptr) {
   int64_t blocks = (hi4 - lo4 + 256 * U - 1) / (256 * U);
   const int64_t cap = (int64_t)cnb_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   k_ddp_adam<MODE, WORLD, U><<<(int)blocks, 256, 0, stream>>>(*comm, *group, reinterpret_cast<float4*>(exp_avg), reinterpret_cast<float4*>(exp_avg_sq), lo4,
-                                                                hi4, a, gz);
+                                                                hi4, a, gz, dev_scalars);
   return cnb_check_launch("ddp_adam_update");
 }
 
@@ -188,8 +192,9 @@ extern "C" int cnb_p2p_barrier(const cnb_p2p_comm* comm, cnb_stream_t stream) {
   return cnb_check_launch("p2p_barrier");
 }
 
-extern "C" int cnb_ddp_adam_update(const cnb_p2p_comm* comm, const cnb_p2p_group* group, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                                   float beta1, float beta2, float eps, int32_t step, float inv_grad_scale, int32_t flags, cnb_stream_t stream) {
+static int ddp_adam_update_impl(const cnb_p2p_comm* comm, const cnb_p2p_group* group, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                float beta1, float beta2, float eps, int32_t step, float inv_grad_scale, int32_t flags, const float* dev_scalars,
+                                cnb_stream_t stream) {
   int rc = check_comm(comm, "ddp_adam_update");
   if (rc) return rc;
   CNB_REQUIRE(group && exp_avg && exp_avg_sq, "ddp_adam_update: null pointer");
@@ -211,16 +216,38 @@ extern "C" int cnb_ddp_adam_update(const cnb_p2p_comm* comm, const cnb_p2p_group
   const int64_t lo4 = lo / 4, hi4 = hi / 4;
   const int gz = ((flags & CNB_P2P_GRADS_ZERO) ? 1 : 0) | ((flags & 16) ? 2 : 0) | ((flags & 32) ? 4 : 0);  // 16 / 32: timing aids (local loads only / local stores only)
   if (multimem) {
-    if (flags & 0x100) return launch_ddp_adam<1, 0, 2>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);  // timing aids
-    if (flags & 0x200) return launch_ddp_adam<1, 0, 4>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
-    return launch_ddp_adam<1, 0, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
+    if (flags & 0x100) return launch_ddp_adam<1, 0, 2>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream, dev_scalars);  // timing aids
+    if (flags & 0x200) return launch_ddp_adam<1, 0, 4>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream, dev_scalars);
+    return launch_ddp_adam<1, 0, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream, dev_scalars);
   }
   switch (comm->world) {
-    case 2: return launch_ddp_adam<0, 2, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
-    case 4: return launch_ddp_adam<0, 4, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
-    case 8: return launch_ddp_adam<0, 8, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
-    default: return launch_ddp_adam<0, 0, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream);
+    case 2: return launch_ddp_adam<0, 2, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream, dev_scalars);
+    case 4: return launch_ddp_adam<0, 4, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream, dev_scalars);
+    case 8: return launch_ddp_adam<0, 8, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream, dev_scalars);
+    default: return launch_ddp_adam<0, 0, 1>(comm, group, exp_avg, exp_avg_sq, lo4, hi4, a, gz, stream, dev_scalars);
   }
+}
+
+extern "C" int cnb_ddp_adam_update(const cnb_p2p_comm* comm, const cnb_p2p_group* group, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                   float beta1, float beta2, float eps, int32_t step, float inv_grad_scale, int32_t flags, cnb_stream_t stream) {
+  return ddp_adam_update_impl(comm, group, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, inv_grad_scale, flags, nullptr, stream);
+}
+
+extern "C" int cnb_ddp_exchange_dev(const cnb_p2p_comm* comm, const cnb_p2p_group* group, float* exp_avg, float* exp_avg_sq, float* grad_own, int64_t n,
+                                    const float* scalars, int32_t flags, int32_t channel, cnb_stream_t stream) {
+  int rc = check_comm(comm, "ddp_exchange_dev");
+  if (rc) return rc;
+  CNB_REQUIRE(scalars != nullptr, "ddp_exchange_dev: null device scalars");
+  CNB_REQUIRE(channel >= 0 && channel < 4, "ddp_exchange_dev: channel %d outside 0..3", channel);
+  cnb_p2p_comm c = *comm;
+  c.channel = channel;
+  if ((rc = cnb_p2p_barrier(&c, stream))) return rc;                      // every rank's gradient of this group is final
+  if ((rc = ddp_adam_update_impl(comm, group, exp_avg, exp_avg_sq, n, 1.0f, 0.9f, 0.999f, 1e-8f, 1, 1.0f, flags, scalars, stream))) return rc;
+  if ((rc = cnb_p2p_barrier(&c, stream))) return rc;                      // every replica written, every rank's gradient consumed
+  if (!(flags & CNB_P2P_GRADS_ZERO) && grad_own != nullptr && n > 0 &&
+      cudaMemsetAsync(grad_own, 0, sizeof(float) * (size_t)n, stream) != cudaSuccess)
+    return cnb_check_launch("ddp_exchange_dev clear");
+  return CNB_OK;
 }
 
 
@@ -265,15 +292,18 @@ extern "C" int cnb_ddp_optimizer_step(const cnb_p2p_comm* comm, const cnb_ddp_gr
   int rc = check_comm(comm, "ddp_optimizer_step");
   if (rc) return rc;
   CNB_REQUIRE(n_groups >= 0 && (n_groups == 0 || groups != nullptr), "ddp_optimizer_step: null groups");
-  bool any_deferred = false;
+  bool any_deferred = false, any_direct = false;
   for (int i = 0; i < n_groups; ++i) any_deferred = any_deferred || groups[i].deferred != 0;
   cnb_p2p_comm c0 = *comm, c1 = *comm;
   c0.channel = 0; c1.channel = 1;
-  if ((rc = cnb_p2p_barrier(&c0, stream))) return rc;  // every rank has finished its backward: all gradients are final
   DdpSide* sd = any_deferred ? ddp_side() : nullptr;
   if (any_deferred && sd == nullptr) any_deferred = false;  // no side stream: everything on the caller's stream
+  for (int i = 0; i < n_groups; ++i) any_direct = any_direct || !(any_deferred && groups[i].deferred);
   if (any_deferred) {
+    // the deferred groups' exchange is self-contained on the side stream (its own barrier channel): it starts when the work enqueued on
+    // `stream` so far -- this step's backward -- has finished, and adds nothing to `stream`
     if (cudaEventRecord(sd->fork, stream) != cudaSuccess || cudaStreamWaitEvent(sd->side, sd->fork, 0) != cudaSuccess) return cnb_check_launch("ddp_optimizer_step fork");
+    if ((rc = cnb_p2p_barrier(&c1, sd->side))) return rc;  // every rank has finished its backward: the gradients are final
     for (int i = 0; i < n_groups; ++i)
       if (groups[i].deferred && (rc = ddp_update_one(comm, groups[i], sd->side))) return rc;
     if ((rc = cnb_p2p_barrier(&c1, sd->side))) return rc;  // every replica of those groups written, every rank's gradient consumed
@@ -282,6 +312,8 @@ extern "C" int cnb_ddp_optimizer_step(const cnb_p2p_comm* comm, const cnb_ddp_gr
     if (cudaEventRecord(sd->fence, sd->side) != cudaSuccess) return cnb_check_launch("ddp_optimizer_step fence");
     sd->pending = true;
   }
+  if (!any_direct) return CNB_OK;
+  if ((rc = cnb_p2p_barrier(&c0, stream))) return rc;
   for (int i = 0; i < n_groups; ++i)
     if (!(any_deferred && groups[i].deferred) && (rc = ddp_update_one(comm, groups[i], stream))) return rc;
   if ((rc = cnb_p2p_barrier(&c0, stream))) return rc;

@@ -278,7 +278,11 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
     for (int i = 0; i < cfg->num_opt_groups; ++i) {
       const cnb_opt_group& og = cfg->opt_groups[i];
       if (og.chain != chain) continue;
-      STAGE(chain == CNB_CHAIN_FIELD ? "adam_fields" : "adam_proposals", 1, cnb_adam_step_zero_dev_live(og.param, og.grad, og.exp_avg, og.exp_avg_sq, og.n, og.scalars, og.live, st));
+      if (og.peer_comm != nullptr)  // data parallel over peer memory: the group's whole exchange on this chain's branch
+        STAGE(chain == CNB_CHAIN_FIELD ? "exchange_fields" : "exchange_proposals", 3, cnb_ddp_exchange_dev(og.peer_comm, og.peer_group, og.exp_avg, og.exp_avg_sq,
+                                                                                                          og.grad, og.n, og.scalars, og.peer_flags, og.peer_channel, st));
+      else
+        STAGE(chain == CNB_CHAIN_FIELD ? "adam_fields" : "adam_proposals", 1, cnb_adam_step_zero_dev_live(og.param, og.grad, og.exp_avg, og.exp_avg_sq, og.n, og.scalars, og.live, st));
       if (rc) return rc;
     }
     return rc;

@@ -211,20 +211,32 @@ class _GraphedStep:
         # that completes its gradient, overlapping the other chain (cnb_opt_group); per-step scalars go through a small device buffer
         self.opt = None
         self.defer_fields = False
-        if trainer.world_size == 1 and trainer.grad_scaler is None and set(trainer.groups) <= {"fields", "proposal_networks"}:
+        peer = trainer.comm is not None
+        if (trainer.world_size == 1 or peer) and trainer.grad_scaler is None and set(trainer.groups) <= {"fields", "proposal_networks"}:
             from . import _lib as L_
 
             # ... except the big "fields" group when the trainer pipelines it: its Adam pass (HBM bound) then runs on a side stream next to the
-            # NEXT step's samplers + proposal forward (L1 bound, reads no field parameter) and only gates that step's field forward
-            self.defer_fields = trainer.defer_fields and "fields" in trainer.groups
+            # NEXT step's samplers + proposal forward (L1 bound, reads no field parameter) and only gates that step's field forward.
+            # Data parallel over peer memory: the same split -- the small proposal group's exchange (barrier, reduce-scatter + Adam +
+            # all-gather, barrier, clear) is a stage INSIDE the graph on the proposal chain's branch, next to the field backward; the fields
+            # group's exchange runs on the library's side stream behind the step (Trainer._p2p_optimizer_step) and gates the next field forward
+            self.defer_fields = (trainer.defer_fields or peer) and "fields" in trainer.groups
             names = [n for n in trainer.groups if not (self.defer_fields and n == "fields")]
             # ring of pinned rows: the host may run several steps ahead of the stream that executes the copies
             self.opt_host = torch.zeros((self.RING, len(names), 8), dtype=torch.float32, pin_memory=True)
             self.opt_np = self.opt_host.numpy()
             self.opt_dev = torch.zeros((len(names), 8), device=dev, dtype=torch.float32)
-            self.opt = [(trainer.groups[n].flat, trainer.groups[n].grad, trainer.groups[n].exp_avg, trainer.groups[n].exp_avg_sq, self.opt_dev[i],
-                         L_.CHAIN_FIELD if n == "fields" else L_.CHAIN_PROPOSALS, trainer.groups[n].live) for i, n in enumerate(names)]
+            self.opt = []
+            for i, n in enumerate(names):
+                g = trainer.groups[n]
+                pinfo = None
+                if peer:
+                    zero = n == "proposal_networks" and not update   # frozen proposal networks: momentum-only step, no peer reads
+                    mm = trainer.ddp == "p2p_multimem" and g.peer.has_multicast
+                    pinfo = (trainer.comm.struct, g.peer.struct, (L_.P2P_GRADS_ZERO if zero else 0) | (L_.P2P_MULTIMEM if mm else 0), 2 + (i & 1))
+                self.opt.append((g.flat, g.grad, g.exp_avg, g.exp_avg_sq, self.opt_dev[i], L_.CHAIN_FIELD if n == "fields" else L_.CHAIN_PROPOSALS, g.live, pinfo))
             self.opt_names = names
+            self.inv_world = 1.0 / trainer.world_size
         self.graph = torch.cuda.CUDAGraph()
         self.graph2 = None
         self.graphB = None
@@ -308,7 +320,7 @@ class _GraphedStep:
         for i, name in enumerate(self.opt_names):
             spec = trainer.optimizers[name]
             b1, b2 = spec.betas
-            self.opt_np[slot, i, :7] = (exponential_decay_lr(step, spec), b1, b2, spec.eps, 1.0 - b1**t, math.sqrt(1.0 - b2**t), 1.0)
+            self.opt_np[slot, i, :7] = (exponential_decay_lr(step, spec), b1, b2, spec.eps, 1.0 - b1**t, math.sqrt(1.0 - b2**t), self.inv_world)
         self.opt_dev.copy_(self.opt_host[slot], non_blocking=True)
 
     def run(self, trainer: "Trainer", ray_bundle, batch):
@@ -610,7 +622,10 @@ class Trainer:
                 losses, outputs = fp.train_step(rb_d, batch_d, update_proposals=updated, grad_scale=self._loss_scale())
             if in_graph_opt:
                 self._grads_clean = True  # the step updated the parameters and cleared the gradients itself
-                if gs.defer_fields:
+                if gs.defer_fields and self.comm is not None:
+                    self._proposals_updated = updated
+                    self._p2p_optimizer_step(step, ["fields"], pipelined=True)   # opt_step was advanced by set_optimizer_scalars
+                elif gs.defer_fields:
                     self._deferred_fields_adam(step)
             else:
                 self.all_reduce_gradients(proposals_updated=updated, wait=False)

@@ -264,11 +264,18 @@ class FusedPipeline:
             # optimiser stage inside the step (cnb_opt_group): (flat param, grad, exp_avg, exp_avg_sq, device scalars [8], chain)
             if len(opt_groups) > L.MAX_OPT_GROUPS:
                 raise ValueError(f"at most {L.MAX_OPT_GROUPS} optimiser groups")
-            for i, (p_, g_, m_, v_, sc_, chain, live_) in enumerate(opt_groups):
+            for i, entry in enumerate(opt_groups):
+                p_, g_, m_, v_, sc_, chain, live_ = entry[:7]
                 og = cfg.opt_groups[i]
                 og.live = live_.data_ptr() if live_ is not None else None
                 og.param, og.grad, og.exp_avg, og.exp_avg_sq = p_.data_ptr(), g_.data_ptr(), m_.data_ptr(), v_.data_ptr()
                 og.n, og.scalars, og.chain = p_.numel(), sc_.data_ptr(), int(chain)
+                if len(entry) > 7 and entry[7] is not None:
+                    # peer-memory data parallelism: this group's whole exchange runs inside the step (cnb_opt_group.peer_*); the structs are
+                    # read at enqueue time, the entry keeps them alive
+                    comm_struct, group_struct, flags, channel = entry[7]
+                    og.peer_comm, og.peer_group = C.addressof(comm_struct), C.addressof(group_struct)
+                    og.peer_flags, og.peer_channel = int(flags), int(channel)
             cfg.num_opt_groups = len(opt_groups)
         d_o = d_d = None
         if ray_grads:

@@ -370,6 +370,8 @@ int cnb_render_rays(const cnb_model* m, const cnb_rays* rays, const cnb_ray_outp
  * so a captured CUDA graph of the step picks up fresh values on every replay. */
 #define CNB_MAX_OPT_GROUPS 4
 enum { CNB_CHAIN_FIELD = 0, CNB_CHAIN_PROPOSALS = 1 };
+struct cnb_p2p_comm;   /* section (e) below */
+struct cnb_p2p_group;
 typedef struct cnb_opt_group {
   float* param; float* grad; float* exp_avg; float* exp_avg_sq;  /* flat, 16-byte aligned, n % 4 == 0 */
   int64_t n;
@@ -377,6 +379,15 @@ typedef struct cnb_opt_group {
   int32_t chain;             /* CNB_CHAIN_*: which backward chain completes this group's gradient */
   int32_t _pad;
   const uint32_t* live;      /* optional: one bit per float4 of the group (cnb_hashgrid_mark_reachable); 0 = unreachable table rows, skipped */
+  /* data-parallel training over peer memory (section (e)): when peer_comm != NULL the stage is the group's whole gradient exchange --
+   * barrier -> reduce-scatter + Adam + all-gather (cnb_ddp_adam_update with the scalars read from `scalars`) -> barrier -> clear own
+   * gradient -- enqueued on the chain's branch of the step, i.e. inside the captured graph and next to the other chain's backward.
+   * HOST pointers to the caller's structs (copied at enqueue time); exp_avg / exp_avg_sq are then the owned-slice moments, param / grad
+   * this rank's replicas (= peer_group->param[rank] / grad[rank]). */
+  const struct cnb_p2p_comm* peer_comm;
+  const struct cnb_p2p_group* peer_group;
+  int32_t peer_flags;        /* CNB_P2P_* */
+  int32_t peer_channel;      /* barrier channel 0..3 reserved for this stage */
 } cnb_opt_group;
 
 typedef struct cnb_train_cfg {
@@ -468,9 +479,14 @@ void cnb_p2p_owned_range(int64_t n, int32_t rank, int32_t world, int64_t* lo, in
 int cnb_p2p_barrier(const cnb_p2p_comm* comm, cnb_stream_t stream);
 int cnb_ddp_adam_update(const cnb_p2p_comm* comm, const cnb_p2p_group* group, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                         float beta1, float beta2, float eps, int32_t step, float inv_grad_scale, int32_t flags, cnb_stream_t stream);
+/* One group's complete exchange on `stream`, graph-capturable: barrier(channel) -> the update above with its seven scalars read from DEVICE
+ * memory (cnb_opt_group.scalars layout; [6] = 1 / (world * loss scale)) -> barrier(channel) -> grad_own cleared (unless CNB_P2P_GRADS_ZERO). */
+int cnb_ddp_exchange_dev(const cnb_p2p_comm* comm, const cnb_p2p_group* group, float* exp_avg, float* exp_avg_sq, float* grad_own, int64_t n,
+                         const float* scalars, int32_t flags, int32_t channel, cnb_stream_t stream);
 
-/* The whole data-parallel optimiser step in one host call.  Groups with deferred != 0 are exchanged on a library-owned side stream with their own
- * barrier channel and only fence later consumers (cnb_ddp_wait_deferred); the others take barrier -> update -> barrier -> gradient clear on `stream`. */
+/* The whole data-parallel optimiser step in one host call.  Groups with deferred != 0 are exchanged on a library-owned side stream that waits for
+ * the work enqueued on `stream` so far and then runs barrier (channel 1) -> update -> barrier -> gradient clear by itself: nothing is added to
+ * `stream`, later consumers are fenced with cnb_ddp_wait_deferred; the other groups take barrier (channel 0) -> update -> barrier -> clear on `stream`. */
 typedef struct cnb_ddp_group_step {
   const cnb_p2p_group* group;
   float* exp_avg; float* exp_avg_sq;
