@@ -155,7 +155,7 @@ class RayOutputs(C.Structure):
 
 
 MAX_OPT_GROUPS = 4
-CHAIN_FIELD, CHAIN_PROPOSALS = 0, 1
+CHAIN_FIELD, CHAIN_PROPOSALS, CHAIN_JOIN = 0, 1, 2
 
 
 class OptGroup(C.Structure):
@@ -180,6 +180,13 @@ class TrainCfg(C.Structure):
         ("phase", C.c_int32),
         ("num_opt_groups", C.c_int32),
         ("opt_groups", OptGroup * MAX_OPT_GROUPS),
+        ("pose_adjustment", C.c_void_p),
+        ("d_pose_adjustment", C.c_void_p),
+        ("camopt_scratch", C.c_void_p),
+        ("num_cameras", C.c_int32),
+        ("trans_l2_penalty", C.c_float),
+        ("rot_l2_penalty", C.c_float),
+        ("_pad_camopt", C.c_int32),
     ]
 
 
@@ -229,6 +236,8 @@ SIGNATURES = {
     "cnb_density_field_bwd_rays": (C.c_int, [C.POINTER(DensityField), C.POINTER(Samples), _P, _P, _P, _P, _P]),
     "cnb_field_bwd_rays": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), _P, _P, _P, _P, _P, _P, _P, _P]),
     "cnb_generate_rays": (C.c_int, [C.POINTER(Camera), _P, _I64, C.POINTER(_F), _P, _P, _P, _P, _P, _P, _P]),
+    "cnb_camera_opt_apply": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
+    "cnb_camera_opt_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _F, _F, _F, _P, _P, _P, _P]),
     "cnb_extract_points_scratch_ints": (_I64, [_I64]),
     "cnb_extract_points": (C.c_int, [_P, _P, _P, _P, _P, _I64, C.POINTER(_F), C.c_int32, _F, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "cnb_generate_rays_boxes": (C.c_int, [C.POINTER(Camera), _P, C.c_int32, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -176,7 +176,8 @@ class FlatGroup:
 
 def _stats_views(losses: Tensor) -> Dict[str, Tensor]:
     """names of the loss buffer cnb_train_step fills (psnr / total are finalised on the device: no per-step torch kernels here)"""
-    return {"rgb_loss": losses[0], "semantics_loss": losses[1], "interlevel_loss": losses[2], "distortion": losses[3], "psnr": losses[4], "loss": losses[5]}
+    return {"rgb_loss": losses[0], "semantics_loss": losses[1], "interlevel_loss": losses[2], "distortion": losses[3], "psnr": losses[4], "loss": losses[5],
+            "camera_opt_regularizer": losses[6]}
 
 
 class _GraphedStep:
@@ -212,7 +213,10 @@ class _GraphedStep:
         self.opt = None
         self.defer_fields = False
         peer = trainer.comm is not None
-        if (trainer.world_size == 1 or peer) and trainer.grad_scaler is None and set(trainer.groups) <= {"fields", "proposal_networks"}:
+        cam_opt = trainer.model.camera_optimizer
+        self.camera_opt = cam_opt if cam_opt.mode != "off" else None
+        allowed = {"fields", "proposal_networks"} | ({"camera_opt"} if (self.camera_opt is not None and trainer.world_size == 1) else set())
+        if (trainer.world_size == 1 or peer) and trainer.grad_scaler is None and set(trainer.groups) <= allowed:
             from . import _lib as L_
 
             # ... except the big "fields" group when the trainer pipelines it: its Adam pass (HBM bound) then runs on a side stream next to the
@@ -234,7 +238,8 @@ class _GraphedStep:
                     zero = n == "proposal_networks" and not update   # frozen proposal networks: momentum-only step, no peer reads
                     mm = trainer.ddp == "p2p_multimem" and g.peer.has_multicast
                     pinfo = (trainer.comm.struct, g.peer.struct, (L_.P2P_GRADS_ZERO if zero else 0) | (L_.P2P_MULTIMEM if mm else 0), 2 + (i & 1))
-                self.opt.append((g.flat, g.grad, g.exp_avg, g.exp_avg_sq, self.opt_dev[i], L_.CHAIN_FIELD if n == "fields" else L_.CHAIN_PROPOSALS, g.live, pinfo))
+                chain = {"fields": L_.CHAIN_FIELD, "proposal_networks": L_.CHAIN_PROPOSALS, "camera_opt": L_.CHAIN_JOIN}[n]
+                self.opt.append((g.flat, g.grad, g.exp_avg, g.exp_avg_sq, self.opt_dev[i], chain, g.live, pinfo))
             self.opt_names = names
             self.inv_world = 1.0 / trainer.world_size
         self.graph = torch.cuda.CUDAGraph()
@@ -263,7 +268,7 @@ class _GraphedStep:
                 if self.jitter_in_graph:
                     self.jitter.uniform_()
                 self.losses, self.outputs, state = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, phase=3,
-                                                                 grad_scale=trainer._loss_scale(), opt_groups=self.opt)
+                                                                 grad_scale=trainer._loss_scale(), opt_groups=self.opt, camera_opt=self.camera_opt)
             self.graphB = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graphB, pool=self.graph.pool()):
                 fp.train_step(self.bundle, self.batch, update_proposals=update, phase=4, state=state)
@@ -274,7 +279,7 @@ class _GraphedStep:
                 if self.jitter_in_graph:
                     self.jitter.uniform_()
                 self.losses, self.outputs = fp.train_step(self.bundle, self.batch, jitter=self.jitter, update_proposals=update, grad_scale=trainer._loss_scale(),
-                                                          opt_groups=self.opt)
+                                                          opt_groups=self.opt, camera_opt=self.camera_opt)
         self.stats = _stats_views(self.losses)
         for g in trainer.groups.values():  # whatever the capture-time warm-up left in the gradients
             g.zero_grad()
@@ -366,6 +371,7 @@ class Trainer:
 
         self.defer_fields = _os.environ.get("CNB_NO_DEFER", "0") != "1"  # one GPU: pipeline the field group's Adam into the next step (graphed steps)
         self.graph_during_anneal = False  # True: capture a graph per distinct anneal value as well (tests)
+        self._camopt_eager = _os.environ.get("CNB_CAMOPT_EAGER", "0") == "1"
         self.check_peers_every = 64       # peer-memory mode: read the barrier time-out flag every N steps (and before checkpoints)
         self.ddp = "nccl"
         if world_size > 1 and ddp != "nccl" and self.grad_scaler is None and next(model.parameters()).is_cuda:
@@ -571,9 +577,11 @@ class Trainer:
             updated = True if self.force_proposal_update else fp.proposals_updated()
             sampler = self.model.proposal_sampler
             cam_opt = self.model.camera_optimizer
-            if cam_opt.mode != "off":
-                # row a17: pose deltas applied with autograd; cnb_train_step returns dLoss/d(origins, directions) and
-                # pipeline.train_step back-propagates them into pose_adjustment.grad (the "camera_opt" flat group)
+            # row a17: the SO3xR3 camera optimizer runs INSIDE the C call (corrections applied before the samplers, dLoss/d rays chained into
+            # pose_adjustment.grad together with the regulariser; csrc/camera_opt.cu) -- graph-replayable like the rest of the step.
+            # CNB_CAMOPT_EAGER=1 keeps the round-1 route (torch pose algebra with autograd around the step) for A/B runs
+            fused_camopt = cam_opt.mode != "off" and not self._camopt_eager
+            if cam_opt.mode != "off" and not fused_camopt:
                 cam_opt.apply_to_raybundle(ray_bundle)
                 reg: Dict[str, Tensor] = {}
                 cam_opt.get_loss_dict(reg)
@@ -592,7 +600,7 @@ class Trainer:
             # proposal_weights_anneal_max_num_iters (1000) iterations: those steps run the same C call eagerly instead of
             # capturing (and throwing away) one graph per step; from then on anneal == 1 and one graph per (R, updated) is replayed
             anneal = float(sampler._anneal)
-            graphable = self.cuda_graph and ray_bundle.nears is None and cam_opt.mode == "off"
+            graphable = self.cuda_graph and ray_bundle.nears is None and (cam_opt.mode == "off" or (fused_camopt and self.world_size == 1 and self.grad_scaler is None))
             if graphable and anneal != 1.0 and (int(ray_bundle.origins.shape[0]), updated, anneal, self._loss_scale()) not in self._graphs:
                 graphable = self.graph_during_anneal
             if graphable:
@@ -605,7 +613,7 @@ class Trainer:
                     # clearing the gradient buffer this warm-up accumulates into, and writing the parameters it reads
                     self.wait_deferred_update()
                     rb_d, batch_d = on_device()
-                    fp.train_step(rb_d, batch_d, update_proposals=False, want_metrics=True)  # eager warm-up (func attributes, workspace)
+                    fp.train_step(rb_d, batch_d, update_proposals=False, want_metrics=True, camera_opt=cam_opt if fused_camopt else None)  # eager warm-up (func attributes, workspace)
                     for g in self.groups.values():
                         g.zero_grad()
                     gs = self._graphs[key] = _GraphedStep(self, rb_d, batch_d, updated)
@@ -619,7 +627,7 @@ class Trainer:
             else:
                 self.wait_deferred_update()
                 rb_d, batch_d = on_device()
-                losses, outputs = fp.train_step(rb_d, batch_d, update_proposals=updated, grad_scale=self._loss_scale())
+                losses, outputs = fp.train_step(rb_d, batch_d, update_proposals=updated, grad_scale=self._loss_scale(), camera_opt=cam_opt if fused_camopt else None)
             if in_graph_opt:
                 self._grads_clean = True  # the step updated the parameters and cleared the gradients itself
                 if gs.defer_fields and self.comm is not None:

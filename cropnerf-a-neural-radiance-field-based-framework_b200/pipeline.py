@@ -222,7 +222,7 @@ class FusedPipeline:
 
     def train_step(self, ray_bundle, batch: Dict[str, Tensor], grad_scale: float = 1.0, want_metrics: bool = True,
                    jitter: Optional[Tensor] = None, update_proposals: Optional[bool] = None, phase: int = 0,
-                   state: Optional[tuple] = None, opt_groups: Optional[list] = None):
+                   state: Optional[tuple] = None, opt_groups: Optional[list] = None, camera_opt=None):
         """forward + losses + backward of one batch; gradients are accumulated into ``param.grad``.
         Returns (losses [8] device tensor: rgb, semantics, interlevel, distortion, ...; per-ray outputs)."""
         m = self.model
@@ -239,7 +239,12 @@ class FusedPipeline:
             return losses, tensors
         # row a17: when the ray origins / directions carry a graph (camera optimizer), the kernels also return dLoss/d rays
         ray_grads = bool(ray_bundle.origins.requires_grad or ray_bundle.directions.requires_grad)
-        ms, keep = self._model_struct(dev, training=True, with_grads=True, ray_gradients=ray_grads)
+        # camera optimizer INSIDE the step (cnb_train_cfg.pose_adjustment): the rays stay as the data manager produced them, the C call
+        # applies the per-camera corrections, collects dLoss/d rays and chains them into pose_adjustment.grad (csrc/camera_opt.cu)
+        fused_camopt = camera_opt is not None and getattr(camera_opt, "mode", "off") != "off"
+        if fused_camopt and ray_grads:
+            raise RuntimeError("rays that already carry an autograd graph cannot be combined with the in-step camera optimizer")
+        ms, keep = self._model_struct(dev, training=True, with_grads=True, ray_gradients=ray_grads or fused_camopt)
         rays, keep2 = self._rays_struct(ray_bundle, training=True)
         R = rays.num_rays
         ws = self._workspace(ms, R, True, dev)
@@ -277,6 +282,21 @@ class FusedPipeline:
                     og.peer_comm, og.peer_group = C.addressof(comm_struct), C.addressof(group_struct)
                     og.peer_flags, og.peer_channel = int(flags), int(channel)
             cfg.num_opt_groups = len(opt_groups)
+        if fused_camopt:
+            pose = camera_opt.pose_adjustment
+            if pose.grad is None:
+                pose.grad = torch.zeros_like(pose)
+            ncam = int(pose.shape[0])
+            key = ("camopt", R, ncam, str(dev))
+            sc = self._ws.get(key)
+            if sc is None:
+                sc = torch.empty((12 * (R + ncam),), device=dev, dtype=torch.float32)
+                self._ws[key] = sc
+            if rays.camera_indices is None:
+                raise AttributeError("Camera indices are not provided.")
+            cfg.pose_adjustment, cfg.d_pose_adjustment, cfg.camopt_scratch = pose.data_ptr(), pose.grad.data_ptr(), sc.data_ptr()
+            cfg.num_cameras = ncam
+            cfg.trans_l2_penalty, cfg.rot_l2_penalty = float(camera_opt.trans_l2_penalty), float(camera_opt.rot_l2_penalty)
         d_o = d_d = None
         if ray_grads:
             if phase != 0:

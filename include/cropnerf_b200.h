@@ -369,7 +369,7 @@ int cnb_render_rays(const cnb_model* m, const cnb_rays* rays, const cnb_ray_outp
  * the proposal networks are still back-propagating on the forked stream, and vice versa.  The per-step scalars live in DEVICE memory
  * so a captured CUDA graph of the step picks up fresh values on every replay. */
 #define CNB_MAX_OPT_GROUPS 4
-enum { CNB_CHAIN_FIELD = 0, CNB_CHAIN_PROPOSALS = 1 };
+enum { CNB_CHAIN_FIELD = 0, CNB_CHAIN_PROPOSALS = 1, CNB_CHAIN_JOIN = 2 /* after all chains: the camera-optimizer group */ };
 struct cnb_p2p_comm;   /* section (e) below */
 struct cnb_p2p_group;
 typedef struct cnb_opt_group {
@@ -410,6 +410,16 @@ typedef struct cnb_train_cfg {
                                 data-parallel caller begin the next step while the field group's parameter exchange is still in flight */
   int32_t num_opt_groups;    /* 0 = the caller runs the optimiser itself (cnb_adam_step_zero / cnb_ddp_adam_update) */
   cnb_opt_group opt_groups[CNB_MAX_OPT_GROUPS];
+  /* camera optimizer inside the step (nerfstudio CameraOptimizer mode "SO3xR3", fruit_nerf.py:114-116,547,614): NULL = off.  The rays
+   * are corrected per camera before the samplers (cnb_camera_opt_apply), dLoss/d(corrected rays) is collected by the backward kernels
+   * (cnb_model.ray_gradients must be set; d_origins / d_directions above must be NULL) and chained into d_pose_adjustment together
+   * with the regulariser's gradient (cnb_camera_opt_bwd); losses_out[6] = regulariser, included in [5]. */
+  const float* pose_adjustment;  /* [num_cameras, 6] (translation | axis-angle) */
+  float* d_pose_adjustment;      /* [num_cameras, 6], ACCUMULATED */
+  float* camopt_scratch;         /* 12 * (R + num_cameras) floats */
+  int32_t num_cameras;
+  float trans_l2_penalty, rot_l2_penalty;
+  int32_t _pad_camopt;
 } cnb_train_cfg;
 
 /* forward + losses + backward of one batch; parameter gradients are ACCUMULATED into the d_* pointers of `m`;
@@ -419,7 +429,8 @@ typedef struct cnb_train_cfg {
  * only state the library keeps (calls from several host threads on one device share them: still correct, merely serialised there).
  * CNB_TRAIN_NO_OVERLAP=1 in the environment keeps everything on `stream`.
  * losses_out (device, 8 floats, overwritten): [0] rgb mse, [1] weighted semantic bce, [2] interlevel (x mult), [3] distortion,
- * [4] psnr = -10 log10([0]) (get_metrics_dict, fruit_nerf.py:639-645), [5] total = [0] + [1] + [2] (sum of get_loss_dict) */
+ * [4] psnr = -10 log10([0]) (get_metrics_dict, fruit_nerf.py:639-645), [5] total = [0] + [1] + [2] + [6] (sum of get_loss_dict),
+ * [6] camera-optimizer regulariser (0 unless cfg->pose_adjustment) */
 int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cnb_train_cfg* cfg, const cnb_ray_outputs* out, float* losses_out,
                    float* workspace, cnb_stream_t stream);
 
@@ -500,6 +511,17 @@ typedef struct cnb_ddp_group_step {
 } cnb_ddp_group_step;
 int cnb_ddp_optimizer_step(const cnb_p2p_comm* comm, const cnb_ddp_group_step* groups, int32_t n_groups, cnb_stream_t stream);
 int cnb_ddp_wait_deferred(cnb_stream_t stream);
+
+/* ---- a17: camera optimizer (nerfstudio cameras/camera_optimizers.py CameraOptimizer mode "SO3xR3", cameras/lie_groups.py exp_map_SO3xR3)
+ * apply: origins_out[r] = origins[r] + t(c), directions_out[r] = R(c) directions[r] with [R|t] = exp_map(pose_adjustment[c]), c = camera_indices[r].
+ * bwd: d_pose_adjustment[c] += dLoss/d pose from the ray gradients (d_origins / d_directions w.r.t. the CORRECTED rays; `directions` are the
+ * uncorrected ones) + grad_scale * d(regulariser)/d pose, regulariser = mean_c |t_c| * trans_l2_penalty + mean_c |w_c| * rot_l2_penalty, whose
+ * value is ADDED to *reg_loss (optional).  scratch: 12 * num_cameras floats. */
+int cnb_camera_opt_apply(const float* pose_adjustment, const int32_t* camera_indices, const float* origins, const float* directions, int64_t R,
+                         int32_t num_cameras, float* origins_out, float* directions_out, cnb_stream_t stream);
+int cnb_camera_opt_bwd(const float* pose_adjustment, const int32_t* camera_indices, const float* directions, const float* d_origins,
+                       const float* d_directions, int64_t R, int32_t num_cameras, float trans_l2_penalty, float rot_l2_penalty, float grad_scale,
+                       float* scratch, float* d_pose_adjustment, float* reg_loss, cnb_stream_t stream);
 
 /* ---- host -> device staging of one batch (rays, targets, optimiser scalars): n cudaMemcpyAsync on `stream` in one call.
  * dst[i] device, src[i] HOST (pinned for a truly asynchronous copy), bytes[i] sizes; the arrays themselves are host arrays. */

@@ -368,3 +368,38 @@ def test_generate_rays_and_aabb_clip(dev, with_pixels):
     assert_close(rb.fars[:, 0].cpu()[both], tmax[both], 1e-4, "fars", floor=1e-2)
     assert int(cnt.item()) == int(hit.sum().item())
     assert torch.allclose(rb.directions.norm(dim=-1).cpu(), torch.ones(rb.directions.shape[0]), atol=1e-5)
+
+
+def test_camera_opt_kernels_against_torch(dev):
+    """cnb_camera_opt_apply / cnb_camera_opt_bwd (csrc/camera_opt.cu) against the torch expression of nerfstudio's CameraOptimizer(SO3xR3):
+    exp_map_SO3xR3, apply_to_raybundle, the regulariser, and autograd for the pose gradient."""
+    from cropnerf_b200.fruit_nerf import exp_map_SO3xR3
+
+    g = torch.Generator().manual_seed(1)
+    C_, R = 9, 2000
+    pose = torch.randn((C_, 6), generator=g) * 0.05
+    pose[0] = 0.0
+    pose[1, 3:] = torch.tensor([1e-3, -2e-3, 5e-4])
+    cam = torch.randint(0, C_, (R,), generator=g)
+    o = torch.randn((R, 3), generator=g)
+    d = torch.nn.functional.normalize(torch.randn((R, 3), generator=g), dim=-1)
+    go, gd = torch.randn((R, 3), generator=g) * 1e-3, torch.randn((R, 3), generator=g) * 1e-3
+    pr = pose.clone().requires_grad_(True)
+    M = exp_map_SO3xR3(pr[cam])
+    o2 = o + M[:, :3, 3]
+    d2 = torch.bmm(M[:, :3, :3], d[..., None]).squeeze(-1)
+    reg = pr[:, :3].norm(dim=-1).mean() * 1e-2 + pr[:, 3:].norm(dim=-1).mean() * 1e-3
+    ((o2 * go).sum() + (d2 * gd).sum() + reg).backward()
+    pd, camd, od, dd = pose.to(dev), cam.to(dev, torch.int32), o.to(dev), d.to(dev)
+    o_out, d_out = torch.empty_like(od), torch.empty_like(dd)
+    L.check(L.lib().cnb_camera_opt_apply(pd.data_ptr(), camd.data_ptr(), od.data_ptr(), dd.data_ptr(), R, C_, o_out.data_ptr(), d_out.data_ptr(), L.stream_ptr(dev)), "apply")
+    assert (o_out.cpu() - o2.detach()).abs().max() < 1e-6 and (d_out.cpu() - d2.detach()).abs().max() < 1e-6
+    scratch = torch.empty((12 * C_,), device=dev)
+    dpose = torch.zeros((C_, 6), device=dev)
+    regl = torch.zeros((1,), device=dev)
+    god, gdd = go.to(dev), gd.to(dev)
+    L.check(L.lib().cnb_camera_opt_bwd(pd.data_ptr(), camd.data_ptr(), dd.data_ptr(), god.data_ptr(), gdd.data_ptr(), R, C_, 1e-2, 1e-3, 1.0,
+                                       scratch.data_ptr(), dpose.data_ptr(), regl.data_ptr(), L.stream_ptr(dev)), "bwd")
+    assert abs(float(regl) - float(reg.detach())) <= 1e-6 * float(reg.detach())
+    err = (dpose.cpu() - pr.grad).abs().max().item() / pr.grad.abs().max().item()
+    assert err < 1e-4, err
