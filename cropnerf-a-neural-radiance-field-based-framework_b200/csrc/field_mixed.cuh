@@ -56,19 +56,51 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], u
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// acc[NT][4] (+)= A[KT][4] x W^T, W = smem [8*NT rows][STRIDE] fp16
-template <int NT, int KT, int STRIDE>
-__device__ __forceinline__ void layer(const __half* __restrict__ W, const uint32_t (&A)[KT][4], float (&acc)[NT][4], int g, int t) {
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const __half* row = W + (nt * 8 + g) * STRIDE + 2 * t;
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+
+// acc[NT][4] (+)= A[KT][4] x W^T, W = smem [8*NT rows][STRIDE] 16-bit (fp16 or bf16; MMA = the matching mma.sync wrapper).
+// B fragments come from ldmatrix: one x4 fetches (k 0-7, k 8-15) of TWO n-tiles -- the thread (g, t) of matrix q receives W[row g][2t, 2t+1],
+// which is exactly the col-major B fragment -- instead of four 32-bit shared loads and their address arithmetic (the MLP kernels are
+// issue / latency bound: 15 % of their instructions were those LDS).  Rows are 16-byte aligned (STRIDE % 8 == 0) and STRIDE = 8 (mod 16)
+// halves spreads the eight 16-byte rows of a matrix over all 32 banks.
+template <int NT, int KT, int STRIDE, typename T, typename MMA>
+__device__ __forceinline__ void layer_ldsm(const T* __restrict__ W, const uint32_t (&A)[KT][4], float (&acc)[NT][4], MMA mma) {
+  static_assert(STRIDE % 8 == 0, "ldmatrix rows must be 16-byte aligned");
+  const int lane = threadIdx.x & 31;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(W);
+  if constexpr (NT == 1) {
+    const uint32_t a0 = base + 2u * ((lane & 7) * STRIDE + ((lane >> 3) & 1) * 8);
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt) {
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(row + kt * 16);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(row + kt * 16 + 8);
-      mma_f16(acc[nt], A[kt], b0, b1);
+      uint32_t b[2];
+      ldsm_x2(b, a0 + 2u * kt * 16);
+      mma(acc[0], A[kt], b[0], b[1]);
+    }
+  } else {
+    static_assert(NT % 2 == 0, "n-tiles are fetched in pairs");
+    const uint32_t a0 = base + 2u * (((lane >> 4) * 8 + (lane & 7)) * STRIDE + ((lane >> 3) & 1) * 8);
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt) {
+        uint32_t b[4];
+        ldsm_x4(b, a0 + 2u * (np * 16 * STRIDE + kt * 16));
+        mma(acc[2 * np], A[kt], b[0], b[1]);
+        mma(acc[2 * np + 1], A[kt], b[2], b[3]);
+      }
     }
   }
+}
+
+template <int NT, int KT, int STRIDE>
+__device__ __forceinline__ void layer(const __half* __restrict__ W, const uint32_t (&A)[KT][4], float (&acc)[NT][4], int g, int t) {
+  (void)g; (void)t;
+  layer_ldsm<NT, KT, STRIDE>(W, A, acc, [](float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) { mma_f16(c, a, b0, b1); });
 }
 
 template <int NT>

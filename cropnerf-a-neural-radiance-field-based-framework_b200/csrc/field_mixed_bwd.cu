@@ -82,16 +82,8 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
 // dX: acc[NT][4] += dY[KT][4] x WT^T, WT = smem bf16 [8*NT rows (= layer inputs)][STRIDE] indexed [in][out]
 template <int NT, int KT, int STRIDE>
 __device__ __forceinline__ void layer_bf(const __nv_bfloat16* __restrict__ W, const uint32_t (&A)[KT][4], float (&acc)[NT][4], int g, int t) {
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const __nv_bfloat16* row = W + (nt * 8 + g) * STRIDE + 2 * t;
-#pragma unroll
-    for (int kt = 0; kt < KT; ++kt) {
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(row + kt * 16);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(row + kt * 16 + 8);
-      mma_bf16(acc[nt], A[kt], b0, b1);
-    }
-  }
+  (void)g; (void)t;
+  layer_ldsm<NT, KT, STRIDE>(W, A, acc, [](float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) { mma_bf16(c, a, b0, b1); });
 }
 
 template <int NT>
