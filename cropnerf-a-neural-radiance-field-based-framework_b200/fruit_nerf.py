@@ -454,12 +454,13 @@ class FruitModel(nn.Module):
                 if not isinstance(output, torch.Tensor):
                     continue
                 if name not in host:
-                    key = (name, n, tuple(output.shape[1:]), output.dtype)
+                    # one grow-only pinned buffer per output (not one per distinct ray count: jagged bundles differ call to call)
+                    key = (name, tuple(output.shape[1:]), output.dtype)
                     buf = self._pinned.get(key)
-                    if buf is None:
+                    if buf is None or buf.shape[0] < n:
                         buf = torch.empty((n, *output.shape[1:]), dtype=output.dtype, pin_memory=True)
                         self._pinned[key] = buf
-                    host[name] = buf
+                    host[name] = buf[:n]
                 host[name][i : i + output.shape[0]].copy_(output, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return host

@@ -161,7 +161,11 @@ class FusedPipeline:
 
     def _workspace(self, ms, R: int, training: bool, dev) -> Tensor:
         n = int(L.lib().cnb_render_workspace_floats(C.byref(ms), R, int(training)))
-        key = (R, training, str(dev))
+        # training workspaces are keyed by the exact ray count: captured CUDA graphs hold their addresses, and a trainer sees one or two
+        # batch sizes.  Eval / export loops see a different remainder chunk on every call (the hit count of a projection pair, the tail
+        # of an image): ONE grow-only buffer per device serves them all (the layout is computed from R inside the C call; it only needs
+        # enough room), instead of one cached allocation per distinct ray count
+        key = (R, True, str(dev)) if training else (0, False, str(dev))
         ws = self._ws.get(key)
         if ws is None or ws.numel() < n:
             ws = torch.empty((max(n, 1),), device=dev, dtype=torch.float32)
