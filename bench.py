@@ -285,6 +285,27 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
         replicas_identical = all(bool(torch.equal(a, allsums[0])) for a in allsums)
         assert replicas_identical, f"rank {rank}: parameter checksums differ across replicas: {[a.tolist() for a in allsums]}"
 
+    # ---- where the N > 1 step spends its extra time (rank 0's view, CUDA events around the two graphs of the pipelined step, a separate
+    # short pass): graph A = samplers + proposal forward; `wait` = the stream idling for the previous step's `fields` exchange (what the
+    # exchange could not hide behind graph A); graph B = field forward + whole backward + the in-graph proposal exchange -------------------
+    ddp_breakdown = None
+    if world > 1 and trainer.comm is not None and not args.no_graph:
+        trainer._probe = []
+        barrier()
+        for i in range(12):
+            train_step(step, *resident[step % nb]); step += 1
+        settle()
+        torch.cuda.synchronize()
+        evs = trainer._probe[2:]
+        trainer._probe = None
+        if evs:
+            a = sum(e[0].elapsed_time(e[1]) for e in evs) / len(evs)
+            w = sum(e[1].elapsed_time(e[2]) for e in evs) / len(evs)
+            b = sum(e[2].elapsed_time(e[3]) for e in evs) / len(evs)
+            ddp_breakdown = {"graph_a_ms": a, "wait_for_fields_exchange_ms": w, "graph_b_ms": b, "steps": len(evs),
+                             "note": "graph_a = samplers + proposal forward (overlaps the previous step's fields exchange); wait = stream idle until that exchange "
+                                     "has landed; graph_b = field forward + backward + in-graph proposal exchange; compare graph_a + graph_b with the N = 1 line's ms_per_step"}
+
     # ---- end to end from DEVICE-resident images (row f1: FruitDataManager.next_train as one kernel, datamanager.DeviceTrainBatches):
     # the pixel sampler + ray generator run on the GPU over uint8 images held in HBM, so no ray / target bytes cross PCIe at all;
     # the loss is still read back every step -----------------------------------------------------------------------------------
@@ -440,7 +461,7 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
         assert not trainer.comm.timed_out(), "a peer-memory barrier timed out during the benchmark"
     del trainer, model, l2_flush
     torch.cuda.empty_cache()
-    return {"ddp": ddp_mode, "replicas_identical": replicas_identical, "t_dev_batches": t_dev_batches, "t_b2b": t_b2b, "steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
+    return {"ddp": ddp_mode, "ddp_breakdown": ddp_breakdown, "replicas_identical": replicas_identical, "t_dev_batches": t_dev_batches, "t_b2b": t_b2b, "steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
             "stage": stage, "n_prof": n_prof, "nonupdate_ms": nonupdate_ms, "camopt_ms": camopt_ms, "adam_ms": adam_ms, "render_stage": render_stage, "loss": loss_host,
             "h2d_train": bytes_of({k: host[0][k] for k in ("origins", "directions", "camera_indices", "image", "fruit_mask")}), "h2d_render": bytes_of({k: rhost[k] for k in ("origins", "directions", "pixel_area", "camera_indices")}),
             "d2h_render": int(d2h_render)}
@@ -520,7 +541,7 @@ def run_product(args):
             "data": "synthetic",
             "config": workload_config(),
             "detail": {"precision": args.precision,
-                       "ms_per_step_l2_flushed_serialised": 1e3 * m["t_b2b"] / steps, "data_parallel": m["ddp"], "replicas_identical": m["replicas_identical"],
+                       "ms_per_step_l2_flushed_serialised": 1e3 * m["t_b2b"] / steps, "data_parallel": m["ddp"], "replicas_identical": m["replicas_identical"], "ddp_breakdown": m["ddp_breakdown"],
                        "note_overlap": "the big 'fields' group is updated on a side stream (one GPU: fused Adam; N>1: reduce-scatter + Adam + all-gather over NVLink) and only gates the "
                                        "NEXT step's field forward; ms_per_step_l2_flushed_serialised flushes L2 (192 MiB fill) before every step and waits for that update inside the step's timed region",
                        "includes": "fwd + losses + bwd (all three networks updated EVERY step) + gradient exchange (N>1) + Adam; "

@@ -332,13 +332,24 @@ class _GraphedStep:
         self._load(ray_bundle, batch)
         if not self.jitter_in_graph:
             trainer.fused.draw_jitter(self.static["origins"].shape[0], self.static["origins"].device, out=self.jitter)
+        probe = trainer._probe  # measurement aid (bench.py): CUDA events around the two graphs of a pipelined step
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if (probe is not None and self.graphB is not None) else None
+        if ev:
+            ev[0].record()
         self.graph.replay()
         if self.graph2 is not None:
             trainer.start_all_reduce("fields")
             self.graph2.replay()
         if self.graphB is not None:
+            if ev:
+                ev[1].record()
             trainer.wait_deferred_update()  # the previous step's field-group exchange must have landed before the field forward
+            if ev:
+                ev[2].record()
             self.graphB.replay()
+            if ev:
+                ev[3].record()
+                probe.append(ev)
         return self.losses, self.outputs
 
 
@@ -370,6 +381,7 @@ class Trainer:
         import os as _os
 
         self.defer_fields = _os.environ.get("CNB_NO_DEFER", "0") != "1"  # one GPU: pipeline the field group's Adam into the next step (graphed steps)
+        self._probe = None                # bench.py sets a list: per-step CUDA events of the pipelined step (graph A | wait | graph B)
         self.graph_during_anneal = False  # True: capture a graph per distinct anneal value as well (tests)
         self._camopt_eager = _os.environ.get("CNB_CAMOPT_EAGER", "0") == "1"
         self.check_peers_every = 64       # peer-memory mode: read the barrier time-out flag every N steps (and before checkpoints)
