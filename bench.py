@@ -234,8 +234,10 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
     barrier()
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     b0.record()
+    h0 = time.perf_counter()
     for i in range(steps):
         train_step(step, *resident[step % nb]); step += 1
+    host_enqueue_ms = 1e3 * (time.perf_counter() - h0) / steps   # host time to ENQUEUE one step (no sync inside): must stay below ms_per_step
     settle()
     b1.record()
     barrier()
@@ -285,11 +287,11 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
         replicas_identical = all(bool(torch.equal(a, allsums[0])) for a in allsums)
         assert replicas_identical, f"rank {rank}: parameter checksums differ across replicas: {[a.tolist() for a in allsums]}"
 
-    # ---- where the N > 1 step spends its extra time (rank 0's view, CUDA events around the two graphs of the pipelined step, a separate
+    # ---- where the step spends its time, and what N > 1 adds (rank 0's view, CUDA events around the two graphs of the pipelined step, a separate
     # short pass): graph A = samplers + proposal forward; `wait` = the stream idling for the previous step's `fields` exchange (what the
     # exchange could not hide behind graph A); graph B = field forward + whole backward + the in-graph proposal exchange -------------------
     ddp_breakdown = None
-    if world > 1 and trainer.comm is not None and not args.no_graph:
+    if not args.no_graph and full:
         trainer._probe = []
         barrier()
         for i in range(12):
@@ -461,7 +463,7 @@ def measure(args, precision, dev, world, rank, local_rank, full=True):
         assert not trainer.comm.timed_out(), "a peer-memory barrier timed out during the benchmark"
     del trainer, model, l2_flush
     torch.cuda.empty_cache()
-    return {"ddp": ddp_mode, "ddp_breakdown": ddp_breakdown, "replicas_identical": replicas_identical, "t_dev_batches": t_dev_batches, "t_b2b": t_b2b, "steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
+    return {"ddp": ddp_mode, "host_enqueue_ms": host_enqueue_ms, "ddp_breakdown": ddp_breakdown, "replicas_identical": replicas_identical, "t_dev_batches": t_dev_batches, "t_b2b": t_b2b, "steps": steps, "t": t, "t_e2e": t_e2e, "t_render": t_render, "t_render_e2e": t_render_e2e, "n_r": n_r, "Rr": Rr, "clk": clk,
             "stage": stage, "n_prof": n_prof, "nonupdate_ms": nonupdate_ms, "camopt_ms": camopt_ms, "adam_ms": adam_ms, "render_stage": render_stage, "loss": loss_host,
             "h2d_train": bytes_of({k: host[0][k] for k in ("origins", "directions", "camera_indices", "image", "fruit_mask")}), "h2d_render": bytes_of({k: rhost[k] for k in ("origins", "directions", "pixel_area", "camera_indices")}),
             "d2h_render": int(d2h_render)}
@@ -542,6 +544,7 @@ def run_product(args):
             "config": workload_config(),
             "detail": {"precision": args.precision,
                        "ms_per_step_l2_flushed_serialised": 1e3 * m["t_b2b"] / steps, "data_parallel": m["ddp"], "replicas_identical": m["replicas_identical"], "ddp_breakdown": m["ddp_breakdown"],
+                       "host_enqueue_ms_per_step": m["host_enqueue_ms"],
                        "note_overlap": "the big 'fields' group is updated on a side stream (one GPU: fused Adam; N>1: reduce-scatter + Adam + all-gather over NVLink) and only gates the "
                                        "NEXT step's field forward; ms_per_step_l2_flushed_serialised flushes L2 (192 MiB fill) before every step and waits for that update inside the step's timed region",
                        "includes": "fwd + losses + bwd (all three networks updated EVERY step) + gradient exchange (N>1) + Adam; "

@@ -264,6 +264,7 @@ SIGNATURES = {
     "cnb_adam_step_zero_live": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P, _P]),
     "cnb_adam_step_zero_dev_live": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P]),
     "cnb_upload": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _I32, _P]),
+    "cnb_stage_inputs": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _I32, _P, C.POINTER(_F), _I32, _P]),
     "cnb_adam_step_zero_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
     "cnb_p2p_owned_range": (None, [_I64, _I32, _I32, C.POINTER(_I64), C.POINTER(_I64)]),
     "cnb_p2p_barrier": (C.c_int, [C.POINTER(P2PComm), _P]),

@@ -197,6 +197,8 @@ class _GraphedStep:
             "image": torch.empty((R, 3), device=dev), "fruit_mask": torch.empty((R, 1), device=dev),
         }
         self.cam64 = torch.zeros((R, 1), device=dev, dtype=torch.int64)
+        self._pending_scalars = None
+        self.opt_dev = None
         self.jitter = fp.draw_jitter(R, dev).clone()
         # torch.rand inside a capture is graph-safe (the generator's philox offset advances per replay): the default jitter is drawn by the
         # graph itself; custom rand_fn feeds (tests) are drawn eagerly into the static buffer before each replay
@@ -289,29 +291,53 @@ class _GraphedStep:
         R = st["origins"].shape[0]
         cam = ray_bundle.camera_indices
         srcs = (ray_bundle.origins, ray_bundle.directions, cam, batch["image"], batch["fruit_mask"])
-        if all((not t.is_cuda) and t.is_pinned() and t.is_contiguous() for t in srcs) and cam.dtype == torch.int64 and batch["image"].shape[-1] == 3 \
-                and all(t.dtype == torch.float32 for t in (srcs[0], srcs[1], srcs[3], srcs[4])):
+        dsts = (st["origins"], st["directions"], self.cam64, st["image"], st["fruit_mask"])
+        plain = cam.dtype == torch.int64 and batch["image"].shape[-1] == 3 and all(t.is_contiguous() for t in srcs) \
+            and all(t.dtype == torch.float32 for t in (srcs[0], srcs[1], srcs[3], srcs[4])) \
+            and all(d.numel() * d.element_size() == t.numel() * t.element_size() for d, t in zip(dsts, srcs))
+        scal = self._pending_scalars
+        self._pending_scalars = None
+        if plain and all((not t.is_cuda) and t.is_pinned() for t in srcs):
             # pinned host batch: raw async copies issued by ONE C call (cnb_upload), no framework dispatch per tensor; the int64 camera
             # indices go up as they are and are narrowed to the kernels' int32 inside the graph
             import ctypes as C
 
             from . import _lib as L
 
-            dsts = (st["origins"], st["directions"], self.cam64, st["image"], st["fruit_mask"])
             n = len(srcs)
-            for d, t in zip(dsts, srcs):
-                if d.numel() * d.element_size() != t.numel() * t.element_size():
-                    raise ValueError("batch tensor sizes do not match the captured step")
             d_arr = (C.c_void_p * n)(*[d.data_ptr() for d in dsts])
             s_arr = (C.c_void_p * n)(*[t.data_ptr() for t in srcs])
             b_arr = (C.c_int64 * n)(*[t.numel() * t.element_size() for t in srcs])
             L.check(L.lib().cnb_upload(d_arr, s_arr, b_arr, n, L.stream_ptr(st["origins"].device)), "upload")
+            if scal is not None:
+                self.opt_dev.copy_(scal, non_blocking=True)
+            return
+        if plain and all(t.is_cuda and t.data_ptr() % 16 == 0 for t in srcs):
+            # device-resident batch: the five copies AND the optimiser's scalars in one kernel launch (cnb_stage_inputs)
+            import ctypes as C
+
+            from . import _lib as L
+
+            n = len(srcs)
+            d_arr = (C.c_void_p * n)(*[d.data_ptr() for d in dsts])
+            s_arr = (C.c_void_p * n)(*[t.data_ptr() for t in srcs])
+            b_arr = (C.c_int64 * n)(*[t.numel() * t.element_size() for t in srcs])
+            ns = 0
+            f_arr = None
+            if scal is not None:
+                vals = scal.reshape(-1).tolist()
+                ns = len(vals)
+                f_arr = (C.c_float * ns)(*vals)
+            L.check(L.lib().cnb_stage_inputs(d_arr, s_arr, b_arr, n, self.opt_dev.data_ptr() if ns else None, f_arr, ns, L.stream_ptr(st["origins"].device)),
+                    "stage_inputs")
             return
         st["origins"].copy_(ray_bundle.origins.reshape(R, 3), non_blocking=True)
         st["directions"].copy_(ray_bundle.directions.reshape(R, 3), non_blocking=True)
         self.cam64.copy_(cam.reshape(R, 1), non_blocking=True)
         st["image"].copy_(batch["image"][:, :3], non_blocking=True)
         st["fruit_mask"].copy_(batch["fruit_mask"].reshape(R, 1), non_blocking=True)
+        if scal is not None:
+            self.opt_dev.copy_(scal, non_blocking=True)
 
     def _narrow_camera_indices(self) -> None:
         """captured at the head of the graph: the kernels' int32 camera indices from the uploaded int64 ones (one tiny kernel)"""
@@ -326,7 +352,7 @@ class _GraphedStep:
             spec = trainer.optimizers[name]
             b1, b2 = spec.betas
             self.opt_np[slot, i, :7] = (exponential_decay_lr(step, spec), b1, b2, spec.eps, 1.0 - b1**t, math.sqrt(1.0 - b2**t), self.inv_world)
-        self.opt_dev.copy_(self.opt_host[slot], non_blocking=True)
+        self._pending_scalars = self.opt_host[slot]   # travels with the step's inputs (_load): kernel parameters or one async H2D copy
 
     def run(self, trainer: "Trainer", ray_bundle, batch):
         self._load(ray_bundle, batch)

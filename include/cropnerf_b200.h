@@ -526,6 +526,11 @@ int cnb_camera_opt_bwd(const float* pose_adjustment, const int32_t* camera_indic
 /* ---- host -> device staging of one batch (rays, targets, optimiser scalars): n cudaMemcpyAsync on `stream` in one call.
  * dst[i] device, src[i] HOST (pinned for a truly asynchronous copy), bytes[i] sizes; the arrays themselves are host arrays. */
 int cnb_upload(void* const* dst, const void* const* src, const int64_t* bytes, int32_t n, cnb_stream_t stream);
+/* the device-resident variant: n (<= 8) device -> device copies (16-byte aligned buffers) and n_scalars (<= 32) floats written from the
+ * HOST array `scalars` into `scalars_dst` (device) as kernel parameters -- ONE kernel launch instead of n + 1 stream operations
+ * (the data manager's batch and the optimiser's per-step scalars of a graph-replayed step). */
+int cnb_stage_inputs(void* const* dst, const void* const* src, const int64_t* bytes, int32_t n, float* scalars_dst, const float* scalars,
+                     int32_t n_scalars, cnb_stream_t stream);
 
 /* ---- measurement aid: per-stage device times of cnb_render_rays / cnb_train_step (CUDA events on the launching stream).
  * cnb_profile_read synchronises, writes "stage:calls:kernels:ms;..." (summed since enable) into buf and clears the log. */
