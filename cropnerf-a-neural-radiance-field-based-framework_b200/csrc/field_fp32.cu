@@ -166,6 +166,7 @@ extern "C" int cnb_field_fwd(const cnb_field* f, const cnb_samples* s, float* de
     }
     CNB_REQUIRE(geo == nullptr || f->geo_feat_dim == 15, "field_fwd: the mixed path exports geo as [N,16]");
     CNB_REQUIRE(!training || ctx != nullptr, "field_fwd: mixed training forward needs ctx scratch (cnb_field_ctx_floats)");
+    CNB_REQUIRE(!training || (rgb != nullptr && sem != nullptr), "field_fwd: the mixed training forward keeps both heads' activations for the backward");
     return cnb_field_mixed_fwd(f, s, density, geo, rgb, sem, positions_out, ctx, training, stream);
   }
   CNB_REQUIRE(ctx != nullptr, "field_fwd: fp32 path needs ctx scratch (cnb_field_ctx_floats)");

@@ -129,12 +129,14 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
     }
     // ---- base MLP: 32 -> 64 -> 16 --------------------------------------------------------------------------------
     uint32_t Abo[1][4];
+    uint32_t mk[2][2] = {{0u, 0u}, {0u, 0u}};   // ReLU flags [fragment row][word]: word 0 = base hidden | semantic hidden 1 << 8, word 1 = rgb hidden 1 | 2 << 8
     {
       float acc[8][4];
       init_bias<8>(acc, Bf + F_BB1, t);
       layer<8, 2, S32>(Wsm + O_WB1, A0, acc, g, t);
       uint32_t AH[4][4];
       to_afrag<4, true>(acc, AH);
+      if (a.mask_out) relu_flags(AH, mk[0][0], mk[1][0]);
       float acc2[2][4];
       init_bias<2>(acc2, Bf + F_BB2, t);
       layer<2, 4, S64>(Wsm + O_WB2, AH, acc2, g, t);
@@ -148,6 +150,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
       if (t == 0) {  // column 0 = density before activation (fruit_field.py:185-193: trunc_exp in fp32, times the selector)
         if (valid[0]) a.density[row[0]] = sel[0] ? expf(acc2[0][0]) : 0.f;
         if (valid[1]) a.density[row[1]] = sel[1] ? expf(acc2[0][2]) : 0.f;
+        if (a.stash_out) {  // the backward's d(density)/d(pre-activation): trunc_exp' in fp32, times the selector
+          if (valid[0]) a.stash_out[4 * row[0]] = sel[0] ? cnb_trunc_exp_grad(acc2[0][0]) : 0.f;
+          if (valid[1]) a.stash_out[4 * row[1]] = sel[1] ? cnb_trunc_exp_grad(acc2[0][2]) : 0.f;
+        }
         acc2[0][0] = 0.f; acc2[0][2] = 0.f;  // clear the dba slot: its weight columns downstream are zero
       }
       to_afrag<1, false>(acc2, Abo);
@@ -159,6 +165,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
       layer<8, 1, S16>(Wsm + O_WS1, Abo, acc, g, t);
       uint32_t AS1[4][4];
       to_afrag<4, true>(acc, AS1);
+      if (a.mask_out) {
+        uint32_t f0, f1;
+        relu_flags(AS1, f0, f1);
+        mk[0][0] |= f0 << 8; mk[1][0] |= f1 << 8;
+      }
       init_bias<8>(acc, Bf + F_BS2, t);
       layer<8, 4, S64>(Wsm + O_WS2, AS1, acc, g, t);
       float s0 = 0.f, s1 = 0.f;
@@ -203,9 +214,18 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
       layer<8, 4, S64>(Wsm + O_WR1, Ain, acc, g, t);
       uint32_t AR[4][4];
       to_afrag<4, true>(acc, AR);
+      if (a.mask_out) relu_flags(AR, mk[0][1], mk[1][1]);
       init_bias<8>(acc, Bf + F_BR2, t);
       layer<8, 4, S64>(Wsm + O_WR2, AR, acc, g, t);
       to_afrag<4, true>(acc, AR);
+      if (a.mask_out) {
+        uint32_t f0, f1;
+        relu_flags(AR, f0, f1);
+        mk[0][1] |= f0 << 8; mk[1][1] |= f1 << 8;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if (valid[h]) a.mask_out[row[h] * 4 + t] = make_uint2(mk[h][0], mk[h][1]);
+      }
       float acc3[1][4];
       init_bias<1>(acc3, Bf + F_BR3, t);
       layer<1, 4, S64>(Wsm + O_WR3, AR, acc3, g, t);
@@ -216,6 +236,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
           const float v0 = 1.f / (1.f + __expf(-acc3[0][2 * h])), v1 = 1.f / (1.f + __expf(-acc3[0][2 * h + 1]));
           if (t == 0) { a.rgb[3 * row[h]] = v0; a.rgb[3 * row[h] + 1] = v1; }
           else a.rgb[3 * row[h] + 2] = v0;
+          if (a.stash_out) {
+            if (t == 0) { a.stash_out[4 * row[h] + 1] = v0; a.stash_out[4 * row[h] + 2] = v1; }
+            else a.stash_out[4 * row[h] + 3] = v0;
+          }
         }
       }
     }
@@ -243,6 +267,8 @@ int cnb_field_mixed_fwd(const cnb_field* f, const cnb_samples* s, float* density
   if (training) {
     a.x0_out = reinterpret_cast<__half*>(ctx);
     a.pos_out = ctx + ctx_pos_off(N);
+    a.stash_out = ctx + ctx_stash_off(N);
+    a.mask_out = reinterpret_cast<uint2*>(ctx + ctx_mask_off(N));
   }
   static bool configured = false;
   if (!configured) {

@@ -43,6 +43,8 @@ struct MixArgs {
   float* density; float* rgb; float* sem; float* pos_out;
   float* geo_out;               // optional [N][16] fp32: base-MLP output [density before activation | geo15] (FruitField.get_density's embedding)
   __half* x0_out;               // optional [N][32] fp16 copy of the encoded features (kept for the backward)
+  float* stash_out;             // optional [N][4] fp32 for the backward: d(density)/d(pre-activation) (trunc_exp' times the selector) | rgb after sigmoid
+  uint2* mask_out;              // optional [N][4] ReLU masks of the four 64-wide hidden layers (relu_flags / field_mixed_bwd_tc5.cu)
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -127,6 +129,20 @@ __device__ __forceinline__ void to_afrag(const float (&acc)[2 * KT][4], uint32_t
   }
 }
 
+// ReLU flags of this thread's 16 values of each of its two fragment rows (A = the packed, already rectified fp16 activations of a 64-wide
+// layer): bit nt <-> column 8 nt + 2 t, bit 16 + nt <-> column 8 nt + 2 t + 1.  A rectified half is +0 or positive, so "non-zero" is bit 15 of
+// half + 0x7fff; three instructions per word.
+__device__ __forceinline__ void relu_flags(const uint32_t (&A)[4][4], uint32_t& row_lo, uint32_t& row_hi) {
+  uint32_t a0 = 0u, a1 = 0u;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {   // n-tile nt = words A[nt/2][2 (nt%2)] (row g) and A[nt/2][2 (nt%2) + 1] (row g + 8)
+    a0 = (a0 >> 1) | ((A[nt >> 1][2 * (nt & 1)] + 0x7FFF7FFFu) & 0x80008000u);
+    a1 = (a1 >> 1) | ((A[nt >> 1][2 * (nt & 1) + 1] + 0x7FFF7FFFu) & 0x80008000u);
+  }
+  row_lo = (a0 >> 8) & 0x00FF00FFu;
+  row_hi = (a1 >> 8) & 0x00FF00FFu;
+}
+
 __device__ __forceinline__ float pick4(int t, float a, float b, float c, float d) { return t == 0 ? a : (t == 1 ? b : (t == 2 ? c : d)); }
 
 __device__ inline void load_weights(const MixArgs& a, __half* Wh_, float* Bf) {
@@ -153,10 +169,16 @@ __device__ inline void load_weights(const MixArgs& a, __half* Wh_, float* Bf) {
   if (tid < 4) Bf[F_BH + tid] = tid == 0 ? __ldg(a.bh) : 0.f;
 }
 
-// ctx (mixed, training): [x0: N*32 fp16][positions: N*3 floats][d_x0: 16 levels x N x 2 floats, level-major], every block 16-byte aligned
+// ctx (mixed, training): [x0: N*32 fp16][positions: N*3 floats][d_x0: 16 levels x N x 2 floats, level-major][stash: N*4 floats]
+// [relu masks: N*8 words][partial weight gradients], every block 16-byte aligned
 inline int64_t ctx_pos_off(int64_t n) { return n * 16; }
 inline int64_t ctx_dx0_off(int64_t n) { return (n * 19 + 3) & ~(int64_t)3; }
-inline int64_t ctx_total(int64_t n) { return ctx_dx0_off(n) + n * 32 + 16; }
+inline int64_t ctx_stash_off(int64_t n) { return ctx_dx0_off(n) + n * 32; }
+inline int64_t ctx_mask_off(int64_t n) { return ctx_stash_off(n) + n * 4; }
+// [per-CTA partial weight gradients of field_mixed_bwd_tc5.cu: CTX_PART_CTAS images of CTX_PART_FLOATS]
+constexpr int64_t CTX_PART_FLOATS = 16896, CTX_PART_CTAS = 160;
+inline int64_t ctx_part_off(int64_t n) { return ctx_mask_off(n) + n * 8; }
+inline int64_t ctx_total(int64_t n) { return ctx_part_off(n) + CTX_PART_FLOATS * CTX_PART_CTAS + 16; }
 
 inline int fill_args(const cnb_field* f, const cnb_samples* s, MixArgs& a) {
   a.table = f->grid.table;
@@ -174,6 +196,8 @@ inline int fill_args(const cnb_field* f, const cnb_samples* s, MixArgs& a) {
   a.embedding = f->appearance_mode == CNB_APP_PER_CAMERA ? f->embedding : (f->appearance_mode == CNB_APP_MEAN ? f->mean_embedding : nullptr);
   a.in0 = f->base.dims[0];
   a.geo_out = nullptr;
+  a.stash_out = nullptr;
+  a.mask_out = nullptr;
   return CNB_OK;
 }
 

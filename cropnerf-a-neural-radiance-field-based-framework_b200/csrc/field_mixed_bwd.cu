@@ -637,10 +637,22 @@ __global__ void __launch_bounds__(FUSED ? THREADS_FUSED : THREADS, 1) k_field_mi
 int cnb_field_mixed_bwd_umma(const cnb_field* f, const cnb_samples* s, const float* d_density, const float* d_rgb, const float* d_sem, float* ctx,
                              cudaStream_t stream);  // field_mixed_bwd_umma.cu: tcgen05 / TMEM variant of the dW contraction
 
+int cnb_field_mixed_bwd_tc5(const cnb_field* f, const cnb_samples* s, const float* d_density, const float* d_rgb, const float* d_sem, float* ctx,
+                            cudaStream_t stream);   // field_mixed_bwd_tc5.cu: every layer a tcgen05.mma tile, row-parallel epilogues
+
 int cnb_field_mixed_bwd(const cnb_field* f, const cnb_samples* s, const float* d_density, const float* d_rgb, const float* d_sem, float* ctx,
                         cudaStream_t stream) {
-  static const bool use_umma = [] { const char* e = getenv("CNB_FIELD_BWD_UMMA"); return e != nullptr && e[0] == '1'; }();
-  if (use_umma) return cnb_field_mixed_bwd_umma(f, s, d_density, d_rgb, d_sem, ctx, stream);
+  // default: the all-tcgen05 kernel (field_mixed_bwd_tc5.cu).  CNB_FIELD_BWD=mma selects this file's mma.sync kernel, CNB_FIELD_BWD=umma the
+  // mma.sync kernel with the dW contraction on tcgen05 (A/B measurements; same numerics contract, same tests).
+  static const int mode = [] {
+    const char* e = getenv("CNB_FIELD_BWD");
+    if (e != nullptr && e[0] == 'm') return 1;
+    if (e != nullptr && e[0] == 'u') return 2;
+    const char* u = getenv("CNB_FIELD_BWD_UMMA");
+    return (u != nullptr && u[0] == '1') ? 2 : 0;
+  }();
+  if (mode == 0) return cnb_field_mixed_bwd_tc5(f, s, d_density, d_rgb, d_sem, ctx, stream);
+  if (mode == 2) return cnb_field_mixed_bwd_umma(f, s, d_density, d_rgb, d_sem, ctx, stream);
   BwdArgs b;
   fill_args(f, s, b.m);
   const int64_t N = s->num_rays * s->samples_per_ray;

@@ -35,6 +35,24 @@ __global__ void __launch_bounds__(256) k_gather(const float2* __restrict__ table
   if (acc == 123.456f) *sink = acc;
 }
 
+// the fp16-table question (SURVEY.md section 7 hard part (c)): the same gather with 4-byte rows (__half2) -- half the footprint, the same
+// number of 32-byte sectors per warp request
+template <bool RANDOM>
+__global__ void __launch_bounds__(256) k_gather4(const uint32_t* __restrict__ table, uint32_t mask, int64_t n, float* __restrict__ sink) {
+  uint32_t acc = 0u;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t row = RANDOM ? (mix((uint32_t)i * 8u + k) & mask) : (((uint32_t)i * 8u + k) & mask);
+      v[k] = __ldg(table + row);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += v[k];
+  }
+  if (acc == 0x12345678u) *sink = (float)acc;
+}
+
 template <bool RANDOM, bool V4>
 __global__ void __launch_bounds__(256) k_scatter(float2* __restrict__ table, uint32_t mask, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -86,6 +104,20 @@ int main() {
     report("gather rand", names[s], time_it([&] { k_gather<true><<<blocks, 256>>>(table, mask, n, sink); }), 8.0 * n);
   }
   report("gather seq", names[2], time_it([&] { k_gather<false><<<blocks, 256>>>(table, max_rows - 1u, n, sink); }), 8.0 * n);
+  // fp16 rows: the same ROW counts, half the bytes (the 16 x 2^19-row field table is 32 MiB); the big preset's 16 x 2^21 rows are 256 MiB in
+  // fp32 (beyond the 126 MB L2) and 128 MiB in fp16 -- measured with the 8-byte gather on a 256 MiB table and the 4-byte one on 128 MiB
+  const char* names4[3] = {"16 KiB fp16 (L1)", "2 MiB fp16 level", "32 MiB fp16 table"};
+  for (int s = 0; s < 3; ++s) {
+    const uint32_t mask = sizes[s] - 1u;
+    report("gather4 rand", names4[s], time_it([&] { k_gather4<true><<<blocks, 256>>>(reinterpret_cast<const uint32_t*>(table), mask, n, sink); }), 8.0 * n);
+  }
+  {
+    float2* big; cudaMalloc(&big, (size_t)(16u << 21) * 8); cudaMemset(big, 0, (size_t)(16u << 21) * 8);
+    const uint32_t mask = (16u << 21) - 1u;
+    report("gather rand", "256 MiB (big preset)", time_it([&] { k_gather<true><<<blocks, 256>>>(big, mask, n, sink); }), 8.0 * n);
+    report("gather4 rand", "128 MiB fp16 (big)", time_it([&] { k_gather4<true><<<blocks, 256>>>(reinterpret_cast<const uint32_t*>(big), mask, n, sink); }), 8.0 * n);
+    cudaFree(big);
+  }
   for (int s = 0; s < 3; ++s) {
     const uint32_t mask = sizes[s] - 1u;
     report("red.v2 rand", names[s], time_it([&] { k_scatter<true, false><<<blocks, 256>>>(table, mask, n); }), 8.0 * n);
