@@ -42,8 +42,9 @@ constexpr int ROWS = 128;            // samples per batch = UMMA M = threads of 
 constexpr int NWG = 2;               // batches in flight per CTA
 constexpr int EPI = NWG * ROWS;
 // + one more warpgroup whose first warp is the issuer: a 9-warp CTA would cap every thread at 168 registers (three warps on one SM
-// sub-partition); with a full third warpgroup the registers are re-split after launch (setmaxnreg: epilogue 224, issuer warpgroup 56)
-constexpr int KTHREADS = EPI + 128;
+// sub-partition); with a full third warpgroup the registers are re-split after launch (setmaxnreg: 4 x 128 at launch = epilogue 200 + 200, issuer / scatter warpgroups 56 + 56)
+constexpr int KTHREADS = EPI + 256;
+constexpr int NSC = 5;               // scatter warps (FUSED): warp 11 and the fourth warpgroup
 constexpr uint32_t FB = 2048;        // bytes of one 8-feature block of an activation matrix (128 rows x 16 B)
 constexpr int NSTEP = 12;
 
@@ -87,6 +88,8 @@ static_assert(I_END <= CTX_PART_FLOATS && I_END % 4 == 0, "partial image size");
 struct BwdArgs {
   MixArgs m;
   float* part;      // [gridDim.x][CTX_PART_FLOATS] per-CTA gradient images
+  float* d_table;   // FUSED: gradient table of the hash grid
+  const float* pos; // FUSED: sample positions kept by the forward
   const __half* x0;
   const float* stash;
   const uint4* masks;
@@ -197,46 +200,51 @@ __device__ __forceinline__ void mask_pack(const float (&v)[NC], const uint32_t (
   }
 }
 
-// One weight matrix into its UMMA layout.  Consecutive threads take consecutive input PAIRS of one output row: the global loads are
-// coalesced (one wavefront per 128 bytes) and four pairs are in flight per thread.  (Chunk-per-thread, 8 strided scalar loads each, was
-// 32 L1 wavefronts per load instruction: 16 k cycles of prologue per CTA.)
-template <int OUT, int IN, typename Src>
-__device__ __forceinline__ void load_matrix_tc5(unsigned char* dst, Src src) {
-  constexpr int PAIRS = OUT * IN / 2;
-  const int nt = blockDim.x;
-  for (int p0 = threadIdx.x; p0 < PAIRS; p0 += 4 * nt) {
-    float v[4][2];
+// One weight matrix into its UMMA layout, in two phases.  Consecutive threads take consecutive input PAIRS of one output row (coalesced
+// global loads); ALL loads of ALL matrices are issued before the first conversion, so the prologue pays one memory round trip, not one per
+// loop iteration (the parameters have usually left L2 since the optimiser wrote them: 14-22 k cycles per CTA with loads issued loop by loop).
+template <int OUT, int IN>
+struct WLoad {
+  static constexpr int PAIRS = OUT * IN / 2;
+  static constexpr int SLOTS = (PAIRS + KTHREADS - 1) / KTHREADS;   // blockDim.x = KTHREADS
+  float v[SLOTS][2];
+  template <typename Src>
+  __device__ __forceinline__ void load(Src src) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int p = p0 + u * nt;
+    for (int u = 0; u < SLOTS; ++u) {
+      const int p = (int)threadIdx.x + u * KTHREADS;
       const int o = p / (IN / 2), i = 2 * (p - o * (IN / 2));
       v[u][0] = p < PAIRS ? src(o, i) : 0.f;
       v[u][1] = p < PAIRS ? src(o, i + 1) : 0.f;
     }
+  }
+  __device__ __forceinline__ void store(unsigned char* dst) const {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int p = p0 + u * nt;
+    for (int u = 0; u < SLOTS; ++u) {
+      const int p = (int)threadIdx.x + u * KTHREADS;
       const int o = p / (IN / 2), i = 2 * (p - o * (IN / 2));
       if (p < PAIRS) *reinterpret_cast<uint32_t*>(dst + (i >> 3) * (OUT * 16) + o * 16 + (i & 7) * 2) = pack_bf2(v[u][0], v[u][1]);
     }
   }
-}
+};
 __device__ inline void load_weights_tc5(const MixArgs& a, unsigned char* Wb, float* Cf, unsigned char* ones) {
   const int in0 = a.in0;
-  load_matrix_tc5<64, 32>(Wb + W_B1, [&](int o, int i) { return i < in0 ? __ldg(a.Wb1 + o * in0 + i) : 0.f; });
-  load_matrix_tc5<16, 64>(Wb + W_B2, [&](int o, int i) { return __ldg(a.Wb2 + o * 64 + i); });
-  load_matrix_tc5<16, 64>(Wb + W_R3, [&](int o, int i) { return o < 3 ? __ldg(a.Wr3 + o * 64 + i) : 0.f; });
-  load_matrix_tc5<64, 64>(Wb + W_R1, [&](int o, int i) { return i == 16 ? 0.f : __ldg(a.Wr1 + o * 63 + (i < 16 ? i : i - 1)); });
-  load_matrix_tc5<64, 64>(Wb + W_R2, [&](int o, int i) { return __ldg(a.Wr2 + o * 64 + i); });
-  load_matrix_tc5<64, 64>(Wb + W_S2, [&](int o, int i) { return __ldg(a.Ws2 + o * 64 + i); });
-  load_matrix_tc5<64, 16>(Wb + W_S1, [&](int o, int i) { return i >= 1 ? __ldg(a.Ws1 + o * 15 + (i - 1)) : 0.f; });
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int e = tid; e < 64; e += nt) {
-    Cf[C_BB1 + e] = __ldg(a.bb1 + e); Cf[C_BR1 + e] = __ldg(a.br1 + e); Cf[C_BR2 + e] = __ldg(a.br2 + e);
-    Cf[C_BS1 + e] = __ldg(a.bs1 + e); Cf[C_BS2 + e] = __ldg(a.bs2 + e); Cf[C_WH + e] = __ldg(a.Wh + e);
-  }
-  if (tid < 16) Cf[C_BB2 + tid] = __ldg(a.bb2 + tid);
+  WLoad<64, 32> b1; WLoad<16, 64> b2, r3; WLoad<64, 64> r1, r2, s2; WLoad<64, 16> s1;
+  b1.load([&](int o, int i) { return i < in0 ? __ldg(a.Wb1 + o * in0 + i) : 0.f; });
+  b2.load([&](int o, int i) { return __ldg(a.Wb2 + o * 64 + i); });
+  r3.load([&](int o, int i) { return o < 3 ? __ldg(a.Wr3 + o * 64 + i) : 0.f; });
+  r1.load([&](int o, int i) { return i == 16 ? 0.f : __ldg(a.Wr1 + o * 63 + (i < 16 ? i : i - 1)); });
+  r2.load([&](int o, int i) { return __ldg(a.Wr2 + o * 64 + i); });
+  s2.load([&](int o, int i) { return __ldg(a.Ws2 + o * 64 + i); });
+  s1.load([&](int o, int i) { return i >= 1 ? __ldg(a.Ws1 + o * 15 + (i - 1)) : 0.f; });
+  float c[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cb2 = 0.f;
+  if (tid < 64) { c[0] = __ldg(a.bb1 + tid); c[1] = __ldg(a.br1 + tid); c[2] = __ldg(a.br2 + tid); c[3] = __ldg(a.bs1 + tid); c[4] = __ldg(a.bs2 + tid); c[5] = __ldg(a.Wh + tid); }
+  if (tid < 16) cb2 = __ldg(a.bb2 + tid);
   for (int e = tid; e < (int)(ONES_BYTES / 4); e += nt) reinterpret_cast<uint32_t*>(ones)[e] = 0x3F803F80u;  // bf16 (1, 1)
+  b1.store(Wb + W_B1); b2.store(Wb + W_B2); r3.store(Wb + W_R3); r1.store(Wb + W_R1); r2.store(Wb + W_R2); s2.store(Wb + W_S2); s1.store(Wb + W_S1);
+  if (tid < 64) { Cf[C_BB1 + tid] = c[0]; Cf[C_BR1 + tid] = c[1]; Cf[C_BR2 + tid] = c[2]; Cf[C_BS1 + tid] = c[3]; Cf[C_BS2 + tid] = c[4]; Cf[C_WH + tid] = c[5]; }
+  if (tid < 16) Cf[C_BB2 + tid] = cb2;
 }
 
 // 32 values per lane -> lane c ends with the warp-wide sum of value c (31 shuffles)
@@ -309,6 +317,45 @@ __device__ __forceinline__ void issue_dw(int step, uint32_t tmem, uint32_t wg_s,
   }
 }
 
+// FUSED (CNB_FIELD_BWD_FUSED=1, NOT the default): the hash-table scatter of d(encoded features) inside this kernel, on the five warps of the
+// issuer warpgroups that issue nothing.  The idea: the MLP part is a latency chain that barely touches the LSU (its operands go from shared
+// memory straight to the tensor core), the scatter is bound by the SM's red.global issue rate (tests/micro/table_access_bench) and needs
+// neither shared memory nor many registers, and no second kernel can co-reside with a 219 KB CTA.  Epilogue threads count finished rows in
+// a shared counter (red.release); the scatter warps take the 32-row groups in completion order.  Measured on B200 (4096-ray step): field
+// backward stage 0.281 ms fused vs 0.220 ms as two kernels (0.814 ms with ONE scatter warp): a (32 samples, level) item is a ~2.4 k-cycle
+// dependent chain (L2 read of d_x0 -> cell hash -> segmented scan -> reds), so five warps per SM deliver 480 cycles per item where the
+// stand-alone kernel, with 48 warps per SM, reaches the LSU bound of ~330.  More scatter warps do not fit the register file next to two
+// 200-register epilogue warpgroups.
+__device__ __forceinline__ void scatter_batch(const MixArgs& a, float* __restrict__ d_table, const float* __restrict__ pos, const float* __restrict__ d_x0,
+                                              int64_t batch, int sw, int lane, int64_t N) {
+  {
+    const int64_t s = batch * ROWS + sw * 32 + lane;
+    const bool in = s < N;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (in) { px = __ldg(pos + 3 * s); py = __ldg(pos + 3 * s + 1); pz = __ldg(pos + 3 * s + 2); }
+#pragma unroll 1
+    for (int l0 = 0; l0 < a.L; l0 += 4) {
+      float2 d[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        d[q] = make_float2(0.f, 0.f);
+        if (in && l0 + q < a.L) d[q] = __ldcg(reinterpret_cast<const float2*>(d_x0) + (int64_t)(l0 + q) * N + s);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int l = l0 + q;
+        if (l < a.L) {  // warp-uniform
+          const bool active = d[q].x != 0.0f || d[q].y != 0.0f;  // zero gradients add nothing (masked samples, App. B-3)
+          CnbCell c = {};
+          if (active) c = cnb_cell(px, py, pz, a.scalings[l]);
+          cnb_scatter_cell(d_table, c, a.mask, (uint32_t)l * a.T, d[q].x, d[q].y, active);
+        }
+      }
+    }
+  }
+}
+
+template <bool FUSED>
 __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_constant__ BwdArgs b) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const MixArgs& a = b.m;
@@ -318,11 +365,13 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
   float* Cf = reinterpret_cast<float*>(smem + O_CONST);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + O_BAR);   // ready[NWG], dwready[NWG] (128 arrivals), done[NWG], dwdone[NWG] (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * NWG);
+  uint32_t* rows_done = tmem_slot + 2;   // FUSED: [NWG] rows whose d(encoded features) are in global memory
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   load_weights_tc5(a, Wb, Cf, ones);
   const long long t_w = b.dbg ? clock64() : 0;
   if (threadIdx.x == 0) {
     for (int w = 0; w < NWG; ++w) {
+      rows_done[w] = 0u;
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bars + w)), "r"(ROWS));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bars + NWG + w)), "r"(ROWS));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bars + 2 * NWG + w)));
@@ -349,7 +398,7 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
   const int64_t nb_cta = nbatches > blockIdx.x ? (nbatches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp >= EPI / 32) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // 4 x 128 at launch = 200 + 200 + 56 + 56 per sub-partition lane
     // ===== three issuers (warp-uniform: all lanes wait, one elected lane issues -- no per-instruction election loop in the SASS) =====
     //   warp 8 + w : the layer MMAs of warpgroup w -- the epilogue's critical path, nothing else in this thread's queue
     //   warp 10    : every dW / bias MMA of both warpgroups -- each dW accumulator has ONE issuing thread
@@ -397,9 +446,29 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
           }
         }
       }
+    } else if (FUSED) {
+      // ===== scatter warps: batch j of this CTA belongs to warpgroup j % NWG and is its (j / NWG)-th; its four 32-row groups are dealt
+      // round-robin over the NSC scatter warps =====
+      const int sc = iw - NWG - 1;   // 0 .. NSC-1
+      const uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared(rows_done);
+      for (int64_t j = 0; j < nb_cta; ++j) {
+        bool waited = false;
+        for (int sw = 0; sw < ROWS / 32; ++sw) {
+          if ((int)((j * (ROWS / 32) + sw) % NSC) != sc) continue;
+          if (!waited) {
+            const uint32_t want = (uint32_t)(j / NWG + 1) * ROWS;
+            uint32_t have;
+            do {
+              asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(have) : "r"(cnt_s + 4u * (uint32_t)(j % NWG)) : "memory");
+            } while (have < want);
+            waited = true;
+          }
+          scatter_batch(a, b.d_table, b.pos, b.d_x0, blockIdx.x + j * gridDim.x, sw, lane, N);
+        }
+      }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     // ===== epilogue warpgroups: thread r owns sample row r of its warpgroup's batch =====
     const int wg = warp >> 2, r = threadIdx.x & (ROWS - 1);
     unsigned char* base = smem + O_WG + (uint32_t)wg * WG_BYTES;
@@ -676,6 +745,8 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
           for (int l = 0; l < 16; ++l)
             if (l < a.L) reinterpret_cast<float2*>(b.d_x0)[(int64_t)l * N + i] = make_float2(v[2 * l], v[2 * l + 1]);
         }
+        if (FUSED)   // release at CTA scope: orders this thread's d_x0 stores before the scatter warp's loads
+          asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(rows_done + wg)) : "memory");
         asm volatile("tcgen05.fence::before_thread_sync;");
         wait_dw();   // step 11 (dWb1 reads D, R1): the next batch starts by overwriting D
         if (dbg_on) { b.dbg[48] += clock64() - te; b.dbg[53] = t_fence; b.dbg[54] = t_dbgrmw; }
@@ -729,7 +800,7 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
       rd(C8{}, T_BR2, [&](int k, float v) { if (k == 0) img[I_BR2 + m] = v; });
       rd(C8{}, T_BR1, [&](int k, float v) { if (k == 0) img[I_BR1 + m] = v; });
       rd(C8{}, T_BH, [&](int k, float v) { if (k == 0 && m == 0) img[I_BH] = v; });
-    } else {
+    } else if (grp == 2) {
       rd(C64{}, T_S2, [&](int k, float v) { img[I_WS2 + m * 64 + k] = v; });
       rd(C8{}, T_BS2, [&](int k, float v) { if (k == 0) img[I_BS2 + m] = v; });
       rd(C8{}, T_BS1, [&](int k, float v) { if (k == 0) img[I_BS1 + m] = v; });
@@ -810,13 +881,22 @@ int cnb_field_mixed_bwd_tc5(const cnb_field* f, const cnb_samples* s, const floa
   }
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(k_field_bwd_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC5) != cudaSuccess) return cnb_check_launch("field_bwd_tc5 attr");
+    if (cudaFuncSetAttribute(k_field_bwd_tc5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC5) != cudaSuccess ||
+        cudaFuncSetAttribute(k_field_bwd_tc5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC5) != cudaSuccess)
+      return cnb_check_launch("field_bwd_tc5 attr");
     configured = true;
   }
   const int64_t nbatches = (N + ROWS - 1) / ROWS;
   int64_t blocks = nbatches < (int64_t)cnb_num_sms() ? nbatches : (int64_t)cnb_num_sms();
   if (blocks > CTX_PART_CTAS) blocks = CTX_PART_CTAS;
-  k_field_bwd_tc5<<<(int)blocks, KTHREADS, SMEM_TC5, stream>>>(b);
+  // default: the table scatter as a second kernel (cnb_hashgrid_bwd_level_major); CNB_FIELD_BWD_FUSED=1: inside this one, same arithmetic
+  static const bool want_fused = [] { const char* e = getenv("CNB_FIELD_BWD_FUSED"); return e != nullptr && e[0] == '1'; }();
+  b.d_table = f->grid.d_table;
+  b.pos = ctx + ctx_pos_off(N);
+  bool fused = want_fused && b.d_table != nullptr;
+  for (int i = 0; i < f->grid.num_levels && fused; ++i) fused = f->grid.scalings[i] < 65535.0f;  // cnb_scatter_cell's 16-bit cell keys
+  if (fused) k_field_bwd_tc5<true><<<(int)blocks, KTHREADS, SMEM_TC5, stream>>>(b);
+  else k_field_bwd_tc5<false><<<(int)blocks, KTHREADS, SMEM_TC5, stream>>>(b);
   int rc = cnb_check_launch("field_bwd_tc5");
   if (rc) return rc;
   k_tc5_reduce<<<dim3((I_END + 255) / 256, 4), 256, 0, stream>>>(b, (int)blocks);
@@ -830,5 +910,6 @@ int cnb_field_mixed_bwd_tc5(const cnb_field* f, const cnb_samples* s, const floa
     fprintf(stderr, "[tc5] final epilogue work %lld ; CTA 0: prologue %lld, batch loop end %lld, kernel end %lld cycles\n", h[48], h[49], h[50], h[51]);
     fprintf(stderr, "[tc5] weights loaded after %lld cycles; fence+arrive total %lld; dbg RMW total %lld\n", h[52], h[53], h[54]);
   }
+  if (fused) return CNB_OK;
   return cnb_hashgrid_bwd_level_major(&f->grid, ctx + ctx_pos_off(N), b.d_x0, N, stream);
 }
