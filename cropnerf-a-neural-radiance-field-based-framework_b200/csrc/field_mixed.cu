@@ -63,6 +63,9 @@ __device__ __forceinline__ uint32_t gather_blend(const LevelLoads& o) {
 //     as one 16-byte load.  The forward gathers are bound by the L1TEX data pipe (one wavefront per distinct sector per
 //     request; ncu: l1tex__data_pipe_lsu_wavefronts 85 % busy, L2 16-42 %), so wavefronts are what is minimised.
 //   features are staged (fp16) in a warp-private 16x32 shared-memory tile and re-read as mma A fragments.
+// KEEP: the training forward, which also writes what the backward needs (encoded features, positions, stash, ReLU flags); the eval / export
+// instantiation carries none of that code (it cost 3-6 % of the render rate as run-time branches: registers)
+template <bool KEEP>
 __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_constant__ MixArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* Wsm = reinterpret_cast<__half*>(smem_raw);
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
       for (int q = 0; q < 2; ++q)
 #pragma unroll
         for (int h = 0; h < 2; ++h) A0[kt][2 * q + h] = X32[(g + 8 * h) * (XS / 2) + 8 * kt + 4 * q + t];
-    if (a.x0_out) {  // encoded features kept for the backward: the tile is one contiguous 1 KB block of the [N,32] fp16 array
+    if (KEEP && a.x0_out) {  // encoded features kept for the backward: the tile is one contiguous 1 KB block of the [N,32] fp16 array
 #pragma unroll
       for (int e = lane; e < 64; e += 32) {
         const int rw = e >> 2, q = e & 3;
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
       layer<8, 2, S32>(Wsm + O_WB1, A0, acc, g, t);
       uint32_t AH[4][4];
       to_afrag<4, true>(acc, AH);
-      if (a.mask_out) relu_flags(AH, mk[0][0], mk[1][0]);
+      if (KEEP && a.mask_out) relu_flags(AH, mk[0][0], mk[1][0]);
       float acc2[2][4];
       init_bias<2>(acc2, Bf + F_BB2, t);
       layer<2, 4, S64>(Wsm + O_WB2, AH, acc2, g, t);
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
       if (t == 0) {  // column 0 = density before activation (fruit_field.py:185-193: trunc_exp in fp32, times the selector)
         if (valid[0]) a.density[row[0]] = sel[0] ? expf(acc2[0][0]) : 0.f;
         if (valid[1]) a.density[row[1]] = sel[1] ? expf(acc2[0][2]) : 0.f;
-        if (a.stash_out) {  // the backward's d(density)/d(pre-activation): trunc_exp' in fp32, times the selector
+        if (KEEP && a.stash_out) {  // the backward's d(density)/d(pre-activation): trunc_exp' in fp32, times the selector
           if (valid[0]) a.stash_out[4 * row[0]] = sel[0] ? cnb_trunc_exp_grad(acc2[0][0]) : 0.f;
           if (valid[1]) a.stash_out[4 * row[1]] = sel[1] ? cnb_trunc_exp_grad(acc2[0][2]) : 0.f;
         }
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
       layer<8, 1, S16>(Wsm + O_WS1, Abo, acc, g, t);
       uint32_t AS1[4][4];
       to_afrag<4, true>(acc, AS1);
-      if (a.mask_out) {
+      if (KEEP && a.mask_out) {
         uint32_t f0, f1;
         relu_flags(AS1, f0, f1);
         mk[0][0] |= f0 << 8; mk[1][0] |= f1 << 8;
@@ -214,11 +217,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
       layer<8, 4, S64>(Wsm + O_WR1, Ain, acc, g, t);
       uint32_t AR[4][4];
       to_afrag<4, true>(acc, AR);
-      if (a.mask_out) relu_flags(AR, mk[0][1], mk[1][1]);
+      if (KEEP && a.mask_out) relu_flags(AR, mk[0][1], mk[1][1]);
       init_bias<8>(acc, Bf + F_BR2, t);
       layer<8, 4, S64>(Wsm + O_WR2, AR, acc, g, t);
       to_afrag<4, true>(acc, AR);
-      if (a.mask_out) {
+      if (KEEP && a.mask_out) {
         uint32_t f0, f1;
         relu_flags(AR, f0, f1);
         mk[0][1] |= f0 << 8; mk[1][1] |= f1 << 8;
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_field_mixed_fwd(const __grid_con
           const float v0 = 1.f / (1.f + __expf(-acc3[0][2 * h])), v1 = 1.f / (1.f + __expf(-acc3[0][2 * h + 1]));
           if (t == 0) { a.rgb[3 * row[h]] = v0; a.rgb[3 * row[h] + 1] = v1; }
           else a.rgb[3 * row[h] + 2] = v0;
-          if (a.stash_out) {
+          if (KEEP && a.stash_out) {
             if (t == 0) { a.stash_out[4 * row[h] + 1] = v0; a.stash_out[4 * row[h] + 2] = v1; }
             else a.stash_out[4 * row[h] + 3] = v0;
           }
@@ -272,13 +275,16 @@ int cnb_field_mixed_fwd(const cnb_field* f, const cnb_samples* s, float* density
   }
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(k_field_mixed_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD2) != cudaSuccess) return cnb_check_launch("field_mixed_fwd attr");
+    if (cudaFuncSetAttribute(k_field_mixed_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD2) != cudaSuccess ||
+        cudaFuncSetAttribute(k_field_mixed_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD2) != cudaSuccess)
+      return cnb_check_launch("field_mixed_fwd attr");
     configured = true;
   }
   int64_t blocks = (N + TILE - 1) / TILE;  // one 16-sample m-tile per warp and round
   const int64_t cap = (int64_t)cnb_num_sms() * 2;
   if (blocks > cap) blocks = cap;
-  k_field_mixed_fwd<<<(int)blocks, THREADS, SMEM_FWD2, stream>>>(a);
+  if (training) k_field_mixed_fwd<true><<<(int)blocks, THREADS, SMEM_FWD2, stream>>>(a);
+  else k_field_mixed_fwd<false><<<(int)blocks, THREADS, SMEM_FWD2, stream>>>(a);
   int rc = cnb_check_launch("field_mixed_fwd");
   if (rc) return rc;
   if (training && positions_out != nullptr &&
