@@ -263,23 +263,39 @@ __device__ __forceinline__ float transpose_reduce32(float (&x)[32], int lane) {
   return x[0];
 }
 
-// The layer MMA of one step of one warpgroup's batch: what the epilogue threads wait for.
-__device__ __forceinline__ void issue_chain(int step, uint32_t tm, uint32_t wg_s, uint32_t w_s) {
+// The layer MMA of one step of one warpgroup's batch: what the epilogue threads wait for.  Its descriptors are prepared BEFORE the issuer
+// waits for the operands (`prepare_chain`), so that after the wake-up only the K-step adds and the MMAs themselves are on the critical path.
+struct ChainOp {
+  uint32_t a_lo, a_hi, b_lo, b_hi, id, a_step, b_step;
+  int ks;
+};
+template <int K, int OUT>
+__device__ __forceinline__ ChainOp op_fwd(uint32_t a_s, uint32_t w_s) {
+  return ChainOp{desc_lo(a_s, FB), desc_hi(128), desc_lo(w_s, OUT * 16), desc_hi(128), idesc(128, OUT, 0, 0), (2 * FB) >> 4, (2 * OUT * 16) >> 4, K / 16};
+}
+template <int KOUT, int OUT, int NIN>
+__device__ __forceinline__ ChainOp op_dx(uint32_t dy_s, uint32_t w_s) {
+  return ChainOp{desc_lo(dy_s, FB), desc_hi(128), desc_lo(w_s, 128), desc_hi(OUT * 16), idesc(128, NIN, 0, 1), (2 * FB) >> 4, 256 >> 4, KOUT / 16};
+}
+__device__ __forceinline__ ChainOp prepare_chain(int step, uint32_t wg_s, uint32_t w_s) {
   const uint32_t DS = wg_s + B_DS, AH = wg_s + B_AH, BO = wg_s + B_BO, AIN = wg_s + B_AIN, R1 = wg_s + B_R1, D = wg_s + B_D;
   switch (step) {
-    case 0: mm_fwd<32, 64>(tm, D, w_s + W_B1); break;
-    case 1: mm_fwd<64, 16>(tm, AH, w_s + W_B2); break;
-    case 2: mm_fwd<64, 64>(tm, AIN, w_s + W_R1); break;
-    case 3: mm_fwd<64, 64>(tm, R1, w_s + W_R2); break;
-    case 4: mm_dx<16, 16, 64>(tm, DS, w_s + W_R3); break;
-    case 5: mm_dx<64, 64, 64>(tm, D, w_s + W_R2); break;
-    case 6: mm_dx<64, 64, 48>(tm, D, w_s + W_R1 + 2 * (64 * 16)); break;   // inputs 16..63: [0, geo15 | emb32]
-    case 7: mm_fwd<16, 64>(tm, BO, w_s + W_S1); break;
-    case 8: mm_fwd<64, 64>(tm, R1, w_s + W_S2); break;
-    case 9: mm_dx<64, 64, 64>(tm, D, w_s + W_S2); break;
-    case 10: mm_dx<16, 16, 64>(tm, DS, w_s + W_B2); break;
-    default: mm_dx<64, 64, 32>(tm, D, w_s + W_B1); break;
+    case 0: return op_fwd<32, 64>(D, w_s + W_B1);
+    case 1: return op_fwd<64, 16>(AH, w_s + W_B2);
+    case 2: return op_fwd<64, 64>(AIN, w_s + W_R1);
+    case 3: return op_fwd<64, 64>(R1, w_s + W_R2);
+    case 4: return op_dx<16, 16, 64>(DS, w_s + W_R3);
+    case 5: return op_dx<64, 64, 64>(D, w_s + W_R2);
+    case 6: return op_dx<64, 64, 48>(D, w_s + W_R1 + 2 * (64 * 16));   // inputs 16..63: [0, geo15 | emb32]
+    case 7: return op_fwd<16, 64>(BO, w_s + W_S1);
+    case 8: return op_fwd<64, 64>(R1, w_s + W_S2);
+    case 9: return op_dx<64, 64, 64>(D, w_s + W_S2);
+    case 10: return op_dx<16, 16, 64>(DS, w_s + W_B2);
+    default: return op_dx<64, 64, 32>(D, w_s + W_B1);
   }
+}
+__device__ __forceinline__ void issue_chain(const ChainOp& o, uint32_t tm) {
+  for (int ks = 0; ks < o.ks; ++ks) umma(tm, desc64(o.a_lo + ks * o.a_step, o.a_hi), desc64(o.b_lo + ks * o.b_step, o.b_hi), o.id, ks > 0 ? 1u : 0u);
 }
 // The weight-gradient MMAs of a step (steps 4-6 and 9-11): off the epilogue's critical path, issued by their own thread.
 __device__ __forceinline__ constexpr bool step_has_dw(int step) { return (step >= 4 && step <= 6) || step >= 9; }
@@ -408,15 +424,13 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
       for (int64_t j = iw; j < nb_cta; j += NWG) {
         for (int step = 0; step < NSTEP; ++step) {
           const long long tq0 = b.dbg ? clock64() : 0;
+          const ChainOp op = prepare_chain(step, smem_s + O_WG + (uint32_t)iw * WG_BYTES, smem_s + O_W);
           mbar_wait(bars_s + 8 * iw, ph);
           ph ^= 1u;
           asm volatile("tcgen05.fence::after_thread_sync;");
           const long long tq1 = b.dbg ? clock64() : 0;
           if (elect_one()) {
-            // opaque bases: otherwise every descriptor of every step is hoisted out of the loops and spilled (56 registers here)
-            uint32_t wg_s = smem_s + O_WG + (uint32_t)iw * WG_BYTES, w_s = smem_s + O_W;
-            asm volatile("" : "+r"(wg_s), "+r"(w_s));
-            issue_chain(step, tmem + T_CHAIN + 64u * (uint32_t)iw, wg_s, w_s);
+            issue_chain(op, tmem + T_CHAIN + 64u * (uint32_t)iw);
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"l"((uint64_t)(bars_s + 8 * (2 * NWG + iw))) : "memory");
             if (b.dbg && blockIdx.x == 0 && iw == 0) { b.dbg[step] += tq1 - tq0; b.dbg[12 + step] += clock64() - tq1; }
           }

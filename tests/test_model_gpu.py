@@ -505,16 +505,19 @@ def test_in_step_camera_optimizer_matches_the_autograd_route(dev, precision):
     assert float(pg[0, :3].abs().max()) > 0 and torch.isfinite(pg).all()
 
 
-def test_field_backward_tcgen05_variant():
-    """The tcgen05 / TMEM variant of the field backward (CNB_FIELD_BWD_UMMA=1, csrc/field_mixed_bwd_umma.cu) passes the same
-    gradient-parity tests as the default mma.sync kernel.  The switch is read once per process, hence the subprocess."""
+@pytest.mark.parametrize("switch", ["CNB_FIELD_BWD=mma", "CNB_FIELD_BWD=umma", "CNB_FIELD_BWD_FUSED=1"])
+def test_field_backward_alternative_kernels(switch):
+    """The default mixed-precision field backward is the all-tcgen05 kernel (csrc/field_mixed_bwd_tc5.cu).  Its measured alternatives -- the
+    round-1 mma.sync kernel, that kernel with the dW contraction on tcgen05, and the tcgen05 kernel with the table scatter fused in -- pass the
+    same gradient-parity tests.  The switches are read once per process, hence the subprocess."""
     import subprocess
     import sys
 
-    env = dict(os.environ, CNB_FIELD_BWD_UMMA="1")
+    k, v = switch.split("=")
+    env = dict(os.environ, **{k: v})
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_model_gpu.py"), "-m", "gpu", "-q", "-x", "-k",
                           "test_field_backward_mixed_precision or test_train_step_ray_gradients_and_camera_optimizer"],
-                         env=env, capture_output=True, text=True, timeout=600)
+                         env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
     assert "passed" in res.stdout
