@@ -20,6 +20,8 @@ import struct
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
+import pickle
+
 import numpy as np
 import torch
 from torch import Tensor
@@ -241,10 +243,37 @@ class PinholeCamera:
     height: int
 
 
-def load_cluster_info(path: str) -> List[dict]:
+class _NumpyOnlyUnpickler(pickle.Unpickler):
+    """The cluster-info file is a pickled object array (the reference writes it with ``np.save(..., allow_pickle=True)``): dicts, lists, ints and
+    numpy arrays.  Unpickling is restricted to the numpy reconstruction helpers, so a crafted file cannot run code."""
+
+    _ALLOWED = {
+        ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"), ("numpy", "ndarray"), ("numpy", "dtype"),
+        ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"), ("numpy.core.numeric", "_frombuffer"),
+        ("numpy._core.numeric", "_frombuffer"),
+    }
+
+    def find_class(self, module, name):
+        if (module, name) in self._ALLOWED:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"cluster info: refusing to unpickle {module}.{name}")
+
+
+def load_cluster_info(path: str, allow_pickle: bool = False) -> List[dict]:
     """``all_super_cluster_info_nsub_*.npy`` written by segmentation/segmenter.py:153-181: a pickled list of
-    ``{'aabb': float[k,2,3] (min,max per sub-cluster), 'pcd': {sub_id: float[n,3]}}`` (read at fruit_nerf.py:265)."""
-    data = np.load(path, allow_pickle=True)
+    ``{'aabb': float[k,2,3] (min,max per sub-cluster), 'pcd': {sub_id: float[n,3]}}`` (read at fruit_nerf.py:265).
+    By default only numpy arrays / plain containers are unpickled; ``allow_pickle=True`` is the reference's unrestricted ``np.load``."""
+    if allow_pickle:
+        data = np.load(path, allow_pickle=True)
+    else:
+        with open(path, "rb") as f:
+            version = np.lib.format.read_magic(f)
+            shape, fortran, dtype = np.lib.format.read_array_header_1_0(f) if version == (1, 0) else np.lib.format.read_array_header_2_0(f)
+            if dtype.hasobject:
+                data = _NumpyOnlyUnpickler(f).load()
+            else:
+                f.seek(0)
+                data = np.load(f, allow_pickle=False)
     out = []
     for item in list(data):
         aabb = np.asarray(item["aabb"], dtype=np.float32)

@@ -121,3 +121,31 @@ def test_aabb_near_far_equals_oracle_intersect_aabb():
     assert 200 < int(hit.sum()) < 3800
     assert torch.equal(n[:, 0] < 1e10, hit)
     assert torch.equal(n[:, 0], tmin) and torch.equal(f[:, 0], tmax)
+
+
+def test_cluster_info_loads_without_running_pickled_code(tmp_path):
+    """the reference's cluster-info file is a pickled object array; the loader only reconstructs numpy arrays / plain containers
+    and refuses anything else unless the caller opts into the reference's unrestricted np.load."""
+    import os
+    import pickle
+
+    import numpy as np
+    import pytest
+
+    import cropnerf_b200.export as E
+
+    good = [{"aabb": np.random.rand(3, 2, 3).astype(np.float32), "pcd": {0: np.random.rand(5, 3)}}, {"aabb": np.random.rand(1, 2, 3), "pcd": {}}]
+    p = str(tmp_path / "good.npy")
+    E.save_cluster_info(p, good)
+    out = E.load_cluster_info(p)
+    assert len(out) == 2 and out[0]["aabb"].shape == (3, 2, 3) and np.allclose(out[0]["pcd"][0], good[0]["pcd"][0])
+    assert np.allclose(E.load_cluster_info(p, allow_pickle=True)[1]["aabb"], out[1]["aabb"])
+
+    class Evil:
+        def __reduce__(self):
+            return (os.getcwd, ())
+
+    q = str(tmp_path / "evil.npy")
+    np.save(q, np.asarray([{"aabb": Evil()}], dtype=object), allow_pickle=True)
+    with pytest.raises(pickle.UnpicklingError):
+        E.load_cluster_info(q)
