@@ -29,6 +29,7 @@ class OptimizerSpec:
     betas: tuple = (0.9, 0.999)
     lr_final: Optional[float] = 1e-4
     max_steps: int = 200000
+    kind: str = "adam"   # "adam" (fruit_nerf_config.py:45-60) | "radam" (the _big / _huge presets, fruit_nerf_config.py:100-108)
 
 
 DEFAULT_OPTIMIZERS = {
@@ -44,6 +45,25 @@ def exponential_decay_lr(step: int, spec: OptimizerSpec) -> float:
         return spec.lr
     t = min(max(step / spec.max_steps, 0.0), 1.0)
     return math.exp(math.log(spec.lr) * (1 - t) + math.log(spec.lr_final) * t)
+
+
+def step_scalars(spec: OptimizerSpec, lr: float, t: int, inv_scale: float = 1.0) -> tuple:
+    """The seven per-step scalars of the flat-group update kernels, ``p -= (s0 / s4) * m / (sqrt(v) / s5 + s3)`` with m, v the Adam moments:
+    ``(lr, beta1, beta2, eps, 1 - beta1^t, sqrt(1 - beta2^t), 1 / grad_scale)`` for torch.optim.Adam.  torch.optim.RAdam is the same kernel with
+    other scalars: rectified steps (rho_t > 5) multiply lr by the rectification term and divide eps by sqrt(1 - beta2^t) (RAdam adds eps
+    BEFORE the bias correction of the denominator); the first steps (rho_t <= 5) have no adaptive denominator, i.e. sqrt(v) / inf + 1."""
+    b1, b2 = spec.betas
+    bc1, bc2 = 1.0 - b1**t, 1.0 - b2**t
+    if spec.kind == "adam":
+        return (lr, b1, b2, spec.eps, bc1, math.sqrt(bc2), inv_scale)
+    if spec.kind != "radam":
+        raise ValueError(f"optimizer kind {spec.kind!r}: 'adam' or 'radam'")
+    rho_inf = 2.0 / (1.0 - b2) - 1.0
+    rho_t = rho_inf - 2.0 * t * (b2**t) / bc2
+    if rho_t > 5.0:
+        rect = math.sqrt((rho_t - 4.0) * (rho_t - 2.0) * rho_inf / ((rho_inf - 4.0) * (rho_inf - 2.0) * rho_t))
+        return (lr * rect, b1, b2, spec.eps / math.sqrt(bc2), bc1, math.sqrt(bc2), inv_scale)
+    return (lr, b1, b2, 1.0, bc1, float("inf"), inv_scale)
 
 
 class GradScaler:
@@ -351,7 +371,7 @@ class _GraphedStep:
         for i, name in enumerate(self.opt_names):
             spec = trainer.optimizers[name]
             b1, b2 = spec.betas
-            self.opt_np[slot, i, :7] = (exponential_decay_lr(step, spec), b1, b2, spec.eps, 1.0 - b1**t, math.sqrt(1.0 - b2**t), self.inv_world)
+            self.opt_np[slot, i, :7] = step_scalars(spec, exponential_decay_lr(step, spec), t, self.inv_world)
         self._pending_scalars = self.opt_host[slot]   # travels with the step's inputs (_load): kernel parameters or one async H2D copy
 
     def run(self, trainer: "Trainer", ray_bundle, batch):
@@ -492,6 +512,11 @@ class Trainer:
             spec = self.optimizers[name]
             lr = exponential_decay_lr(step, spec)
             # Adam and the gradient clear of the next step in one pass over the flat group
+            if spec.kind != "adam":
+                if flag is not None:
+                    raise NotImplementedError("RAdam with a GradScaler: the guarded update kernel computes Adam's bias corrections itself")
+                ops.adam_step_scalars(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, step_scalars(spec, lr, self.opt_step, inv), live=g.live)
+                continue
             ops.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, lr, self.opt_step, spec.betas[0], spec.betas[1], spec.eps,
                           inv_grad_scale=inv, zero_grad=True, skip_flag=flag, live=g.live)
         self._grads_clean = True
@@ -512,6 +537,8 @@ class Trainer:
         from . import _lib as L
 
         comm = self.comm
+        if any(self.optimizers[name].kind != "adam" for name in order):
+            raise NotImplementedError("RAdam over the peer-memory exchange (its kernel computes Adam's bias corrections from the step count): use ddp='nccl'")
         if self._ddp_steps is None or len(self._ddp_steps) != len(order):
             self._ddp_steps = (L.DdpGroupStep * len(order))()
             for i, name in enumerate(order):
@@ -557,8 +584,11 @@ class Trainer:
         g = self.groups["fields"]
         spec = self.optimizers["fields"]
         with torch.cuda.stream(self._side_stream):
-            ops.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, exponential_decay_lr(step, spec), self.opt_step, spec.betas[0], spec.betas[1], spec.eps,
-                          inv_grad_scale=1.0, zero_grad=True, live=g.live)
+            if spec.kind != "adam":
+                ops.adam_step_scalars(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, step_scalars(spec, exponential_decay_lr(step, spec), self.opt_step), live=g.live)
+            else:
+                ops.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, exponential_decay_lr(step, spec), self.opt_step, spec.betas[0], spec.betas[1],
+                              spec.eps, inv_grad_scale=1.0, zero_grad=True, live=g.live)
             self._deferred_event.record(self._side_stream)
         self._deferred_pending = True
         self.model._param_fence = self.wait_deferred_update

@@ -584,6 +584,20 @@ def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, 
     )
 
 
+def adam_step_scalars(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, scalars, live: Optional[Tensor] = None) -> None:
+    """The flat-group update + gradient clear with the step's seven scalars given explicitly (engine.step_scalars: Adam or RAdam):
+    ``p -= (s0 / s4) * m / (sqrt(v) / s5 + s3)``.  The scalars travel as one 28-byte device tensor (cnb_adam_step_zero_dev[_live])."""
+    dev = _dev(param)
+    sc = torch.tensor([float(x) for x in scalars] + [0.0], dtype=torch.float32).to(dev, non_blocking=False)
+    if live is not None:
+        L.check(L.lib().cnb_adam_step_zero_dev_live(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+                                                    sc.data_ptr(), live.data_ptr(), L.stream_ptr(dev)), "adam_step_dev_live")
+    else:
+        L.check(L.lib().cnb_adam_step_zero_dev(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+                                               sc.data_ptr(), L.stream_ptr(dev)), "adam_step_dev")
+    sc.record_stream(torch.cuda.current_stream(dev))
+
+
 def grad_check_finite(grad: Tensor, found_inf: Tensor) -> None:
     """found_inf (device int32 [1]) |= any(!isfinite(grad))  -- torch.amp.GradScaler's inf check over one flat gradient group."""
     dev = _dev(grad)

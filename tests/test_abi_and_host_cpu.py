@@ -252,3 +252,28 @@ def test_live_bitmap_bit_packing_of_nonzero_moments():
     g.live[0] |= 2  # bits already set stay set
     g.include_nonzero_moments()
     assert int((g.live[0] >> 1) & 1) == 1
+
+
+def test_step_scalars_reproduce_torch_adam_and_radam():
+    """engine.step_scalars: the update kernels compute p -= (s0 / s4) * m / (sqrt(v) / s5 + s3); with the scalars chosen per optimizer kind the
+    same formula is torch.optim.Adam and torch.optim.RAdam (rectified and unrectified steps).  Emulated in float64 on the host."""
+    import torch
+
+    from cropnerf_b200.engine import OptimizerSpec, step_scalars
+
+    for kind, cls in (("adam", torch.optim.Adam), ("radam", torch.optim.RAdam)):
+        g = torch.Generator().manual_seed(3)
+        p = torch.randn(64, generator=g, dtype=torch.float64)
+        ref = torch.nn.Parameter(p.clone())
+        opt = cls([ref], lr=1e-2, eps=1e-15)
+        spec = OptimizerSpec(lr=1e-2, eps=1e-15, lr_final=None, kind=kind)
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        for t in range(1, 15):
+            gr = torch.randn(64, generator=g, dtype=torch.float64)
+            s = step_scalars(spec, 1e-2, t)
+            m = m + (1 - s[1]) * (gr - m)
+            v = s[2] * v + (1 - s[2]) * gr * gr
+            p = p - (s[0] / s[4]) * (m / (v.sqrt() / s[5] + s[3]))
+            ref.grad = gr.clone()
+            opt.step()
+            assert float((p - ref.detach()).abs().max()) < 1e-12, (kind, t)

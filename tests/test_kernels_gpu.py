@@ -335,6 +335,30 @@ def test_adam_matches_torch(dev):
         assert_close(p, ref.detach(), 1e-5, f"adam step {step}", floor=1e-3)
 
 
+@pytest.mark.parametrize("kind", ["adam", "radam"])
+def test_explicit_scalar_update_matches_torch_adam_and_radam(dev, kind):
+    """The flat-group update kernel with host-computed scalars (engine.step_scalars) against torch.optim.Adam / torch.optim.RAdam (the
+    optimizer of the _big / _huge presets, fruit_nerf_config.py:100-108): the unrectified first steps (rho_t <= 5, no adaptive denominator),
+    the rectified ones, and the gradient clear."""
+    from cropnerf_b200.engine import OptimizerSpec, step_scalars
+
+    g = torch.Generator().manual_seed(6)
+    p0 = torch.randn((10007,), generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = (torch.optim.RAdam if kind == "radam" else torch.optim.Adam)([ref], lr=1e-2, eps=1e-15)
+    spec = OptimizerSpec(lr=1e-2, eps=1e-15, lr_final=None, kind=kind)
+    p = p0.clone().to(dev)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 13):
+        grad = torch.randn((10007,), generator=g) * 10.0 ** float((step % 5) - 2)
+        ref.grad = grad.clone()
+        opt.step()
+        gd = grad.to(dev)
+        ops.adam_step_scalars(p, gd, m, v, step_scalars(spec, 1e-2, step))
+        assert float(gd.abs().max()) == 0.0, "the update clears the gradient"
+        assert_close(p, ref.detach(), 1e-5, f"{kind} step {step}", floor=1e-3)
+
+
 @pytest.mark.parametrize("with_pixels", [False, True])
 def test_generate_rays_and_aabb_clip(dev, with_pixels):
     """Device ray generation + AABB slab test ("next" row f1) against the restated nerfstudio generate_rays / intersect_aabb."""
