@@ -52,7 +52,9 @@ def step_scalars(spec: OptimizerSpec, lr: float, t: int, inv_scale: float = 1.0)
     ``(lr, beta1, beta2, eps, 1 - beta1^t, sqrt(1 - beta2^t), 1 / grad_scale)`` for torch.optim.Adam.  torch.optim.RAdam is the same kernel with
     other scalars: rectified steps (rho_t > 5) multiply lr by the rectification term and divide eps by sqrt(1 - beta2^t) (RAdam adds eps
     BEFORE the bias correction of the denominator); the first steps (rho_t <= 5) have no adaptive denominator, i.e. sqrt(v) / inf + 1."""
-    b1, b2 = spec.betas
+    # the kernels hold the betas as fp32: the bias corrections are taken of THOSE values (as the C entries that compute them do), otherwise
+    # (1 - beta2) of the moment update and 1 - beta2^t of its correction disagree by 1e-5 relative at t = 1
+    b1, b2 = (float(torch.tensor(x, dtype=torch.float32)) for x in spec.betas)
     bc1, bc2 = 1.0 - b1**t, 1.0 - b2**t
     if spec.kind == "adam":
         return (lr, b1, b2, spec.eps, bc1, math.sqrt(bc2), inv_scale)

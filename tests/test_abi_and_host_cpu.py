@@ -276,4 +276,5 @@ def test_step_scalars_reproduce_torch_adam_and_radam():
             p = p - (s[0] / s[4]) * (m / (v.sqrt() / s[5] + s[3]))
             ref.grad = gr.clone()
             opt.step()
-            assert float((p - ref.detach()).abs().max()) < 1e-12, (kind, t)
+            # the scalars carry the betas as the kernels hold them (fp32-rounded): 0.999 -> 0.99900001287, hence not 1e-12
+            assert float((p - ref.detach()).abs().max()) < 2e-6, (kind, t)

@@ -339,24 +339,25 @@ def test_adam_matches_torch(dev):
 def test_explicit_scalar_update_matches_torch_adam_and_radam(dev, kind):
     """The flat-group update kernel with host-computed scalars (engine.step_scalars) against torch.optim.Adam / torch.optim.RAdam (the
     optimizer of the _big / _huge presets, fruit_nerf_config.py:100-108): the unrectified first steps (rho_t <= 5, no adaptive denominator),
-    the rectified ones, and the gradient clear."""
+    the rectified ones, and the gradient clear.  (Flat groups are 16-byte aligned with n % 4 == 0: engine.FlatGroup pads every tensor to 256 bytes.)"""
     from cropnerf_b200.engine import OptimizerSpec, step_scalars
 
     g = torch.Generator().manual_seed(6)
-    p0 = torch.randn((10007,), generator=g)
+    p0 = torch.randn((10008,), generator=g)
     ref = torch.nn.Parameter(p0.clone())
     opt = (torch.optim.RAdam if kind == "radam" else torch.optim.Adam)([ref], lr=1e-2, eps=1e-15)
     spec = OptimizerSpec(lr=1e-2, eps=1e-15, lr_final=None, kind=kind)
     p = p0.clone().to(dev)
     m, v = torch.zeros_like(p), torch.zeros_like(p)
     for step in range(1, 13):
-        grad = torch.randn((10007,), generator=g) * 10.0 ** float((step % 5) - 2)
+        grad = torch.randn((10008,), generator=g) * 10.0 ** float((step % 5) - 2)
         ref.grad = grad.clone()
         opt.step()
         gd = grad.to(dev)
         ops.adam_step_scalars(p, gd, m, v, step_scalars(spec, 1e-2, step))
         assert float(gd.abs().max()) == 0.0, "the update clears the gradient"
-        assert_close(p, ref.detach(), 1e-5, f"{kind} step {step}", floor=1e-3)
+        # unrectified RAdam steps are lr * m_hat, O(1) with these gradients: fp32 rounding of the update is ~1e-7 absolute, so the floor is 0.1
+        assert_close(p, ref.detach(), 1e-5, f"{kind} step {step}", floor=1e-1)
 
 
 @pytest.mark.parametrize("with_pixels", [False, True])
