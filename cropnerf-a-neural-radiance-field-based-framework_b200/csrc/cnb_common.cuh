@@ -188,6 +188,7 @@ __device__ __forceinline__ void cnb_red4(float* table, uint32_t even_row, float 
 // reductions.  The two x-neighbours of a corner pair (hash prime of x is 1) are adjacent table
 // rows whenever floor(x) is even: those go out as ONE 16-byte red.global.add.v4.f32.
 // Requires integer cell coordinates < 65536 (scalings < 65535).
+template <int CAP = 8>
 __device__ __forceinline__ void cnb_scatter_cell(float* d_table, const CnbCell& c, uint32_t mask, uint32_t level_offset, float d0, float d1,
                                                  bool active) {
   const unsigned FULL = 0xffffffffu;
@@ -197,7 +198,7 @@ __device__ __forceinline__ void cnb_scatter_cell(float* d_table, const CnbCell& 
   const uint32_t k0 = active ? (c.fx | (c.fy << 16)) : FULL;
   const uint32_t k1 = active ? (c.fz | ((c.cx - c.fx) << 16) | ((c.cy - c.fy) << 17) | ((c.cz - c.fz) << 18)) : (uint32_t)lane;
   const uint32_t p0 = __shfl_up_sync(FULL, k0, 1), p1 = __shfl_up_sync(FULL, k1, 1);
-  const bool head = (lane & 7) == 0 || k0 != p0 || k1 != p1;
+  const bool head = (lane & (CAP - 1)) == 0 || k0 != p0 || k1 != p1;
   const uint32_t heads = __ballot_sync(FULL, head);
   float w[8];
   cnb_corner_weights(c.ox, c.oy, c.oz, w);
@@ -207,7 +208,7 @@ __device__ __forceinline__ void cnb_scatter_cell(float* d_table, const CnbCell& 
   if (heads != FULL) {  // at least one run of two or more lanes in this warp
     const int start = 31 - __clz(heads & (FULL >> (31 - lane)));
 #pragma unroll
-    for (int off = 1; off < 8; off <<= 1) {
+    for (int off = 1; off < CAP; off <<= 1) {
       const bool take = lane - off >= start;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {

@@ -381,7 +381,15 @@ __global__ void __launch_bounds__(BLOCK, SPLIT ? 5 : 6) k_density_bwd_tc(DfArgs 
         const bool on = active && (d0 != 0.0f || d1 != 0.0f);
         CnbCell c = {};
         if (on) c = cnb_cell(x, y, z, a.scalings[l]);
-        cnb_scatter_cell(a.d_table, c, a.mask, (uint32_t)l * a.T, d0, d1, on);
+        // run-aggregation cap per level (the level loop is unrolled, the branches fold): a scan round is 16 shuffles + adds and this kernel is
+        // issue-bound, so the finer levels, whose runs are short, stop earlier.  Measured on B200 (proposal0 / proposal1 backward stage, ms):
+        // caps {8,8,8,8,8} 0.178 / 0.083, {4,4,4,4,4} 0.169 / 0.087, {8,8,4,4,4} 0.165 / 0.080, {8,8,4,2,2} 0.160 / 0.079, {8,4,2,2,2} 0.164 / 0.082
+#ifndef CNB_PROP_CAP_SPLIT
+#define CNB_PROP_CAP_SPLIT 2
+#endif
+        if (l < CNB_PROP_CAP_SPLIT) cnb_scatter_cell<8>(a.d_table, c, a.mask, (uint32_t)l * a.T, d0, d1, on);
+        else if (l < CNB_PROP_CAP_SPLIT + 1) cnb_scatter_cell<4>(a.d_table, c, a.mask, (uint32_t)l * a.T, d0, d1, on);
+        else cnb_scatter_cell<2>(a.d_table, c, a.mask, (uint32_t)l * a.T, d0, d1, on);
       }
     }
     __syncthreads();
