@@ -20,8 +20,9 @@
 // derivative with full weight -- trunc_exp' of the density and sigmoid' of the colour -- take the FORWARD's fp32 values instead (the
 // 4-float-per-sample stash k_field_mixed_fwd writes in training), as autograd does.
 //
-// dW: eight accumulators (+ eight 8-column bias accumulators: dY^T x ones) stay in TMEM across all batches of the persistent CTA (344 of
-// 512 columns; 2 x 64 more are the two warpgroups' layer accumulators) and are flushed once per CTA through a shared-memory image.
+// dW: eight accumulators stay in TMEM across all batches of the persistent CTA (304 of 512 columns; 2 x 64 more are the two warpgroups' layer
+// accumulators) and are flushed once per CTA through a shared-memory image.  The bias gradients ride along as one extra row / column of each dW
+// GEMM, read from a constant that sits behind (or inside) its operand -- see the buffer order below.
 //
 // Three single-thread issuers: one per warpgroup for the layer MMAs (the only thing the epilogue threads wait for), one for all dW / bias MMAs
 // (every dW accumulator has one issuing thread; its completion is only needed before the next overwrite of D / DS / the X buffers).
@@ -48,16 +49,22 @@ constexpr int NSC = 5;               // scatter warps (FUSED): warp 11 and the f
 constexpr uint32_t FB = 2048;        // bytes of one 8-feature block of an activation matrix (128 rows x 16 B)
 constexpr int NSTEP = 12;
 
-// per-warpgroup activation buffers (byte offsets inside the warpgroup's region).  DS first: as the M = 64 operand of a bias GEMM it is read
-// 8 feature blocks deep (it has 2); the overrun lands in AH and only feeds accumulator rows nobody reads.
+// per-warpgroup activation buffers (byte offsets inside the warpgroup's region).  The ORDER carries the bias gradients: every dW GEMM gets
+// its bias row / column from a block of the NEXT buffer (or a spare column of its own) that holds a constant --
+//   AH | BO      : dWb2^T = [AH | BO ...]^T DS with M = 128: row 64 is BO's column 0, which is set to 1 (the cleared dba slot; its weight columns are 0)
+//   R1 | ONES    : dWr2 / dWs2 = dY^T [R1 | ones] with N = 72: column 64;   dWb1 = dY^T [X0 (4 blocks) | ones written behind it], N = 40: column 32
+//   R2 | AIN     : dWr3^T / dWh^T = [R2 | AIN ...]^T DS with M = 128: row 64 is AIN's column 0 = SH component 0, the constant 0.2820948 (bf16)
+//   AIN itself   : column 16 (the dba slot, = BO's column 0 = 1): dWr1's column 16;   BO: dWs1's column 0
+// (bias gradients as separate dY^T x ones GEMMs were 64 of the dW issuer's 128 MMAs per batch)
 constexpr uint32_t B_DS = 0;                   // 16-feature matrices: d(rgb pre-activation) | [d_sem] | d(base output)
 constexpr uint32_t B_AH = B_DS + 2 * FB;       // base hidden
-constexpr uint32_t B_BO = B_AH + 8 * FB;       // [0 | geo15]
-constexpr uint32_t B_AIN = B_BO + 2 * FB;      // [SH16 | 0, geo15 | emb32]
-constexpr uint32_t B_R1 = B_AIN + 8 * FB;      // rgb hidden 1      | later: semantic hidden 1 | later: encoded features (for dWb1)
-constexpr uint32_t B_R2 = B_R1 + 8 * FB;       // rgb hidden 2      | later: semantic hidden 2
-constexpr uint32_t B_D = B_R2 + 8 * FB;        // encoded features (step 0) | later: every 64-wide dY
-constexpr uint32_t WG_BYTES = B_D + 8 * FB;    // 90 112
+constexpr uint32_t B_BO = B_AH + 8 * FB;       // [1 | geo15]
+constexpr uint32_t B_R1 = B_BO + 2 * FB;       // rgb hidden 1      | later: semantic hidden 1 | later: encoded features + ones (for dWb1)
+constexpr uint32_t B_ONES = B_R1 + 8 * FB;     // one block of ones, written once
+constexpr uint32_t B_R2 = B_ONES + FB;         // rgb hidden 2      | later: semantic hidden 2
+constexpr uint32_t B_AIN = B_R2 + 8 * FB;      // [SH16 | 1, geo15 | emb32]
+constexpr uint32_t B_D = B_AIN + 8 * FB;       // encoded features (step 0) | later: every 64-wide dY
+constexpr uint32_t WG_BYTES = B_D + 8 * FB;    // 92 160
 // weights (bf16, layout above)
 constexpr uint32_t W_B1 = 0;                   // [64][32]
 constexpr uint32_t W_B2 = W_B1 + 64 * 32 * 2;  // [16][64]
@@ -67,16 +74,24 @@ constexpr uint32_t W_R3 = W_R2 + 64 * 64 * 2;  // [16][64]  rows 3..15 zero
 constexpr uint32_t W_S1 = W_R3 + 16 * 64 * 2;  // [64][16]  in = [0 | geo15]
 constexpr uint32_t W_S2 = W_S1 + 64 * 16 * 2;
 constexpr uint32_t W_BYTES = W_S2 + 64 * 64 * 2;   // 34 816
-constexpr uint32_t ONES_BYTES = ROWS * 16;     // B operand [8][128 samples] of ones
 // fp32 constants
 constexpr int C_BB1 = 0, C_BB2 = 64, C_BR1 = 80, C_BR2 = 144, C_BS1 = 208, C_BS2 = 272, C_WH = 336, C_FLOATS = 400;
-constexpr uint32_t O_WG = 0, O_W = NWG * WG_BYTES, O_ONES = O_W + W_BYTES, O_CONST = O_ONES + ONES_BYTES, O_BAR = O_CONST + C_FLOATS * 4,
+constexpr uint32_t O_WG = 0, O_W = NWG * WG_BYTES, O_CONST = O_W + W_BYTES, O_BAR = O_CONST + C_FLOATS * 4,
                    SMEM_TC5 = O_BAR + 128;   // 4 NWG mbarriers + the TMEM base slot
 static_assert(SMEM_TC5 <= 232448, "227 KB of dynamic shared memory per CTA");
 // TMEM columns
 constexpr uint32_t T_CHAIN = 0;   // + 64 * warpgroup
-constexpr uint32_t T_R3 = 128, T_R2 = 144, T_R1 = 208, T_H = 272, T_S2 = 280, T_S1 = 344, T_B2 = 360, T_B1 = 376;
-constexpr uint32_t T_BR3 = 408, T_BR2 = 416, T_BR1 = 424, T_BH = 432, T_BS2 = 440, T_BS1 = 448, T_BB2 = 456, T_BB1 = 464, T_END = 472;
+// dW accumulators (fp32 columns).  M = 64 GEMMs keep row m in lane (m % 16) + 32 (m / 16); the three transposed ones are M = 128 (row r in lane r).
+constexpr uint32_t T_R3 = 128;          // [64 in + bias row 64][16]   M = 128
+constexpr uint32_t T_R2 = T_R3 + 16;    // [64 out][64 in | bias col 64 ...]  72 columns
+constexpr uint32_t T_R1 = T_R2 + 72;    // [64][64], column 16 = bias
+constexpr uint32_t T_H = T_R1 + 64;     // [64 in + bias row 64][8]    M = 128
+constexpr uint32_t T_S2 = T_H + 8;      // 72 columns
+constexpr uint32_t T_S1 = T_S2 + 72;    // [64][16], column 0 = bias
+constexpr uint32_t T_B2 = T_S1 + 16;    // [64 in + bias row 64][16]   M = 128
+constexpr uint32_t T_B1 = T_B2 + 16;    // [64][32 | bias col 32 ...]  40 columns
+constexpr uint32_t T_END = T_B1 + 40;   // 432
+static_assert(T_END <= 512, "TMEM columns");
 
 // gradient image: every weight / bias gradient in its global element order (one image per CTA, reduced by k_tc5_reduce)
 constexpr int I_WR3 = 0, I_BR3 = 192, I_WR2 = 196, I_BR2 = I_WR2 + 4096, I_WR1 = I_BR2 + 64, I_BR1 = I_WR1 + 4032, I_WH = I_BR1 + 64, I_BH = I_WH + 64,
@@ -144,10 +159,11 @@ template <int KOUT, int OUT, int NIN>
 __device__ __forceinline__ void mm_dx(uint32_t tm, uint32_t dy_s, uint32_t w_s) {
   mm_loop<KOUT / 16, 2 * FB, 256>(tm, desc_lo(dy_s, FB), desc_hi(128), desc_lo(w_s, 128), desc_hi(OUT * 16), idesc(128, NIN, 0, 1), false);
 }
-// weight gradient: TM[64 features of A][N features of B] (+)= A^T B over the 128 samples
-template <int N>
+// weight gradient: TM[M features of A][N features of B] (+)= A^T B over the 128 samples (M = 64, or 128 for the transposed GEMMs whose
+// bias row lives in the block behind A's 64 features)
+template <int N, int M = 64>
 __device__ __forceinline__ void mm_dw(uint32_t tm, uint32_t a_s, uint32_t b_s, bool first) {
-  mm_loop<ROWS / 16, 256, 256>(tm, desc_lo(a_s, 128), desc_hi(FB), desc_lo(b_s, 128), desc_hi(FB), idesc(64, N, 1, 1), !first);
+  mm_loop<ROWS / 16, 256, 256>(tm, desc_lo(a_s, 128), desc_hi(FB), desc_lo(b_s, 128), desc_hi(FB), idesc(M, N, 1, 1), !first);
 }
 
 template <int NC>
@@ -227,9 +243,9 @@ struct WLoad {
     }
   }
 };
-__device__ inline void load_weights_tc5(const MixArgs& a, unsigned char* Wb, float* Cf, unsigned char* ones, long long* tmark) {
+__device__ inline void load_weights_tc5(const MixArgs& a, unsigned char* Wb, float* Cf, long long* tmark) {
   const int in0 = a.in0;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x;
   WLoad<64, 32> b1; WLoad<16, 64> b2, r3; WLoad<64, 64> r1, r2, s2; WLoad<64, 16> s1;
   b1.load([&](int o, int i) { return i < in0 ? __ldg(a.Wb1 + o * in0 + i) : 0.f; });
   b2.load([&](int o, int i) { return __ldg(a.Wb2 + o * 64 + i); });
@@ -242,7 +258,6 @@ __device__ inline void load_weights_tc5(const MixArgs& a, unsigned char* Wb, flo
   if (tid < 64) { c[0] = __ldg(a.bb1 + tid); c[1] = __ldg(a.br1 + tid); c[2] = __ldg(a.br2 + tid); c[3] = __ldg(a.bs1 + tid); c[4] = __ldg(a.bs2 + tid); c[5] = __ldg(a.Wh + tid); }
   if (tid < 16) cb2 = __ldg(a.bb2 + tid);
   if (tmark) tmark[0] = clock64();   // all loads issued
-  for (int e = tid; e < (int)(ONES_BYTES / 4); e += nt) reinterpret_cast<uint32_t*>(ones)[e] = 0x3F803F80u;  // bf16 (1, 1)
   b1.store(Wb + W_B1);
   if (tmark) tmark[1] = clock64();   // first matrix converted and stored: its loads have landed
   b2.store(Wb + W_B2); r3.store(Wb + W_R3); r1.store(Wb + W_R1); r2.store(Wb + W_R2); s2.store(Wb + W_S2); s1.store(Wb + W_S1);
@@ -302,37 +317,21 @@ __device__ __forceinline__ void issue_chain(const ChainOp& o, uint32_t tm) {
 }
 // The weight-gradient MMAs of a step (steps 4-6 and 9-11): off the epilogue's critical path, issued by their own thread.
 __device__ __forceinline__ constexpr bool step_has_dw(int step) { return (step >= 4 && step <= 6) || step >= 9; }
-__device__ __forceinline__ void issue_dw(int step, uint32_t tmem, uint32_t wg_s, uint32_t ones_s, bool first) {
+__device__ __forceinline__ void issue_dw(int step, uint32_t tmem, uint32_t wg_s, bool first) {
   const uint32_t DS = wg_s + B_DS, AH = wg_s + B_AH, BO = wg_s + B_BO, AIN = wg_s + B_AIN, R1 = wg_s + B_R1, R2 = wg_s + B_R2, D = wg_s + B_D;
   switch (step) {
-    case 4:
-      mm_dw<16>(tmem + T_R3, R2, DS, first);        // dWr3^T [in][out]
-      mm_dw<8>(tmem + T_BR3, DS, ones_s, first);
-      break;
-    case 5:
-      mm_dw<64>(tmem + T_R2, D, R1, first);
-      mm_dw<8>(tmem + T_BR2, D, ones_s, first);
-      break;
-    case 6:
-      mm_dw<64>(tmem + T_R1, D, AIN, first);
-      mm_dw<8>(tmem + T_BR1, D, ones_s, first);
-      break;
+    case 4: mm_dw<16, 128>(tmem + T_R3, R2, DS, first); break;       // dWr3^T [in | AIN col 0][out]
+    case 5: mm_dw<72>(tmem + T_R2, D, R1, first); break;             // [R1 | ones]
+    case 6: mm_dw<64>(tmem + T_R1, D, AIN, first); break;            // AIN column 16 = 1
     case 9:
-      mm_dw<8>(tmem + T_H, R2, DS, first);          // dWh^T [in][1]
-      mm_dw<8>(tmem + T_BH, DS, ones_s, first);
-      mm_dw<64>(tmem + T_S2, D, R1, first);
-      mm_dw<8>(tmem + T_BS2, D, ones_s, first);
+      mm_dw<8, 128>(tmem + T_H, R2, DS, first);                      // dWh^T [in | AIN col 0][1]
+      mm_dw<72>(tmem + T_S2, D, R1, first);
       break;
     case 10:
-      mm_dw<16>(tmem + T_S1, D, BO, first);
-      mm_dw<8>(tmem + T_BS1, D, ones_s, first);
-      mm_dw<16>(tmem + T_B2, AH, DS, first);        // dWb2^T [in][out]
-      mm_dw<8>(tmem + T_BB2, DS, ones_s, first);
+      mm_dw<16>(tmem + T_S1, D, BO, first);                          // BO column 0 = 1
+      mm_dw<16, 128>(tmem + T_B2, AH, DS, first);                    // dWb2^T [in | BO col 0][out]
       break;
-    default:
-      mm_dw<32>(tmem + T_B1, D, R1, first);
-      mm_dw<8>(tmem + T_BB1, D, ones_s, first);
-      break;
+    default: mm_dw<40>(tmem + T_B1, D, R1, first); break;            // [X0 | ones]
   }
 }
 
@@ -380,14 +379,15 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
   const MixArgs& a = b.m;
   const long long t_start = b.dbg ? clock64() : 0;
   unsigned char* Wb = smem + O_W;
-  unsigned char* ones = smem + O_ONES;
   float* Cf = reinterpret_cast<float*>(smem + O_CONST);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + O_BAR);   // ready[NWG], dwready[NWG] (128 arrivals), done[NWG], dwdone[NWG] (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * NWG);
   uint32_t* rows_done = tmem_slot + 2;   // FUSED: [NWG] rows whose d(encoded features) are in global memory
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long tmark[2] = {0, 0};
-  load_weights_tc5(a, Wb, Cf, ones, b.dbg ? tmark : nullptr);
+  load_weights_tc5(a, Wb, Cf, b.dbg ? tmark : nullptr);
+  for (int e = threadIdx.x; e < (int)(NWG * FB / 4); e += KTHREADS)   // the ones block of each warpgroup, bf16 (1, 1)
+    reinterpret_cast<uint32_t*>(smem + O_WG + (uint32_t)(e / (FB / 4)) * WG_BYTES + B_ONES)[e % (FB / 4)] = 0x3F803F80u;
   const long long t_w = b.dbg ? clock64() : 0;
   if (threadIdx.x == 0) {
     for (int w = 0; w < NWG; ++w) {
@@ -455,9 +455,9 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
             ph[w] ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;");
             if (elect_one()) {
-              uint32_t wg_s = smem_s + O_WG + (uint32_t)w * WG_BYTES, ones_s = smem_s + O_ONES;
-              asm volatile("" : "+r"(wg_s), "+r"(ones_s));
-              issue_dw(step, tmem, wg_s, ones_s, j0 == 0 && w == 0);
+              uint32_t wg_s = smem_s + O_WG + (uint32_t)w * WG_BYTES;
+              asm volatile("" : "+r"(wg_s));
+              issue_dw(step, tmem, wg_s, j0 == 0 && w == 0);
               asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"l"((uint64_t)(bars_s + 8 * (3 * NWG + w))) : "memory");
             }
             __syncwarp();
@@ -610,7 +610,8 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
         tm_load<16>(trow, v);
         uint32_t w[8];
         bias_act_pack<16, false>(v, Cf + C_BB2, w);
-        w[0] &= 0xFFFF0000u;   // column 0 is the density pre-activation: its slot in every downstream input is zero
+        w[0] = (w[0] & 0xFFFF0000u) | 0x3F80u;   // column 0 is the density pre-activation: its slot in every downstream input has zero WEIGHTS, and
+                                               // carries the constant 1 whose dW column / row is the bias gradient of the layers that read BO / AIN
         row_store<2>(base + B_BO, r, w);
 #pragma unroll
         for (int c = 0; c < 8; ++c) ain[8 + c] = w[c];
@@ -751,6 +752,7 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
         wait_dw();   // step 10 (dWs1, dWb2: D, BO, AH, DS)
         row_store<8>(base + B_D, r, w);
         row_store<4>(base + B_R1, r, x0w);
+        *reinterpret_cast<uint4*>(base + B_R1 + 4 * FB + r * 16) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);   // dWb1's bias column
         ready(true);
       }
       // ---- 12: d(encoded features), level-major [L][N][2] -------------------------------------------------------------------------------------
@@ -779,14 +781,17 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
   if (b.dbg && blockIdx.x == 0 && threadIdx.x == 0) b.dbg[50] = clock64() - t_start;
   const int in0 = a.in0;
   float* img = reinterpret_cast<float*>(smem + O_WG);   // gradient image, every tensor in its global element order
-  // M = 64 accumulators keep row m in TMEM lane (m % 16) + 32 * (m / 16): lanes 0..15 of the warps with warp % 4 == q hold rows 16 q + lane.
-  // tcgen05.ld is warp-collective (.sync.aligned): all 32 lanes take part, lanes 16..31 discard what they read.  All 12 warps read (the
-  // warp's quarter of the lanes, a third of the accumulators each); column indices are compile-time, so a value costs one shared store.
+  // M = 64 accumulators keep row m in TMEM lane (m % 16) + 32 * (m / 16): lanes 0..15 of the warps with warp % 4 == q hold rows 16 q + lane;
+  // M = 128 accumulators (the transposed GEMMs) keep row r in lane r: warp quarter q holds rows 32 q + lane.  tcgen05.ld is warp-collective
+  // (.sync.aligned): all 32 lanes take part and discard what they do not own.  Twelve warps read (the warp's quarter of the lanes, a third of
+  // the accumulators each); column indices are compile-time, so a value costs one shared store.
   if (nb_cta > 0) {
-    const int q = warp & 3, m = 16 * q + (lane & 15);
+    const int q = warp & 3, m = 16 * q + (lane & 15), r128 = 32 * q + lane;
     const bool own = lane < 16;
     const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16);
-    auto rd = [&](auto ncols_tag, uint32_t col0, auto put) {
+    // the bias row of dWr3^T / dWh^T was accumulated against AIN's column 0 = SH component 0 (bf16): a constant
+    const float inv_sh0 = 1.0f / __bfloat162float(__float2bfloat16_rn(0.28209479177387814f));
+    auto rd = [&](auto ncols_tag, uint32_t col0, bool mine, auto put) {
       constexpr int NC = decltype(ncols_tag)::value;
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 8) {
@@ -795,7 +800,7 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
                      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                      : "r"(taddr + col0 + c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (own) {
+        if (mine) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) put(c0 + e, __uint_as_float(v[e]));
         }
@@ -803,27 +808,20 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
       }
     };
     using C8 = std::integral_constant<int, 8>; using C16 = std::integral_constant<int, 16>;
-    using C32 = std::integral_constant<int, 32>; using C64 = std::integral_constant<int, 64>;
+    using C40 = std::integral_constant<int, 40>; using C64 = std::integral_constant<int, 64>; using C72 = std::integral_constant<int, 72>;
     const int grp = warp >> 2;
+    const bool t_own = r128 <= 64;   // transposed accumulators: rows 0..63 = the layer's inputs, row 64 = the bias
     if (grp == 0) {
-      rd(C64{}, T_R2, [&](int k, float v) { img[I_WR2 + m * 64 + k] = v; });
-      rd(C16{}, T_R3, [&](int k, float v) { if (k < 3) img[I_WR3 + k * 64 + m] = v; });            // dWr3^T: row = input
-      rd(C8{}, T_H, [&](int k, float v) { if (k == 0) img[I_WH + m] = v; });                        // dWh^T
-      rd(C32{}, T_B1, [&](int k, float v) { if (k < in0) img[I_WB1 + m * in0 + k] = v; });
+      rd(C72{}, T_R2, own, [&](int k, float v) { if (k < 64) img[I_WR2 + m * 64 + k] = v; else if (k == 64) img[I_BR2 + m] = v; });
+      rd(C16{}, T_R3, t_own, [&](int k, float v) { if (k < 3) { if (r128 < 64) img[I_WR3 + k * 64 + r128] = v; else img[I_BR3 + k] = v * inv_sh0; } });
+      rd(C8{}, T_H, t_own, [&](int k, float v) { if (k == 0) { if (r128 < 64) img[I_WH + r128] = v; else img[I_BH] = v * inv_sh0; } });
     } else if (grp == 1) {
-      rd(C64{}, T_R1, [&](int k, float v) { if (k != 16) img[I_WR1 + m * 63 + (k < 16 ? k : k - 1)] = v; });
-      rd(C16{}, T_S1, [&](int k, float v) { if (k >= 1) img[I_WS1 + m * 15 + (k - 1)] = v; });
-      rd(C16{}, T_B2, [&](int k, float v) { img[I_WB2 + k * 64 + m] = v; });                        // dWb2^T
-      rd(C8{}, T_BR3, [&](int k, float v) { if (k == 0 && m < 3) img[I_BR3 + m] = v; });
-      rd(C8{}, T_BR2, [&](int k, float v) { if (k == 0) img[I_BR2 + m] = v; });
-      rd(C8{}, T_BR1, [&](int k, float v) { if (k == 0) img[I_BR1 + m] = v; });
-      rd(C8{}, T_BH, [&](int k, float v) { if (k == 0 && m == 0) img[I_BH] = v; });
+      rd(C64{}, T_R1, own, [&](int k, float v) { if (k == 16) img[I_BR1 + m] = v; else img[I_WR1 + m * 63 + (k < 16 ? k : k - 1)] = v; });
+      rd(C16{}, T_S1, own, [&](int k, float v) { if (k == 0) img[I_BS1 + m] = v; else img[I_WS1 + m * 15 + (k - 1)] = v; });
+      rd(C16{}, T_B2, t_own, [&](int k, float v) { if (r128 < 64) img[I_WB2 + k * 64 + r128] = v; else img[I_BB2 + k] = v; });
     } else if (grp == 2) {
-      rd(C64{}, T_S2, [&](int k, float v) { img[I_WS2 + m * 64 + k] = v; });
-      rd(C8{}, T_BS2, [&](int k, float v) { if (k == 0) img[I_BS2 + m] = v; });
-      rd(C8{}, T_BS1, [&](int k, float v) { if (k == 0) img[I_BS1 + m] = v; });
-      rd(C8{}, T_BB2, [&](int k, float v) { if (k == 0 && m < 16) img[I_BB2 + m] = v; });
-      rd(C8{}, T_BB1, [&](int k, float v) { if (k == 0) img[I_BB1 + m] = v; });
+      rd(C72{}, T_S2, own, [&](int k, float v) { if (k < 64) img[I_WS2 + m * 64 + k] = v; else if (k == 64) img[I_BS2 + m] = v; });
+      rd(C40{}, T_B1, own, [&](int k, float v) { if (k < 32) { if (k < in0) img[I_WB1 + m * in0 + k] = v; } else if (k == 32) img[I_BB1 + m] = v; });
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
