@@ -62,8 +62,8 @@ constexpr uint32_t B_BO = B_AH + 8 * FB;       // [1 | geo15]
 constexpr uint32_t B_R1 = B_BO + 2 * FB;       // rgb hidden 1      | later: semantic hidden 1 | later: encoded features + ones (for dWb1)
 constexpr uint32_t B_ONES = B_R1 + 8 * FB;     // one block of ones, written once
 constexpr uint32_t B_R2 = B_ONES + FB;         // rgb hidden 2      | later: semantic hidden 2
-constexpr uint32_t B_AIN = B_R2 + 8 * FB;      // [SH16 | 1, geo15 | emb32]
-constexpr uint32_t B_D = B_AIN + 8 * FB;       // encoded features (step 0) | later: every 64-wide dY
+constexpr uint32_t B_AIN = B_R2 + 8 * FB;      // encoded features (step 0) | [SH16 | 1, geo15 | emb32]
+constexpr uint32_t B_D = B_AIN + 8 * FB;       // every 64-wide dY
 constexpr uint32_t WG_BYTES = B_D + 8 * FB;    // 92 160
 // weights (bf16, layout above)
 constexpr uint32_t W_B1 = 0;                   // [64][32]
@@ -298,7 +298,7 @@ __device__ __forceinline__ ChainOp op_dx(uint32_t dy_s, uint32_t w_s) {
 __device__ __forceinline__ ChainOp prepare_chain(int step, uint32_t wg_s, uint32_t w_s) {
   const uint32_t DS = wg_s + B_DS, AH = wg_s + B_AH, BO = wg_s + B_BO, AIN = wg_s + B_AIN, R1 = wg_s + B_R1, D = wg_s + B_D;
   switch (step) {
-    case 0: return op_fwd<32, 64>(D, w_s + W_B1);
+    case 0: return op_fwd<32, 64>(AIN, w_s + W_B1);   // the encoded features are staged in the (still free) AIN buffer
     case 1: return op_fwd<64, 16>(AH, w_s + W_B2);
     case 2: return op_fwd<64, 64>(AIN, w_s + W_R1);
     case 3: return op_fwd<64, 64>(R1, w_s + W_R2);
@@ -579,8 +579,8 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
         }
       }
       if (dbg_on) { te = clock64(); estep = 0; }
-      // ---- 0: encoded features -> D ------------------------------------------------------------------------------------------------
-      row_store<4>(base + B_D, r, x0w);
+      // ---- 0: encoded features -> AIN's first four blocks (free until step 2; D and R1 may still be read by the previous batch's dWb1 GEMM) ----
+      row_store<4>(base + B_AIN, r, x0w);
       ready();
       load_row(j + NWG, nxt);
       // ---- 1: base hidden -----------------------------------------------------------------------------------------------------------
@@ -625,6 +625,7 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
         tm_load<64>(trow, v);
         uint32_t w[32];
         bias_act_pack<64, true>(v, Cf + C_BR1, w);
+        if (j > wg) wait_dw();   // step 11 of this warpgroup's PREVIOUS batch (dWb1 reads D, R1): waited for here, three layers later, not at its end
         row_store<8>(base + B_R1, r, w);
         ready();
       }
@@ -768,10 +769,10 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_field_bwd_tc5(const __grid_cons
         if (FUSED)   // release at CTA scope: orders this thread's d_x0 stores before the scatter warp's loads
           asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(rows_done + wg)) : "memory");
         asm volatile("tcgen05.fence::before_thread_sync;");
-        wait_dw();   // step 11 (dWb1 reads D, R1): the next batch starts by overwriting D
         if (dbg_on) { b.dbg[48] += clock64() - te; b.dbg[53] = t_fence; b.dbg[54] = t_dbgrmw; }
       }
     }
+    if (wg < nb_cta) wait_dw();   // the last batch's dWb1
   }
 
   // ---- one read-out + flush per CTA ----------------------------------------------------------------------------------------------------
