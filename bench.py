@@ -479,12 +479,12 @@ STAGE_BYTES_PER_RAY = {
 
 
 # DRAM traffic per launch of each stage (dram__bytes_read.sum + dram__bytes_write.sum of its kernels, one `ncu --set full`
-# capture of this same command, third training step: profiles/r2b_top_kernels_ncu_full.csv).  field_bwd = k_field_bwd_tc5 + k_tc5_reduce +
+# capture of this same command, third training step: profiles/r2c_top_kernels_ncu_full.csv).  field_bwd = k_field_bwd_tc5 + k_tc5_reduce +
 # k_hashgrid_bwd<1>.  Far below the algorithmic bytes because the tables live in L2: the forward gathers are bound by the L1TEX data
 # pipe, the backward by the SM's red issue rate.
-NCU_DRAM_SOURCE = "profiles/r2b_top_kernels_ncu_full.csv: ncu --set full --clock-control none, round-2 final code state (field backward on tcgen05)"
+NCU_DRAM_SOURCE = "profiles/r2c_top_kernels_ncu_full.csv: ncu --set full --clock-control none, round-2 final code state (field backward on tcgen05)"
 NCU_DRAM_BYTES_PER_LAUNCH = {
-    "field_bwd": (26.28 + 1.26 + 10.06 + 0.0 + 73.32 + 1.58) * 1e6, "field_fwd": (49.26 + 11.51) * 1e6, "proposal0_bwd": (53.41 + 2.11) * 1e6,
+    "field_bwd": (26.26 + 0.63 + 10.06 + 0.0 + 73.31 + 1.19) * 1e6, "field_fwd": (49.70 + 10.00) * 1e6, "proposal0_bwd": (53.41 + 1.78) * 1e6,
     "proposal1_bwd": (4.79 + 0.01) * 1e6, "proposal0_fwd": (7.19 + 1.47) * 1e6, "proposal1_fwd": 5.16e6,
 }
 
