@@ -42,8 +42,9 @@ namespace {
 constexpr int ROWS = 128;            // samples per batch = UMMA M = threads of one epilogue warpgroup
 constexpr int NWG = 2;               // batches in flight per CTA
 constexpr int EPI = NWG * ROWS;
-// + one more warpgroup whose first warp is the issuer: a 9-warp CTA would cap every thread at 168 registers (three warps on one SM
-// sub-partition); with a full third warpgroup the registers are re-split after launch (setmaxnreg: 4 x 128 at launch = epilogue 200 + 200, issuer / scatter warpgroups 56 + 56)
+// + two more warpgroups: warps 8, 9 = the layer-MMA issuers of the two epilogue warpgroups, warp 10 = the dW issuer, warps 11..15 = scatter
+// warps (FUSED) or idle.  Registers are re-split after launch with setmaxnreg: 4 x 128 at launch = epilogue 200 + 200, the others 56 + 56
+// (the increase blocks until the decreases have released enough: the sum must not exceed what the CTA was launched with).
 constexpr int KTHREADS = EPI + 256;
 constexpr int NSC = 5;               // scatter warps (FUSED): warp 11 and the fourth warpgroup
 constexpr uint32_t FB = 2048;        // bytes of one 8-feature block of an activation matrix (128 rows x 16 B)
