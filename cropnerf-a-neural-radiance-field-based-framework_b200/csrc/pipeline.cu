@@ -330,7 +330,9 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
     if (rc) return rc;
     if (cfg->update_proposals) {
       const cnb_samples sm = make_samples(rays, ws + L.eu[lv], S);
-      if (rays_grad) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 2, cnb_density_field_bwd_rays(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pg_scratch,
+      // every level has its OWN d(features) scratch: the two levels back-propagate on concurrent branches (handing both the first level's
+      // buffer was the "7 % off, unexplained" pose gradient of the two-branch order: a plain race on that scratch)
+      if (rays_grad) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 2, cnb_density_field_bwd_rays(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pg_level[lv],
                                                                                                      d_origins, d_directions, st));
       else if (L.pfeat[lv] >= 0) STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd_kept(&m->proposal[lv], &sm, ws + L.d_dens[lv], ws + L.pfeat[lv], st));
       else STAGE(lv == 0 ? "proposal0_bwd" : "proposal1_bwd", 1, cnb_density_field_bwd(&m->proposal[lv], &sm, ws + L.d_dens[lv], st));
@@ -360,10 +362,7 @@ extern "C" int cnb_train_step(const cnb_model* m, const cnb_rays* rays, const cn
     // are independent: each only needs its own interlevel gradient; the level-1 backward is a short, latency-bound kernel that fills the gaps
     // of the level-0 one); side[1] joins side[0] before the proposal group's tail (loss scaling, metrics, Adam), side[0] joins the caller's stream
     cudaStream_t s0 = fk->side[0], s1 = fk->side[1];
-    // with ray gradients the two proposal levels stay on ONE branch (field chain || proposal chain): run on two branches their pose
-    // gradient came out 7 % off on B200 (deterministically; tests/micro/camopt_debug.py) although they share no buffer we could find,
-    // whereas this order reproduces the serial result to fp32 atomics noise -- measured, not yet explained
-    bool two = lf >= 2 && cfg->update_proposals && !rays_grad && stream_after(s1, stream, fk->fork2);
+    bool two = lf >= 2 && cfg->update_proposals && stream_after(s1, stream, fk->fork2);
     rc = proposal_level(0, s0);
     if (lf >= 2) { const int r1 = proposal_level(1, two ? s1 : s0); if (!rc) rc = r1; }
     bool joined = true;
