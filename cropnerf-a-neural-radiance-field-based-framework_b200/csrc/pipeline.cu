@@ -50,7 +50,7 @@ struct Layout {
   int64_t o_rgb, o_acc, o_sem, o_depth, o_pd[2];
   int64_t g_rgb, g_sem, d_w[MAX_LEVELS_P], d_dens[MAX_LEVELS_P], d_rgb, d_sem;
   int64_t ctx, ctx_floats;
-  int64_t pg_scratch;    // d(features) of one proposal level, for the ray gradients (row a17)
+  int64_t pg_scratch;    // (= pg_level[0]; kept for the workspace-size accounting)
   int64_t pg_level[MAX_LEVELS_P];  // one scratch per proposal level: the levels back-propagate concurrently
   int64_t pfeat[MAX_LEVELS_P];  // (training) encoded features of each proposal level kept by the forward for the backward; -1 = not kept
   int64_t total;
