@@ -20,7 +20,8 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "cropnerf_b200.h")
 
 MAX_LEVELS = 16
 MAX_LAYERS = 4
-MAX_WIDTH = 64
+MAX_WIDTH = 64        # fused (shared-memory resident) MLP operators
+WIDE_MAX_WIDTH = 256  # wider layers run layer by layer in exact fp32 (csrc/mlp_wide.cu)
 
 PREC_FP32, PREC_MIXED = 0, 1
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
@@ -430,8 +431,8 @@ def make_mlp(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], ou
     m.out_activation = out_activation
     m.dims[0] = weights[0].shape[1]
     for i, (w, b) in enumerate(zip(weights, biases)):
-        if w.shape[0] > MAX_WIDTH or w.shape[1] > MAX_WIDTH:
-            raise ValueError(f"MLP layer {i} of shape {tuple(w.shape)} exceeds the compiled maximum width {MAX_WIDTH}")
+        if w.shape[0] > WIDE_MAX_WIDTH or w.shape[1] > WIDE_MAX_WIDTH:
+            raise ValueError(f"MLP layer {i} of shape {tuple(w.shape)} exceeds the compiled maximum width {WIDE_MAX_WIDTH}")
         m.dims[i + 1] = w.shape[0]
         m.W[i] = ptr(w)
         m.b[i] = ptr(b)

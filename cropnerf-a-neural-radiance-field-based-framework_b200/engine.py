@@ -39,6 +39,14 @@ DEFAULT_OPTIMIZERS = {
 }
 
 
+# the optimizers of `fruit_nerf_big` / `fruit_nerf_huge` (fruit_nerf_config.py:100-118,152-170): RAdam, no schedule on the proposal networks
+BIG_PRESET_OPTIMIZERS = {
+    "proposal_networks": OptimizerSpec(lr=1e-2, eps=1e-15, lr_final=None, kind="radam"),
+    "fields": OptimizerSpec(lr=1e-2, eps=1e-15, lr_final=1e-4, max_steps=50000, kind="radam"),
+    "camera_opt": OptimizerSpec(lr=1e-3, eps=1e-15, lr_final=1e-4, max_steps=5000),
+}
+
+
 def exponential_decay_lr(step: int, spec: OptimizerSpec) -> float:
     """nerfstudio ExponentialDecayScheduler (no warm-up): log-linear interpolation lr -> lr_final over max_steps."""
     if spec.lr_final is None:

@@ -18,11 +18,13 @@ from typing import Dict, List, Type
 
 UNAVAILABLE = None
 fruit_nerf_b200_method = None
+fruit_nerf_b200_method_big = None    # fruit_nerf_config.py:66-118
+fruit_nerf_b200_method_huge = None   # fruit_nerf_config.py:120-190
 
 try:
     from nerfstudio.cameras.camera_optimizers import CameraOptimizerConfig  # type: ignore
     from nerfstudio.configs.base_config import ViewerConfig  # type: ignore
-    from nerfstudio.engine.optimizers import AdamOptimizerConfig  # type: ignore
+    from nerfstudio.engine.optimizers import AdamOptimizerConfig, RAdamOptimizerConfig  # type: ignore
     from nerfstudio.engine.schedulers import ExponentialDecaySchedulerConfig  # type: ignore
     from nerfstudio.engine.trainer import TrainerConfig  # type: ignore
     from nerfstudio.models.base_model import Model  # type: ignore
@@ -125,4 +127,48 @@ else:
             vis="viewer",
         ),
         description="FruitNeRF / CropNeRF ray-render path on hand-written sm_100a kernels (cropnerf_b200)",
+    )
+
+    def _ropt(lr_final, max_steps) -> dict:
+        return {"optimizer": RAdamOptimizerConfig(lr=1e-2, eps=1e-15),
+                "scheduler": None if lr_final is None else ExponentialDecaySchedulerConfig(lr_final=lr_final, max_steps=max_steps)}
+
+    # The two larger presets (fruit_nerf_config.py:66-190).  Their FruitField is wider than the tensor-core kernels are compiled for (128-wide
+    # three-layer semantic MLP, geo_feat_dim 30), so they run in exact fp32 (`precision="fp32"`: layers above 64 on csrc/mlp_wide.cu); the
+    # optimizers are the reference's (nerfstudio's RAdam; `engine.BIG_PRESET_OPTIMIZERS` is the same for this package's own Trainer).
+    fruit_nerf_b200_method_big = MethodSpecification(
+        config=TrainerConfig(
+            method_name="fruit_nerf_b200_big", steps_per_eval_batch=500, steps_per_save=2000, max_num_iterations=100000, mixed_precision=False,
+            pipeline=FruitPipelineConfig(
+                datamanager=FruitDataManagerConfig(train_num_images_to_sample_from=200, train_num_times_to_repeat_images=1000,
+                                                   dataparser=CottonNerfDataParserConfig(train_split_fraction=0.99),
+                                                   train_num_rays_per_batch=4096 * 2, eval_num_rays_per_batch=4096),
+                model=FruitNerfB200ModelConfig(eval_num_rays_per_chunk=1 << 15, num_nerf_samples_per_ray=128, num_proposal_samples_per_ray=(512, 256),
+                                               hidden_dim=128, geo_feat_dim=30, hidden_dim_color=128, hidden_dim_semantics=128, num_layers_semantic=3,
+                                               appearance_embed_dim=128, max_res=4096, proposal_weights_anneal_max_num_iters=5000,
+                                               log2_hashmap_size=21, precision="fp32"),
+            ),
+            optimizers={"proposal_networks": _ropt(None, 0), "fields": _ropt(1e-4, 50000), "camera_opt": _opt(1e-3, 1e-4, 5000)},
+            viewer=ViewerConfig(num_rays_per_chunk=1 << 15),
+            vis="viewer",
+        ),
+        description="FruitNeRF-Big on the cropnerf_b200 kernels (exact fp32 mode)",
+    )
+    fruit_nerf_b200_method_huge = MethodSpecification(
+        config=TrainerConfig(
+            method_name="fruit_nerf_b200_huge", steps_per_eval_batch=500, steps_per_save=2000, max_num_iterations=100000, mixed_precision=False,
+            pipeline=FruitPipelineConfig(
+                datamanager=FruitDataManagerConfig(dataparser=CottonNerfDataParserConfig(), train_num_rays_per_batch=4096 * 4, eval_num_rays_per_batch=4096),
+                model=FruitNerfB200ModelConfig(
+                    eval_num_rays_per_chunk=1 << 15, num_nerf_samples_per_ray=64, num_proposal_samples_per_ray=(512, 512),
+                    proposal_net_args_list=[{"hidden_dim": 16, "log2_hashmap_size": 17, "num_levels": 5, "max_res": 512, "use_linear": False},
+                                            {"hidden_dim": 16, "log2_hashmap_size": 17, "num_levels": 7, "max_res": 2048, "use_linear": False}],
+                    hidden_dim=256, hidden_dim_color=256, appearance_embed_dim=32, geo_feat_dim=30, hidden_dim_semantics=128, num_layers_semantic=3,
+                    max_res=8192, proposal_weights_anneal_max_num_iters=5000, log2_hashmap_size=21, precision="fp32"),
+            ),
+            optimizers={"proposal_networks": _ropt(None, 0), "fields": _ropt(1e-4, 50000), "camera_opt": _opt(1e-3, 1e-4, 5000)},
+            viewer=ViewerConfig(num_rays_per_chunk=1 << 15),
+            vis="viewer",
+        ),
+        description="FruitNeRF-Huge on the cropnerf_b200 kernels (exact fp32 mode)",
     )

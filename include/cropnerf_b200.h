@@ -31,7 +31,8 @@ extern "C" {
 #define CNB_VERSION 100
 #define CNB_MAX_LEVELS 16
 #define CNB_MAX_LAYERS 4
-#define CNB_MAX_WIDTH 64
+#define CNB_MAX_WIDTH 64        /* widest layer of the fused (shared-memory resident) MLP operators */
+#define CNB_WIDE_MAX_WIDTH 256  /* wider MLPs (the _big / _huge presets) run layer by layer in exact fp32: csrc/mlp_wide.cu */
 
 typedef struct CUstream_st* cnb_stream_t;
 
@@ -63,7 +64,7 @@ typedef struct cnb_grid {
  * ReLU between layers, out_activation after the last.  W[l] is [dims[l+1], dims[l]] row-major (nn.Linear.weight). */
 typedef struct cnb_mlp {
   int32_t num_layers;                 /* 1..CNB_MAX_LAYERS */
-  int32_t dims[CNB_MAX_LAYERS + 1];   /* in, hidden..., out ; each <= CNB_MAX_WIDTH */
+  int32_t dims[CNB_MAX_LAYERS + 1];   /* in, hidden..., out ; each <= CNB_WIDE_MAX_WIDTH (fused kernels up to CNB_MAX_WIDTH) */
   int32_t out_activation;             /* CNB_ACT_* */
   int32_t _pad;
   const float* W[CNB_MAX_LAYERS];

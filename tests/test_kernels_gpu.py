@@ -72,7 +72,9 @@ def test_hashgrid_empty_and_errors(dev):
         mine.to("cpu")(torch.rand(4, 3))  # no CPU fallback
 
 
-@pytest.mark.parametrize("dims,act", [((32, 64, 16), None), ((15, 64, 64), None), ((64, 1), None), ((63, 64, 64, 3), "sigmoid"), ((10, 16, 1), None)])
+@pytest.mark.parametrize("dims,act", [((32, 64, 16), None), ((15, 64, 64), None), ((64, 1), None), ((63, 64, 64, 3), "sigmoid"), ((10, 16, 1), None),
+                                      # the big / huge presets' layers (above 64 wide: csrc/mlp_wide.cu, layer by layer)
+                                      ((30, 128, 128, 128), None), ((128, 1), None), ((78, 64, 64, 3), "sigmoid"), ((32, 64, 31), None)])
 def test_mlp_forward_backward(dev, dims, act):
     torch.manual_seed(3)
     nl = len(dims) - 1

@@ -27,11 +27,17 @@ def _field_samples(R, S, seed):
     return rays, edges
 
 
+# the FruitField dimensions the reference's other presets forward (fruit_nerf_config.py:86-98 `fruit_nerf_big`, :141-150 `fruit_nerf_huge`):
+# a 128-wide three-layer semantic MLP and geo_feat_dim = 30, i.e. a 78-wide RGB input -- layers above 64 run on csrc/mlp_wide.cu (exact mode)
+BIG_PRESET = dict(geo_feat_dim=30, hidden_dim_semantics=128, num_layers_semantic=3, max_res=4096)
+
+
+@pytest.mark.parametrize("preset", [{}, BIG_PRESET], ids=["base", "big"])
 @pytest.mark.parametrize("contraction", [True, False])
 @pytest.mark.parametrize("training", [True, False])
-def test_field_forward_backward(dev, contraction, training):
+def test_field_forward_backward(dev, contraction, training, preset):
     R, S, num_images = 160, 48, 20
-    cfg = cases.make_config(dict(log2_hashmap_size=14, disable_scene_contraction=not contraction))
+    cfg = cases.make_config(dict(log2_hashmap_size=14, disable_scene_contraction=not contraction, **preset))
     oracle, state = cases.build_oracle(cfg, num_images, seed=0, table_scale=0.5)
     oracle.train(training)
     model = product_model(cfg, state, num_images, dev, training)
@@ -195,6 +201,62 @@ def test_full_size_config_vs_oracle(dev):
         out = model(product_bundle(rays, dev))
     ref_np = {k: v.numpy() for k, v in ref.items() if isinstance(v, torch.Tensor)}
     _check_outputs(out, ref_np, "full-size")
+
+
+@pytest.mark.parametrize("preset", ["big", "huge"])
+@pytest.mark.parametrize("training", [False, True])
+def test_big_preset_model_vs_oracle(dev, training, preset):
+    """The models of the reference's `fruit_nerf_big` / `fruit_nerf_huge` presets (fruit_nerf_config.py:86-98, 141-150): 128 / (512, 256) resp.
+    64 / (512, 512) samples per ray, three-layer 128-wide semantic MLP, geo_feat_dim 30, 5000 anneal iterations, a 7-level proposal grid --
+    through the same fused render / training step in exact fp32 (the wide layers on csrc/mlp_wide.cu), against the oracle: per-ray outputs
+    in eval mode; the five losses and every parameter-gradient norm in training.  (Table sizes reduced, as in every small case.)"""
+    big = dict(BIG_PRESET, num_nerf_samples_per_ray=128, num_proposal_samples_per_ray=(512, 256), proposal_weights_anneal_max_num_iters=5000,
+               log2_hashmap_size=15)
+    if preset == "huge":   # fruit_nerf_config.py:141-150: 7-level second proposal grid, (512, 512) + 64 samples, max_res 8192
+        big.update(num_nerf_samples_per_ray=64, num_proposal_samples_per_ray=(512, 512), max_res=8192, proposal_net_args_list=[
+            {"hidden_dim": 16, "log2_hashmap_size": 13, "num_levels": 5, "max_res": 512, "use_linear": False},
+            {"hidden_dim": 16, "log2_hashmap_size": 13, "num_levels": 7, "max_res": 2048, "use_linear": False}])
+    cfg = cases.make_config(big)
+    num_images, R = 20, 96
+    oracle, state = cases.build_oracle(cfg, num_images, 0, 0.5)
+    oracle.train(training)
+    rays = synthetic.make_rays(R, seed=4, num_cameras=num_images)
+    model = product_model(cfg, state, num_images, dev, training)
+    if not training:
+        with torch.no_grad():
+            ref = oracle(cases.oracle_bundle(rays))
+            out = model(product_bundle(rays, dev))
+        _check_outputs(out, {k: v.numpy() for k, v in ref.items() if isinstance(v, torch.Tensor)}, "big preset")
+        return
+    jit = synthetic.make_jitter(R, 3, seed=2)
+    for mdl in (oracle, model):   # the same uniform draws on both sides (initial sampler + two PDF levels)
+        feed = synthetic.JitterFeed(jit)
+        mdl.proposal_sampler.initial_sampler.rand_fn = feed
+        mdl.proposal_sampler.pdf_sampler.rand_fn = feed
+    oracle.set_anneal(2500)   # mid-anneal of the preset's 5000 iterations
+    for cb in model.get_training_callbacks():
+        if "BEFORE_TRAIN_ITERATION" in cb.where_to_run:
+            cb.func(2500)
+    targets = synthetic.make_targets(R, seed=3)
+    ref = oracle(cases.oracle_bundle(rays))
+    loss_ref = oracle.get_loss_dict(ref, targets)
+    sum(loss_ref.values()).backward()
+    out = model(product_bundle(rays, dev))
+    loss = model.get_loss_dict(out, {k: v.to(dev) for k, v in targets.items()})
+    for k, v in loss.items():
+        r = float(loss_ref[k])
+        assert abs(float(v) - r) <= 5e-4 * abs(r) + 1e-8, f"{k}: {float(v)} vs {r}"
+    sum(loss.values()).backward()
+    ref_params = dict(oracle.named_parameters())
+    checked = 0
+    for name, p in model.named_parameters():
+        gr = ref_params[name].grad if name in ref_params else None
+        if gr is None or p.grad is None:
+            continue
+        gn, rn = p.grad.double().norm().item(), gr.double().norm().item()
+        assert abs(gn - rn) <= 2e-2 * rn + 1e-12, f"grad norm {name}: {gn} vs {rn}"
+        checked += 1
+    assert checked >= 20
 
 
 def test_export_mode_and_density_projection(dev):

@@ -130,9 +130,13 @@ def test_adam_zero_matches_torch_adam(dev):
     assert_close(p, ref.detach(), 1e-5, "adam params")
 
 
-def test_cuda_graph_step_equals_eager(dev):
-    """The captured-graph training step replays exactly the kernels of the eager one-call step."""
+@pytest.mark.parametrize("optimizer", ["adam", "radam"])
+def test_cuda_graph_step_equals_eager(dev, optimizer):
+    """The captured-graph training step replays exactly the kernels of the eager one-call step.  radam: the optimizer of the big / huge presets
+    (engine.BIG_PRESET_OPTIMIZERS), whose update is the same kernel with other per-step scalars -- in-graph from the device scalar slots, eagerly
+    through cnb_adam_step_zero_dev."""
     R = 256
+    optimizers = engine.BIG_PRESET_OPTIMIZERS if optimizer == "radam" else None
     a, b = _models(dev, True, "mixed", small=False)
     rays = synthetic.make_rays(R, seed=6, num_cameras=20)
     targets = {k: v.to(dev) for k, v in synthetic.make_targets(R, seed=3).items()}
@@ -142,7 +146,7 @@ def test_cuda_graph_step_equals_eager(dev):
         feed = synthetic.JitterFeed(jit)
         model.proposal_sampler.initial_sampler.rand_fn = feed
         model.proposal_sampler.pdf_sampler.rand_fn = feed
-        tr = engine.Trainer(model, cuda_graph=graph, force_proposal_update=True)
+        tr = engine.Trainer(model, optimizers=optimizers, cuda_graph=graph, force_proposal_update=True)
         for step in (3000, 3001, 3002):
             feed.reset()
             st = tr.train_iteration(step, product_bundle(rays, dev), targets)
