@@ -686,6 +686,10 @@ bool cnb_mlp_is_wide(const cnb_mlp* m);
 int cnb_mlp_wide_fwd(const cnb_mlp* m, const float* x, int64_t x_stride, int64_t n, float* y, float* hidden, cudaStream_t stream);
 int cnb_mlp_wide_bwd(const cnb_mlp* m, const float* x, int64_t x_stride, const float* hidden, const float* y, const float* dy, int64_t n, float* dx,
                      int64_t dx_stride, cudaStream_t stream);
+bool cnb_mlp_is_lin1(const cnb_mlp* m);   // Linear(in -> 1): the semantic head
+int cnb_mlp_lin1_fwd(const cnb_mlp* m, const float* x, int64_t x_stride, int64_t n, float* y, cudaStream_t stream);
+int cnb_mlp_lin1_bwd(const cnb_mlp* m, const float* x, int64_t x_stride, const float* y, const float* dy, int64_t n, float* dx, int64_t dx_stride,
+                     cudaStream_t stream);
 
 extern "C" int64_t cnb_mlp_hidden_floats(const cnb_mlp* m) {
   if (!m) return 0;
@@ -695,10 +699,11 @@ extern "C" int64_t cnb_mlp_hidden_floats(const cnb_mlp* m) {
 }
 
 extern "C" int cnb_mlp_fwd(const cnb_mlp* m, const float* x, int64_t x_stride, int64_t n, float* y, float* hidden, cnb_stream_t stream) {
-  if (cnb_mlp_is_wide(m)) {
+  if (cnb_mlp_is_lin1(m) || cnb_mlp_is_wide(m)) {
     CNB_REQUIRE(n >= 0 && (n == 0 || (x && y)), "mlp_fwd: null x/y");
     CNB_REQUIRE(x_stride >= m->dims[0], "mlp_fwd: x_stride %lld < in dim %d", (long long)x_stride, m->dims[0]);
-    return n == 0 ? CNB_OK : cnb_mlp_wide_fwd(m, x, x_stride, n, y, hidden, stream);
+    if (n == 0) return CNB_OK;
+    return cnb_mlp_is_lin1(m) ? cnb_mlp_lin1_fwd(m, x, x_stride, n, y, stream) : cnb_mlp_wide_fwd(m, x, x_stride, n, y, hidden, stream);
   }
   MlpArgs a;
   int rc = make_args(m, a);
@@ -735,6 +740,12 @@ extern "C" int cnb_mlp_fwd(const cnb_mlp* m, const float* x, int64_t x_stride, i
 
 extern "C" int cnb_mlp_bwd(const cnb_mlp* m, const float* x, int64_t x_stride, const float* hidden, const float* y, const float* dy, int64_t n,
                            float* dx, int64_t dx_stride, cnb_stream_t stream) {
+  if (cnb_mlp_is_lin1(m)) {
+    CNB_REQUIRE(n >= 0 && (n == 0 || (x && dy)), "mlp_bwd: null x/dy");
+    CNB_REQUIRE(m->out_activation == CNB_ACT_NONE || y != nullptr, "mlp_bwd: forward output required for the output activation");
+    CNB_REQUIRE(dx == nullptr || dx_stride >= m->dims[0], "mlp_bwd: dx_stride too small");
+    return n == 0 ? CNB_OK : cnb_mlp_lin1_bwd(m, x, x_stride, y, dy, n, dx, dx_stride, stream);
+  }
   if (cnb_mlp_is_wide(m)) {
     CNB_REQUIRE(n >= 0 && (n == 0 || (x && dy)), "mlp_bwd: null x/dy");
     CNB_REQUIRE(m->num_layers == 1 || hidden != nullptr, "mlp_bwd: hidden activations required for %d layers", m->num_layers);
