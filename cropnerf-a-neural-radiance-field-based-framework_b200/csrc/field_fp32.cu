@@ -58,29 +58,38 @@ __global__ void __launch_bounds__(256) k_positions(cnb_samples sm, cnb_warp w, f
 }
 
 // density = trunc_exp(bo[:,0]) * selector ; rgb_in = [SH16 | geo | appearance] (fruit_field.py:186-193,244-279)
+// One WARP per sample, lanes = columns of the row: the 256-byte rows go out as coalesced stores (a thread per sample wrote 32 rows per store
+// instruction, 256 bytes apart: 87 us for 196 608 samples, several times its HBM time).  Every lane evaluates the 16 SH components of the
+// ray (40 flops) and keeps the one of its column.
 __global__ void __launch_bounds__(256) k_mid_fwd(cnb_samples sm, const float* __restrict__ bo, int ob, const float* __restrict__ sel,
                                                  const float* __restrict__ embedding, const float* __restrict__ mean_embedding, int app_mode,
                                                  int app_dim, int rip, float* __restrict__ density, float* __restrict__ geo_out,
                                                  float* __restrict__ rin) {
   const int S = sm.samples_per_ray;
   const int64_t total = sm.num_rays * S;
-  const int geo = ob - 1;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  const int geo = ob - 1, lane = threadIdx.x & 31;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); i < total; i += wstride) {
     const int64_t r = cnb_ray_of(i, S);
     const float* b = bo + i * ob;
-    density[i] = sel[i] != 0.0f ? expf(b[0]) : 0.0f;
-    if (geo_out) for (int k = 0; k < ob; ++k) geo_out[i * ob + k] = b[k];
+    if (lane == 0) density[i] = sel[i] != 0.0f ? expf(b[0]) : 0.0f;
+    if (geo_out) for (int k = lane; k < ob; k += 32) geo_out[i * ob + k] = b[k];
     float c[16];
     cnb_sh16(__ldg(sm.directions + 3 * r), __ldg(sm.directions + 3 * r + 1), __ldg(sm.directions + 3 * r + 2), c);
-    float* o = rin + i * rip;
+    float mine = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) o[k] = c[k];
-    for (int k = 0; k < geo; ++k) o[16 + k] = b[1 + k];
+    for (int q = 0; q < 16; ++q) mine = (lane == q) ? c[q] : mine;
     const float* e = nullptr;
     if (app_mode == CNB_APP_PER_CAMERA) e = embedding + (int64_t)__ldg(sm.camera_indices + r) * app_dim;
     else if (app_mode == CNB_APP_MEAN) e = mean_embedding;
-    for (int k = 0; k < app_dim; ++k) o[16 + geo + k] = e ? __ldg(e + k) : 0.0f;
-    for (int k = 16 + geo + app_dim; k < rip; ++k) o[k] = 0.0f;
+    float* o = rin + i * rip;
+    for (int k = lane; k < rip; k += 32) {
+      float v = 0.0f;
+      if (k < 16) v = mine;
+      else if (k < 16 + geo) v = b[1 + (k - 16)];
+      else if (k < 16 + geo + app_dim) v = e ? __ldg(e + (k - 16 - geo)) : 0.0f;
+      o[k] = v;
+    }
   }
 }
 
