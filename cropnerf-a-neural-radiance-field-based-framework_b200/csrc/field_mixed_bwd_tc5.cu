@@ -117,9 +117,6 @@ struct BwdArgs {
 };
 
 // ---- tcgen05 plumbing ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
-}
 // bf16 x bf16 -> f32 ; major: 0 = K, 1 = MN
 __device__ __forceinline__ constexpr uint32_t idesc(int M, int N, int amajor, int bmajor) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)amajor << 15) | ((uint32_t)bmajor << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
