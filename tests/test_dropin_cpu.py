@@ -40,5 +40,7 @@ def test_method_plugin_module_is_import_guarded():
     from cropnerf_b200 import method_config
 
     assert (method_config.fruit_nerf_b200_method is None) == (method_config.UNAVAILABLE is not None)
+    for preset in ("fruit_nerf_b200_method_big", "fruit_nerf_b200_method_huge"):   # the two larger presets (exact fp32 mode)
+        assert (getattr(method_config, preset) is None) == (method_config.UNAVAILABLE is not None)
     if method_config.fruit_nerf_b200_method is None:
         assert "nerfstudio" in method_config.UNAVAILABLE or "fruit_nerf" in method_config.UNAVAILABLE
