@@ -44,3 +44,22 @@ def test_method_plugin_module_is_import_guarded():
         assert (getattr(method_config, preset) is None) == (method_config.UNAVAILABLE is not None)
     if method_config.fruit_nerf_b200_method is None:
         assert "nerfstudio" in method_config.UNAVAILABLE or "fruit_nerf" in method_config.UNAVAILABLE
+
+
+def test_big_preset_modules_have_the_reference_shapes():
+    """The FruitField dimensions of `fruit_nerf_big` / `_huge` (fruit_nerf_config.py:86-98,141-150) build the same modules in the product as the
+    reference's own fruit_field.py does through the oracle shims: a strict state-dict load both ways (host side only; the kernels' side is
+    tests/test_model_gpu.py::test_big_preset_model_vs_oracle)."""
+    from cropnerf_b200.fruit_nerf import FruitModel, FruitNerfModelConfig
+    from oracle import cases
+
+    cfg = cases.make_config(dict(log2_hashmap_size=12, geo_feat_dim=30, hidden_dim_semantics=128, num_layers_semantic=3, max_res=4096,
+                                 num_nerf_samples_per_ray=128, num_proposal_samples_per_ray=(512, 256)))
+    oracle, state = cases.build_oracle(cfg, 7, seed=0, table_scale=0.5)
+    kw = {k: getattr(cfg, k) for k in cfg.__dataclass_fields__ if k in FruitNerfModelConfig.__dataclass_fields__}
+    model = FruitModel(FruitNerfModelConfig(**kw), num_train_data=7)
+    model.load_state_dict(state, strict=True)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert shapes["field.mlp_semantics.layers.0.weight"] == (128, 30) and shapes["field.mlp_semantics.layers.2.weight"] == (64, 128)
+    assert shapes["field.mlp_head.layers.0.weight"] == (64, 78) and shapes["field.mlp_base_mlp.layers.1.weight"] == (31, 64)
+    oracle.load_state_dict(model.state_dict(), strict=True)
